@@ -1,0 +1,226 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+ctypes face over oracle/oracle_api.h.  Loads either checker:
+
+  kind="reference"  oracle/_ref/libtesseract_ref.so    (the reference's own sources, prebuilt)
+  kind="port"       oracle/_build/libtesseract_port.so (the CPU restatement, oracle/port.cc)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PATHS = {
+    "reference": os.path.join(HERE, "_ref", "libtesseract_ref.so"),
+    "port": os.path.join(HERE, "_build", "libtesseract_port.so"),
+}
+INF_DET_BEAM = 65535
+U64_MAX = (1 << 64) - 1
+
+
+class OrcConfig(C.Structure):
+    _fields_ = [
+        ("det_beam", C.c_int32),
+        ("beam_climbing", C.c_int32),
+        ("no_revisit_dets", C.c_int32),
+        ("merge_errors", C.c_int32),
+        ("pqlimit", C.c_uint64),
+        ("det_penalty", C.c_double),
+        ("num_det_orders", C.c_uint64),
+        ("det_orders", C.POINTER(C.c_uint64)),
+        ("num_threads", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+def build(kind: str) -> None:
+    """Compile a checker with oracle/Makefile ("ref" needs /root/reference)."""
+    target = "ref" if kind == "reference" else "port"
+    subprocess.run(["make", "-s", "-C", HERE, target], check=True)
+
+
+def available(kind: str) -> bool:
+    return os.path.exists(PATHS[kind])
+
+
+_libs: dict[str, C.CDLL] = {}
+
+
+def _lib(kind: str) -> C.CDLL:
+    if kind in _libs:
+        return _libs[kind]
+    lib = C.CDLL(PATHS[kind])
+    u64p, f64p, u8p, i32p = (C.POINTER(t) for t in (C.c_uint64, C.c_double, C.c_uint8, C.c_int32))
+    lib.orc_last_error.restype = C.c_char_p
+    lib.orc_kind.restype = C.c_char_p
+    lib.orc_create.restype = C.c_void_p
+    lib.orc_create.argtypes = [C.c_char_p, C.POINTER(OrcConfig)]
+    lib.orc_destroy.argtypes = [C.c_void_p]
+    for name in ("orc_num_detectors", "orc_num_observables", "orc_num_errors", "orc_num_dem_errors",
+                 "orc_last_batch_nnz"):
+        getattr(lib, name).restype = C.c_uint64
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.orc_error_costs.argtypes = [C.c_void_p, f64p]
+    lib.orc_maps.argtypes = [C.c_void_p, u64p, u64p]
+    lib.orc_csr.restype = C.c_int64
+    lib.orc_csr.argtypes = [C.c_void_p, C.c_int, u64p, i32p]
+    lib.orc_decode.argtypes = [C.c_void_p, u64p, C.c_uint64, C.c_int64, C.c_uint64, u64p, C.c_uint64,
+                               u64p, f64p, i32p]
+    lib.orc_decode_batch_b8.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_uint64, u8p, f64p, u8p, f64p, f64p]
+    lib.orc_last_batch_errors.argtypes = [C.c_void_p, u64p, u64p]
+    lib.orc_cost_from_errors.argtypes = [C.c_void_p, u64p, C.c_uint64, f64p]
+    lib.orc_flipped_observables.argtypes = [C.c_void_p, u64p, C.c_uint64, u8p]
+    lib.orc_build_det_orders.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64, u64p]
+    lib.orc_merge_weights.restype = C.c_double
+    lib.orc_merge_weights.argtypes = [C.c_double, C.c_double]
+    lib.orc_counters.argtypes = [C.c_void_p, u64p, C.c_int]
+    _libs[kind] = lib
+    return lib
+
+
+def _p(arr, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def build_det_orders(dem_text: str, num_det_orders: int, method: int = 1, seed: int = 0,
+                     kind: str = "reference") -> np.ndarray:
+    """utils.cc:192-205; method 0=DetBFS 1=DetIndex 2=DetCoordinate."""
+    lib = _lib(kind)
+    tmp = OracleDecoder(dem_text, kind=kind)
+    D = tmp.num_detectors
+    tmp.close()
+    out = np.zeros((num_det_orders, D), dtype=np.uint64)
+    if lib.orc_build_det_orders(dem_text.encode(), num_det_orders, method, seed, _p(out, C.c_uint64)) != 0:
+        raise OracleError(lib.orc_last_error().decode())
+    return out
+
+
+def merge_weights(a: float, b: float, kind: str = "reference") -> float:
+    return _lib(kind).orc_merge_weights(a, b)
+
+
+class OracleDecoder:
+    """A pool of CPU decoders (one per worker thread) behind oracle_api.h."""
+
+    def __init__(self, dem_text: str, *, det_beam: int = 5, beam_climbing: bool = False,
+                 no_revisit_dets: bool = True, merge_errors: bool = True, pqlimit: int = 200000,
+                 det_penalty: float = 0.0, det_orders=None, num_threads: int = 1, kind: str = "reference"):
+        self.lib = _lib(kind)
+        self.kind = kind
+        cfg = OrcConfig()
+        cfg.det_beam = det_beam
+        cfg.beam_climbing = int(beam_climbing)
+        cfg.no_revisit_dets = int(no_revisit_dets)
+        cfg.merge_errors = int(merge_errors)
+        cfg.pqlimit = U64_MAX if pqlimit is None or pqlimit >= U64_MAX else int(pqlimit)
+        cfg.det_penalty = det_penalty
+        self._orders = None
+        if det_orders is not None and len(det_orders):
+            self._orders = np.ascontiguousarray(det_orders, dtype=np.uint64)
+            cfg.num_det_orders = self._orders.shape[0]
+            cfg.det_orders = _p(self._orders, C.c_uint64)
+        cfg.num_threads = num_threads
+        self.h = self.lib.orc_create(dem_text.encode(), C.byref(cfg))
+        if not self.h:
+            raise OracleError(self.lib.orc_last_error().decode())
+        self.num_detectors = self.lib.orc_num_detectors(self.h)
+        self.num_observables = self.lib.orc_num_observables(self.h)
+        self.num_errors = self.lib.orc_num_errors(self.h)
+        self.num_dem_errors = self.lib.orc_num_dem_errors(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OracleError(self.lib.orc_last_error().decode())
+
+    # ---- tables -------------------------------------------------------------------------------
+    def error_costs(self) -> np.ndarray:
+        out = np.zeros(self.num_errors, dtype=np.float64)
+        self._check(self.lib.orc_error_costs(self.h, _p(out, C.c_double)))
+        return out
+
+    def maps(self):
+        a = np.zeros(self.num_dem_errors, dtype=np.uint64)
+        b = np.zeros(self.num_errors, dtype=np.uint64)
+        self._check(self.lib.orc_maps(self.h, _p(a, C.c_uint64), _p(b, C.c_uint64)))
+        return a, b
+
+    def csr(self, which: int):
+        rows = self.num_detectors if which == 0 else self.num_errors
+        nnz = self.lib.orc_csr(self.h, which, None, None)
+        if nnz < 0:
+            raise OracleError(self.lib.orc_last_error().decode())
+        off = np.zeros(rows + 1, dtype=np.uint64)
+        idx = np.zeros(max(nnz, 1), dtype=np.int32)
+        self.lib.orc_csr(self.h, which, _p(off, C.c_uint64), _p(idx, C.c_int32))
+        return off, idx[:nnz]
+
+    def rows(self, which: int):
+        off, idx = self.csr(which)
+        return [idx[int(off[r]):int(off[r + 1])].tolist() for r in range(len(off) - 1)]
+
+    # ---- decoding -----------------------------------------------------------------------------
+    def decode_to_errors(self, hits, order: int = -1, beam: int = 0):
+        hits = np.ascontiguousarray(hits, dtype=np.uint64)
+        cap = 4096
+        errs = np.zeros(cap, dtype=np.uint64)
+        n = C.c_uint64()
+        cost = C.c_double()
+        low = C.c_int32()
+        self._check(self.lib.orc_decode(self.h, _p(hits, C.c_uint64), len(hits), order, beam,
+                                        _p(errs, C.c_uint64), cap, C.byref(n), C.byref(cost), C.byref(low)))
+        return errs[: n.value].tolist(), cost.value, bool(low.value)
+
+    def decode_batch_b8(self, dets_b8: np.ndarray):
+        dets_b8 = np.ascontiguousarray(dets_b8, dtype=np.uint8)
+        shots, stride = dets_b8.shape
+        obs = np.zeros((shots, (self.num_observables + 7) // 8), dtype=np.uint8)
+        cost = np.zeros(shots, dtype=np.float64)
+        low = np.zeros(shots, dtype=np.uint8)
+        wall = C.c_double()
+        cpu = C.c_double()
+        self._check(self.lib.orc_decode_batch_b8(self.h, _p(dets_b8, C.c_uint8), stride, shots,
+                                                 _p(obs, C.c_uint8), _p(cost, C.c_double), _p(low, C.c_uint8),
+                                                 C.byref(wall), C.byref(cpu)))
+        nnz = self.lib.orc_last_batch_nnz(self.h)
+        off = np.zeros(shots + 1, dtype=np.uint64)
+        idx = np.zeros(max(nnz, 1), dtype=np.uint64)
+        self._check(self.lib.orc_last_batch_errors(self.h, _p(off, C.c_uint64), _p(idx, C.c_uint64)))
+        return {"obs": obs, "cost": cost, "low_confidence": low, "err_offsets": off, "err_idx": idx[:nnz],
+                "wall_seconds": wall.value, "sum_shot_seconds": cpu.value}
+
+    def cost_from_errors(self, errs) -> float:
+        errs = np.ascontiguousarray(errs, dtype=np.uint64)
+        out = C.c_double()
+        self._check(self.lib.orc_cost_from_errors(self.h, _p(errs, C.c_uint64), len(errs), C.byref(out)))
+        return out.value
+
+    def flipped_observables(self, errs):
+        errs = np.ascontiguousarray(errs, dtype=np.uint64)
+        out = np.zeros((self.num_observables + 7) // 8 or 1, dtype=np.uint8)
+        self._check(self.lib.orc_flipped_observables(self.h, _p(errs, C.c_uint64), len(errs), _p(out, C.c_uint8)))
+        bits = np.unpackbits(out, bitorder="little")[: self.num_observables]
+        return np.nonzero(bits)[0].tolist()
+
+    def counters(self, reset: bool = False):
+        out = np.zeros(8, dtype=np.uint64)
+        self._check(self.lib.orc_counters(self.h, _p(out, C.c_uint64), int(reset)))
+        names = ["Q", "P", "X", "L", "S", "A", "V", "searches"]
+        return dict(zip(names, out.tolist()))
