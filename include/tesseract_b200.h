@@ -1,0 +1,146 @@
+/* tesseract_b200 — C ABI of the B200-native Tesseract decode path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own for this path
+ * (its Python module binds the C++ class directly, src/tesseract.pybind.h); each entry point below
+ * names the reference C++ interface it stands in for, so that a maintainer can rebind
+ * TesseractDecoder's methods onto it (INTEGRATION.md shows the stubs).
+ *
+ * Conventions: plain C, opaque handles, caller-owned buffers, no torch types.  Functions returning
+ * int return TSR_OK (0) or a negative TSR_E_* code; tsr_last_error() then gives the message of the
+ * last failure on the calling thread (texts follow the reference's exception texts where it has
+ * one).  A decoder handle is not re-entrant (like the reference object, tesseract.h:109-131): use
+ * one handle per host thread or serialise calls.  There is NO CPU fallback: every decode entry
+ * point fails with TSR_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef TESSERACT_B200_H
+#define TESSERACT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSR_OK 0
+#define TSR_E_INVALID_ARGUMENT (-1) /* std::invalid_argument in the reference */
+#define TSR_E_RUNTIME (-2)          /* std::runtime_error in the reference */
+#define TSR_E_CUDA (-3)             /* no device / CUDA failure */
+#define TSR_E_DEVICE_MEMORY (-4)    /* a search outgrew every retry tier of the node pool */
+
+#define TSR_INF_DET_BEAM 65535u          /* tesseract.h:33 */
+#define TSR_PQLIMIT_UNBOUNDED UINT64_MAX /* std::numeric_limits<size_t>::max(), tesseract_main.cc:503 */
+#define TSR_NO_ERROR_INDEX UINT64_MAX    /* "removed" in dem_error_to_error, common.cc:228-239 */
+
+typedef struct tsr_decoder tsr_decoder;
+
+/* Mirrors TesseractConfig (tesseract.h:39-58) minus the DEM (passed as text) and the
+ * verbose/visualization switches, which are host-only debugging aids in the reference. */
+typedef struct tsr_config {
+  int32_t det_beam;        /* default 5; TSR_INF_DET_BEAM = unbounded */
+  int32_t beam_climbing;   /* tesseract.cc:307-328 */
+  int32_t no_revisit_dets; /* tesseract.cc:475-476, 563-565 */
+  int32_t merge_errors;    /* tesseract.cc:162-166 */
+  int32_t at_most_two_errors_per_detector; /* README.md:59 only; no reference code — see DESIGN.md */
+  int32_t device;          /* CUDA device ordinal; -1 = current device */
+  uint64_t pqlimit;        /* default 200000; TSR_PQLIMIT_UNBOUNDED */
+  double det_penalty;      /* tesseract.cc:153 */
+  uint64_t num_det_orders; /* 0 = one identity order (tesseract.cc:175-177) */
+  const uint64_t* det_orders; /* [num_det_orders][num_detectors] row-major, position -> detector */
+  /* Device resources; 0 = choose automatically. */
+  uint32_t search_slots;       /* concurrent searches (one warp each) */
+  uint32_t warps_per_block;
+  uint64_t node_pool_bytes;    /* HBM set aside for heaps / chains / visited sets */
+  uint64_t max_batch_shots;    /* shots staged per kernel launch */
+} tsr_config;
+
+/* Fills the reference's C++ defaults (tesseract.h:39-58). */
+void tsr_config_init(tsr_config* cfg);
+
+const char* tsr_last_error(void);
+const char* tsr_version(void);
+
+/* ---- construction: TesseractDecoder::TesseractDecoder(TesseractConfig) (tesseract.cc:156-205) ----
+ * dem_text is what str(stim.DetectorErrorModel) prints (stim_utils.pybind.h:22-26).  Ingestion runs on
+ * the host; the resulting tables are uploaded to `device`.  With TSR_CREATE_HOST_ONLY in `flags` no
+ * CUDA call is made: the handle serves the table getters, cost_from_errors and
+ * get_flipped_observables only, and every decode call fails with TSR_E_CUDA. */
+#define TSR_CREATE_HOST_ONLY 1u
+int tsr_create(const char* dem_text, const tsr_config* cfg, uint32_t flags, tsr_decoder** out);
+void tsr_destroy(tsr_decoder* h);
+
+/* Public fields of TesseractDecoder (tesseract.h:112-130). */
+uint64_t tsr_num_detectors(const tsr_decoder* h);
+uint64_t tsr_num_observables(const tsr_decoder* h);
+uint64_t tsr_num_errors(const tsr_decoder* h);     /* errors.size() */
+uint64_t tsr_num_dem_errors(const tsr_decoder* h); /* dem_error_to_error.size() */
+uint64_t tsr_num_det_orders(const tsr_decoder* h); /* config.det_orders.size() */
+int tsr_error_costs(const tsr_decoder* h, double* out /* [num_errors] */);
+int tsr_maps(const tsr_decoder* h, uint64_t* dem_error_to_error /* [num_dem_errors] or NULL */,
+             uint64_t* error_to_dem_error /* [num_errors] or NULL */);
+/* which: 0 = d2e rows (sorted, tesseract.cc:223-227), 1 = edets, 2 = eneighbors (get_eneighbors()),
+ * 3 = per-error observables.  Either pointer may be NULL.  Returns the index count or a negative code. */
+int64_t tsr_csr(const tsr_decoder* h, int which, uint64_t* offsets, int32_t* idx);
+/* The compiled DEM (config.dem after merge / zero-strip) as text; caller frees with tsr_free. */
+int tsr_compiled_dem_text(const tsr_decoder* h, char** out);
+void tsr_free(void* p);
+
+/* ---- decode --------------------------------------------------------------------------------------
+ * tsr_decode_batch_b8: the batched hot path behind decode_shots (tesseract.cc:665-671),
+ * decode_batch (tesseract.pybind.h:450-511) and decode_shots_bit_packed
+ * (tesseract_sinter_compat.pybind.h:45-97).  dets: [shots][stride] bytes, bit k of byte j = detector
+ * 8j+k.  All outputs are optional (NULL to skip): obs_out [shots][ceil(O/8)] same bit order;
+ * cost_out [shots] = cost_from_errors(predicted_errors_buffer); low_conf_out [shots].  The per-shot
+ * error lists (predicted_errors_buffer: original flattened-DEM indices, root-to-leaf order) stay in
+ * the handle until the next decode and are read with tsr_last_batch_errors.
+ * The *_device variant takes and fills device pointers on the handle's device (inputs already in
+ * HBM) and enqueues on tsr_stream(h) without a final host sync of the outputs' consumers. */
+int tsr_decode_batch_b8(tsr_decoder* h, const uint8_t* dets, uint64_t stride, uint64_t shots,
+                        uint8_t* obs_out, double* cost_out, uint8_t* low_conf_out);
+int tsr_decode_batch_b8_device(tsr_decoder* h, const uint8_t* d_dets, uint64_t stride, uint64_t shots,
+                               uint8_t* d_obs_out, double* d_cost_out, uint8_t* d_low_conf_out);
+uint64_t tsr_last_batch_nnz(const tsr_decoder* h);
+int tsr_last_batch_errors(const tsr_decoder* h, uint64_t* offsets /* [shots+1] */, uint64_t* idx /* [nnz] */);
+
+/* tsr_decode: one shot from a sparse list of fired detectors.
+ * order < 0: decode_to_errors(detections) — the det-order ensemble / beam climbing (tesseract.cc:295-347).
+ * order >= 0: decode_to_errors(detections, order, beam) (tesseract.cc:371-378).
+ * errs_out receives predicted_errors_buffer (fails with TSR_E_INVALID_ARGUMENT if errs_cap is too
+ * small; *n_errs is set either way).  A detector id >= num_detectors fails with TSR_E_RUNTIME and the
+ * reference's message (tesseract.cc:400-404). */
+int tsr_decode(tsr_decoder* h, const uint64_t* detections, uint64_t n, int64_t order, uint64_t beam,
+               uint64_t* errs_out, uint64_t errs_cap, uint64_t* n_errs, double* cost, int32_t* low_confidence);
+
+/* cost_from_errors (tesseract.cc:618-628) and get_flipped_observables (tesseract.cc:630-658) over
+ * original flattened-DEM error indices; both fail with TSR_E_INVALID_ARGUMENT ("error index does not
+ * map to a retained decoder error") on removed errors.  obs_bits_out: ceil(O/8) bytes. */
+int tsr_cost_from_errors(const tsr_decoder* h, const uint64_t* errs, uint64_t n, double* out);
+int tsr_flipped_observables(const tsr_decoder* h, const uint64_t* errs, uint64_t n, uint8_t* obs_bits_out);
+
+/* Search counters since the last reset, summed over every search this handle ran:
+ * [0]=Q pushes [1]=P pops [2]=X expanded nodes [3]=L chain-walk steps [4]=S scanned row entries
+ * [5]=A sum(|edets|+|fired neighbours|) over evaluated children [6]=V visited inserts+probes
+ * [7]=searches run (distinct (order, beam) trials only). */
+int tsr_counters(tsr_decoder* h, uint64_t out[8], int reset);
+/* Timing of the last batch, measured with CUDA events on tsr_stream(h): [0]=search kernel ms,
+ * [1]=whole device pipeline ms (stage + search + resolve), [2]=search kernel launches,
+ * [3]=items rerun in a larger node-pool tier. */
+int tsr_last_batch_timing(const tsr_decoder* h, double out[4]);
+void* tsr_stream(tsr_decoder* h); /* cudaStream_t the decoder launches on */
+int tsr_device(const tsr_decoder* h);
+
+/* ---- helpers either side of the path -------------------------------------------------------------*/
+/* build_det_orders (utils.cc:192-205); method 0=DetBFS 1=DetIndex 2=DetCoordinate; out [n][D]. */
+int tsr_build_det_orders(const char* dem_text, uint64_t num_det_orders, int method, uint64_t seed, uint64_t* out);
+uint64_t tsr_dem_count_detectors(const char* dem_text); /* UINT64_MAX on parse failure */
+double tsr_merge_weights(double a, double b);           /* common.cc:118-123 */
+/* Stand-ins for the stim services the reference CLI uses (tesseract_main.cc:191-211, utils.cc:207-251):
+ * circuit text -> DEM text (caller frees with tsr_free) and an i.i.d. DEM shot sampler into bit-packed
+ * rows ([shots][ceil(D/8)], [shots][ceil(O/8)]; obs_out may be NULL). */
+int tsr_circuit_to_dem(const char* circuit_text, char** dem_text_out);
+int tsr_sample_dem_b8(const char* dem_text, uint64_t seed, uint64_t shots, uint8_t* dets_out, uint8_t* obs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TESSERACT_B200_H */

@@ -1,0 +1,323 @@
+"""ctypes binding of the C ABI in include/tesseract_b200.h (libtesseract_b200.so, built in-tree).
+
+This is the thin, torch-free Python face of the boundary: tests and bench.py call the decode path
+through it so that what is measured and checked is exactly what a reference maintainer would bind.
+There is no CPU fallback: decode calls raise CudaUnavailable without an sm_100 device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtesseract_b200.so")
+
+INF_DET_BEAM = 65535
+PQLIMIT_UNBOUNDED = (1 << 64) - 1
+NO_ERROR_INDEX = (1 << 64) - 1
+CREATE_HOST_ONLY = 1
+
+TSR_E_INVALID_ARGUMENT, TSR_E_RUNTIME, TSR_E_CUDA, TSR_E_DEVICE_MEMORY = -1, -2, -3, -4
+
+
+class CudaUnavailable(RuntimeError):
+    pass
+
+
+class DeviceMemoryError(RuntimeError):
+    pass
+
+
+class TsrConfig(C.Structure):
+    _fields_ = [
+        ("det_beam", C.c_int32),
+        ("beam_climbing", C.c_int32),
+        ("no_revisit_dets", C.c_int32),
+        ("merge_errors", C.c_int32),
+        ("at_most_two_errors_per_detector", C.c_int32),
+        ("device", C.c_int32),
+        ("pqlimit", C.c_uint64),
+        ("det_penalty", C.c_double),
+        ("num_det_orders", C.c_uint64),
+        ("det_orders", C.POINTER(C.c_uint64)),
+        ("search_slots", C.c_uint32),
+        ("warps_per_block", C.c_uint32),
+        ("node_pool_bytes", C.c_uint64),
+        ("max_batch_shots", C.c_uint64),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C tesseract_decoder_b200/csrc).  There is no fallback implementation.")
+    L = C.CDLL(LIB_PATH)
+    u64p, f64p, u8p, i32p = (C.POINTER(t) for t in (C.c_uint64, C.c_double, C.c_uint8, C.c_int32))
+    L.tsr_config_init.argtypes = [C.POINTER(TsrConfig)]
+    L.tsr_last_error.restype = C.c_char_p
+    L.tsr_version.restype = C.c_char_p
+    L.tsr_create.argtypes = [C.c_char_p, C.POINTER(TsrConfig), C.c_uint32, C.POINTER(C.c_void_p)]
+    L.tsr_destroy.argtypes = [C.c_void_p]
+    for name in ("tsr_num_detectors", "tsr_num_observables", "tsr_num_errors", "tsr_num_dem_errors",
+                 "tsr_num_det_orders", "tsr_last_batch_nnz"):
+        getattr(L, name).restype = C.c_uint64
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.tsr_error_costs.argtypes = [C.c_void_p, f64p]
+    L.tsr_maps.argtypes = [C.c_void_p, u64p, u64p]
+    L.tsr_csr.restype = C.c_int64
+    L.tsr_csr.argtypes = [C.c_void_p, C.c_int, u64p, i32p]
+    L.tsr_compiled_dem_text.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.tsr_free.argtypes = [C.c_void_p]
+    L.tsr_decode_batch_b8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.tsr_decode_batch_b8_device.argtypes = L.tsr_decode_batch_b8.argtypes
+    L.tsr_last_batch_errors.argtypes = [C.c_void_p, u64p, u64p]
+    L.tsr_decode.argtypes = [C.c_void_p, u64p, C.c_uint64, C.c_int64, C.c_uint64, u64p, C.c_uint64, u64p, f64p, i32p]
+    L.tsr_cost_from_errors.argtypes = [C.c_void_p, u64p, C.c_uint64, f64p]
+    L.tsr_flipped_observables.argtypes = [C.c_void_p, u64p, C.c_uint64, u8p]
+    L.tsr_counters.argtypes = [C.c_void_p, u64p, C.c_int]
+    L.tsr_last_batch_timing.argtypes = [C.c_void_p, f64p]
+    L.tsr_stream.restype = C.c_void_p
+    L.tsr_stream.argtypes = [C.c_void_p]
+    L.tsr_device.argtypes = [C.c_void_p]
+    L.tsr_build_det_orders.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64, u64p]
+    L.tsr_dem_count_detectors.restype = C.c_uint64
+    L.tsr_dem_count_detectors.argtypes = [C.c_char_p]
+    L.tsr_merge_weights.restype = C.c_double
+    L.tsr_merge_weights.argtypes = [C.c_double, C.c_double]
+    L.tsr_circuit_to_dem.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.tsr_sample_dem_b8.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, u8p, u8p]
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "tsr_config_init", "tsr_last_error", "tsr_version", "tsr_create", "tsr_destroy", "tsr_num_detectors",
+    "tsr_num_observables", "tsr_num_errors", "tsr_num_dem_errors", "tsr_num_det_orders", "tsr_error_costs",
+    "tsr_maps", "tsr_csr", "tsr_compiled_dem_text", "tsr_free", "tsr_decode_batch_b8",
+    "tsr_decode_batch_b8_device", "tsr_last_batch_nnz", "tsr_last_batch_errors", "tsr_decode",
+    "tsr_cost_from_errors", "tsr_flipped_observables", "tsr_counters", "tsr_last_batch_timing", "tsr_stream",
+    "tsr_device", "tsr_build_det_orders", "tsr_dem_count_detectors", "tsr_merge_weights", "tsr_circuit_to_dem",
+    "tsr_sample_dem_b8",
+]
+
+
+def _p(arr, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+def _raise(rc: int):
+    msg = lib().tsr_last_error().decode()
+    if rc == TSR_E_INVALID_ARGUMENT:
+        raise ValueError(msg)
+    if rc == TSR_E_CUDA:
+        raise CudaUnavailable(msg)
+    if rc == TSR_E_DEVICE_MEMORY:
+        raise DeviceMemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def _check(rc: int):
+    if rc != 0:
+        _raise(rc)
+
+
+def _take_text(ptr: C.c_void_p) -> str:
+    try:
+        return C.string_at(ptr).decode()
+    finally:
+        lib().tsr_free(ptr)
+
+
+def circuit_to_dem(circuit_text: str) -> str:
+    out = C.c_void_p()
+    _check(lib().tsr_circuit_to_dem(circuit_text.encode(), C.byref(out)))
+    return _take_text(out)
+
+
+def dem_count_detectors(dem_text: str) -> int:
+    n = lib().tsr_dem_count_detectors(dem_text.encode())
+    if n == (1 << 64) - 1:
+        raise ValueError(lib().tsr_last_error().decode())
+    return n
+
+
+def build_det_orders(dem_text: str, num_det_orders: int, method: int = 1, seed: int = 0) -> np.ndarray:
+    """utils.cc:192-205; method 0=DetBFS 1=DetIndex 2=DetCoordinate."""
+    D = dem_count_detectors(dem_text)
+    out = np.zeros((num_det_orders, D), dtype=np.uint64)
+    _check(lib().tsr_build_det_orders(dem_text.encode(), num_det_orders, method, seed, _p(out, C.c_uint64)))
+    return out
+
+
+def merge_weights(a: float, b: float) -> float:
+    return lib().tsr_merge_weights(a, b)
+
+
+def sample_dem_b8(dem_text: str, seed: int, shots: int, num_detectors: int, num_observables: int):
+    dets = np.zeros((shots, (num_detectors + 7) // 8), dtype=np.uint8)
+    obs = np.zeros((shots, max((num_observables + 7) // 8, 1)), dtype=np.uint8)
+    _check(lib().tsr_sample_dem_b8(dem_text.encode(), seed, shots, _p(dets, C.c_uint8), _p(obs, C.c_uint8)))
+    return dets, obs[:, : (num_observables + 7) // 8]
+
+
+class Decoder:
+    """Owns one tsr_decoder handle."""
+
+    def __init__(self, dem_text: str, *, det_beam: int = 5, beam_climbing: bool = False,
+                 no_revisit_dets: bool = True, merge_errors: bool = True, pqlimit: int | None = 200000,
+                 det_penalty: float = 0.0, det_orders=None, at_most_two_errors_per_detector: bool = False,
+                 device: int = -1, host_only: bool = False, search_slots: int = 0, warps_per_block: int = 0,
+                 node_pool_bytes: int = 0, max_batch_shots: int = 0):
+        L = lib()
+        cfg = TsrConfig()
+        L.tsr_config_init(C.byref(cfg))
+        cfg.det_beam = det_beam
+        cfg.beam_climbing = int(beam_climbing)
+        cfg.no_revisit_dets = int(no_revisit_dets)
+        cfg.merge_errors = int(merge_errors)
+        cfg.at_most_two_errors_per_detector = int(at_most_two_errors_per_detector)
+        cfg.device = device
+        cfg.pqlimit = PQLIMIT_UNBOUNDED if pqlimit is None or pqlimit >= PQLIMIT_UNBOUNDED else int(pqlimit)
+        cfg.det_penalty = det_penalty
+        self._orders = None
+        if det_orders is not None and len(det_orders):
+            self._orders = np.ascontiguousarray(det_orders, dtype=np.uint64)
+            cfg.num_det_orders = self._orders.shape[0]
+            cfg.det_orders = _p(self._orders, C.c_uint64)
+        cfg.search_slots = search_slots
+        cfg.warps_per_block = warps_per_block
+        cfg.node_pool_bytes = node_pool_bytes
+        cfg.max_batch_shots = max_batch_shots
+        h = C.c_void_p()
+        self.h = None
+        _check(L.tsr_create(dem_text.encode(), C.byref(cfg), CREATE_HOST_ONLY if host_only else 0, C.byref(h)))
+        self.h = h
+        self.num_detectors = L.tsr_num_detectors(h)
+        self.num_observables = L.tsr_num_observables(h)
+        self.num_errors = L.tsr_num_errors(h)
+        self.num_dem_errors = L.tsr_num_dem_errors(h)
+        self.num_det_orders = L.tsr_num_det_orders(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tsr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables -------------------------------------------------------------------------------
+    def error_costs(self) -> np.ndarray:
+        out = np.zeros(self.num_errors, dtype=np.float64)
+        _check(lib().tsr_error_costs(self.h, _p(out, C.c_double)))
+        return out
+
+    def maps(self):
+        a = np.zeros(self.num_dem_errors, dtype=np.uint64)
+        b = np.zeros(self.num_errors, dtype=np.uint64)
+        _check(lib().tsr_maps(self.h, _p(a, C.c_uint64), _p(b, C.c_uint64)))
+        return a, b
+
+    def csr(self, which: int):
+        rows = self.num_detectors if which == 0 else self.num_errors
+        nnz = lib().tsr_csr(self.h, which, None, None)
+        if nnz < 0:
+            _raise(int(nnz))
+        off = np.zeros(rows + 1, dtype=np.uint64)
+        idx = np.zeros(max(nnz, 1), dtype=np.int32)
+        lib().tsr_csr(self.h, which, _p(off, C.c_uint64), _p(idx, C.c_int32))
+        return off, idx[:nnz]
+
+    def rows(self, which: int):
+        off, idx = self.csr(which)
+        return [idx[int(off[r]):int(off[r + 1])].tolist() for r in range(len(off) - 1)]
+
+    def compiled_dem_text(self) -> str:
+        out = C.c_void_p()
+        _check(lib().tsr_compiled_dem_text(self.h, C.byref(out)))
+        return _take_text(out)
+
+    # ---- decoding -----------------------------------------------------------------------------
+    def decode_to_errors(self, detections, order: int = -1, beam: int = 0):
+        """(predicted_errors_buffer, cost_from_errors(buffer), low_confidence_flag)."""
+        det = np.ascontiguousarray(detections, dtype=np.uint64)
+        cap = 1 << 16
+        errs = np.zeros(cap, dtype=np.uint64)
+        n, cost, low = C.c_uint64(), C.c_double(), C.c_int32()
+        _check(lib().tsr_decode(self.h, _p(det, C.c_uint64), len(det), order, beam, _p(errs, C.c_uint64), cap,
+                                C.byref(n), C.byref(cost), C.byref(low)))
+        return errs[: n.value].tolist(), cost.value, bool(low.value)
+
+    def last_batch_errors(self):
+        nnz = lib().tsr_last_batch_nnz(self.h)
+        off = np.zeros(self._last_shots + 1, dtype=np.uint64)
+        idx = np.zeros(max(nnz, 1), dtype=np.uint64)
+        _check(lib().tsr_last_batch_errors(self.h, _p(off, C.c_uint64), _p(idx, C.c_uint64)))
+        return off, idx[:nnz]
+
+    def decode_batch_b8(self, dets_b8: np.ndarray, want_errors: bool = True):
+        """Host buffers in, host buffers out (H2D and D2H inside the call)."""
+        dets_b8 = np.ascontiguousarray(dets_b8, dtype=np.uint8)
+        if dets_b8.ndim != 2:
+            raise ValueError("dets_b8 must be a 2D uint8 array [shots, ceil(num_detectors/8)]")
+        shots, stride = dets_b8.shape
+        obs = np.zeros((shots, (self.num_observables + 7) // 8), dtype=np.uint8)
+        cost = np.zeros(shots, dtype=np.float64)
+        low = np.zeros(shots, dtype=np.uint8)
+        _check(lib().tsr_decode_batch_b8(self.h, dets_b8.ctypes.data, stride, shots, obs.ctypes.data, cost.ctypes.data,
+                                         low.ctypes.data))
+        self._last_shots = shots
+        out = {"obs": obs, "cost": cost, "low_confidence": low}
+        if want_errors:
+            out["err_offsets"], out["err_idx"] = self.last_batch_errors()
+        return out
+
+    def decode_batch_b8_device(self, d_dets: int, stride: int, shots: int, d_obs: int = 0, d_cost: int = 0,
+                               d_low: int = 0):
+        """Device pointers (ints) in and out; inputs already resident in HBM."""
+        _check(lib().tsr_decode_batch_b8_device(self.h, d_dets, stride, shots, d_obs or None, d_cost or None,
+                                                d_low or None))
+        self._last_shots = shots
+
+    def cost_from_errors(self, errs) -> float:
+        errs = np.ascontiguousarray(errs, dtype=np.uint64)
+        out = C.c_double()
+        _check(lib().tsr_cost_from_errors(self.h, _p(errs, C.c_uint64), len(errs), C.byref(out)))
+        return out.value
+
+    def flipped_observables(self, errs):
+        errs = np.ascontiguousarray(errs, dtype=np.uint64)
+        out = np.zeros(max((self.num_observables + 7) // 8, 1), dtype=np.uint8)
+        _check(lib().tsr_flipped_observables(self.h, _p(errs, C.c_uint64), len(errs), _p(out, C.c_uint8)))
+        bits = np.unpackbits(out, bitorder="little")[: self.num_observables]
+        return np.nonzero(bits)[0].tolist()
+
+    def counters(self, reset: bool = False):
+        out = np.zeros(8, dtype=np.uint64)
+        _check(lib().tsr_counters(self.h, _p(out, C.c_uint64), int(reset)))
+        return dict(zip(["Q", "P", "X", "L", "S", "A", "V", "searches"], out.tolist()))
+
+    def last_batch_timing(self):
+        out = np.zeros(4, dtype=np.float64)
+        _check(lib().tsr_last_batch_timing(self.h, _p(out, C.c_double)))
+        return {"search_ms": out[0], "pipeline_ms": out[1], "search_launches": int(out[2]), "rerun_items": int(out[3])}
+
+    @property
+    def stream(self) -> int:
+        return lib().tsr_stream(self.h) or 0
+
+    @property
+    def device(self) -> int:
+        return lib().tsr_device(self.h)

@@ -1,0 +1,827 @@
+// C ABI (include/tesseract_b200.h): host-side decoder object, device memory and the launch pipeline.
+//
+// Per batch:  stage_kernel (syndrome statistics)  ->  search_kernel (one warp per (shot, trial),
+// persistent warps claiming work from an atomic counter, like utils.h:88-92)  ->  resolve_kernel
+// (ensemble minimum, observables, costs, pooled error lists).  Searches that outgrow their slot's
+// heap/chain/visited capacity are re-run in the next "tier": fewer slots over the same node pool,
+// each proportionally larger — never on the CPU.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/tesseract_b200.h"
+#include "circuit.h"
+#include "dem.h"
+#include "ingest.h"
+#include "search.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct DeviceMemoryError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+void cuda_check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw CudaError(std::string("CUDA: ") + what + ": " + cudaGetErrorString(e));
+}
+#define CUDA_OK(expr) cuda_check((expr), #expr)
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return TSR_OK;
+  } catch (const std::invalid_argument& e) {
+    g_error = e.what();
+    return TSR_E_INVALID_ARGUMENT;
+  } catch (const CudaError& e) {
+    g_error = e.what();
+    return TSR_E_CUDA;
+  } catch (const DeviceMemoryError& e) {
+    g_error = e.what();
+    return TSR_E_DEVICE_MEMORY;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return TSR_E_RUNTIME;
+  }
+}
+
+// A device allocation that frees itself.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    release();
+    CUDA_OK(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+  template <typename T>
+  void upload(const std::vector<T>& v) {
+    ensure(std::max<size_t>(v.size() * sizeof(T), 16));
+    if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+};
+
+struct Tier {
+  uint32_t slots;
+  uint64_t node_cap, visit_cap;
+};
+
+// The (order, beam) trials of one decode call: the reference's literal loop (tesseract.cc:307-344)
+// and the distinct searches behind it (identical detector orders are searched once).
+struct TrialSet {
+  std::vector<uint32_t> perm, beam;        // distinct trials
+  std::vector<uint32_t> literal_to_trial;  // literal trial -> distinct trial
+  DevBuf d_perm, d_beam, d_literal;
+  void upload() {
+    d_perm.upload(perm);
+    d_beam.upload(beam);
+    d_literal.upload(literal_to_trial);
+  }
+};
+
+}  // namespace
+
+struct tsr_decoder {
+  tsr_config cfg{};
+  tsr::DemTables T;
+  std::vector<std::vector<uint64_t>> det_orders;
+  std::vector<uint32_t> order_to_perm;  // det order index -> distinct permutation id
+  uint32_t n_perms = 0;
+  bool host_only = true;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  // Device tables.
+  DevBuf row_off, row_err, rec_a, rec_b, rec_c, e_off, e_det, e_rank, e_cost, e_nnbr, eo_off, eo_obs, e2dem, adj,
+      zobrist, order_det, order_pos;
+  tsr::DeviceTables dt;
+  TrialSet ensemble;
+
+  // Node pool and tiers.
+  uint32_t wpb = 4, blocks = 0;
+  std::vector<Tier> tiers;
+  DevBuf pool, hcache, vlist;
+  uint32_t vlist_cap = 256;
+
+  // Per-batch buffers.
+  uint64_t max_batch = 0;
+  DevBuf d_dets, d_status, d_sol_len, d_fcost, d_sol, d_obs, d_cost, d_low, d_err_off, d_err_len, d_err, d_retry,
+      d_items, d_scalars, d_counters;
+  uint32_t sol_stride = 0;
+
+  // Results of the last decode call.
+  std::vector<uint64_t> last_off{0};
+  std::vector<uint64_t> last_idx;
+  double timing[4] = {0, 0, 0, 0};
+
+  ~tsr_decoder() {
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+using tsr::DemModel;
+
+uint64_t splitmix(uint64_t& s) {
+  s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+void make_ensemble(const tsr_decoder& h, TrialSet& ts) {
+  // tesseract.cc:307-344.
+  std::map<std::pair<uint32_t, uint32_t>, uint32_t> seen;
+  auto add = [&](size_t order, uint32_t beam) {
+    auto key = std::make_pair(h.order_to_perm[order], beam);
+    auto it = seen.find(key);
+    if (it == seen.end()) {
+      it = seen.emplace(key, (uint32_t)ts.perm.size()).first;
+      ts.perm.push_back(key.first);
+      ts.beam.push_back(beam);
+    }
+    ts.literal_to_trial.push_back(it->second);
+  };
+  const size_t n_orders = h.det_orders.size();
+  if (h.cfg.beam_climbing) {
+    const int trials = std::max(h.cfg.det_beam + 1, (int)n_orders);
+    int beam = 0;
+    size_t order = 0;
+    for (int t = 0; t < trials; ++t) {
+      add(order, (uint32_t)beam);
+      beam = (beam + 1) % (h.cfg.det_beam + 1);
+      order = (order + 1) % n_orders;
+    }
+  } else {
+    for (size_t order = 0; order < n_orders; ++order) add(order, (uint32_t)h.cfg.det_beam);
+  }
+}
+
+void init_device(tsr_decoder& h) {
+  if (h.cfg.device >= 0) {
+    CUDA_OK(cudaSetDevice(h.cfg.device));
+    h.device = h.cfg.device;
+  } else {
+    CUDA_OK(cudaGetDevice(&h.device));
+  }
+  cudaDeviceProp prop{};
+  CUDA_OK(cudaGetDeviceProperties(&prop, h.device));
+  if (prop.major < 10)
+    throw CudaError(std::string("tesseract_b200 needs an sm_100 (Blackwell) device; found ") + prop.name + " (sm_" +
+                    std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+  h.sm_count = prop.multiProcessorCount;
+  CUDA_OK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+  for (auto& e : h.ev) CUDA_OK(cudaEventCreate(&e));
+
+  const tsr::DemTables& T = h.T;
+  const uint32_t D = (uint32_t)T.num_detectors, E = (uint32_t)T.num_errors;
+  h.row_off.upload(T.row_off);
+  h.row_err.upload(T.row_err);
+  h.rec_a.upload(T.rec_a);
+  h.rec_b.upload(T.rec_b);
+  h.rec_c.upload(T.rec_c);
+  h.e_off.upload(T.e_off);
+  h.e_det.upload(T.e_det);
+  h.e_rank.upload(T.e_rank);
+  h.e_cost.upload(T.e_cost);
+  h.eo_off.upload(T.eo_off);
+  h.eo_obs.upload(T.eo_obs);
+  h.e2dem.upload(T.error_to_dem_error);
+  h.adj.upload(T.adj);
+  {
+    // |eneighbors[e]| for counter A, from the adjacency matrix.
+    std::vector<uint16_t> nn(E);
+    std::vector<uint32_t> acc(T.adj_words);
+    for (uint32_t e = 0; e < E; ++e) {
+      std::fill(acc.begin(), acc.end(), 0u);
+      for (int d : T.errors[e].detectors)
+        for (uint32_t w = 0; w < T.adj_words; ++w) acc[w] |= T.adj[(size_t)d * T.adj_words + w];
+      uint32_t n = 0;
+      for (uint32_t w : acc) n += (uint32_t)__builtin_popcount(w);
+      nn[e] = (uint16_t)std::min<uint32_t>(n - (uint32_t)T.errors[e].detectors.size(), 0xFFFF);
+    }
+    h.e_nnbr.upload(nn);
+  }
+  {
+    std::vector<uint64_t> z((size_t)D * 2 + 2);
+    uint64_t s = 0x7E55E7AC7DEC0DE5ull;
+    for (auto& v : z) v = splitmix(s);
+    h.zobrist.upload(z);
+  }
+  {
+    std::vector<uint32_t> od((size_t)h.n_perms * D + 1), op((size_t)h.n_perms * D + 1, 0xFFFFFFFFu);
+    std::vector<char> done(h.n_perms, 0);
+    for (size_t k = 0; k < h.det_orders.size(); ++k) {
+      uint32_t q = h.order_to_perm[k];
+      if (done[q]) continue;
+      done[q] = 1;
+      for (uint32_t pos = 0; pos < D; ++pos) {
+        uint64_t det = h.det_orders[k][pos];
+        if (det >= D) throw std::invalid_argument("detector order entries must be < num_detectors");
+        od[(size_t)q * D + pos] = (uint32_t)det;
+        uint32_t& inv = op[(size_t)q * D + det];
+        inv = std::min(inv, pos);
+      }
+    }
+    h.order_det.upload(od);
+    h.order_pos.upload(op);
+  }
+  tsr::DeviceTables& dt = h.dt;
+  dt.D = D;
+  dt.E = E;
+  dt.O = (uint32_t)T.num_observables;
+  dt.nwords = T.adj_words;
+  dt.row_off = h.row_off.as<uint32_t>();
+  dt.row_err = h.row_err.as<int32_t>();
+  dt.rec_a = h.rec_a.as<uint4>();
+  dt.rec_b = h.rec_b.as<uint4>();
+  dt.rec_c = h.rec_c.as<uint4>();
+  dt.e_off = h.e_off.as<uint32_t>();
+  dt.e_det = h.e_det.as<int32_t>();
+  dt.e_rank = h.e_rank.as<int32_t>();
+  dt.e_cost = h.e_cost.as<double>();
+  dt.e_nnbr = h.e_nnbr.as<uint16_t>();
+  dt.eo_off = h.eo_off.as<uint32_t>();
+  dt.eo_obs = h.eo_obs.as<int32_t>();
+  dt.e2dem = h.e2dem.as<uint64_t>();
+  dt.adj = h.adj.as<uint32_t>();
+  dt.zobrist = h.zobrist.as<uint4>();
+  dt.order_det = h.order_det.as<uint32_t>();
+  dt.order_pos = h.order_pos.as<uint32_t>();
+
+  make_ensemble(h, h.ensemble);
+  h.ensemble.upload();
+
+  // Grid shape: persistent warps filling every SM.
+  h.wpb = h.cfg.warps_per_block ? std::min<uint32_t>(h.cfg.warps_per_block, 8) : 4;
+  int occ = tsr::search_max_blocks_per_sm(h.wpb, D);
+  while (occ == 0 && h.wpb > 1) {
+    h.wpb /= 2;
+    occ = tsr::search_max_blocks_per_sm(h.wpb, D);
+  }
+  if (occ == 0) throw CudaError("the search kernel does not fit on this device for this many detectors");
+  h.blocks = (uint32_t)(h.sm_count * occ);
+  uint32_t slots = h.blocks * h.wpb;
+  if (h.cfg.search_slots && h.cfg.search_slots < slots) {
+    slots = std::max<uint32_t>(h.cfg.search_slots, 1);
+    h.blocks = (slots + h.wpb - 1) / h.wpb;
+    slots = h.blocks * h.wpb;
+  }
+
+  // Node pool: 32 B per node (heap + chain) + 16 B per visited entry (half as many as nodes).
+  const bool revisit_tab = h.cfg.no_revisit_dets != 0;
+  const double per_node = 32.0 + (revisit_tab ? 8.0 : 0.0);
+  const uint64_t want_nodes = h.cfg.pqlimit == TSR_PQLIMIT_UNBOUNDED ? ~uint64_t{0} : h.cfg.pqlimit + 1;
+  size_t free_b = 0, total_b = 0;
+  CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+  uint64_t budget = h.cfg.node_pool_bytes ? h.cfg.node_pool_bytes : (uint64_t)(free_b * 0.30);
+  budget = std::min<uint64_t>(budget, (uint64_t)(free_b * 0.85));
+  uint64_t cap0 = (uint64_t)((double)budget / slots / per_node);
+  cap0 = std::min<uint64_t>(cap0, want_nodes);
+  cap0 = std::max<uint64_t>(cap0, 64);
+  auto visit_of = [&](uint64_t cap) { return revisit_tab ? std::max<uint64_t>(cap / 2, 64) : 0; };
+  h.tiers.push_back({slots, cap0, visit_of(cap0)});
+  const uint64_t pool_nodes = (uint64_t)slots * cap0;
+  while (h.tiers.back().node_cap < want_nodes && h.tiers.back().slots > 1) {
+    uint32_t s = std::max<uint32_t>(h.tiers.back().slots / 16, 1);
+    uint64_t cap = std::min<uint64_t>(pool_nodes / s, want_nodes);
+    h.tiers.push_back({s, cap, visit_of(cap)});
+  }
+  // Layout inside the pool for tier k: [heap: slots*cap*16][chain: slots*cap*16][visited: slots*vcap*16].
+  size_t pool_bytes = 0;
+  for (const Tier& t : h.tiers)
+    pool_bytes = std::max<size_t>(pool_bytes, (size_t)t.slots * (t.node_cap * 32 + t.visit_cap * 16));
+  h.pool.ensure(pool_bytes + 256);
+  h.hcache.ensure((size_t)slots * std::max<uint32_t>(D, 1) * sizeof(double));
+  h.vlist.ensure((size_t)slots * h.vlist_cap * sizeof(uint32_t));
+  CUDA_OK(cudaMemsetAsync(h.pool.p, 0, h.pool.bytes, h.stream));  // visited tables start empty
+  h.d_scalars.ensure(64);
+  h.d_counters.ensure(8 * sizeof(unsigned long long));
+  CUDA_OK(cudaMemsetAsync(h.d_counters.p, 0, 64, h.stream));
+  CUDA_OK(cudaStreamSynchronize(h.stream));
+  h.max_batch = h.cfg.max_batch_shots ? h.cfg.max_batch_shots : (uint64_t{1} << 16);
+}
+
+void require_device(const tsr_decoder& h) {
+  if (h.host_only) throw CudaError("CUDA: this decoder was created host-only; decoding needs an sm_100 GPU (no CPU fallback)");
+}
+
+// d_scalars layout (4-byte units): [0] work counter, [1] max fired, [2..3] total fired (u64),
+// [4..5] error cursor (u64), [6] retry count.
+struct Scalars {
+  unsigned int work, max_fired;
+  unsigned long long total_fired, err_cursor;
+  unsigned int retry_count, pad;
+};
+
+// Decodes `shots` shots whose bit-packed syndromes are at device pointer d_dets.  Outputs go to the
+// given device pointers (nullable).  Error lists are appended to h.last_off / h.last_idx.
+void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t shots, const TrialSet& ts,
+               uint8_t* d_obs, double* d_cost, uint8_t* d_low) {
+  const tsr::DemTables& T = h.T;
+  const uint32_t U = (uint32_t)ts.perm.size();
+  const uint64_t items64 = (uint64_t)shots * U;
+  if (items64 > 0xFFFFFFF0ull) throw std::invalid_argument("batch too large: shots x trials must fit in 32 bits");
+  const uint32_t items = (uint32_t)items64;
+  cudaStream_t s = h.stream;
+  Scalars* sc = h.d_scalars.as<Scalars>();
+  CUDA_OK(cudaMemsetAsync(sc, 0, sizeof(Scalars), s));
+  CUDA_OK(cudaEventRecord(h.ev[0], s));
+
+  tsr::StageParams sp;
+  sp.dets = d_dets;
+  sp.stride = stride;
+  sp.shots = shots;
+  sp.D = (uint32_t)T.num_detectors;
+  sp.max_fired = &sc->max_fired;
+  sp.total_fired = &sc->total_fired;
+  CUDA_OK((cudaError_t)tsr::launch_stage(sp, s));
+  Scalars hs{};
+  CUDA_OK(cudaMemcpyAsync(&hs, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  const uint32_t stride_need =
+      (uint32_t)std::min<uint64_t>(std::max<uint64_t>(T.num_errors, 1), 4ull * hs.max_fired + 32);
+  h.sol_stride = stride_need;
+
+  h.d_status.ensure(items);
+  h.d_sol_len.ensure((size_t)items * 4);
+  h.d_fcost.ensure((size_t)items * 8);
+  h.d_sol.ensure((size_t)items * h.sol_stride * 4);
+  h.d_err_off.ensure((size_t)shots * 8);
+  h.d_err_len.ensure((size_t)shots * 4);
+  const uint64_t err_cap = (uint64_t)shots * h.sol_stride;
+  h.d_err.ensure(err_cap * 8);
+  h.d_retry.ensure((size_t)shots * 4 * 2);
+
+  auto search_params = [&](const Tier& tier, const uint32_t* item_ids, uint32_t n_work) {
+    tsr::SearchParams p;
+    p.t = h.dt;
+    p.dets = d_dets;
+    p.stride = stride;
+    p.n_work = n_work;
+    p.item_ids = item_ids;
+    p.n_trials = U;
+    p.trial_perm = ts.d_perm.as<uint32_t>();
+    p.trial_beam = ts.d_beam.as<uint32_t>();
+    p.det_penalty = h.cfg.det_penalty;
+    p.pqlimit = h.cfg.pqlimit;
+    p.no_revisit = h.cfg.no_revisit_dets != 0;
+    p.at_most_two = h.cfg.at_most_two_errors_per_detector != 0;
+    p.n_slots = tier.slots;
+    p.node_cap = tier.node_cap;
+    p.visit_cap = tier.visit_cap;
+    p.vlist_cap = h.vlist_cap;
+    char* base = h.pool.as<char>();
+    p.heap = reinterpret_cast<tsr::HeapNode*>(base);
+    p.chain = reinterpret_cast<tsr::ChainNode*>(base + (size_t)tier.slots * tier.node_cap * 16);
+    p.visited = reinterpret_cast<uint4*>(base + (size_t)tier.slots * tier.node_cap * 32);
+    p.vlist = h.vlist.as<uint32_t>();
+    p.hcache = h.hcache.as<double>();
+    p.sol_stride = h.sol_stride;
+    p.sol = h.d_sol.as<uint32_t>();
+    p.sol_len = h.d_sol_len.as<uint32_t>();
+    p.status = h.d_status.as<uint8_t>();
+    p.fcost = h.d_fcost.as<double>();
+    p.work_counter = &sc->work;
+    p.counters = h.d_counters.as<unsigned long long>();
+    return p;
+  };
+  auto resolve_params = [&](const uint32_t* shot_ids, uint32_t n, uint32_t* retry_out) {
+    tsr::ResolveParams r;
+    r.t = h.dt;
+    r.n_shots = n;
+    r.shot_ids = shot_ids;
+    r.n_trials = U;
+    r.n_literal = (uint32_t)ts.literal_to_trial.size();
+    r.literal_to_trial = ts.d_literal.as<uint32_t>();
+    r.sol_stride = h.sol_stride;
+    r.sol = h.d_sol.as<uint32_t>();
+    r.sol_len = h.d_sol_len.as<uint32_t>();
+    r.status = h.d_status.as<uint8_t>();
+    r.obs_out = d_obs;
+    r.obs_stride = (uint32_t)((T.num_observables + 7) / 8);
+    r.cost_out = d_cost;
+    r.low_conf_out = d_low;
+    r.err_out = h.d_err.as<uint64_t>();
+    r.err_cap = err_cap;
+    r.err_cursor = &sc->err_cursor;
+    r.err_off = h.d_err_off.as<uint64_t>();
+    r.err_len = h.d_err_len.as<uint32_t>();
+    r.retry_shots = retry_out;
+    r.retry_count = &sc->retry_count;
+    return r;
+  };
+
+  // Tier 0 over every item.
+  const Tier& t0 = h.tiers[0];
+  uint32_t blocks0 = std::min<uint32_t>((t0.slots + h.wpb - 1) / h.wpb, (items + h.wpb - 1) / h.wpb);
+  CUDA_OK(cudaEventRecord(h.ev[1], s));
+  CUDA_OK((cudaError_t)tsr::launch_search(search_params(t0, nullptr, items), blocks0, h.wpb, s));
+  CUDA_OK(cudaEventRecord(h.ev[2], s));
+  uint32_t* retry_a = h.d_retry.as<uint32_t>();
+  uint32_t* retry_b = retry_a + shots;
+  CUDA_OK((cudaError_t)tsr::launch_resolve(resolve_params(nullptr, shots, retry_a), s));
+  CUDA_OK(cudaMemcpyAsync(&hs, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  double launches = 1, rerun = 0;
+  float ms_search = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms_search, h.ev[1], h.ev[2]));
+
+  // Retry tiers for searches that outgrew their slot.
+  for (size_t tier = 1; hs.retry_count > 0; ++tier) {
+    if (tier >= h.tiers.size())
+      throw DeviceMemoryError("a search outgrew the device node pool (" + std::to_string(hs.retry_count) +
+                              " shot(s)); raise node_pool_bytes, lower pqlimit or set a finite beam");
+    const uint32_t n_retry = hs.retry_count;
+    std::vector<uint32_t> shot_ids(n_retry), item_ids((size_t)n_retry * U);
+    CUDA_OK(cudaMemcpy(shot_ids.data(), retry_a, (size_t)n_retry * 4, cudaMemcpyDeviceToHost));
+    std::sort(shot_ids.begin(), shot_ids.end());
+    for (uint32_t i = 0; i < n_retry; ++i)
+      for (uint32_t u = 0; u < U; ++u) item_ids[(size_t)i * U + u] = shot_ids[i] * U + u;
+    h.d_items.ensure(item_ids.size() * 4 + (size_t)n_retry * 4);
+    uint32_t* d_item_ids = h.d_items.as<uint32_t>();
+    uint32_t* d_shot_ids = d_item_ids + item_ids.size();
+    CUDA_OK(cudaMemcpyAsync(d_item_ids, item_ids.data(), item_ids.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(d_shot_ids, shot_ids.data(), (size_t)n_retry * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(&sc->work, 0, 4, s));
+    CUDA_OK(cudaMemsetAsync(&sc->retry_count, 0, 4, s));
+    // A differently-shaped tier reuses the pool: visited tables must start empty.
+    const Tier& tk = h.tiers[tier];
+    if (tk.visit_cap)
+      CUDA_OK(cudaMemsetAsync(h.pool.as<char>() + (size_t)tk.slots * tk.node_cap * 32, 0, (size_t)tk.slots * tk.visit_cap * 16, s));
+    CUDA_OK(cudaEventRecord(h.ev[1], s));
+    uint32_t nb = std::min<uint32_t>((tk.slots + h.wpb - 1) / h.wpb, ((uint32_t)item_ids.size() + h.wpb - 1) / h.wpb);
+    CUDA_OK((cudaError_t)tsr::launch_search(search_params(tk, d_item_ids, (uint32_t)item_ids.size()), nb, h.wpb, s));
+    CUDA_OK(cudaEventRecord(h.ev[2], s));
+    CUDA_OK((cudaError_t)tsr::launch_resolve(resolve_params(d_shot_ids, n_retry, retry_b), s));
+    // Restore the tier-0 invariant (empty visited tables in the tier-0 layout).
+    if (t0.visit_cap)
+      CUDA_OK(cudaMemsetAsync(h.pool.as<char>() + (size_t)t0.slots * t0.node_cap * 32, 0, (size_t)t0.slots * t0.visit_cap * 16, s));
+    CUDA_OK(cudaMemcpyAsync(&hs, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, h.ev[1], h.ev[2]));
+    ms_search += ms;
+    launches += 1;
+    rerun += (double)item_ids.size();
+    std::swap(retry_a, retry_b);
+  }
+  if (hs.err_cursor > err_cap) throw DeviceMemoryError("pooled error lists overflowed their buffer");
+
+  // Error lists -> host CSR.
+  std::vector<uint64_t> off(shots), pooled(hs.err_cursor);
+  std::vector<uint32_t> len(shots);
+  CUDA_OK(cudaMemcpyAsync(off.data(), h.d_err_off.p, (size_t)shots * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(len.data(), h.d_err_len.p, (size_t)shots * 4, cudaMemcpyDeviceToHost, s));
+  if (!pooled.empty())
+    CUDA_OK(cudaMemcpyAsync(pooled.data(), h.d_err.p, pooled.size() * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaEventRecord(h.ev[3], s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  for (uint32_t k = 0; k < shots; ++k) {
+    h.last_idx.insert(h.last_idx.end(), pooled.begin() + (std::ptrdiff_t)off[k], pooled.begin() + (std::ptrdiff_t)(off[k] + len[k]));
+    h.last_off.push_back(h.last_idx.size());
+  }
+  float ms_all = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms_all, h.ev[0], h.ev[3]));
+  h.timing[0] += ms_search;
+  h.timing[1] += ms_all;
+  h.timing[2] += launches;
+  h.timing[3] += rerun;
+}
+
+void begin_call(tsr_decoder& h) {
+  h.last_off.assign(1, 0);
+  h.last_idx.clear();
+  for (double& v : h.timing) v = 0;
+}
+
+void decode_batch(tsr_decoder& h, const uint8_t* dets, uint64_t stride, uint64_t shots, bool on_device,
+                  const TrialSet& ts, uint8_t* obs, double* cost, uint8_t* low) {
+  require_device(h);
+  CUDA_OK(cudaSetDevice(h.device));
+  const uint64_t min_stride = (h.T.num_detectors + 7) / 8;
+  if (shots && stride < min_stride)
+    throw std::invalid_argument("stride (" + std::to_string(stride) + ") is smaller than ceil(num_detectors/8) (" +
+                                std::to_string(min_stride) + ")");
+  begin_call(h);
+  const uint64_t obs_stride = (h.T.num_observables + 7) / 8;
+  for (uint64_t at = 0; at < shots; at += h.max_batch) {
+    const uint32_t n = (uint32_t)std::min<uint64_t>(h.max_batch, shots - at);
+    if (on_device) {
+      run_chunk(h, dets + at * stride, stride, n, ts, obs ? obs + at * obs_stride : nullptr, cost ? cost + at : nullptr,
+                low ? low + at : nullptr);
+    } else {
+      h.d_dets.ensure((size_t)n * stride);
+      h.d_obs.ensure(std::max<size_t>((size_t)n * obs_stride, 16));
+      h.d_cost.ensure((size_t)n * 8);
+      h.d_low.ensure(n);
+      CUDA_OK(cudaMemcpyAsync(h.d_dets.p, dets + at * stride, (size_t)n * stride, cudaMemcpyHostToDevice, h.stream));
+      run_chunk(h, h.d_dets.as<uint8_t>(), stride, n, ts, h.d_obs.as<uint8_t>(), h.d_cost.as<double>(), h.d_low.as<uint8_t>());
+      if (obs && obs_stride)
+        CUDA_OK(cudaMemcpyAsync(obs + at * obs_stride, h.d_obs.p, (size_t)n * obs_stride, cudaMemcpyDeviceToHost, h.stream));
+      if (cost) CUDA_OK(cudaMemcpyAsync(cost + at, h.d_cost.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h.stream));
+      if (low) CUDA_OK(cudaMemcpyAsync(low + at, h.d_low.p, n, cudaMemcpyDeviceToHost, h.stream));
+      CUDA_OK(cudaStreamSynchronize(h.stream));
+    }
+  }
+}
+
+uint64_t mapped_error(const tsr_decoder& h, uint64_t dem_error) {
+  // dem_error_to_error.at(i) and the "removed" check (tesseract.cc:620-624).
+  if (dem_error >= h.T.dem_error_to_error.size()) throw std::out_of_range("vector::_M_range_check: error index out of range");
+  uint64_t e = h.T.dem_error_to_error[dem_error];
+  if (e == tsr::kNoError) throw std::invalid_argument("error index does not map to a retained decoder error");
+  return e;
+}
+
+char* dup_text(const std::string& s) {
+  char* out = (char*)std::malloc(s.size() + 1);
+  if (!out) throw std::bad_alloc();
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return out;
+}
+
+}  // namespace
+
+extern "C" {
+
+void tsr_config_init(tsr_config* cfg) {
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->det_beam = 5;
+  cfg->no_revisit_dets = 1;
+  cfg->merge_errors = 1;
+  cfg->pqlimit = 200000;
+  cfg->device = -1;
+}
+
+const char* tsr_last_error(void) {
+  return g_error.c_str();
+}
+const char* tsr_version(void) {
+  return "tesseract_b200 0.1.0 (sm_100a)";
+}
+
+int tsr_create(const char* dem_text, const tsr_config* cfg, uint32_t flags, tsr_decoder** out) {
+  *out = nullptr;
+  return guarded([&] {
+    auto h = std::make_unique<tsr_decoder>();
+    h->cfg = *cfg;
+    h->cfg.det_orders = nullptr;
+    DemModel dem = DemModel::parse(dem_text);
+    h->T = tsr::ingest(dem, cfg->merge_errors != 0);
+    const uint64_t D = h->T.num_detectors;
+    // tesseract.cc:175-188.
+    if (cfg->num_det_orders == 0) {
+      h->det_orders.emplace_back(D);
+      for (uint64_t i = 0; i < D; ++i) h->det_orders[0][i] = i;
+    } else {
+      if (!cfg->det_orders) throw std::invalid_argument("det_orders is null but num_det_orders > 0");
+      for (uint64_t k = 0; k < cfg->num_det_orders; ++k)
+        h->det_orders.emplace_back(cfg->det_orders + k * D, cfg->det_orders + (k + 1) * D);
+    }
+    if (cfg->det_beam < 0) throw std::invalid_argument("det_beam must be >= 0");
+    if (h->T.max_degree > 32)
+      throw std::invalid_argument("tesseract_b200: errors touching more than 32 detectors are not supported");
+    std::map<std::vector<uint64_t>, uint32_t> perm_ids;
+    for (const auto& o : h->det_orders) {
+      auto it = perm_ids.emplace(o, (uint32_t)perm_ids.size()).first;
+      h->order_to_perm.push_back(it->second);
+    }
+    h->n_perms = (uint32_t)perm_ids.size();
+    h->host_only = (flags & TSR_CREATE_HOST_ONLY) != 0;
+    if (!h->host_only) init_device(*h);
+    *out = h.release();
+  });
+}
+
+void tsr_destroy(tsr_decoder* h) {
+  if (!h) return;
+  if (!h->host_only) cudaSetDevice(h->device);
+  delete h;
+}
+
+uint64_t tsr_num_detectors(const tsr_decoder* h) { return h->T.num_detectors; }
+uint64_t tsr_num_observables(const tsr_decoder* h) { return h->T.num_observables; }
+uint64_t tsr_num_errors(const tsr_decoder* h) { return h->T.num_errors; }
+uint64_t tsr_num_dem_errors(const tsr_decoder* h) { return h->T.num_dem_errors; }
+uint64_t tsr_num_det_orders(const tsr_decoder* h) { return h->det_orders.size(); }
+
+int tsr_error_costs(const tsr_decoder* h, double* out) {
+  std::copy(h->T.e_cost.begin(), h->T.e_cost.end(), out);
+  return TSR_OK;
+}
+
+int tsr_maps(const tsr_decoder* h, uint64_t* dem_error_to_error, uint64_t* error_to_dem_error) {
+  if (dem_error_to_error) std::copy(h->T.dem_error_to_error.begin(), h->T.dem_error_to_error.end(), dem_error_to_error);
+  if (error_to_dem_error) std::copy(h->T.error_to_dem_error.begin(), h->T.error_to_dem_error.end(), error_to_dem_error);
+  return TSR_OK;
+}
+
+int64_t tsr_csr(const tsr_decoder* h, int which, uint64_t* offsets, int32_t* idx) {
+  const tsr::DemTables& T = h->T;
+  auto emit = [&](const std::vector<uint32_t>& off, const std::vector<int32_t>& v) -> int64_t {
+    if (offsets) std::copy(off.begin(), off.end(), offsets);
+    if (idx) std::copy(v.begin(), v.end(), idx);
+    return (int64_t)v.size();
+  };
+  switch (which) {
+    case 0:
+      return emit(T.row_off, T.row_err);
+    case 1:
+      return emit(T.e_off, T.e_det);
+    case 2: {
+      auto nb = T.eneighbors();
+      uint64_t n = 0;
+      for (size_t e = 0; e < nb.size(); ++e) {
+        if (offsets) offsets[e] = n;
+        for (int v : nb[e]) {
+          if (idx) idx[n] = v;
+          ++n;
+        }
+      }
+      if (offsets) offsets[nb.size()] = n;
+      return (int64_t)n;
+    }
+    case 3:
+      return emit(T.eo_off, T.eo_obs);
+    default:
+      g_error = "unknown table id";
+      return TSR_E_INVALID_ARGUMENT;
+  }
+}
+
+int tsr_compiled_dem_text(const tsr_decoder* h, char** out) {
+  return guarded([&] { *out = dup_text(h->T.compiled_dem.str()); });
+}
+
+void tsr_free(void* p) {
+  std::free(p);
+}
+
+int tsr_decode_batch_b8(tsr_decoder* h, const uint8_t* dets, uint64_t stride, uint64_t shots, uint8_t* obs_out,
+                        double* cost_out, uint8_t* low_conf_out) {
+  return guarded([&] { decode_batch(*h, dets, stride, shots, false, h->ensemble, obs_out, cost_out, low_conf_out); });
+}
+
+int tsr_decode_batch_b8_device(tsr_decoder* h, const uint8_t* d_dets, uint64_t stride, uint64_t shots,
+                               uint8_t* d_obs_out, double* d_cost_out, uint8_t* d_low_conf_out) {
+  return guarded([&] { decode_batch(*h, d_dets, stride, shots, true, h->ensemble, d_obs_out, d_cost_out, d_low_conf_out); });
+}
+
+uint64_t tsr_last_batch_nnz(const tsr_decoder* h) {
+  return h->last_idx.size();
+}
+
+int tsr_last_batch_errors(const tsr_decoder* h, uint64_t* offsets, uint64_t* idx) {
+  if (offsets) std::copy(h->last_off.begin(), h->last_off.end(), offsets);
+  if (idx) std::copy(h->last_idx.begin(), h->last_idx.end(), idx);
+  return TSR_OK;
+}
+
+int tsr_decode(tsr_decoder* h, const uint64_t* detections, uint64_t n, int64_t order, uint64_t beam, uint64_t* errs_out,
+               uint64_t errs_cap, uint64_t* n_errs, double* cost, int32_t* low_confidence) {
+  return guarded([&] {
+    require_device(*h);
+    const uint64_t D = h->T.num_detectors;
+    const uint64_t stride = std::max<uint64_t>((D + 7) / 8, 1);
+    std::vector<uint8_t> packed(stride, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint64_t d = detections[i];
+      if (d >= D)  // tesseract.cc:400-404
+        throw std::runtime_error("Symptom " + std::to_string(d) + " references a detector >= num_detectors (= " +
+                                 std::to_string(D) + ").");
+      packed[d >> 3] |= (uint8_t)(1u << (d & 7));
+    }
+    double c = 0;
+    uint8_t low = 0;
+    if (order < 0) {
+      decode_batch(*h, packed.data(), stride, 1, false, h->ensemble, nullptr, &c, &low);
+    } else {
+      if ((uint64_t)order >= h->det_orders.size()) throw std::invalid_argument("detector_order is out of range");
+      if (beam > TSR_INF_DET_BEAM) beam = TSR_INF_DET_BEAM;
+      TrialSet one;
+      one.perm = {h->order_to_perm[(size_t)order]};
+      one.beam = {(uint32_t)beam};
+      one.literal_to_trial = {0};
+      CUDA_OK(cudaSetDevice(h->device));
+      one.upload();
+      decode_batch(*h, packed.data(), stride, 1, false, one, nullptr, &c, &low);
+    }
+    if (cost) *cost = c;
+    if (low_confidence) *low_confidence = low;
+    if (n_errs) *n_errs = h->last_idx.size();
+    if (errs_out) {
+      if (h->last_idx.size() > errs_cap) throw std::invalid_argument("errs_out is too small for the predicted errors");
+      std::copy(h->last_idx.begin(), h->last_idx.end(), errs_out);
+    }
+  });
+}
+
+int tsr_cost_from_errors(const tsr_decoder* h, const uint64_t* errs, uint64_t n, double* out) {
+  return guarded([&] {
+    double total = 0;
+    for (uint64_t i = 0; i < n; ++i) total += h->T.e_cost[mapped_error(*h, errs[i])];
+    *out = total;
+  });
+}
+
+int tsr_flipped_observables(const tsr_decoder* h, const uint64_t* errs, uint64_t n, uint8_t* obs_bits_out) {
+  return guarded([&] {
+    const uint64_t nb = (h->T.num_observables + 7) / 8;
+    std::vector<uint8_t> bits(nb, 0);
+    for (uint64_t i = 0; i < n; ++i)
+      for (int ob : h->T.errors[mapped_error(*h, errs[i])].observables) bits[(size_t)ob >> 3] ^= (uint8_t)(1u << (ob & 7));
+    std::copy(bits.begin(), bits.end(), obs_bits_out);
+  });
+}
+
+int tsr_counters(tsr_decoder* h, uint64_t out[8], int reset) {
+  return guarded([&] {
+    require_device(*h);
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaMemcpy(out, h->d_counters.p, 64, cudaMemcpyDeviceToHost));
+    if (reset) CUDA_OK(cudaMemset(h->d_counters.p, 0, 64));
+  });
+}
+
+int tsr_last_batch_timing(const tsr_decoder* h, double out[4]) {
+  for (int i = 0; i < 4; ++i) out[i] = h->timing[i];
+  return TSR_OK;
+}
+
+void* tsr_stream(tsr_decoder* h) {
+  return h->stream;
+}
+int tsr_device(const tsr_decoder* h) {
+  return h->host_only ? -1 : h->device;
+}
+
+int tsr_build_det_orders(const char* dem_text, uint64_t num_det_orders, int method, uint64_t seed, uint64_t* out) {
+  return guarded([&] {
+    if (method < 0 || method > 2) throw std::invalid_argument("Unknown det order method");
+    DemModel dem = DemModel::parse(dem_text);
+    auto orders = tsr::build_det_orders(dem, num_det_orders, (tsr::DetOrder)method, seed);
+    const uint64_t D = dem.count_detectors();
+    for (size_t k = 0; k < orders.size(); ++k) std::copy(orders[k].begin(), orders[k].end(), out + k * D);
+  });
+}
+
+uint64_t tsr_dem_count_detectors(const char* dem_text) {
+  uint64_t n = UINT64_MAX;
+  guarded([&] { n = DemModel::parse(dem_text).count_detectors(); });
+  return n;
+}
+
+double tsr_merge_weights(double a, double b) {
+  return tsr::merge_weights(a, b);
+}
+
+int tsr_circuit_to_dem(const char* circuit_text, char** dem_text_out) {
+  return guarded([&] { *dem_text_out = dup_text(tsr::circuit_to_dem_text(circuit_text)); });
+}
+
+int tsr_sample_dem_b8(const char* dem_text, uint64_t seed, uint64_t shots, uint8_t* dets_out, uint8_t* obs_out) {
+  return guarded([&] {
+    DemModel dem = DemModel::parse(dem_text);
+    const uint64_t ds = (dem.count_detectors() + 7) / 8, os = (dem.count_observables() + 7) / 8;
+    std::memset(dets_out, 0, (size_t)(shots * ds));
+    if (obs_out) std::memset(obs_out, 0, (size_t)(shots * os));
+    tsr::sample_dem_b8(dem, seed, shots, dets_out, ds, obs_out, os);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,351 @@
+#include "ingest.h"
+
+#include <algorithm>
+#include <cmath>
+#include <iostream>
+#include <map>
+#include <numeric>
+#include <queue>
+#include <random>
+#include <set>
+#include <stdexcept>
+
+namespace tsr {
+
+double CompiledError::probability() const {
+  return 1.0 / (1.0 + std::exp(cost));
+}
+
+double merge_weights(double a, double b) {
+  // common.cc:118-123: the log-likelihood weight of "exactly one of two independent mechanisms".
+  double sign = std::copysign(1, a) * std::copysign(1, b);
+  double smaller = sign * std::min(std::abs(a), std::abs(b));
+  return smaller + std::log(1 + std::exp(-std::abs(a + b))) - std::log(1 + std::exp(-std::abs(a - b)));
+}
+
+namespace {
+
+// common.cc:52-88.  Targets are XOR-accumulated (a detector listed twice cancels); separators are
+// ignored; the surviving ids come out ascending.
+CompiledError compile_error(const DemInstruction& inst) {
+  if (inst.kind != DemKind::Error)
+    throw std::invalid_argument("Error must be loaded from an error dem instruction, but received: " + inst.str());
+  double p = inst.args.at(0);
+  if (p < 0 || p > 1)
+    throw std::invalid_argument("Probability must be between 0 and 1, but received: " + std::to_string(p));
+  std::set<int> dets, obs;
+  for (const DemTarget& t : inst.targets) {
+    if (t.is_sep()) continue;
+    std::set<int>& into = t.is_obs() ? obs : dets;
+    int id = (int)t.id();
+    if (!into.erase(id)) into.insert(id);
+  }
+  CompiledError e;
+  e.cost = -1 * std::log(p / (1 - p));
+  e.detectors.assign(dets.begin(), dets.end());
+  e.observables.assign(obs.begin(), obs.end());
+  return e;
+}
+
+std::vector<DemTarget> symptom_targets(const CompiledError& e) {
+  std::vector<DemTarget> t;
+  for (int d : e.detectors) t.push_back(DemTarget::det((uint64_t)d));
+  for (int o : e.observables) t.push_back(DemTarget::obs((uint64_t)o));
+  return t;
+}
+
+}  // namespace
+
+DemTables ingest(const DemModel& flat, bool merge_errors) {
+  DemTables T;
+  T.num_dem_errors = flat.count_errors();
+  std::vector<uint64_t> to_compiled(T.num_dem_errors);
+  std::iota(to_compiled.begin(), to_compiled.end(), uint64_t{0});
+
+  // Stage 1 (common.cc:139-190): merge errors with identical symptoms; first-seen order defines the
+  // merged index; DETECTOR / LOGICAL_OBSERVABLE instructions keep their order and move to the front.
+  DemModel stage1;
+  if (merge_errors) {
+    std::map<std::pair<std::vector<int>, std::vector<int>>, uint64_t> index_of;
+    std::vector<CompiledError> merged;
+    std::vector<uint64_t> merge_map;
+    for (const DemInstruction& inst : flat.instructions) {
+      if (inst.kind != DemKind::Error) {
+        stage1.instructions.push_back(inst);
+        continue;
+      }
+      CompiledError e = compile_error(inst);
+      if (e.detectors.empty()) std::cout << "Warning: the circuit has errors that do not flip any detectors \n";
+      auto key = std::make_pair(e.detectors, e.observables);
+      auto it = index_of.find(key);
+      if (it == index_of.end()) {
+        index_of.emplace(std::move(key), merged.size());
+        merge_map.push_back(merged.size());
+        merged.push_back(std::move(e));
+      } else {
+        merged[it->second].cost = merge_weights(e.cost, merged[it->second].cost);
+        merge_map.push_back(it->second);
+      }
+    }
+    for (const CompiledError& e : merged) stage1.append_error(e.probability(), symptom_targets(e));
+    for (uint64_t& v : to_compiled) v = merge_map[v];
+  } else {
+    stage1 = flat;
+  }
+
+  // Stage 2 (common.cc:192-218): drop errors whose probability is not > 0.
+  std::vector<uint64_t> keep_map;
+  uint64_t kept = 0;
+  for (const DemInstruction& inst : stage1.instructions) {
+    if (inst.kind == DemKind::Error) {
+      if (inst.args[0] > 0) {
+        keep_map.push_back(kept++);
+        T.compiled_dem.instructions.push_back(inst);
+      } else {
+        keep_map.push_back(kNoError);
+      }
+    } else {
+      T.compiled_dem.instructions.push_back(inst);
+    }
+  }
+  for (uint64_t& v : to_compiled) v = keep_map[v];
+  T.dem_error_to_error = to_compiled;
+
+  // Stage 3 (utils.cc:253-261): the compiled error list; costs are recomputed from the printed
+  // probabilities, i.e. after the cost -> p -> cost round trip.
+  for (const DemInstruction& inst : T.compiled_dem.instructions)
+    if (inst.kind == DemKind::Error && inst.args[0] > 0) T.errors.push_back(compile_error(inst));
+  T.num_errors = T.errors.size();
+  T.num_detectors = T.compiled_dem.count_detectors();
+  T.num_observables = T.compiled_dem.count_observables();
+
+  // common.cc:228-239: first original index for each compiled error.
+  T.error_to_dem_error.assign(T.num_errors, kNoError);
+  for (uint64_t i = 0; i < T.dem_error_to_error.size(); ++i) {
+    uint64_t c = T.dem_error_to_error[i];
+    if (c != kNoError && T.error_to_dem_error[c] == kNoError) T.error_to_dem_error[c] = i;
+  }
+
+  const uint64_t D = T.num_detectors, E = T.num_errors;
+  if (D >= 0xFFFF) throw std::invalid_argument("tesseract_b200: at most 65534 detectors are supported");
+
+  // Rows (tesseract.cc:211-227).  Filled in ascending error index, then std::sort by cost/degree —
+  // an unstable sort whose tie order is part of the contract, so it is the same
+  // libstdc++ call on the same input sequence.
+  std::vector<std::vector<int>> rows(D);
+  std::vector<double> per_detector_cost(E);
+  for (uint64_t e = 0; e < E; ++e) {
+    for (int d : T.errors[e].detectors) rows[(size_t)d].push_back((int)e);
+    per_detector_cost[e] = T.errors[e].cost / T.errors[e].detectors.size();
+  }
+  for (auto& row : rows)
+    std::sort(row.begin(), row.end(), [&](size_t a, size_t b) { return per_detector_cost[a] < per_detector_cost[b]; });
+
+  T.row_off.assign(D + 1, 0);
+  for (uint64_t d = 0; d < D; ++d) {
+    T.row_off[d + 1] = T.row_off[d] + (uint32_t)rows[d].size();
+    T.max_row_len = std::max<uint32_t>(T.max_row_len, (uint32_t)rows[d].size());
+  }
+  if (T.max_row_len > 0x7FFE) throw std::invalid_argument("tesseract_b200: detector rows longer than 32766 are not supported");
+  const size_t nnz = T.row_off[D];
+  T.row_err.resize(nnz);
+  for (uint64_t d = 0; d < D; ++d) std::copy(rows[d].begin(), rows[d].end(), T.row_err.begin() + T.row_off[d]);
+
+  T.e_off.assign(E + 1, 0);
+  T.eo_off.assign(E + 1, 0);
+  T.e_cost.resize(E);
+  for (uint64_t e = 0; e < E; ++e) {
+    T.e_off[e + 1] = T.e_off[e] + (uint32_t)T.errors[e].detectors.size();
+    T.eo_off[e + 1] = T.eo_off[e] + (uint32_t)T.errors[e].observables.size();
+    T.e_cost[e] = T.errors[e].cost;
+    T.max_degree = std::max<uint32_t>(T.max_degree, (uint32_t)T.errors[e].detectors.size());
+  }
+  T.e_det.resize(nnz);
+  T.e_rank.assign(nnz, -1);
+  T.eo_obs.resize(T.eo_off[E]);
+  for (uint64_t e = 0; e < E; ++e) {
+    std::copy(T.errors[e].detectors.begin(), T.errors[e].detectors.end(), T.e_det.begin() + T.e_off[e]);
+    std::copy(T.errors[e].observables.begin(), T.errors[e].observables.end(), T.eo_obs.begin() + T.eo_off[e]);
+  }
+  for (uint64_t d = 0; d < D; ++d) {
+    for (uint32_t k = 0; k < rows[d].size(); ++k) {
+      uint64_t e = (uint64_t)rows[d][k];
+      const auto& dets = T.errors[e].detectors;
+      size_t j = (size_t)(std::lower_bound(dets.begin(), dets.end(), (int)d) - dets.begin());
+      T.e_rank[T.e_off[e] + j] = (int32_t)k;
+    }
+  }
+
+  // Row records.
+  const RowSlot unused{(uint16_t)D, 0xFFFF};
+  T.rec_a.resize(nnz);
+  T.rec_b.assign(nnz * 4, unused);
+  T.rec_c.assign(nnz * 4, unused);
+  for (uint64_t d = 0; d < D; ++d) {
+    for (uint32_t k = 0; k < rows[d].size(); ++k) {
+      size_t at = T.row_off[d] + k;
+      uint64_t e = (uint64_t)rows[d][k];
+      const auto& dets = T.errors[e].detectors;
+      RowRecordA a;
+      a.cost = T.errors[e].cost;
+      a.size = (uint16_t)std::min<size_t>(dets.size(), 0xFFFF);
+      a.flags = dets.size() > (size_t)kMaxInlineDegree ? 1 : 0;
+      a.other0 = unused;
+      int slot = 0;
+      for (size_t j = 0; j < dets.size() && slot < kMaxInlineDegree - 1; ++j) {
+        if ((uint64_t)dets[j] == d) continue;
+        RowSlot s{(uint16_t)dets[j], (uint16_t)T.e_rank[T.e_off[e] + j]};
+        if (slot == 0) {
+          a.other0 = s;
+        } else if (slot <= 4) {
+          T.rec_b[at * 4 + (size_t)(slot - 1)] = s;
+        } else {
+          T.rec_c[at * 4 + (size_t)(slot - 5)] = s;
+        }
+        ++slot;
+      }
+      T.rec_a[at] = a;
+    }
+  }
+
+  // Detector adjacency (replaces eneighbors, tesseract.cc:229-254).
+  T.adj_words = (uint32_t)((D + 31) / 32);
+  T.adj.assign((size_t)D * T.adj_words, 0);
+  for (const CompiledError& e : T.errors)
+    for (int a : e.detectors)
+      for (int b : e.detectors) T.adj[(size_t)a * T.adj_words + ((size_t)b >> 5)] |= 1u << (b & 31);
+  return T;
+}
+
+std::vector<std::vector<int>> DemTables::eneighbors() const {
+  std::vector<std::vector<int>> out(num_errors);
+  std::vector<uint32_t> acc(adj_words);
+  for (uint64_t e = 0; e < num_errors; ++e) {
+    std::fill(acc.begin(), acc.end(), 0u);
+    for (int d : errors[e].detectors)
+      for (uint32_t w = 0; w < adj_words; ++w) acc[w] |= adj[(size_t)d * adj_words + w];
+    for (int d : errors[e].detectors) acc[(size_t)d >> 5] &= ~(1u << (d & 31));
+    for (uint32_t w = 0; w < adj_words; ++w)
+      for (uint32_t m = acc[w]; m; m &= m - 1) out[e].push_back((int)(w * 32 + (uint32_t)__builtin_ctz(m)));
+  }
+  return out;
+}
+
+// ---- detector orders (utils.cc:32-205) -----------------------------------------------------------
+
+std::vector<std::vector<double>> get_detector_coords(const DemModel& dem) {
+  // One entry per DETECTOR instruction, in order of appearance (utils.cc:42-48).
+  std::vector<std::vector<double>> coords;
+  for (const DemInstruction& inst : dem.instructions)
+    if (inst.kind == DemKind::Detector) coords.push_back(inst.args);
+  return coords;
+}
+
+std::vector<std::vector<uint64_t>> build_detector_graph(const DemModel& dem) {
+  std::vector<std::vector<uint64_t>> nb(dem.count_detectors());
+  for (const DemInstruction& inst : dem.instructions) {
+    if (inst.kind != DemKind::Error) continue;
+    std::vector<uint64_t> dets;
+    for (const DemTarget& t : inst.targets)
+      if (t.is_det()) dets.push_back(t.id());
+    for (size_t i = 0; i < dets.size(); ++i)
+      for (size_t j = i + 1; j < dets.size(); ++j) {
+        nb[dets[i]].push_back(dets[j]);
+        nb[dets[j]].push_back(dets[i]);
+      }
+  }
+  for (auto& v : nb) {
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+  }
+  return nb;
+}
+
+std::vector<std::vector<uint64_t>> build_det_orders(const DemModel& dem, uint64_t num_det_orders, DetOrder method,
+                                                    uint64_t seed) {
+  std::mt19937_64 rng(seed);
+  const size_t n = dem.count_detectors();
+  std::vector<std::vector<uint64_t>> orders(num_det_orders);
+  switch (method) {
+    case DetOrder::DetIndex: {
+      // utils.cc:173-190: one coin per order, heads = descending.
+      std::uniform_int_distribution<int> coin(0, 1);
+      for (auto& order : orders) {
+        order.resize(n);
+        bool descending = coin(rng) != 0;
+        for (size_t i = 0; i < n; ++i) order[i] = descending ? n - 1 - i : i;
+      }
+      return orders;
+    }
+    case DetOrder::DetBFS: {
+      // utils.cc:89-133: randomised breadth-first sweeps; the stored list is the INVERSE of the
+      // visiting sequence (a quirk the search then reads as position -> detector).
+      auto graph = build_detector_graph(dem);
+      std::uniform_int_distribution<size_t> pick(0, graph.size() - 1);
+      for (auto& order : orders) {
+        std::vector<size_t> seq;
+        seq.reserve(graph.size());
+        std::vector<char> seen(graph.size(), 0);
+        std::queue<size_t> frontier;
+        size_t start = pick(rng);
+        while (seq.size() < graph.size()) {
+          if (!seen[start]) {
+            seen[start] = 1;
+            frontier.push(start);
+            seq.push_back(start);
+          }
+          while (!frontier.empty()) {
+            size_t cur = frontier.front();
+            frontier.pop();
+            std::vector<uint64_t> nb = graph[cur];
+            std::shuffle(nb.begin(), nb.end(), rng);
+            for (uint64_t v : nb)
+              if (!seen[v]) {
+                seen[v] = 1;
+                frontier.push(v);
+                seq.push_back(v);
+              }
+          }
+          if (seq.size() < graph.size()) {
+            do {
+              start = pick(rng);
+            } while (seen[start]);
+          }
+        }
+        order.resize(graph.size());
+        for (size_t i = 0; i < seq.size(); ++i) order[seq[i]] = i;
+      }
+      return orders;
+    }
+    case DetOrder::DetCoordinate: {
+      // utils.cc:135-171: sort detectors by their projection on a random Gaussian direction.
+      auto coords = get_detector_coords(dem);
+      std::normal_distribution<double> gauss(0, 1);
+      if (coords.empty() || coords.at(0).empty()) {
+        for (auto& order : orders) {
+          order.resize(n);
+          std::iota(order.begin(), order.end(), uint64_t{0});
+        }
+        return orders;
+      }
+      std::vector<double> proj(n);
+      for (auto& order : orders) {
+        std::vector<double> dir;
+        for (size_t i = 0; i < coords.at(0).size(); ++i) dir.push_back(gauss(rng));
+        for (size_t i = 0; i < coords.size(); ++i) {
+          proj[i] = 0;
+          for (size_t j = 0; j < dir.size(); ++j) proj[i] += coords[i][j] * dir[j];
+        }
+        std::vector<size_t> seq(n);
+        std::iota(seq.begin(), seq.end(), size_t{0});
+        std::sort(seq.begin(), seq.end(), [&](const size_t& a, const size_t& b) { return proj[a] > proj[b]; });
+        order.resize(n);
+        for (size_t i = 0; i < seq.size(); ++i) order[seq[i]] = i;
+      }
+      return orders;
+    }
+  }
+  throw std::invalid_argument("Unknown det order method");
+}
+
+}  // namespace tsr

@@ -1,0 +1,134 @@
+// Device-side data layout and launch interface of the A* search kernels (search.cu).
+#pragma once
+#include <cstdint>
+
+namespace tsr {
+
+// ---- device-resident DEM tables (read-only during decoding, L2-resident: <= ~20 MB) --------------
+struct DeviceTables {
+  uint32_t D = 0, E = 0, O = 0;
+  uint32_t nwords = 0;  // ceil(D/32): words per detector bitset and per adjacency row
+  // Detector rows (host-sorted), and per-entry records; see ingest.h.
+  const uint32_t* row_off = nullptr;  // [D+1]
+  const int32_t* row_err = nullptr;   // [nnz]
+  const uint4* rec_a = nullptr;       // [nnz]   {cost f64, size u16, flags u16, slot0}
+  const uint4* rec_b = nullptr;       // [nnz]   slots 1..4
+  const uint4* rec_c = nullptr;       // [nnz]   slots 5..8
+  // Errors.
+  const uint32_t* e_off = nullptr;    // [E+1]
+  const int32_t* e_det = nullptr;     // [nnz]  ascending detectors
+  const int32_t* e_rank = nullptr;    // [nnz]  rank of the error in that detector's row
+  const double* e_cost = nullptr;     // [E]
+  const uint16_t* e_nnbr = nullptr;   // [E]    |eneighbors[e]| of the reference (counter A only)
+  const uint32_t* eo_off = nullptr;   // [E+1]
+  const int32_t* eo_obs = nullptr;    // observables per error
+  const uint64_t* e2dem = nullptr;    // [E]    error_to_dem_error
+  // Detector adjacency bit matrix [D][nwords] and 128-bit Zobrist keys [D].
+  const uint32_t* adj = nullptr;
+  const uint4* zobrist = nullptr;
+  // Distinct detector orders: position -> detector and its inverse, [n_perm][D].
+  const uint32_t* order_det = nullptr;
+  const uint32_t* order_pos = nullptr;
+};
+
+struct alignas(16) HeapNode {
+  double cost;       // f = g + h
+  uint32_t chain;    // index into the chain arena, kNoChain for the root
+  uint16_t num_dets;
+  uint16_t depth;
+};
+struct alignas(16) ChainNode {
+  uint32_t error;
+  uint32_t parent;
+  uint32_t mind_pos;  // (min_detector << 16) | rank of `error` in that detector's row
+  uint32_t off_mask;  // bit j: detector j of `error` was fired before it (at-most-two heuristic)
+};
+constexpr uint32_t kNoChain = 0xFFFFFFFFu;
+
+enum ItemStatus : uint8_t {
+  kItemOk = 0,
+  kItemLowConfidence = 1,   // the reference's low_confidence_flag
+  kItemNodeOverflow = 2,    // outgrew this tier's per-slot heap / chain / visited capacity
+  kItemSolutionOverflow = 3 // solution longer than sol_stride
+};
+
+struct SearchParams {
+  DeviceTables t;
+  // Work: item i = (shot, distinct trial) with i = shot * n_trials + trial; `item_ids` (nullable)
+  // restricts the launch to a list of items (retry tiers).
+  const uint8_t* dets = nullptr;  // [shots][stride] bit-packed
+  uint64_t stride = 0;
+  uint32_t n_work = 0;
+  const uint32_t* item_ids = nullptr;
+  uint32_t n_trials = 1;
+  const uint32_t* trial_perm = nullptr;  // [n_trials] distinct order id
+  const uint32_t* trial_beam = nullptr;  // [n_trials]
+  // Config.
+  double det_penalty = 0;
+  uint64_t pqlimit = 0;
+  int no_revisit = 1;
+  int at_most_two = 0;
+  // Per-slot scratch (slot = one warp).
+  uint32_t n_slots = 0;
+  uint64_t node_cap = 0;   // heap and chain entries per slot
+  uint64_t visit_cap = 0;  // visited-table entries per slot
+  uint32_t vlist_cap = 0;
+  HeapNode* heap = nullptr;
+  ChainNode* chain = nullptr;
+  uint4* visited = nullptr;
+  uint32_t* vlist = nullptr;
+  double* hcache = nullptr;  // [n_slots][D]
+  // Per-item outputs.
+  uint32_t sol_stride = 0;
+  uint32_t* sol = nullptr;      // [items][sol_stride] compiled error ids, root -> leaf
+  uint32_t* sol_len = nullptr;  // [items]
+  uint8_t* status = nullptr;    // [items] ItemStatus
+  double* fcost = nullptr;      // [items] f of the goal node (diagnostic)
+  unsigned int* work_counter = nullptr;
+  unsigned long long* counters = nullptr;  // [8], see tsr_counters
+};
+
+struct ResolveParams {
+  DeviceTables t;
+  uint32_t n_shots = 0;          // shots of the batch (or length of shot_ids)
+  const uint32_t* shot_ids = nullptr;  // nullable: restrict to these shots (retry tiers)
+  uint32_t n_trials = 1;         // distinct trials per shot
+  uint32_t n_literal = 1;        // literal trials of the reference loop
+  const uint32_t* literal_to_trial = nullptr;  // [n_literal]
+  uint32_t sol_stride = 0;
+  const uint32_t* sol = nullptr;
+  const uint32_t* sol_len = nullptr;
+  const uint8_t* status = nullptr;
+  // Outputs (any may be null).
+  uint8_t* obs_out = nullptr;  // [shots][obs_stride]
+  uint32_t obs_stride = 0;
+  double* cost_out = nullptr;
+  uint8_t* low_conf_out = nullptr;
+  uint64_t* err_out = nullptr;           // pooled predicted errors (original DEM indices)
+  uint64_t err_cap = 0;
+  unsigned long long* err_cursor = nullptr;
+  uint64_t* err_off = nullptr;           // [shots] start in err_out
+  uint32_t* err_len = nullptr;           // [shots]
+  uint32_t* retry_shots = nullptr;       // shots with an overflowed trial
+  unsigned int* retry_count = nullptr;
+};
+
+struct StageParams {
+  const uint8_t* dets = nullptr;
+  uint64_t stride = 0;
+  uint32_t shots = 0;
+  uint32_t D = 0;
+  unsigned int* max_fired = nullptr;  // out: largest number of fired detectors in the batch
+  unsigned long long* total_fired = nullptr;
+};
+
+// Launchers (search.cu).  All enqueue on `stream` and return the cudaError_t of the launch.
+int launch_stage(const StageParams& p, void* stream);
+int launch_search(const SearchParams& p, uint32_t blocks, uint32_t warps_per_block, void* stream);
+int launch_resolve(const ResolveParams& p, void* stream);
+// Shared memory bytes one search warp needs for a DEM with D detectors.
+uint32_t search_smem_bytes_per_warp(uint32_t D);
+// Resident blocks per SM of the search kernel for this block shape (0 on failure).
+int search_max_blocks_per_sm(uint32_t warps_per_block, uint32_t D);
+
+}  // namespace tsr
