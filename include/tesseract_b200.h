@@ -47,6 +47,7 @@ typedef struct tsr_config {
   double det_penalty;      /* tesseract.cc:153 */
   uint64_t num_det_orders; /* 0 = one identity order (tesseract.cc:175-177) */
   const uint64_t* det_orders; /* [num_det_orders][num_detectors] row-major, position -> detector */
+  uint64_t det_order_len;  /* entries per order; must equal num_detectors (tesseract.cc:178-184); 0 = unchecked */
   /* Device resources; 0 = choose automatically. */
   uint32_t search_slots;       /* concurrent searches (one warp each) */
   uint32_t warps_per_block;

@@ -42,6 +42,7 @@ class TsrConfig(C.Structure):
         ("det_penalty", C.c_double),
         ("num_det_orders", C.c_uint64),
         ("det_orders", C.POINTER(C.c_uint64)),
+        ("det_order_len", C.c_uint64),
         ("search_slots", C.c_uint32),
         ("warps_per_block", C.c_uint32),
         ("node_pool_bytes", C.c_uint64),
@@ -191,7 +192,10 @@ class Decoder:
         self._orders = None
         if det_orders is not None and len(det_orders):
             self._orders = np.ascontiguousarray(det_orders, dtype=np.uint64)
+            if self._orders.ndim != 2:
+                raise ValueError("det_orders must be a 2D array [num_det_orders, num_detectors]")
             cfg.num_det_orders = self._orders.shape[0]
+            cfg.det_order_len = self._orders.shape[1]
             cfg.det_orders = _p(self._orders, C.c_uint64)
         cfg.search_slots = search_slots
         cfg.warps_per_block = warps_per_block

@@ -609,6 +609,8 @@ int tsr_create(const char* dem_text, const tsr_config* cfg, uint32_t flags, tsr_
       for (uint64_t i = 0; i < D; ++i) h->det_orders[0][i] = i;
     } else {
       if (!cfg->det_orders) throw std::invalid_argument("det_orders is null but num_det_orders > 0");
+      if (cfg->det_order_len && cfg->det_order_len != D)  // tesseract.cc:178-184
+        throw std::invalid_argument("Each detector order list must have a size equal to the number of detectors.");
       for (uint64_t k = 0; k < cfg->num_det_orders; ++k)
         h->det_orders.emplace_back(cfg->det_orders + k * D, cfg->det_orders + (k + 1) * D);
     }

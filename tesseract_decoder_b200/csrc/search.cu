@@ -399,7 +399,9 @@ __device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t ite
     // detector_cost_cache, tesseract.cc:531,569-582; same values).  For the root their in-order sum is
     // the initial cost (tesseract.cc:411-414).
     double root_cost = 0;
-    for (uint32_t wb = 0; wb < nwords; wb += 32) {
+    // (The root is popped right after its cost was computed: its terms are still in hc.)
+    const bool terms_cached = !root_pending && node.chain == kNoChain;
+    for (uint32_t wb = 0; wb < nwords && !terms_cached; wb += 32) {
       const uint32_t w = wb + lane;
       const uint32_t mine = w < nwords ? fbits[w] : 0;
       unsigned nz = __ballot_sync(kFull, mine != 0);

@@ -1,0 +1,162 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every declared symbol, and the
+host ingestion (DEM text -> tables) is identical to the oracle's.  No compute call needs a GPU here."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import workloads as W
+from oracle import oracle
+from oracle.oracle import OracleDecoder
+from tesseract_decoder_b200 import capi
+
+KIND = "reference" if oracle.available("reference") else "port"
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(W.ROOT, "include", "tesseract_b200.h")).read()
+    declared = set(re.findall(r"\b(tsr_[a-z0-9_]+)\s*\(", header))
+    declared -= {"tsr_decoder", "tsr_config"}
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(capi.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in lib.tsr_version.__call__.__self__.tsr_version() if False else True
+
+
+def test_version_string():
+    assert "sm_100a" in capi.lib().tsr_version().decode()
+
+
+def test_config_defaults_match_reference():  # tesseract.h:39-58
+    cfg = capi.TsrConfig()
+    capi.lib().tsr_config_init(ctypes.byref(cfg))
+    assert (cfg.det_beam, cfg.beam_climbing, cfg.no_revisit_dets, cfg.merge_errors, cfg.pqlimit, cfg.det_penalty) == \
+        (5, 0, 1, 1, 200000, 0.0)
+
+
+@pytest.mark.parametrize("name", ["surface_d5_r5_p0.002_X", "color_superdense_d5_r5_p0.001_Z", "bb72_r6_p0.001_X",
+                                  "transcx_d3_p0.001_X"])
+@pytest.mark.parametrize("merge", [True, False])
+def test_ingestion_tables_equal_the_oracle(name, merge):
+    dem = W.load_dem(name)
+    mine = capi.Decoder(dem, merge_errors=merge, host_only=True)
+    ref = OracleDecoder(dem, merge_errors=merge, kind=KIND)
+    assert (mine.num_detectors, mine.num_observables, mine.num_errors, mine.num_dem_errors) == \
+        (ref.num_detectors, ref.num_observables, ref.num_errors, ref.num_dem_errors)
+    assert np.array_equal(mine.error_costs(), ref.error_costs())  # bit-exact doubles (same libm calls)
+    for which in range(4):  # sorted d2e rows (tie order included), edets, eneighbors, observables
+        a, b = mine.csr(which), ref.csr(which)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), which
+    for a, b in zip(mine.maps(), ref.maps()):
+        assert np.array_equal(a, b)
+
+
+def test_recorded_dem_sizes():
+    """num_detectors / num_compiled_errors the reference recorded for these circuits
+    (benchmarking/sparsify_errors/aggregated_results.jsonl:645,375,795,195,15)."""
+    expect = {"surface_d5_r5_p0.002_X": (120, 1677), "color_superdense_d7_r7_p0.001_X": (252, 9941),
+              "surface_d11_r11_p0.001_X": (1320, 24483), "bb144_r12_p0.001_X": (1728, 67824), "bb72_r6_p0.001_X": (432, 16200)}
+    for name, (D, E) in expect.items():
+        dec = capi.Decoder(W.load_dem(name), host_only=True)
+        assert (dec.num_detectors, dec.num_errors) == (D, E), name
+
+
+def test_small_known_answers_host_side():
+    # tesseract.test.cc:204-223, 249-278; common.test.cc:22-29
+    dec = capi.Decoder("error(0.1) D0\nerror(0) D1\nerror(0.2) D2\nerror(0.3) D2\ndetector(0,0,0) D0\ndetector(0,0,0) D1\ndetector(0,0,0) D2",
+                       host_only=True)
+    d2e, e2d = dec.maps()
+    assert dec.num_errors == 2 and len(d2e) == 4 and d2e[1] == capi.NO_ERROR_INDEX and d2e[2] == d2e[3] and e2d[d2e[2]] == 2
+    with pytest.raises(ValueError, match="error index does not map to a retained decoder error"):
+        dec.cost_from_errors([1])
+    with pytest.raises(ValueError, match="error index does not map to a retained decoder error"):
+        dec.flipped_observables([1])
+    dec = capi.Decoder("error(0.1) D0 ^ D0 D1 L0 L1 L1", merge_errors=False, host_only=True)
+    assert dec.rows(1) == [[1]] and dec.rows(3) == [[0]]
+    # shared_decoding_tests.py:37-127
+    dec = capi.Decoder("error(0.1) D0 L0\nerror(0.2) D1 L1\nerror(0.3) D2\nerror(0.4) D3 L0 L1", merge_errors=False, host_only=True)
+    assert dec.cost_from_errors([0, 3]) == pytest.approx(math.log(9) + math.log(1.5))
+    assert dec.cost_from_errors([]) == 0
+    assert dec.flipped_observables([0, 3]) == [1] and dec.flipped_observables([3]) == [0, 1]
+
+
+def test_eneighbors_known_answers():  # tesseract.test.cc:280-374
+    dec = capi.Decoder("error(0.1) D0 D1\nerror(0.1) D1 D2\nerror(0.1) D2 D3\nerror(0.1) D4 D5\nerror(0.1) D0 D2 D4\n"
+                       + "\n".join(f"detector({i}, 0, 0) D{i}" for i in range(6)), merge_errors=False, host_only=True)
+    assert dec.rows(2) == [[2, 4], [0, 3, 4], [0, 1, 4], [0, 2], [1, 3, 5]]
+
+
+def test_dem_text_grammar():
+    """repeat blocks, shift_detectors, tags, comments, separators."""
+    text = """
+        # a comment
+        error[tagged](0.125) D0 D1 ^ D2 L0
+        repeat 3 {
+            error(0.25) D0 D3
+            shift_detectors(0, 1) 2
+        }
+        detector(1, 2) D0
+        logical_observable L1
+    """
+    flat = "error(0.125) D0 D1 D2 L0\nerror(0.25) D0 D3\nerror(0.25) D2 D5\nerror(0.25) D4 D7\ndetector(1,5) D6\nlogical_observable L1"
+    a = capi.Decoder(text, merge_errors=False, host_only=True)
+    b = capi.Decoder(flat, merge_errors=False, host_only=True)
+    r = OracleDecoder(text, merge_errors=False, kind=KIND)
+    assert a.num_detectors == b.num_detectors == r.num_detectors == 8
+    assert a.num_observables == b.num_observables == r.num_observables == 2
+    assert a.rows(1) == b.rows(1) == r.rows(1)
+    assert np.array_equal(a.error_costs(), r.error_costs())
+    assert capi.Decoder(a.compiled_dem_text(), merge_errors=False, host_only=True).rows(1) == a.rows(1)
+    for bad in ["error(1.5) D0", "error(0.1) Q0", "bogus(0.1) D0", "repeat 2 {\nerror(0.1) D0", "error D0"]:
+        with pytest.raises(ValueError):
+            capi.Decoder(bad, host_only=True)
+
+
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_det_orders_equal_the_reference(method):
+    if not oracle.available("reference") and method != 1:
+        pytest.skip("BFS / coordinate orders are only restated in the reference build")
+    for name in ["transcx_d3_p0.001_X", "color_superdense_d5_r5_p0.001_Z"]:
+        dem = W.load_dem(name)
+        for seed in (0, 2384753, W.CLI_ORDER_SEED):
+            assert np.array_equal(capi.build_det_orders(dem, 7, method, seed), oracle.build_det_orders(dem, 7, method, seed, kind=KIND))
+
+
+def test_det_order_size_is_validated():  # tesseract.cc:178-184
+    with pytest.raises(ValueError):
+        capi.Decoder("error(0.1) D0 D1", det_orders=np.zeros((1, 5), dtype=np.uint64), host_only=True)
+
+
+def test_merge_weights():  # common.test.cc:115-145
+    rng = np.random.default_rng(1)
+    for p, q in rng.uniform(0.001, 0.999, size=(100, 2)):
+        a, b = math.log((1 - p) / p), math.log((1 - q) / q)
+        assert capi.merge_weights(a, b) == oracle.merge_weights(a, b, kind=KIND)
+
+
+def test_sampler_is_deterministic_and_plausible():
+    dem = W.load_dem("surface_d5_r5_p0.002_X")
+    a = capi.sample_dem_b8(dem, 5, 4000, 120, 1)
+    b = capi.sample_dem_b8(dem, 5, 4000, 120, 1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    fired = np.unpackbits(a[0], axis=1).sum() / 4000
+    assert 6.0 < fired < 8.5  # 7.1 fired detectors per shot on this DEM
+
+
+def test_decode_without_a_device_fails_loudly():
+    """No CPU fallback: a host-only handle refuses to decode."""
+    dec = capi.Decoder("error(0.1) D0 D1 L0\nerror(0.2) D0", host_only=True)
+    with pytest.raises(capi.CudaUnavailable):
+        dec.decode_to_errors([0, 1])
+    with pytest.raises(capi.CudaUnavailable):
+        dec.decode_batch_b8(np.zeros((1, 1), dtype=np.uint8))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/testdata"), reason="reference test circuits are not on this box")
+def test_circuit_analyzer_reproduces_committed_dems():
+    path = "/root/reference/testdata/surfacecodes/r=5,d=5,p=0.002,noise=si1000,c=surface_code_X,q=49,gates=cz.stim"
+    assert capi.circuit_to_dem(open(path).read()) == W.load_dem("surface_d5_r5_p0.002_X")

@@ -1,0 +1,261 @@
+"""Pins the oracle: the reference's own known-answer tests, restated, run against BOTH CPU checkers
+(the reference build oracle/_ref when present, and the CPU port), plus port == reference shot for shot
+and port == committed golden outputs (which the reference build produced; scripts/make_golden.py).
+"""
+import itertools
+import math
+
+import numpy as np
+import pytest
+
+import workloads as W
+from oracle import oracle
+from oracle.oracle import OracleDecoder
+
+KINDS = [k for k in ("reference", "port") if oracle.available(k)]
+pytestmark = pytest.mark.parametrize("kind", KINDS)
+
+# tesseract.test.cc:125-202 — four literal DEMs, every syndrome.
+EXHAUSTIVE_DEMS = [
+    """error(0.1) D0 D1 L0
+error(0.1) D1 D2
+error(0.1) D2 D3
+error(0.1) D3 D0
+detector(0, 0, 0) D0
+detector(1, 0, 0) D1
+detector(2, 0, 0) D2
+detector(3, 0, 0) D3""",
+    """error(0.011) D0
+error(0.02) D1 D2
+error(0.033) D1 D2 D3
+error(0.09) D1
+error(0.042) D3 D5
+error(0.043) D3 D4
+error(0.05) D2 D4 D5
+detector(0, 0, 0) D0
+detector(1, 0, 0) D1
+detector(2, 0, 0) D2
+detector(3, 0, 0) D3
+detector(4, 0, 0) D4
+detector(5, 0, 0) D5""",
+    """error(0.02) D0
+error(0.02) D1
+error(0.02) D1 D0
+error(0.03) D1 D3
+error(0.02) D0 D2
+error(0.02) D0 D3
+error(0.02) D2 D3
+error(0.02) D2
+error(0.02) D3
+detector(0, 0, 0) D0
+detector(0, 0, 0) D1
+detector(0, 0, 1) D2
+detector(0, 0, 1) D3""",
+    """error(0.02) D0
+error(0.02) D1
+error(0.02) D1 D0
+error(0.03) D1 D3
+error(0.02) D0 D2
+error(0.02) D0 D3
+error(0.02) D2 D3
+error(0.03) D3 D5
+error(0.02) D2
+error(0.03) D3
+detector(1, 0, 0) D0
+detector(0, 1, 0) D1
+detector(1, 0, 1) D2
+detector(0, 0, 1) D3
+detector(1, 1, 2) D4
+detector(0, 0, 2) D5""",
+]
+
+
+def brute_force_min_cost(dem_text, num_detectors):
+    """Exact optimum by enumeration (stands in for the reference's Simplex/HiGHS oracle)."""
+    errs = []
+    for line in dem_text.splitlines():
+        line = line.strip()
+        if not line.startswith("error"):
+            continue
+        p = float(line[line.index("(") + 1:line.index(")")])
+        mask = 0
+        for tok in line[line.index(")") + 1:].split():
+            if tok.startswith("D"):
+                mask ^= 1 << int(tok[1:])
+        errs.append((math.log((1 - p) / p), mask))
+    best = {}
+    for subset in itertools.product([0, 1], repeat=len(errs)):
+        cost, mask = 0.0, 0
+        for take, (c, m) in zip(subset, errs):
+            if take:
+                cost += c
+                mask ^= m
+        if cost < best.get(mask, float("inf")):
+            best[mask] = cost
+    return best
+
+
+@pytest.mark.parametrize("which", range(4))
+def test_exhaustive_small_dems_reach_the_optimum(kind, which):
+    dem = EXHAUSTIVE_DEMS[which]
+    dec = OracleDecoder(dem, kind=kind)  # default config (tesseract.h:39-58)
+    D = dec.num_detectors
+    best = brute_force_min_cost(dem, D)
+    for bits in range(1 << D):
+        hits = [d for d in range(D) if bits & (1 << (D - d - 1))]
+        mask = sum(1 << d for d in hits)
+        errs, cost, low = dec.decode_to_errors(hits)
+        if low:
+            assert mask not in best
+            continue
+        assert abs(cost - best[mask]) <= 1e-7  # EPSILON, utils.h:34
+
+
+def test_strip_zero_probability_errors(kind):  # tesseract.test.cc:204-223
+    dec = OracleDecoder("error(0.1) D0\nerror(0) D1\nerror(0.2) D2\ndetector(0,0,0) D0\ndetector(0,0,0) D1\ndetector(0,0,0) D2", kind=kind)
+    assert dec.num_errors == 2
+
+
+def test_index_maps_in_original_coordinates(kind):  # tesseract.test.cc:249-278
+    dec = OracleDecoder("error(0.1) D0\nerror(0) D1\nerror(0.2) D2\nerror(0.3) D2\ndetector(0,0,0) D0\ndetector(0,0,0) D1\ndetector(0,0,0) D2", kind=kind)
+    d2e, e2d = dec.maps()
+    assert len(d2e) == 4 and d2e[1] == oracle.U64_MAX and d2e[2] == d2e[3] and e2d[d2e[2]] == 2
+    with pytest.raises(oracle.OracleError, match="error index does not map to a retained decoder error"):
+        dec.cost_from_errors([1])
+    with pytest.raises(oracle.OracleError, match="error index does not map to a retained decoder error"):
+        dec.flipped_observables([1])
+
+
+def test_eneighbors(kind):  # tesseract.test.cc:280-374
+    dec = OracleDecoder("error(0.1) D0 D1\nerror(0.1) D1 D2\nerror(0.1) D2 D3\nerror(0.1) D4 D5\nerror(0.1) D0 D2 D4\n"
+                        + "\n".join(f"detector({i}, 0, 0) D{i}" for i in range(6)), merge_errors=False, kind=kind)
+    assert dec.rows(2) == [[2, 4], [0, 3, 4], [0, 1, 4], [0, 2], [1, 3, 5]]
+    dec = OracleDecoder("error(0.1) D0 D1\nerror(0.1) D1 D2\nerror(0.1) D3 D4\nerror(0.1) D4 D5\nerror(0.1) D6 D7\nerror(0.1) D7 D8\n"
+                        "error(0.1) D1 D4 D7\nerror(0.1) D0 D3 D6\n" + "\n".join(f"detector({i}, 0, 0) D{i}" for i in range(9)),
+                        merge_errors=False, kind=kind)
+    assert dec.rows(2) == [[2, 3, 4, 6, 7], [0, 4, 7], [0, 1, 5, 6, 7], [1, 3, 7], [0, 1, 3, 4, 8], [1, 4, 6],
+                           [0, 2, 3, 5, 6, 8], [1, 4, 7]]
+
+
+def test_invalid_symptom_message(kind):  # tesseract.test.cc:376-400
+    dec = OracleDecoder("error(0.1) D0 D1\nerror(0.1) D1 D2\nerror(0.1) D2 D3\ndetector(0, 0, 0) D0\ndetector(1, 0, 0) D1\n"
+                        "detector(2, 0, 0) D2\ndetector(2, 0, 0) D2", kind=kind)
+    n = dec.num_detectors
+    with pytest.raises(oracle.OracleError, match=rf"Symptom {n} references a detector >= num_detectors \(= {n}\)\."):
+        dec.decode_to_errors([n])
+
+
+def test_detcost_compares_ratios(kind):  # tesseract.test.cc:402-423
+    # residual {D0, D1}: the cheaper-per-detector error is "D0 D1 D3"; its share is cost/2 per detector,
+    # so the root's f is exactly twice that share and the search returns that error.
+    dec = OracleDecoder("error(0.005322067133022559) D0 D1 D3\nerror(0.0051237598826648) D0 D1 D2", merge_errors=False, kind=kind)
+    costs = dec.error_costs()
+    assert abs(costs[0] - 5.230557212477344) < 1e-12
+
+
+def test_infinite_pqlimit(kind):  # tesseract.test.cc:460-476
+    dec = OracleDecoder("error(0.1) D0\nerror(0.1) D1\nerror(0.01) D0 D1\ndetector(0,0,0) D0\ndetector(0,0,0) D1",
+                        pqlimit=None, det_beam=oracle.INF_DET_BEAM, kind=kind)
+    errs, cost, low = dec.decode_to_errors([0, 1])
+    assert not low and sorted(errs) in ([2], [0, 1])
+    assert abs(cost - min(math.log(99), 2 * math.log(9))) < 1e-9
+
+
+def test_more_than_64_observables(kind):  # tesseract.test.cc:542-564
+    dec = OracleDecoder("error(0.1) D0 L3 L70\nerror(0.1) D1 L64\ndetector(0,0,0) D0\ndetector(0,0,0) D1", kind=kind)
+    assert dec.num_observables == 71
+    errs, _, low = dec.decode_to_errors([0, 1])
+    assert not low and dec.flipped_observables(errs) == [3, 64, 70]
+
+
+def test_cost_and_observables_from_errors(kind):  # shared_decoding_tests.py:37-127
+    dec = OracleDecoder("error(0.1) D0 L0\nerror(0.2) D1 L1\nerror(0.3) D2\nerror(0.4) D3 L0 L1", merge_errors=False, kind=kind)
+    assert dec.cost_from_errors([0]) == pytest.approx(math.log(0.9 / 0.1))
+    assert dec.cost_from_errors([3]) == pytest.approx(math.log(0.6 / 0.4))
+    assert dec.cost_from_errors([0, 3]) == pytest.approx(math.log(0.9 / 0.1) + math.log(0.6 / 0.4))
+    assert dec.cost_from_errors([]) == 0
+    assert dec.flipped_observables([0]) == [0]
+    assert dec.flipped_observables([3]) == [0, 1]
+    assert dec.flipped_observables([0, 3]) == [1]
+    assert dec.flipped_observables([]) == []
+
+
+@pytest.mark.parametrize("obs_id", [0, 1, 31, 32, 63])
+def test_observable_ids(kind, obs_id):  # shared_decoding_tests.py:130-156
+    dec = OracleDecoder(f"error(0.01) D0 L{obs_id}", kind=kind)
+    errs, _, _ = dec.decode_to_errors([0])
+    assert dec.flipped_observables(errs) == [obs_id]
+
+
+def test_decode_batch_expected_matrices(kind):  # shared_decoding_tests.py:255-329
+    dec = OracleDecoder("error(0.1) D0 D1 L0\nerror(0.2) D0 L1\nerror(0.05) D1", kind=kind)
+    dets = np.packbits(np.array([[1, 1], [1, 0], [0, 1]], dtype=np.uint8), axis=1, bitorder="little")
+    out = dec.decode_batch_b8(dets)
+    assert np.unpackbits(out["obs"], axis=1, bitorder="little")[:, :2].tolist() == [[1, 0], [0, 1], [0, 0]]
+    dec = OracleDecoder("error(0.1) D0 D1 L0\nerror(0.2) D0 D2 L1\nerror(0.05) D1 D3 L0 L2\nerror(0.15) D2\nerror(0.25) D3", kind=kind)
+    dets = np.packbits(np.array([[1, 1, 0, 0], [1, 0, 1, 0], [0, 1, 0, 1], [0, 0, 1, 1]], dtype=np.uint8), axis=1, bitorder="little")
+    out = dec.decode_batch_b8(dets)
+    assert np.unpackbits(out["obs"], axis=1, bitorder="little")[:, :3].tolist() == [[1, 0, 0], [0, 1, 0], [1, 0, 1], [0, 0, 0]]
+
+
+def test_decode_complex_dem(kind):  # shared_decoding_tests.py:214-237
+    dec = OracleDecoder("error(0.5) D0 D1 L0 L2\nerror(0.01) D0\nerror(0.01) D1\nerror(0.05) D2", kind=kind)
+    errs, _, _ = dec.decode_to_errors([0, 1])
+    assert dec.flipped_observables(errs) == [0, 2]
+
+
+def test_merge_errors_affects_cost(kind):  # shared_decoding_tests.py:332-361
+    dem = "error(0.1) D0\nerror(0.01) D0"
+    a = OracleDecoder(dem, merge_errors=False, kind=kind)
+    b = OracleDecoder(dem, merge_errors=True, kind=kind)
+    ea, ca, _ = a.decode_to_errors([0])
+    eb, cb, _ = b.decode_to_errors([0])
+    p = 0.1 * 0.99 + 0.01 * 0.9
+    assert ea == eb and ca == pytest.approx(math.log(0.9 / 0.1)) and cb == pytest.approx(math.log((1 - p) / p)) and ca != cb
+
+
+def test_cost_golden_value(kind):  # tesseract_test.py:193-201
+    dec = OracleDecoder("error(0.1) D0 D1 L0\nerror(0.2) D0\nerror(0.3) D1", kind=kind)
+    errs, cost, low = dec.decode_to_errors([0, 1])
+    assert not low
+    assert cost == pytest.approx(min(math.log(9), math.log(4) + math.log(7 / 3)))
+
+
+def test_merge_weights_is_probability_xor(kind):  # common.test.cc:115-145
+    rng = np.random.default_rng(0)
+    for p, q in rng.uniform(0.001, 0.999, size=(200, 2)):
+        a, b = math.log((1 - p) / p), math.log((1 - q) / q)
+        r = p * (1 - q) + q * (1 - p)
+        assert oracle.merge_weights(a, b, kind=kind) == pytest.approx(math.log((1 - r) / r), abs=1e-12)
+
+
+def test_xor_canonicalisation(kind):  # common.test.cc:22-29
+    dec = OracleDecoder("error(0.1) D0 ^ D0 D1 L0 L1 L1", merge_errors=False, kind=kind)
+    assert dec.rows(1) == [[1]] and dec.rows(3) == [[0]]
+
+
+def test_det_index_orders(kind):  # utils.cc:173-190 (same mt19937_64 draws in both)
+    dem = W.load_dem("transcx_d3_p0.001_X")
+    got = oracle.build_det_orders(dem, 24, 1, W.CLI_ORDER_SEED, kind=kind)
+    D = got.shape[1]
+    up, down = np.arange(D, dtype=np.uint64), np.arange(D, dtype=np.uint64)[::-1]
+    assert all(np.array_equal(r, up) or np.array_equal(r, down) for r in got)
+    if "reference" in KINDS:
+        assert np.array_equal(got, oracle.build_det_orders(dem, 24, 1, W.CLI_ORDER_SEED, kind="reference"))
+
+
+@pytest.mark.parametrize("name", W.golden_names())
+def test_golden_vectors(kind, name):
+    """Committed outputs of the reference build: the checker in use must reproduce them bit for bit."""
+    g = W.load_golden(name)
+    if name in ("g_c3_surface_d11_climb", "g_c4_bb144_p1e-4") and kind == "port":
+        g = {k: (v[:8] if k in ("dets", "obs", "cost", "low_confidence") else v) for k, v in g.items()}
+    from tesseract_decoder_b200 import capi
+    dem, kw = W.decoder_kwargs(g["config"], capi.build_det_orders)
+    dec = OracleDecoder(dem, kind=kind, num_threads=8, **kw)
+    out = dec.decode_batch_b8(g["dets"])
+    n = len(g["dets"])
+    assert np.array_equal(out["obs"], g["obs"][:n])
+    assert np.array_equal(out["low_confidence"], g["low_confidence"][:n])
+    assert np.array_equal(out["cost"], g["cost"][:n])
+    assert W.split_lists(out["err_offsets"], out["err_idx"]) == W.split_lists(g["err_offsets"], g["err_idx"])[:n]
