@@ -100,6 +100,9 @@ int tsr_decode_batch_b8(tsr_decoder* h, const uint8_t* dets, uint64_t stride, ui
                         uint8_t* obs_out, double* cost_out, uint8_t* low_conf_out);
 int tsr_decode_batch_b8_device(tsr_decoder* h, const uint8_t* d_dets, uint64_t stride, uint64_t shots,
                                uint8_t* d_obs_out, double* d_cost_out, uint8_t* d_low_conf_out);
+/* Whether batch decodes keep the per-shot error lists for tsr_last_batch_errors (default 1).  Callers that
+ * only consume observables (decode_batch, decode_shots_bit_packed) switch it off and save the D2H copy. */
+int tsr_set_collect_errors(tsr_decoder* h, int on);
 uint64_t tsr_last_batch_nnz(const tsr_decoder* h);
 int tsr_last_batch_errors(const tsr_decoder* h, uint64_t* offsets /* [shots+1] */, uint64_t* idx /* [nnz] */);
 

@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
     L.tsr_decode_batch_b8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.tsr_decode_batch_b8_device.argtypes = L.tsr_decode_batch_b8.argtypes
     L.tsr_last_batch_errors.argtypes = [C.c_void_p, u64p, u64p]
+    L.tsr_set_collect_errors.argtypes = [C.c_void_p, C.c_int]
     L.tsr_decode.argtypes = [C.c_void_p, u64p, C.c_uint64, C.c_int64, C.c_uint64, u64p, C.c_uint64, u64p, f64p, i32p]
     L.tsr_cost_from_errors.argtypes = [C.c_void_p, u64p, C.c_uint64, f64p]
     L.tsr_flipped_observables.argtypes = [C.c_void_p, u64p, C.c_uint64, u8p]
@@ -104,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "tsr_config_init", "tsr_last_error", "tsr_version", "tsr_create", "tsr_destroy", "tsr_num_detectors",
     "tsr_num_observables", "tsr_num_errors", "tsr_num_dem_errors", "tsr_num_det_orders", "tsr_error_costs",
     "tsr_maps", "tsr_csr", "tsr_compiled_dem_text", "tsr_free", "tsr_decode_batch_b8",
-    "tsr_decode_batch_b8_device", "tsr_last_batch_nnz", "tsr_last_batch_errors", "tsr_decode",
+    "tsr_decode_batch_b8_device", "tsr_set_collect_errors", "tsr_last_batch_nnz", "tsr_last_batch_errors", "tsr_decode",
     "tsr_cost_from_errors", "tsr_flipped_observables", "tsr_counters", "tsr_last_batch_timing", "tsr_stream",
     "tsr_device", "tsr_build_det_orders", "tsr_dem_count_detectors", "tsr_merge_weights", "tsr_circuit_to_dem",
     "tsr_sample_dem_b8",
@@ -264,6 +265,9 @@ class Decoder:
                                 C.byref(n), C.byref(cost), C.byref(low)))
         return errs[: n.value].tolist(), cost.value, bool(low.value)
 
+    def set_collect_errors(self, on: bool):
+        _check(lib().tsr_set_collect_errors(self.h, int(on)))
+
     def last_batch_errors(self):
         nnz = lib().tsr_last_batch_nnz(self.h)
         off = np.zeros(self._last_shots + 1, dtype=np.uint64)
@@ -287,6 +291,12 @@ class Decoder:
         if want_errors:
             out["err_offsets"], out["err_idx"] = self.last_batch_errors()
         return out
+
+    def decode_batch_b8_raw(self, dets_ptr: int, stride: int, shots: int, obs_ptr: int = 0, cost_ptr: int = 0,
+                            low_ptr: int = 0):
+        """tsr_decode_batch_b8 on caller-owned HOST buffers given as addresses (e.g. pinned memory)."""
+        _check(lib().tsr_decode_batch_b8(self.h, dets_ptr, stride, shots, obs_ptr or None, cost_ptr or None, low_ptr or None))
+        self._last_shots = shots
 
     def decode_batch_b8_device(self, d_dets: int, stride: int, shots: int, d_obs: int = 0, d_cost: int = 0,
                                d_low: int = 0):

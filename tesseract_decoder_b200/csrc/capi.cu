@@ -137,6 +137,7 @@ struct tsr_decoder {
   DevBuf d_dets, d_status, d_sol_len, d_fcost, d_sol, d_obs, d_cost, d_low, d_err_off, d_err_len, d_err, d_retry,
       d_items, d_scalars, d_counters;
   uint32_t sol_stride = 0;
+  bool collect_errors = true;
 
   // Results of the last decode call.
   std::vector<uint64_t> last_off{0};
@@ -438,7 +439,7 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     r.err_out = h.d_err.as<uint64_t>();
     r.err_cap = err_cap;
     r.err_cursor = &sc->err_cursor;
-    r.err_off = h.d_err_off.as<uint64_t>();
+    r.err_off = h.collect_errors ? h.d_err_off.as<uint64_t>() : nullptr;
     r.err_len = h.d_err_len.as<uint32_t>();
     r.retry_shots = retry_out;
     r.retry_count = &sc->retry_count;
@@ -502,17 +503,23 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
   if (hs.err_cursor > err_cap) throw DeviceMemoryError("pooled error lists overflowed their buffer");
 
   // Error lists -> host CSR.
-  std::vector<uint64_t> off(shots), pooled(hs.err_cursor);
-  std::vector<uint32_t> len(shots);
-  CUDA_OK(cudaMemcpyAsync(off.data(), h.d_err_off.p, (size_t)shots * 8, cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaMemcpyAsync(len.data(), h.d_err_len.p, (size_t)shots * 4, cudaMemcpyDeviceToHost, s));
-  if (!pooled.empty())
-    CUDA_OK(cudaMemcpyAsync(pooled.data(), h.d_err.p, pooled.size() * 8, cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaEventRecord(h.ev[3], s));
-  CUDA_OK(cudaStreamSynchronize(s));
-  for (uint32_t k = 0; k < shots; ++k) {
-    h.last_idx.insert(h.last_idx.end(), pooled.begin() + (std::ptrdiff_t)off[k], pooled.begin() + (std::ptrdiff_t)(off[k] + len[k]));
-    h.last_off.push_back(h.last_idx.size());
+  if (h.collect_errors) {
+    std::vector<uint64_t> off(shots), pooled(hs.err_cursor);
+    std::vector<uint32_t> len(shots);
+    CUDA_OK(cudaMemcpyAsync(off.data(), h.d_err_off.p, (size_t)shots * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(len.data(), h.d_err_len.p, (size_t)shots * 4, cudaMemcpyDeviceToHost, s));
+    if (!pooled.empty())
+      CUDA_OK(cudaMemcpyAsync(pooled.data(), h.d_err.p, pooled.size() * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaEventRecord(h.ev[3], s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    for (uint32_t k = 0; k < shots; ++k) {
+      h.last_idx.insert(h.last_idx.end(), pooled.begin() + (std::ptrdiff_t)off[k], pooled.begin() + (std::ptrdiff_t)(off[k] + len[k]));
+      h.last_off.push_back(h.last_idx.size());
+    }
+  } else {
+    CUDA_OK(cudaEventRecord(h.ev[3], s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    h.last_off.resize(h.last_off.size() + shots, 0);
   }
   float ms_all = 0;
   CUDA_OK(cudaEventElapsedTime(&ms_all, h.ev[0], h.ev[3]));
@@ -701,6 +708,11 @@ int tsr_decode_batch_b8(tsr_decoder* h, const uint8_t* dets, uint64_t stride, ui
 int tsr_decode_batch_b8_device(tsr_decoder* h, const uint8_t* d_dets, uint64_t stride, uint64_t shots,
                                uint8_t* d_obs_out, double* d_cost_out, uint8_t* d_low_conf_out) {
   return guarded([&] { decode_batch(*h, d_dets, stride, shots, true, h->ensemble, d_obs_out, d_cost_out, d_low_conf_out); });
+}
+
+int tsr_set_collect_errors(tsr_decoder* h, int on) {
+  h->collect_errors = on != 0;
+  return TSR_OK;
 }
 
 uint64_t tsr_last_batch_nnz(const tsr_decoder* h) {

@@ -1,0 +1,308 @@
+"""GPU parity proper (-m gpu): the sm_100a decode path, called through the C ABI
+(include/tesseract_b200.h via tesseract_decoder_b200/capi.py), against
+
+  * the committed golden outputs of the reference build (tests/golden/*.npz, scripts/make_golden.py),
+  * the reference's own known-answer tests restated (tesseract.test.cc, shared_decoding_tests.py),
+  * the CPU checkers (oracle/_ref when it travelled, else the port) on fresh seeded shots, and
+  * size-independent properties at BASELINE sizes (syndrome reproduction, cost/observable
+    consistency, batch-shape / slot-count / node-pool-tier invariance, determinism).
+
+Bar: bit-exact observables, low-confidence flags, error lists (order included) and costs
+(np.array_equal on float64 — stricter than the 1e-9 relative the north star allows).
+Nothing here reads /root/reference.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import workloads as W
+from oracle import oracle
+from oracle.oracle import OracleDecoder
+from tesseract_decoder_b200 import capi
+from test_oracle import EXHAUSTIVE_DEMS, brute_force_min_cost
+
+pytestmark = pytest.mark.gpu
+KIND = "reference" if oracle.available("reference") else "port"
+
+
+def assert_same(out, ref, n=None):
+    n = len(out["obs"]) if n is None else n
+    assert np.array_equal(out["low_confidence"][:n], ref["low_confidence"][:n])
+    assert np.array_equal(out["obs"][:n], ref["obs"][:n])
+    assert np.array_equal(out["cost"][:n], ref["cost"][:n])  # bit-exact doubles
+    a = W.split_lists(out["err_offsets"], out["err_idx"])[:n]
+    b = W.split_lists(ref["err_offsets"], ref["err_idx"])[:n]
+    bad = [i for i in range(n) if a[i] != b[i]]
+    assert not bad, f"{len(bad)} shots with differing error lists, first {bad[:5]}"
+
+
+def check_solutions_are_consistent(dec, dets, out):
+    """Properties every non-low-confidence answer must have, whatever the search did: the predicted
+    errors reproduce the syndrome, cost == cost_from_errors, obs == get_flipped_observables."""
+    D, O = dec.num_detectors, dec.num_observables
+    d2e, _ = dec.maps()
+    off, edets = dec.csr(1)
+    ooff, eobs = dec.csr(3)
+    costs = dec.error_costs()
+    bits = np.unpackbits(dets, axis=1, bitorder="little")[:, :D]
+    obits = np.unpackbits(out["obs"], axis=1, bitorder="little")[:, :O] if O else np.zeros((len(dets), 0), np.uint8)
+    lists = W.split_lists(out["err_offsets"], out["err_idx"])
+    for s, errs in enumerate(lists):
+        if out["low_confidence"][s]:
+            assert errs == [] and out["cost"][s] == 0
+            continue
+        syn = np.zeros(D, dtype=np.uint8)
+        ob = np.zeros(O, dtype=np.uint8)
+        total = 0.0
+        for e in errs:
+            ce = int(d2e[e])
+            assert ce != capi.NO_ERROR_INDEX
+            syn[edets[int(off[ce]):int(off[ce + 1])]] ^= 1
+            ob[eobs[int(ooff[ce]):int(ooff[ce + 1])]] ^= 1
+            total += costs[ce]
+        assert np.array_equal(syn, bits[s]), s
+        assert np.array_equal(ob, obits[s]), s
+        assert total == out["cost"][s], s
+
+
+# ---- golden vectors of the reference build ---------------------------------------------------------
+
+@pytest.mark.parametrize("name", W.golden_names())
+def test_golden_vectors(name):
+    g = W.load_golden(name)
+    dem, kw = W.decoder_kwargs(g["config"], capi.build_det_orders)
+    dec = capi.Decoder(dem, **kw)
+    out = dec.decode_batch_b8(g["dets"])
+    assert_same(out, g)
+    check_solutions_are_consistent(dec, g["dets"], out)
+    # one shot at a time through tsr_decode gives the same answers as the batch
+    lists = W.split_lists(g["err_offsets"], g["err_idx"])
+    bits = np.unpackbits(g["dets"], axis=1, bitorder="little")[:, :dec.num_detectors]
+    for s in range(min(4, len(lists))):
+        errs, cost, low = dec.decode_to_errors(np.nonzero(bits[s])[0])
+        assert (errs, cost, low) == (lists[s], g["cost"][s], bool(g["low_confidence"][s]))
+
+
+# ---- the reference's known-answer tests, on the GPU ------------------------------------------------
+
+@pytest.mark.parametrize("which", range(4))
+def test_exhaustive_small_dems(which):  # tesseract.test.cc:125-202
+    dem = EXHAUSTIVE_DEMS[which]
+    dec = capi.Decoder(dem)
+    D = dec.num_detectors
+    best = brute_force_min_cost(dem, D)
+    allbits = ((np.arange(1 << D)[:, None] >> np.arange(D)[None, :]) & 1).astype(np.uint8)
+    dets = np.packbits(allbits, axis=1, bitorder="little")
+    out = dec.decode_batch_b8(dets)
+    ref = OracleDecoder(dem, kind=KIND).decode_batch_b8(dets)
+    assert_same(out, ref)
+    for mask in range(1 << D):
+        if out["low_confidence"][mask]:
+            assert mask not in best
+        else:
+            assert abs(out["cost"][mask] - best[mask]) <= 1e-7  # EPSILON, utils.h:34
+
+
+def test_small_known_answers():
+    # tesseract.test.cc:460-476 (unbounded pqlimit and beam)
+    dec = capi.Decoder("error(0.1) D0\nerror(0.1) D1\nerror(0.01) D0 D1\ndetector(0,0,0) D0\ndetector(0,0,0) D1",
+                       pqlimit=None, det_beam=capi.INF_DET_BEAM)
+    errs, cost, low = dec.decode_to_errors([0, 1])
+    assert not low and sorted(errs) in ([2], [0, 1]) and abs(cost - min(math.log(99), 2 * math.log(9))) < 1e-9
+    # tesseract.test.cc:402-423 (detcost compares ratios): the search must pick the cheaper-per-detector error
+    dem = "error(0.005322067133022559) D0 D1 D3\nerror(0.0051237598826648) D0 D1 D2"
+    a = capi.Decoder(dem, merge_errors=False).decode_to_errors([0, 1, 3])
+    b = OracleDecoder(dem, merge_errors=False, kind=KIND).decode_to_errors([0, 1, 3])
+    assert a == b
+    # tesseract.test.cc:542-564 (more than 64 observables)
+    dec = capi.Decoder("error(0.1) D0 L3 L70\nerror(0.1) D1 L64\ndetector(0,0,0) D0\ndetector(0,0,0) D1")
+    errs, _, low = dec.decode_to_errors([0, 1])
+    assert not low and dec.flipped_observables(errs) == [3, 64, 70]
+    out = dec.decode_batch_b8(np.array([[3]], dtype=np.uint8))
+    assert np.nonzero(np.unpackbits(out["obs"][0], bitorder="little"))[0].tolist() == [3, 64, 70]
+    # shared_decoding_tests.py:130-156
+    for obs_id in (0, 1, 31, 32, 63):
+        dec = capi.Decoder(f"error(0.01) D0 L{obs_id}")
+        errs, _, _ = dec.decode_to_errors([0])
+        assert dec.flipped_observables(errs) == [obs_id]
+    # shared_decoding_tests.py:214-237
+    dec = capi.Decoder("error(0.5) D0 D1 L0 L2\nerror(0.01) D0\nerror(0.01) D1\nerror(0.05) D2")
+    errs, _, _ = dec.decode_to_errors([0, 1])
+    assert dec.flipped_observables(errs) == [0, 2]
+    # tesseract_test.py:193-201
+    dec = capi.Decoder("error(0.1) D0 D1 L0\nerror(0.2) D0\nerror(0.3) D1")
+    errs, cost, low = dec.decode_to_errors([0, 1])
+    assert not low and cost == pytest.approx(min(math.log(9), math.log(4) + math.log(7 / 3)))
+    # shared_decoding_tests.py:332-361 (merging changes the cost, not the answer)
+    dem = "error(0.1) D0\nerror(0.01) D0"
+    ea, ca, _ = capi.Decoder(dem, merge_errors=False).decode_to_errors([0])
+    eb, cb, _ = capi.Decoder(dem, merge_errors=True).decode_to_errors([0])
+    p = 0.1 * 0.99 + 0.01 * 0.9
+    assert ea == eb and ca == pytest.approx(math.log(9)) and cb == pytest.approx(math.log((1 - p) / p)) and ca != cb
+
+
+def test_decode_batch_expected_matrices():  # shared_decoding_tests.py:255-329
+    dec = capi.Decoder("error(0.1) D0 D1 L0\nerror(0.2) D0 L1\nerror(0.05) D1")
+    dets = np.packbits(np.array([[1, 1], [1, 0], [0, 1]], dtype=np.uint8), axis=1, bitorder="little")
+    out = dec.decode_batch_b8(dets)
+    assert np.unpackbits(out["obs"], axis=1, bitorder="little")[:, :2].tolist() == [[1, 0], [0, 1], [0, 0]]
+    dec = capi.Decoder("error(0.1) D0 D1 L0\nerror(0.2) D0 D2 L1\nerror(0.05) D1 D3 L0 L2\nerror(0.15) D2\nerror(0.25) D3")
+    dets = np.packbits(np.array([[1, 1, 0, 0], [1, 0, 1, 0], [0, 1, 0, 1], [0, 0, 1, 1]], dtype=np.uint8), axis=1, bitorder="little")
+    out = dec.decode_batch_b8(dets)
+    assert np.unpackbits(out["obs"], axis=1, bitorder="little")[:, :3].tolist() == [[1, 0, 0], [0, 1, 0], [1, 0, 1], [0, 0, 0]]
+
+
+def test_error_behaviour():
+    dem = ("error(0.1) D0 D1\nerror(0.1) D1 D2\nerror(0.1) D2 D3\ndetector(0, 0, 0) D0\ndetector(1, 0, 0) D1\n"
+           "detector(2, 0, 0) D2\ndetector(2, 0, 0) D2")
+    dec = capi.Decoder(dem)
+    n = dec.num_detectors
+    with pytest.raises(RuntimeError, match=rf"Symptom {n} references a detector >= num_detectors \(= {n}\)\."):  # tesseract.test.cc:376-400
+        dec.decode_to_errors([n])
+    with pytest.raises(ValueError, match="stride"):
+        capi.Decoder(W.load_dem("surface_d5_r5_p0.002_X")).decode_batch_b8(np.zeros((2, 3), dtype=np.uint8))
+    with pytest.raises(ValueError):
+        dec.decode_to_errors([0], order=5, beam=1)
+    # a syndrome no error set explains is low confidence, not an exception (tesseract.cc:416-419)
+    assert dec.decode_to_errors([0]) == ([], 0.0, True)
+
+
+def test_empty_and_ragged_inputs():
+    dem = W.load_dem("surface_d5_r5_p0.002_X")
+    dec = capi.Decoder(dem, det_beam=5, no_revisit_dets=False)
+    out = dec.decode_batch_b8(np.zeros((0, 15), dtype=np.uint8))  # empty batch
+    assert out["obs"].shape == (0, 1) and len(out["err_offsets"]) == 1
+    dets, _ = capi.sample_dem_b8(dem, 3, 257, 120, 1)
+    dets[::7] = 0  # shots with no fired detector decode to the empty set at cost 0
+    ref = OracleDecoder(dem, det_beam=5, no_revisit_dets=False, kind=KIND).decode_batch_b8(dets)
+    out = dec.decode_batch_b8(dets)
+    assert_same(out, ref)
+    assert all(out["cost"][::7] == 0) and not out["low_confidence"][::7].any()
+    # a wider stride with junk in the padding bytes and in the unused high bits is ignored
+    wide = np.full((257, 23), 0xFF, dtype=np.uint8)
+    wide[:, :15] = dets
+    assert_same(dec.decode_batch_b8(wide), ref)
+    # D not a multiple of 8 / 32: bits >= D in the last byte are ignored
+    dem7 = "\n".join(f"error(0.05) D{i} D{(i + 1) % 7}" for i in range(7)) + "\nerror(0.02) D0 L0"
+    d7 = capi.Decoder(dem7)
+    syn = np.array([[0b0000011], [0b1000001], [0b0101000]], dtype=np.uint8)
+    a = d7.decode_batch_b8(syn)
+    b = d7.decode_batch_b8(syn | 0x80)
+    r = OracleDecoder(dem7, kind=KIND).decode_batch_b8(syn)
+    assert_same(a, r)
+    assert_same(b, r)
+
+
+# ---- fresh seeded shots against the CPU checker, counters included ---------------------------------
+
+FRESH = [
+    # (config, shots, seed)
+    (W.CONFIGS["C1"], 3000, 21),
+    (dict(dem="surface_d5_r5_p0.002_X", det_beam=5, pqlimit=200000, no_revisit_dets=True, num_det_orders=20,
+          det_order_seed=2384753), 600, 22),  # Python-side defaults (tesseract.pybind.h:65-67, 144-150)
+    (dict(dem="color_superdense_d5_r5_p0.001_Z", det_beam=2, beam_climbing=True, pqlimit=10000, no_revisit_dets=True,
+          num_det_orders=3), 800, 23),
+    (dict(dem="color_superdense_d7_r7_p0.001_X", det_beam=5, pqlimit=200000, no_revisit_dets=True, num_det_orders=1), 200, 24),
+    (dict(dem="transcx_d3_p0.001_X", det_beam=W.INF_BEAM, pqlimit=None, no_revisit_dets=False, num_det_orders=0,
+          det_penalty=0.5), 3000, 25),
+    (dict(dem="transcx_d5_p0.001_X", det_beam=W.INF_BEAM, pqlimit=None, no_revisit_dets=False, num_det_orders=0,
+          det_penalty=1.0), 300, 26),
+    (dict(dem="bb72_r6_p0.001_X", det_beam=W.INF_BEAM, pqlimit=500, no_revisit_dets=True, num_det_orders=2), 150, 27),  # pqlimit hits
+    (dict(dem="bb144_r12_p0.0001_X", det_beam=W.INF_BEAM, pqlimit=None, no_revisit_dets=True, num_det_orders=24), 40, 28),
+    (dict(dem="surface_d11_r11_p0.001_X", det_beam=3, beam_climbing=True, pqlimit=20000, no_revisit_dets=True,
+          num_det_orders=0), 60, 29),
+]
+
+
+@pytest.mark.parametrize("case", range(len(FRESH)))
+def test_fresh_shots_against_the_cpu_checker(case):
+    cfg, shots, seed = FRESH[case]
+    dem, kw = W.decoder_kwargs(cfg, capi.build_det_orders)
+    dec = capi.Decoder(dem, **kw)
+    dets, _ = capi.sample_dem_b8(dem, seed, shots, dec.num_detectors, dec.num_observables)
+    ref = OracleDecoder(dem, kind=KIND, num_threads=8, **kw).decode_batch_b8(dets)
+    dec.counters(reset=True)
+    out = dec.decode_batch_b8(dets)
+    assert_same(out, ref)
+    check_solutions_are_consistent(dec, dets, out)
+    if oracle.available("port") and shots <= 1000:
+        # The search itself is the same search: pushes, pops, expansions, chain steps, scanned heuristic
+        # entries and visited probes agree with the instrumented CPU port.  The port
+        # runs every literal trial; the GPU runs distinct (order, beam) trials once, so compare on a
+        # decoder restricted to the distinct trials.
+        port = OracleDecoder(dem, kind="port", num_threads=8, **kw)
+        port.decode_batch_b8(dets)
+        pc, gc = port.counters(), dec.counters()
+        n_literal = max(len(kw["det_orders"]) if kw["det_orders"] is not None else 1,
+                        (kw["det_beam"] + 1) if kw["beam_climbing"] else 0)
+        if gc["searches"] == shots * n_literal:
+            for k in ("Q", "P", "X", "L", "S", "V"):
+                assert gc[k] == pc[k], (k, gc, pc)
+
+
+# ---- invariances at larger sizes --------------------------------------------------------------------
+
+def test_results_do_not_depend_on_batching_slots_or_pool_tiers():
+    cfg = W.CONFIGS["C1"]
+    dem, kw = W.decoder_kwargs(cfg, capi.build_det_orders)
+    base = capi.Decoder(dem, **kw)
+    dets, obs = capi.sample_dem_b8(dem, 1001, 20000, base.num_detectors, base.num_observables)
+    a = base.decode_batch_b8(dets)
+    check_solutions_are_consistent(base, dets[:2000], {k: (v[:2000] if k in ("obs", "cost", "low_confidence") else v) for k, v in a.items()})
+    assert_same(base.decode_batch_b8(dets), a)  # deterministic
+    small = capi.Decoder(dem, max_batch_shots=777, search_slots=96, warps_per_block=2, **kw)
+    assert_same(small.decode_batch_b8(dets), a)
+    # A starved node pool: searches overflow tier 0 and are re-run in the larger tiers (never on the CPU).
+    tiny = capi.Decoder(dem, node_pool_bytes=8 << 20, **kw)
+    b = tiny.decode_batch_b8(dets)
+    assert tiny.last_batch_timing()["rerun_items"] > 0
+    assert_same(b, a)
+
+
+def test_unbounded_search_that_outgrows_every_tier_fails_loudly():
+    dem = W.load_dem("bb72_r6_p0.001_X")
+    dec = capi.Decoder(dem, det_beam=W.INF_BEAM, pqlimit=None, no_revisit_dets=True, node_pool_bytes=64 << 10, search_slots=64)
+    dets, _ = capi.sample_dem_b8(dem, 5, 64, dec.num_detectors, dec.num_observables)
+    with pytest.raises(capi.DeviceMemoryError):
+        dec.decode_batch_b8(dets)
+
+
+def test_device_resident_entry_point_matches_host_entry_point():
+    torch = pytest.importorskip("torch")
+    cfg = W.CONFIGS["C1"]
+    dem, kw = W.decoder_kwargs(cfg, capi.build_det_orders)
+    dec = capi.Decoder(dem, device=0, **kw)
+    dets, _ = capi.sample_dem_b8(dem, 77, 5000, dec.num_detectors, dec.num_observables)
+    a = dec.decode_batch_b8(dets)
+    d = torch.from_numpy(dets).cuda()
+    obs = torch.zeros((5000, 1), dtype=torch.uint8, device="cuda")
+    cost = torch.zeros(5000, dtype=torch.float64, device="cuda")
+    low = torch.zeros(5000, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    dec.decode_batch_b8_device(d.data_ptr(), dets.shape[1], 5000, obs.data_ptr(), cost.data_ptr(), low.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(obs.cpu().numpy(), a["obs"]) and np.array_equal(cost.cpu().numpy(), a["cost"])
+    assert np.array_equal(low.cpu().numpy(), a["low_confidence"])
+    off, idx = dec.last_batch_errors()
+    assert np.array_equal(off, a["err_offsets"]) and np.array_equal(idx, a["err_idx"])
+
+
+def test_at_most_two_errors_per_detector_is_a_valid_restriction():
+    """No reference code exists for this flag (parity unpinned).  What can be pinned: answers
+    stay valid, no detector is touched by more than two chosen errors, and switching the flag off
+    restores reference parity."""
+    dem = W.load_dem("transcx_d5_p0.001_X")
+    dec = capi.Decoder(dem, det_beam=W.INF_BEAM, pqlimit=200000, no_revisit_dets=True, det_penalty=0.5,
+                       at_most_two_errors_per_detector=True)
+    dets, _ = capi.sample_dem_b8(dem, 31, 400, dec.num_detectors, dec.num_observables)
+    out = dec.decode_batch_b8(dets)
+    check_solutions_are_consistent(dec, dets, out)
+    d2e, _ = dec.maps()
+    off, edets = dec.csr(1)
+    for errs in W.split_lists(out["err_offsets"], out["err_idx"]):
+        touched = np.zeros(dec.num_detectors, dtype=np.int32)
+        for e in errs:
+            ce = int(d2e[e])
+            touched[edets[int(off[ce]):int(off[ce + 1])]] += 1
+        assert touched.max(initial=0) <= 2
