@@ -224,6 +224,15 @@ def run_b200(args, wl, rank, world, local):
         bad = int(((h_obs.numpy() != true_obs).any(axis=1) & (low == 0)).sum())
         return reduce_counts(bad, int(low.sum()))
 
+    # Algorithmic bytes of one batch, from the search's own operation counters.  Counter S
+    # (row entries the reference's early-exit loop visits) needs the instrumented kernel variant, so it is
+    # taken from one untimed pass over the same batch; the timed steps run the production variant.
+    dec.set_instrumented(True)
+    dec.counters(reset=True)
+    step_device()
+    ctr1 = dec.counters(reset=True)
+    dec.set_instrumented(False)
+
     def timed(step):
         for _ in range(args.warmup):
             step()
@@ -253,13 +262,15 @@ def run_b200(args, wl, rank, world, local):
     value, e2e = total / dt, total / dt2
 
     peak, peak_src = measured_peak_gbs()
-    alg = algorithmic_bytes(ctr, S * args.steps, D, O)  # rank 0's launches
+    alg = algorithmic_bytes(ctr1, S, D, O) * args.steps  # rank 0's launches: the same batch every step
+    assert all(ctr[k] == ctr1[k] * args.steps for k in ("Q", "P", "X", "L", "V")), (ctr, ctr1)
     n_launch = args.steps * ((S + (1 << 16) - 1) >> 16)  # tier-0 search launches (one per 65536-shot chunk)
     achieved = alg / (a["search_ms"] * 1e-3) / 1e9 if a["search_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "tsr::search_kernel", "algorithmic_bytes_per_launch": alg / n_launch,
+                "peak_source": peak_src, "kernel": "tsr::search_fast_kernel" if dec.search_path == "fast" else "tsr::search_kernel", "algorithmic_bytes_per_launch": alg / n_launch,
                 "algorithmic_bytes_per_shot": alg / (S * args.steps), "kernel_ms_per_launch": a["search_ms"] / n_launch,
-                "launches_timed": n_launch, "scanned_entries_per_shot": ctr["S"] / (S * args.steps)}
+                "launches_timed": n_launch, "scanned_entries_per_shot": ctr1["S"] / S, "search_path": dec.search_path,
+                "counters_per_batch": ctr1}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:

@@ -53,6 +53,8 @@ typedef struct tsr_config {
   uint32_t warps_per_block;
   uint64_t node_pool_bytes;    /* HBM set aside for heaps / chains / visited sets */
   uint64_t max_batch_shots;    /* shots staged per kernel launch */
+  int32_t force_generic_kernel; /* 1 = always use the event-replay kernel (search.cu), even for certified DEMs */
+  int32_t reserved;
 } tsr_config;
 
 /* Fills the reference's C++ defaults (tesseract.h:39-58). */
@@ -120,6 +122,16 @@ int tsr_decode(tsr_decoder* h, const uint64_t* detections, uint64_t n, int64_t o
  * map to a retained decoder error") on removed errors.  obs_bits_out: ceil(O/8) bytes. */
 int tsr_cost_from_errors(const tsr_decoder* h, const uint64_t* errs, uint64_t n, double* out);
 int tsr_flipped_observables(const tsr_decoder* h, const uint64_t* errs, uint64_t n, uint8_t* obs_bits_out);
+
+/* Which search kernel this handle decodes with: 1 = the CTA-per-search integer-rank kernel (search_fast.cu),
+ * taken when the DEM passes the host-side certificate of csrc/fast.h; 0 = the generic kernel (search.cu) that
+ * replays get_detcost's floating-point scan event by event.  Both are CUDA; results are identical.
+ * tsr_search_path_reason says why a DEM was not certified ("" when it was). */
+int tsr_search_path(const tsr_decoder* h);
+const char* tsr_search_path_reason(const tsr_decoder* h);
+/* Fast path only: also count the row entries the reference's early-exit loop would visit (counter S below);
+ * off by default because it costs a warp scan per 32 entries.  The generic kernel always counts. */
+int tsr_set_instrumented(tsr_decoder* h, int on);
 
 /* Search counters since the last reset, summed over every search this handle ran:
  * [0]=Q pushes [1]=P pops [2]=X expanded nodes [3]=L chain-walk steps [4]=S scanned row entries

@@ -47,6 +47,8 @@ class TsrConfig(C.Structure):
         ("warps_per_block", C.c_uint32),
         ("node_pool_bytes", C.c_uint64),
         ("max_batch_shots", C.c_uint64),
+        ("force_generic_kernel", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -82,6 +84,10 @@ def lib() -> C.CDLL:
     L.tsr_decode_batch_b8_device.argtypes = L.tsr_decode_batch_b8.argtypes
     L.tsr_last_batch_errors.argtypes = [C.c_void_p, u64p, u64p]
     L.tsr_set_collect_errors.argtypes = [C.c_void_p, C.c_int]
+    L.tsr_set_instrumented.argtypes = [C.c_void_p, C.c_int]
+    L.tsr_search_path.argtypes = [C.c_void_p]
+    L.tsr_search_path_reason.argtypes = [C.c_void_p]
+    L.tsr_search_path_reason.restype = C.c_char_p
     L.tsr_decode.argtypes = [C.c_void_p, u64p, C.c_uint64, C.c_int64, C.c_uint64, u64p, C.c_uint64, u64p, f64p, i32p]
     L.tsr_cost_from_errors.argtypes = [C.c_void_p, u64p, C.c_uint64, f64p]
     L.tsr_flipped_observables.argtypes = [C.c_void_p, u64p, C.c_uint64, u8p]
@@ -105,7 +111,8 @@ EXPORTED_SYMBOLS = [
     "tsr_config_init", "tsr_last_error", "tsr_version", "tsr_create", "tsr_destroy", "tsr_num_detectors",
     "tsr_num_observables", "tsr_num_errors", "tsr_num_dem_errors", "tsr_num_det_orders", "tsr_error_costs",
     "tsr_maps", "tsr_csr", "tsr_compiled_dem_text", "tsr_free", "tsr_decode_batch_b8",
-    "tsr_decode_batch_b8_device", "tsr_set_collect_errors", "tsr_last_batch_nnz", "tsr_last_batch_errors", "tsr_decode",
+    "tsr_decode_batch_b8_device", "tsr_set_collect_errors", "tsr_set_instrumented", "tsr_search_path",
+    "tsr_search_path_reason", "tsr_last_batch_nnz", "tsr_last_batch_errors", "tsr_decode",
     "tsr_cost_from_errors", "tsr_flipped_observables", "tsr_counters", "tsr_last_batch_timing", "tsr_stream",
     "tsr_device", "tsr_build_det_orders", "tsr_dem_count_detectors", "tsr_merge_weights", "tsr_circuit_to_dem",
     "tsr_sample_dem_b8",
@@ -178,7 +185,7 @@ class Decoder:
                  no_revisit_dets: bool = True, merge_errors: bool = True, pqlimit: int | None = 200000,
                  det_penalty: float = 0.0, det_orders=None, at_most_two_errors_per_detector: bool = False,
                  device: int = -1, host_only: bool = False, search_slots: int = 0, warps_per_block: int = 0,
-                 node_pool_bytes: int = 0, max_batch_shots: int = 0):
+                 node_pool_bytes: int = 0, max_batch_shots: int = 0, force_generic_kernel: bool = False):
         L = lib()
         cfg = TsrConfig()
         L.tsr_config_init(C.byref(cfg))
@@ -202,6 +209,7 @@ class Decoder:
         cfg.warps_per_block = warps_per_block
         cfg.node_pool_bytes = node_pool_bytes
         cfg.max_batch_shots = max_batch_shots
+        cfg.force_generic_kernel = int(force_generic_kernel)
         h = C.c_void_p()
         self.h = None
         _check(L.tsr_create(dem_text.encode(), C.byref(cfg), CREATE_HOST_ONLY if host_only else 0, C.byref(h)))
@@ -264,6 +272,17 @@ class Decoder:
         _check(lib().tsr_decode(self.h, _p(det, C.c_uint64), len(det), order, beam, _p(errs, C.c_uint64), cap,
                                 C.byref(n), C.byref(cost), C.byref(low)))
         return errs[: n.value].tolist(), cost.value, bool(low.value)
+
+    @property
+    def search_path(self) -> str:
+        return "fast" if lib().tsr_search_path(self.h) else "generic"
+
+    @property
+    def search_path_reason(self) -> str:
+        return lib().tsr_search_path_reason(self.h).decode()
+
+    def set_instrumented(self, on: bool):
+        _check(lib().tsr_set_instrumented(self.h, int(on)))
 
     def set_collect_errors(self, on: bool):
         _check(lib().tsr_set_collect_errors(self.h, int(on)))

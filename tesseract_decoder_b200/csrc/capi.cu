@@ -19,6 +19,7 @@
 #include "../../include/tesseract_b200.h"
 #include "circuit.h"
 #include "dem.h"
+#include "fast.h"
 #include "ingest.h"
 #include "search.h"
 
@@ -111,6 +112,10 @@ struct TrialSet {
 struct tsr_decoder {
   tsr_config cfg{};
   tsr::DemTables T;
+  tsr::FastTables F;
+  bool fast = false;          // decode with search_fast.cu (CTA per search) instead of search.cu
+  bool instrumented = false;  // fast path: also count the reference's scanned row entries (counter S)
+  bool hc_shared = false;
   std::vector<std::vector<uint64_t>> det_orders;
   std::vector<uint32_t> order_to_perm;  // det order index -> distinct permutation id
   uint32_t n_perms = 0;
@@ -122,7 +127,7 @@ struct tsr_decoder {
 
   // Device tables.
   DevBuf row_off, row_err, rec_a, rec_b, rec_c, e_off, e_det, e_rank, e_cost, e_nnbr, eo_off, eo_obs, e2dem, adj,
-      zobrist, order_det, order_pos;
+      zobrist, order_det, order_pos, frec_a, frec_b, frank, fquot;
   tsr::DeviceTables dt;
   TrialSet ensemble;
 
@@ -282,24 +287,61 @@ void init_device(tsr_decoder& h) {
   dt.zobrist = h.zobrist.as<uint4>();
   dt.order_det = h.order_det.as<uint32_t>();
   dt.order_pos = h.order_pos.as<uint32_t>();
+  dt.max_row_len = std::max<uint32_t>(T.max_row_len, 1);
+  if (h.fast) {
+    h.frec_a.upload(h.F.rec_a);
+    h.frec_b.upload(h.F.rec_b);
+    h.frank.upload(h.F.rank);
+    h.fquot.upload(h.F.quotient);
+    dt.frec_a = h.frec_a.as<uint4>();
+    dt.frec_b = h.frec_b.as<uint4>();
+    dt.frank = h.frank.as<uint16_t>();
+    dt.fquot = h.fquot.as<double>();
+    dt.fa_slots = h.F.a_slots;
+    dt.fnstride = h.F.nstride;
+    dt.fn_costs = h.F.n_costs;
+  }
 
   make_ensemble(h, h.ensemble);
   h.ensemble.upload();
 
-  // Grid shape: persistent warps filling every SM.
-  h.wpb = h.cfg.warps_per_block ? std::min<uint32_t>(h.cfg.warps_per_block, 8) : 4;
-  int occ = tsr::search_max_blocks_per_sm(h.wpb, D);
-  while (occ == 0 && h.wpb > 1) {
-    h.wpb /= 2;
-    occ = tsr::search_max_blocks_per_sm(h.wpb, D);
+  // Grid shape: persistent CTAs (fast path: one search each) or warps (generic path) filling every SM.
+  uint32_t slots = 0;
+  if (h.fast) {
+    // Warps per search: enough to split a row's children, few enough that short rows do not idle them.
+    uint32_t w = h.cfg.warps_per_block ? h.cfg.warps_per_block : (T.max_row_len > 96 ? 8 : T.max_row_len > 48 ? 4 : 2);
+    w = std::max<uint32_t>(1, std::min<uint32_t>(w, 16));
+    h.hc_shared = (size_t)D * 8 <= 32 * 1024;
+    int occ = tsr::search_fast_max_blocks_per_sm(dt, w, h.hc_shared);
+    while (occ == 0 && (w > 1 || h.hc_shared)) {
+      if (h.hc_shared && w <= 2) h.hc_shared = false; else w = std::max<uint32_t>(w / 2, 1);
+      occ = tsr::search_fast_max_blocks_per_sm(dt, w, h.hc_shared);
+    }
+    if (occ == 0) {
+      h.fast = false;  // state does not fit in shared memory: generic kernel
+      h.F.why_not = "the per-search state does not fit in shared memory";
+    } else {
+      h.wpb = w;
+      h.blocks = (uint32_t)(h.sm_count * occ);
+      slots = h.blocks;
+      if (h.cfg.search_slots && h.cfg.search_slots < slots) slots = h.blocks = std::max<uint32_t>(h.cfg.search_slots, 1);
+    }
   }
-  if (occ == 0) throw CudaError("the search kernel does not fit on this device for this many detectors");
-  h.blocks = (uint32_t)(h.sm_count * occ);
-  uint32_t slots = h.blocks * h.wpb;
-  if (h.cfg.search_slots && h.cfg.search_slots < slots) {
-    slots = std::max<uint32_t>(h.cfg.search_slots, 1);
-    h.blocks = (slots + h.wpb - 1) / h.wpb;
+  if (!h.fast) {
+    h.wpb = h.cfg.warps_per_block ? std::min<uint32_t>(h.cfg.warps_per_block, 8) : 4;
+    int occ = tsr::search_max_blocks_per_sm(h.wpb, D);
+    while (occ == 0 && h.wpb > 1) {
+      h.wpb /= 2;
+      occ = tsr::search_max_blocks_per_sm(h.wpb, D);
+    }
+    if (occ == 0) throw CudaError("the search kernel does not fit on this device for this many detectors");
+    h.blocks = (uint32_t)(h.sm_count * occ);
     slots = h.blocks * h.wpb;
+    if (h.cfg.search_slots && h.cfg.search_slots < slots) {
+      slots = std::max<uint32_t>(h.cfg.search_slots, 1);
+      h.blocks = (slots + h.wpb - 1) / h.wpb;
+      slots = h.blocks * h.wpb;
+    }
   }
 
   // Node pool: 32 B per node (heap + chain) + 16 B per visited entry (half as many as nodes).
@@ -411,6 +453,7 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     p.visited = reinterpret_cast<uint4*>(base + (size_t)tier.slots * tier.node_cap * 32);
     p.vlist = h.vlist.as<uint32_t>();
     p.hcache = h.hcache.as<double>();
+    p.hc_shared = h.hc_shared ? 1 : 0;
     p.sol_stride = h.sol_stride;
     p.sol = h.d_sol.as<uint32_t>();
     p.sol_len = h.d_sol_len.as<uint32_t>();
@@ -448,9 +491,12 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
 
   // Tier 0 over every item.
   const Tier& t0 = h.tiers[0];
-  uint32_t blocks0 = std::min<uint32_t>((t0.slots + h.wpb - 1) / h.wpb, (items + h.wpb - 1) / h.wpb);
+  auto launch = [&](const tsr::SearchParams& sp_, uint32_t tier_slots, uint32_t n_work) {
+    if (h.fast) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, h.instrumented, s);
+    return tsr::launch_search(sp_, std::min<uint32_t>((tier_slots + h.wpb - 1) / h.wpb, (n_work + h.wpb - 1) / h.wpb), h.wpb, s);
+  };
   CUDA_OK(cudaEventRecord(h.ev[1], s));
-  CUDA_OK((cudaError_t)tsr::launch_search(search_params(t0, nullptr, items), blocks0, h.wpb, s));
+  CUDA_OK((cudaError_t)launch(search_params(t0, nullptr, items), t0.slots, items));
   CUDA_OK(cudaEventRecord(h.ev[2], s));
   uint32_t* retry_a = h.d_retry.as<uint32_t>();
   uint32_t* retry_b = retry_a + shots;
@@ -484,8 +530,7 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     if (tk.visit_cap)
       CUDA_OK(cudaMemsetAsync(h.pool.as<char>() + (size_t)tk.slots * tk.node_cap * 32, 0, (size_t)tk.slots * tk.visit_cap * 16, s));
     CUDA_OK(cudaEventRecord(h.ev[1], s));
-    uint32_t nb = std::min<uint32_t>((tk.slots + h.wpb - 1) / h.wpb, ((uint32_t)item_ids.size() + h.wpb - 1) / h.wpb);
-    CUDA_OK((cudaError_t)tsr::launch_search(search_params(tk, d_item_ids, (uint32_t)item_ids.size()), nb, h.wpb, s));
+    CUDA_OK((cudaError_t)launch(search_params(tk, d_item_ids, (uint32_t)item_ids.size()), tk.slots, (uint32_t)item_ids.size()));
     CUDA_OK(cudaEventRecord(h.ev[2], s));
     CUDA_OK((cudaError_t)tsr::launch_resolve(resolve_params(d_shot_ids, n_retry, retry_b), s));
     // Restore the tier-0 invariant (empty visited tables in the tier-0 layout).
@@ -630,6 +675,9 @@ int tsr_create(const char* dem_text, const tsr_config* cfg, uint32_t flags, tsr_
       h->order_to_perm.push_back(it->second);
     }
     h->n_perms = (uint32_t)perm_ids.size();
+    h->F = tsr::build_fast_tables(h->T);
+    h->fast = h->F.certified && !cfg->force_generic_kernel;
+    if (h->F.certified && cfg->force_generic_kernel) h->F.why_not = "force_generic_kernel is set";
     h->host_only = (flags & TSR_CREATE_HOST_ONLY) != 0;
     if (!h->host_only) init_device(*h);
     *out = h.release();
@@ -713,6 +761,19 @@ int tsr_decode_batch_b8_device(tsr_decoder* h, const uint8_t* d_dets, uint64_t s
 int tsr_set_collect_errors(tsr_decoder* h, int on) {
   h->collect_errors = on != 0;
   return TSR_OK;
+}
+
+int tsr_set_instrumented(tsr_decoder* h, int on) {
+  h->instrumented = on != 0;
+  return TSR_OK;
+}
+
+int tsr_search_path(const tsr_decoder* h) {
+  return h->fast ? 1 : 0;
+}
+
+const char* tsr_search_path_reason(const tsr_decoder* h) {
+  return h->fast ? "" : h->F.why_not.c_str();
 }
 
 uint64_t tsr_last_batch_nnz(const tsr_decoder* h) {

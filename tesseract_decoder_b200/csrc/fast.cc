@@ -1,0 +1,139 @@
+// See fast.h.
+#include "fast.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+namespace tsr {
+namespace {
+
+struct Cls {
+  uint32_t cost_id, n;
+  double cost;
+};
+
+// The reference's predicate, with its arithmetic: double * (double)integer on both sides, each product
+// rounded to double, then compared (tesseract.cc:139-140, 146).
+inline bool P(const Cls& a, const Cls& b) {
+  volatile double lhs = a.cost * (double)b.n;
+  volatile double rhs = b.cost * (double)a.n;
+  return lhs < rhs;
+}
+
+// Exact order of cost/n: a 53-bit significand times an integer <= 11 is exact in x87 extended precision.
+inline bool exact_less(const Cls& a, const Cls& b) {
+  static_assert(sizeof(long double) >= 10, "needs a 64-bit significand");
+  return (long double)a.cost * (long double)b.n < (long double)b.cost * (long double)a.n;
+}
+
+void put_slot(uint8_t* plane, int byte_off, uint32_t det, uint32_t rank) {
+  const uint32_t v = (det & 0x3FFF) | (rank << 14);
+  plane[byte_off] = (uint8_t)v;
+  plane[byte_off + 1] = (uint8_t)(v >> 8);
+  plane[byte_off + 2] = (uint8_t)(v >> 16);
+}
+
+}  // namespace
+
+FastTables build_fast_tables(const DemTables& T) {
+  FastTables F;
+  const uint64_t D = T.num_detectors, E = T.num_errors;
+  auto fail = [&](std::string why) {
+    F.certified = false;
+    F.why_not = std::move(why);
+    return F;
+  };
+  if (D > kFastMaxDetectors) return fail("more than 16383 detectors");
+  if (T.max_degree > kFastMaxDegree) return fail("an error touches more than 11 detectors");
+  if (T.max_row_len > kFastMaxRowLen) return fail("a detector row is longer than 1024 errors");
+
+  std::map<double, uint32_t> ids;
+  for (uint64_t e = 0; e < E; ++e) {
+    const double c = T.e_cost[e];
+    if (!(c > 0) || !std::isfinite(c)) return fail("an error has a non-positive or non-finite cost (p >= 0.5)");
+    ids.emplace(c, 0);
+  }
+  if (ids.size() > kFastMaxCosts) return fail("more than 128 distinct error costs");
+  uint32_t next = 0;
+  for (auto& kv : ids) kv.second = next++;
+  F.n_costs = (uint32_t)ids.size();
+  F.nstride = std::max<uint32_t>(T.max_degree, 1) + 1;
+  F.cost_id.resize(E);
+  std::vector<uint32_t> max_size(F.n_costs, 0);
+  std::vector<double> cost_of(F.n_costs, 0);
+  for (uint64_t e = 0; e < E; ++e) {
+    const uint32_t k = ids[T.e_cost[e]];
+    F.cost_id[e] = (uint8_t)k;
+    cost_of[k] = T.e_cost[e];
+    max_size[k] = std::max<uint32_t>(max_size[k], (uint32_t)T.errors[e].detectors.size());
+  }
+
+  // (1) P is a strict weak order on the classes.
+  std::vector<Cls> cls;
+  for (uint32_t k = 0; k < F.n_costs; ++k)
+    for (uint32_t n = 1; n <= max_size[k]; ++n) cls.push_back({k, n, cost_of[k]});
+  std::stable_sort(cls.begin(), cls.end(), exact_less);
+  std::vector<uint32_t> r(cls.size(), 0);
+  for (size_t i = 1; i < cls.size(); ++i) r[i] = r[i - 1] + (P(cls[i - 1], cls[i]) ? 1u : 0u);
+  for (size_t i = 0; i < cls.size(); ++i)
+    for (size_t j = i; j < cls.size(); ++j)
+      if (P(cls[i], cls[j]) != (r[i] < r[j]) || P(cls[j], cls[i]))
+        return fail("the heuristic's rounded ratio comparison is not a strict weak order on this DEM's costs");
+  if (!cls.empty() && r.back() >= 0xFFFF) return fail("too many distinct cost/count ratios");
+  F.rank.assign((size_t)F.n_costs * F.nstride, 0xFFFF);
+  F.quotient.assign((size_t)F.n_costs * F.nstride, INFINITY);
+  for (size_t i = 0; i < cls.size(); ++i) {
+    const size_t at = (size_t)cls[i].cost_id * F.nstride + cls[i].n;
+    F.rank[at] = (uint16_t)r[i];
+    volatile double q = cls[i].cost / (double)cls[i].n;  // tesseract.cc:153
+    F.quotient[at] = q;
+  }
+
+  // (2) rank(cost, size) never decreases along a row.
+  for (uint64_t d = 0; d < D; ++d) {
+    uint32_t prev = 0;
+    for (uint32_t k = T.row_off[d]; k < T.row_off[d + 1]; ++k) {
+      const uint64_t e = (uint64_t)T.row_err[k];
+      const uint32_t rk = F.rank[(size_t)F.cost_id[e] * F.nstride + T.errors[e].detectors.size()];
+      if (rk < prev) return fail("a detector row is not sorted by the rank of cost/size");
+      prev = rk;
+    }
+  }
+
+  // Records.
+  const size_t nnz = T.row_err.size();
+  F.rec_a.assign(nnz * 16 + 16, 0);
+  F.rec_b.assign(nnz * 16 + 16, 0);
+  F.a_slots = std::min<uint32_t>(5, T.max_degree > 0 ? T.max_degree - 1 : 0);
+  for (uint64_t d = 0; d < D; ++d) {
+    for (uint32_t at = T.row_off[d]; at < T.row_off[d + 1]; ++at) {
+      const uint64_t e = (uint64_t)T.row_err[at];
+      const auto& dets = T.errors[e].detectors;
+      uint8_t* a = &F.rec_a[(size_t)at * 16];
+      uint8_t* b = &F.rec_b[(size_t)at * 16];
+      for (int s = 0; s < 5; ++s) {
+        put_slot(a, 1 + 3 * s, (uint32_t)D, kFastSlotDummyRank);
+        put_slot(b, 3 * s, (uint32_t)D, kFastSlotDummyRank);
+      }
+      int slot = 0;
+      for (size_t j = 0; j < dets.size(); ++j) {
+        if ((uint64_t)dets[j] == d) continue;
+        const uint32_t rank = (uint32_t)T.e_rank[T.e_off[e] + j];
+        if (slot < 5)
+          put_slot(a, 1 + 3 * slot, (uint32_t)dets[j], rank);
+        else
+          put_slot(b, 3 * (slot - 5), (uint32_t)dets[j], rank);
+        ++slot;
+      }
+      const bool has_b = slot > 5;
+      F.any_plane_b |= has_b;
+      a[0] = (uint8_t)(F.cost_id[e] | (has_b ? 0x80 : 0));
+    }
+  }
+  F.certified = true;
+  return F;
+}
+
+}  // namespace tsr

@@ -29,6 +29,13 @@ struct DeviceTables {
   // Distinct detector orders: position -> detector and its inverse, [n_perm][D].
   const uint32_t* order_det = nullptr;
   const uint32_t* order_pos = nullptr;
+  // Fast path (fast.h; null / 0 when the DEM is not certified for it).
+  const uint4* frec_a = nullptr;     // [nnz] packed records, plane A
+  const uint4* frec_b = nullptr;     // [nnz] plane B (entries with header bit 7)
+  const uint16_t* frank = nullptr;   // [fn_costs * fnstride] rank of class (cost id, count)
+  const double* fquot = nullptr;     // [fn_costs * fnstride] fl(cost / count)
+  uint32_t fa_slots = 0, fnstride = 0, fn_costs = 0;
+  uint32_t max_row_len = 0;
 };
 
 struct alignas(16) HeapNode {
@@ -78,6 +85,7 @@ struct SearchParams {
   uint4* visited = nullptr;
   uint32_t* vlist = nullptr;
   double* hcache = nullptr;  // [n_slots][D]
+  int hc_shared = 0;         // fast path: the per-detector terms of the expanded node live in shared memory
   // Per-item outputs.
   uint32_t sol_stride = 0;
   uint32_t* sol = nullptr;      // [items][sol_stride] compiled error ids, root -> leaf
@@ -126,6 +134,10 @@ struct StageParams {
 int launch_stage(const StageParams& p, void* stream);
 int launch_search(const SearchParams& p, uint32_t blocks, uint32_t warps_per_block, void* stream);
 int launch_resolve(const ResolveParams& p, void* stream);
+// Fast path (search_fast.cu): one CTA of `warps` warps per search.
+int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, void* stream);
+uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared);
+int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared);
 // Shared memory bytes one search warp needs for a DEM with D detectors.
 uint32_t search_smem_bytes_per_warp(uint32_t D);
 // Resident blocks per SM of the search kernel for this block shape (0 on failure).

@@ -1,0 +1,894 @@
+// The A* most-likely-error search, fast path: one CTA per (shot, trial) search, W warps per CTA.
+//
+// Same search as search.cu (reference: tesseract.cc:380-616, 128-154, 349-369, 119-121, bits/stl_heap.h),
+// reorganised around what the v0 profile showed (profiles/r01_v0_*): the warp-per-search kernel was
+// latency bound (long-scoreboard stalls on L2 row records, 2 % L1 hit rate, 16 warps/SM) and lost half
+// the machine to the tail of a batch.  Here
+//
+//   * a search owns a CTA.  The children of an expanded node are independent (each is the parent state
+//     with the error's detectors toggled and a longer blocked prefix of the min-detector's row), so the
+//     W warps evaluate them round-robin, each on a private copy of the 16-bit-per-detector state, and
+//     warp 0 then pushes the results in row order — which keeps the reference's queue order.  All W
+//     warps scan the same few detector rows, so the row records become L1 hits, and a batch needs 8-16x
+//     fewer concurrent searches to fill the machine (smaller tail, larger node pool per search).
+//   * a row scan is integer-only.  Under the host-checked certificate (fast.h) get_detcost is "the first
+//     unblocked row entry of minimal rank(cost, count)", so a lane keeps min(rank << 12 | position) over
+//     its entries, the warp takes one REDUX.MIN, and the winner's host-computed quotient fl(cost/count)
+//     is looked up.  No per-chunk ballots, no FP64 in the loop, and chunk loads are independent.
+//   * row records are 16 bytes (5 neighbours) + 16 bytes (5 more, only for errors of degree > 6) with
+//     24-bit (detector, rank) slots instead of 16 + 16 + 16 bytes with an 8-byte cost.
+//
+// Exactness: the child cost is still node.cost + cost(e) then -= / += detector terms in the reference's
+// order with round-to-nearest adds; pushes happen in row order; the queue is the same libstdc++ heap.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "search.h"
+
+namespace tsr {
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr uint32_t kFired = 0x8000u;
+constexpr uint32_t kThr = 0x7FFu;
+constexpr uint32_t kKeyInf = 0xFFFFFFFFu;
+
+enum Action : int { kActExpand = 0, kActSkip = 1, kActDone = 2 };
+enum ChildStatus : uint32_t { kChildOk = 0, kChildDropped = 1 };
+
+struct alignas(16) Ctl {
+  // the popped node
+  double cost;
+  uint32_t chain;
+  uint32_t num_dets, depth;
+  // search state (owned by warp 0)
+  uint32_t min_dets, max_dets;
+  uint32_t root_dets;
+  int root_pending;
+  int terms_cached;
+  unsigned long long heap_size, chain_size, pushed, n_visited;
+  uint4 key, root_key;
+  // expansion
+  uint32_t mind, m_off, m_len, nchild;
+  // control
+  int action;
+  uint32_t status;
+  uint32_t work;
+  uint32_t item;
+};
+
+struct Smem {
+  Ctl* ctl;
+  uint16_t* rank;   // [n_costs * nstride]
+  uint32_t* rbits;  // [nwords]
+  uint32_t* fbits;  // [nwords]
+  uint16_t* pst;    // [dpad]
+  double* hc;       // [D] (shared or global)
+  double* res_cost;  // [max_row_len]
+  uint4* res_meta;   // [max_row_len] {error, fired_mask, next_dets | pos << 16, status}
+  uint16_t* clist;   // [max_row_len]
+  uint16_t* st;      // this warp's private state [dpad]
+};
+
+__host__ __device__ inline uint32_t round16(uint32_t bytes) {
+  return (bytes + 15u) & ~15u;
+}
+__host__ __device__ inline uint32_t dpad_of(uint32_t D) {
+  return (D + 1 + 7) & ~7u;  // u16 entries, multiple of 16 bytes
+}
+
+struct Layout {
+  uint32_t off_rank, off_rbits, off_fbits, off_pst, off_hc, off_cost, off_meta, off_clist, off_st, total;
+};
+__host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint32_t rank_entries, uint32_t max_row_len,
+                                               uint32_t warps, bool hc_shared) {
+  Layout L;
+  uint32_t at = round16(sizeof(Ctl));
+  L.off_rank = at;
+  at += round16(rank_entries * 2);
+  L.off_rbits = at;
+  at += round16(nwords * 4);
+  L.off_fbits = at;
+  at += round16(nwords * 4);
+  L.off_pst = at;
+  at += dpad_of(D) * 2;
+  L.off_hc = at;
+  if (hc_shared) at += round16(D * 8);
+  L.off_cost = at;
+  at += round16(max_row_len * 8);
+  L.off_meta = at;
+  at += max_row_len * 16;
+  L.off_clist = at;
+  at += round16(max_row_len * 2);
+  L.off_st = at;
+  at += warps * dpad_of(D) * 2;
+  L.total = at;
+  return L;
+}
+
+__device__ __forceinline__ uint4 ldg16(const uint4* p) {
+  return __ldg(p);
+}
+
+// ---- row records -----------------------------------------------------------------------------------
+
+__device__ __forceinline__ void slot_apply(uint32_t slot, const uint16_t* st, uint32_t& count, bool& blocked) {
+  const uint32_t v = st[slot & 0x3FFF];
+  count += v >> 15;
+  blocked |= ((slot >> 14) & 0x3FF) < (v & kThr);
+}
+
+struct Eval {
+  uint32_t count;
+  bool blocked;
+  uint32_t cost_id;
+};
+
+// Entry `idx` of the row at `roff` whose own detector has block threshold Td, in state st.
+__device__ __forceinline__ Eval eval_entry(const DeviceTables& t, const uint16_t* st, uint32_t roff, uint32_t idx,
+                                           uint32_t Td) {
+  const uint4 a = ldg16(t.frec_a + roff + idx);
+  Eval e;
+  e.count = 1;
+  e.blocked = idx < Td;
+  e.cost_id = a.x & 0x7F;
+  const uint32_t ns = t.fa_slots;
+  if (ns > 0) slot_apply(a.x >> 8, st, e.count, e.blocked);
+  if (ns > 1) slot_apply(a.y & 0xFFFFFF, st, e.count, e.blocked);
+  if (ns > 2) slot_apply((a.y >> 24) | ((a.z & 0xFFFF) << 8), st, e.count, e.blocked);
+  if (ns > 3) slot_apply((a.z >> 16) | ((a.w & 0xFF) << 16), st, e.count, e.blocked);
+  if (ns > 4) slot_apply(a.w >> 8, st, e.count, e.blocked);
+  if (a.x & 0x80) {
+    const uint4 b = ldg16(t.frec_b + roff + idx);
+    slot_apply(b.x & 0xFFFFFF, st, e.count, e.blocked);
+    slot_apply((b.x >> 24) | ((b.y & 0xFFFF) << 8), st, e.count, e.blocked);
+    slot_apply((b.y >> 16) | ((b.z & 0xFF) << 16), st, e.count, e.blocked);
+    slot_apply(b.z >> 8, st, e.count, e.blocked);
+    slot_apply(b.w & 0xFFFFFF, st, e.count, e.blocked);
+  }
+  return e;
+}
+
+// Number of detectors of the error behind a record (instrumented builds only: the early-exit position).
+__device__ __forceinline__ uint32_t entry_size(const DeviceTables& t, uint32_t roff, uint32_t idx) {
+  const uint32_t e = (uint32_t)__ldg(t.row_err + roff + idx);
+  return __ldg(t.e_off + e + 1) - __ldg(t.e_off + e);
+}
+
+// get_detcost (tesseract.cc:128-154) without det_penalty for fired detector x in state st; +inf when no
+// unblocked error touches x.  kInstr additionally counts the row entries the reference loop would have
+// visited before its early exit (counter S of SURVEY.md §8d).
+template <bool kInstr>
+__device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t* st, const uint16_t* rank, uint32_t x,
+                                           uint32_t lane, unsigned long long& scanned) {
+  const uint32_t roff = __ldg(t.row_off + x);
+  const uint32_t rlen = __ldg(t.row_off + x + 1) - roff;
+  const uint32_t Td = st[x] & kThr;
+  uint32_t best = kKeyInf, best_cls = 0;
+  uint32_t carry = kKeyInf;  // kInstr: best rank before this chunk
+  bool counting = true;
+#pragma unroll 2
+  for (uint32_t base = 0; base < rlen; base += 32) {
+    const uint32_t idx = base + lane;
+    uint32_t urank = kKeyInf;
+    if (idx < rlen) {
+      const Eval e = eval_entry(t, st, roff, idx, Td);
+      const uint32_t cls = e.cost_id * t.fnstride + e.count;
+      if (!e.blocked) {
+        urank = rank[cls];
+        const uint32_t key = (urank << 12) | idx;
+        if (key < best) {
+          best = key;
+          best_cls = cls;
+        }
+      }
+    }
+    if (kInstr && counting) {
+      uint32_t rs = 0;
+      if (idx < rlen) rs = rank[(ldg16(t.frec_a + roff + idx).x & 0x7F) * t.fnstride + entry_size(t, roff, idx)];
+      uint32_t incl = urank;
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(kFull, incl, off);
+        if ((int)lane >= off) incl = min(incl, o);
+      }
+      uint32_t excl = __shfl_up_sync(kFull, incl, 1);
+      if (lane == 0) excl = kKeyInf;
+      const uint32_t before = min(carry, excl);
+      const unsigned mb = __ballot_sync(kFull, idx < rlen && before != kKeyInf && rs >= before);
+      if (mb) {
+        scanned += (unsigned long long)__ffs((int)mb);
+        counting = false;
+      } else {
+        scanned += min(32u, rlen - base);
+        carry = min(carry, __shfl_sync(kFull, incl, 31));
+      }
+    }
+  }
+  const uint32_t m = __reduce_min_sync(kFull, best);
+  if (m == kKeyInf) return __longlong_as_double(0x7FF0000000000000LL);
+  const int winner = __ffs((int)__ballot_sync(kFull, best == m)) - 1;
+  const uint32_t cls = __shfl_sync(kFull, best_cls, winner);
+  return __ldg(t.fquot + cls);
+}
+
+// ---- queue: exact libstdc++ std::priority_queue<Node, vector<Node>, std::greater<Node>> -------------
+
+__device__ __forceinline__ bool node_greater(const HeapNode& a, const HeapNode& b) {
+  return a.cost > b.cost || (a.cost == b.cost && a.num_dets < b.num_dets);  // Node::operator>, tesseract.cc:119-121
+}
+__device__ __forceinline__ HeapNode heap_ld(const HeapNode* p) {
+  const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p));
+  HeapNode n;
+  n.cost = __hiloint2double((int)v.y, (int)v.x);
+  n.chain = v.z;
+  n.num_dets = (uint16_t)(v.w & 0xFFFF);
+  n.depth = (uint16_t)(v.w >> 16);
+  return n;
+}
+__device__ __forceinline__ void heap_st(HeapNode* p, const HeapNode& n) {
+  uint4 v;
+  v.x = (uint32_t)__double2loint(n.cost);
+  v.y = (uint32_t)__double2hiint(n.cost);
+  v.z = n.chain;
+  v.w = (uint32_t)n.num_dets | ((uint32_t)n.depth << 16);
+  __stcg(reinterpret_cast<uint4*>(p), v);
+}
+
+// std::push_heap after push_back (bits/stl_heap.h:135-148), by a whole warp: lane k fetches the ancestor
+// k+1 levels above the new leaf, the sift stops at the first ancestor that is not greater than the value,
+// and the ancestors below it move down one level — the same moves the sequential loop makes, in one
+// memory round trip.
+__device__ __forceinline__ void heap_push_warp(HeapNode* heap, unsigned long long size_before, const HeapNode& value,
+                                               uint32_t lane) {
+  const unsigned long long leaf1 = size_before + 1;  // 1-based index of the new leaf
+  const unsigned long long anc1 = leaf1 >> (lane + 1);
+  const bool valid = anc1 >= 1;
+  HeapNode pn;
+  pn.cost = 0;
+  pn.chain = 0;
+  pn.num_dets = 0;
+  pn.depth = 0;
+  if (valid) pn = heap_ld(heap + (anc1 - 1));
+  const bool up = valid && node_greater(pn, value);
+  const unsigned not_up = ~__ballot_sync(kFull, up);
+  const uint32_t stop = not_up ? (uint32_t)__ffs((int)not_up) - 1 : 32;  // ancestors 0..stop-1 move down
+  if (lane < stop) heap_st(heap + ((leaf1 >> lane) - 1), pn);
+  if (lane == 0) heap_st(heap + ((leaf1 >> stop) - 1), value);
+  __syncwarp();
+}
+
+// top(); pop(): std::pop_heap (bits/stl_heap.h:224-267) then pop_back.  One lane.
+__device__ HeapNode heap_pop(HeapNode* heap, unsigned long long& size) {
+  HeapNode top = heap_ld(heap);
+  if (size > 1) {
+    const long long len = (long long)size - 1;
+    HeapNode value = heap_ld(heap + len);
+    long long hole = 0, child = 0;
+    while (child < (len - 1) / 2) {
+      child = 2 * (child + 1);
+      HeapNode r = heap_ld(heap + child), l = heap_ld(heap + child - 1);
+      if (node_greater(r, l)) {
+        --child;
+        r = l;
+      }
+      heap_st(heap + hole, r);
+      hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+      child = 2 * (child + 1);
+      heap_st(heap + hole, heap_ld(heap + child - 1));
+      hole = child - 1;
+    }
+    while (hole > 0) {
+      long long parent = (hole - 1) / 2;
+      HeapNode pn = heap_ld(heap + parent);
+      if (!node_greater(pn, value)) break;
+      heap_st(heap + hole, pn);
+      hole = parent;
+    }
+    heap_st(heap + hole, value);
+  }
+  --size;
+  return top;
+}
+
+// ---- visited set: open addressing over 128-bit Zobrist fingerprints of the fired set ----------------
+
+__device__ __forceinline__ bool key_eq(const uint4& a, const uint4& b) {
+  return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w;
+}
+__device__ __forceinline__ uint4 key_fix(uint4 k) {
+  if ((k.x | k.y | k.z | k.w) == 0) k.w = 1;  // all-zero marks an empty slot
+  return k;
+}
+__device__ bool visited_contains(const uint4* tab, uint64_t cap, uint4 key) {
+  key = key_fix(key);
+  uint64_t i = ((uint64_t)key.x * cap) >> 32;
+  while (true) {
+    const uint4 v = __ldcg(tab + i);
+    if ((v.x | v.y | v.z | v.w) == 0) return false;
+    if (key_eq(v, key)) return true;
+    if (++i == cap) i = 0;
+  }
+}
+__device__ int visited_insert(uint4* tab, uint64_t cap, uint4 key, uint64_t& where) {
+  key = key_fix(key);
+  uint64_t i = ((uint64_t)key.x * cap) >> 32;
+  while (true) {
+    const uint4 v = __ldcg(tab + i);
+    if ((v.x | v.y | v.z | v.w) == 0) {
+      __stcg(tab + i, key);
+      where = i;
+      return 1;
+    }
+    if (key_eq(v, key)) return 0;
+    if (++i == cap) i = 0;
+  }
+}
+__device__ __forceinline__ uint4 warp_xor(uint4 k) {
+  k.x = __reduce_xor_sync(kFull, k.x);
+  k.y = __reduce_xor_sync(kFull, k.y);
+  k.z = __reduce_xor_sync(kFull, k.z);
+  k.w = __reduce_xor_sync(kFull, k.w);
+  return k;
+}
+__device__ __forceinline__ void key_xor(uint4& a, const uint4& b) {
+  a.x ^= b.x;
+  a.y ^= b.y;
+  a.z ^= b.z;
+  a.w ^= b.w;
+}
+
+struct Counters {
+  unsigned long long Q = 0, P = 0, X = 0, L = 0, S = 0, A = 0, V = 0;
+};
+
+// ---- one child (one warp): tesseract.cc:533-606 up to, not including, the push ----------------------
+
+template <bool kInstr>
+__device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm, uint32_t j, uint32_t lane,
+                                           const uint4* vtab, Counters& ctr) {
+  const DeviceTables& t = p.t;
+  const Ctl& c = *sm.ctl;
+  uint16_t* st = sm.st;
+  const uint32_t D = t.D, nwords = t.nwords;
+  const uint32_t pos = sm.clist[j];
+  const uint32_t mind = c.mind;
+  const uint32_t ei = (uint32_t)__ldg(t.row_err + c.m_off + pos);
+  const uint32_t eb = __ldg(t.e_off + ei), deg = __ldg(t.e_off + ei + 1) - eb;
+  uint32_t dj = D;
+  uint32_t sj = 0;
+  if (lane < deg) {
+    dj = (uint32_t)__ldg(t.e_det + eb + lane);
+    sj = st[dj];
+  }
+  const unsigned fired_mask = __ballot_sync(kFull, (sj & kFired) != 0);
+  const uint32_t next_dets = c.num_dets + deg - 2 * (uint32_t)__popc(fired_mask);
+  uint32_t status = kChildOk;
+  double cost = 0;
+  if (next_dets > c.max_dets) status = kChildDropped;  // tesseract.cc:561
+  if (status == kChildOk && p.no_revisit) {            // tesseract.cc:563-565
+    uint4 z = make_uint4(0, 0, 0, 0);
+    if (lane < deg) z = ldg16(t.zobrist + dj);
+    z = warp_xor(z);
+    key_xor(z, c.key);
+    int seen = 0;
+    if (lane == 0) seen = visited_contains(vtab, p.visit_cap, z) ? 1 : 0;
+    seen = __shfl_sync(kFull, seen, 0);
+    ++ctr.V;
+    if (seen) status = kChildDropped;
+  }
+  if (status == kChildOk) {
+    // The child's state: toggle the error's detectors, block the min-detector row up to this entry.
+    if (lane < deg) {
+      uint32_t nv = sj ^ kFired;
+      if (p.at_most_two && (sj & kFired)) nv = (nv & kFired) | kThr;
+      st[dj] = (uint16_t)nv;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t s = st[mind];
+      if ((s & kThr) < pos + 1) st[mind] = (uint16_t)((s & kFired) | (pos + 1));
+    }
+    __syncwarp();
+
+    // The reference's add/sub chain, in its order (tesseract.cc:549-585).
+    cost = __dadd_rn(c.cost, __ldg(t.e_cost + ei));
+    for (uint32_t k = 0; k < deg; ++k) {
+      const uint32_t d = __shfl_sync(kFull, dj, (int)k);
+      if ((fired_mask >> k) & 1) {
+        cost = __dsub_rn(cost, sm.hc[d]);
+      } else {
+        const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, d, lane, ctr.S), p.det_penalty);
+        cost = __dadd_rn(cost, h);
+      }
+    }
+    // eneighbors[ei] ∩ fired: detectors adjacent to one of the error's detectors, fired in the parent
+    // (hence in the child), not in the error itself; ascending.
+    for (uint32_t wb = 0; wb < nwords; wb += 32) {
+      const uint32_t w = wb + lane;
+      uint32_t mine = 0;
+      for (uint32_t k = 0; k < deg; ++k) {
+        const uint32_t d = __shfl_sync(kFull, dj, (int)k);
+        if (w < nwords) mine |= __ldg(t.adj + (size_t)d * nwords + w);
+      }
+      for (uint32_t k = 0; k < deg; ++k) {
+        const uint32_t d = __shfl_sync(kFull, dj, (int)k);
+        if ((d >> 5) == w) mine &= ~(1u << (d & 31));
+      }
+      if (w < nwords) mine &= sm.fbits[w];
+      unsigned nz = __ballot_sync(kFull, mine != 0);
+      while (nz) {
+        const uint32_t l = (uint32_t)__ffs((int)nz) - 1;
+        nz &= nz - 1;
+        uint32_t word = __shfl_sync(kFull, mine, (int)l);
+        while (word) {
+          const uint32_t od = (wb + l) * 32 + (uint32_t)__ffs((int)word) - 1;
+          word &= word - 1;
+          cost = __dsub_rn(cost, sm.hc[od]);
+          const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, od, lane, ctr.S), p.det_penalty);
+          cost = __dadd_rn(cost, h);
+        }
+      }
+    }
+    ctr.A += deg + __ldg(t.e_nnbr + ei);
+    if (lane < deg) st[dj] = (uint16_t)sj;  // back to the parent state (the min detector is one of them)
+    __syncwarp();
+    if (cost == __longlong_as_double(0x7FF0000000000000LL)) status = kChildDropped;  // tesseract.cc:587
+  }
+  if (lane == 0) {
+    sm.res_cost[j] = cost;
+    sm.res_meta[j] = make_uint4(ei, fired_mask, next_dets | (pos << 16), status);
+  }
+}
+
+// ---- one search (whole CTA).  Returns the item status; on kItemOk the solution has been written. ------
+
+template <bool kInstr>
+__device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t slot, uint32_t item, Counters& ctr) {
+  const DeviceTables& t = p.t;
+  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+  const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  const uint32_t D = t.D, nwords = t.nwords, dpad = dpad_of(D);
+  Ctl& c = *sm.ctl;
+  const uint32_t shot = item / p.n_trials, trial = item - shot * p.n_trials;
+  const uint32_t perm = __ldg(p.trial_perm + trial);
+  const uint32_t beam = __ldg(p.trial_beam + trial);
+  const uint32_t* order_det = t.order_det + (size_t)perm * D;
+  const uint32_t* order_pos = t.order_pos + (size_t)perm * D;
+  HeapNode* heap = p.heap + (size_t)slot * p.node_cap;
+  ChainNode* chain = p.chain + (size_t)slot * p.node_cap;
+  uint4* vtab = p.no_revisit ? p.visited + (size_t)slot * p.visit_cap : nullptr;
+  uint32_t* vlist = p.no_revisit ? p.vlist + (size_t)slot * p.vlist_cap : nullptr;
+  const double kInf = __longlong_as_double(0x7FF0000000000000LL);
+
+  // Stage the shot: bit-packed syndrome -> root fired bitset (warp 0).
+  if (warp == 0) {
+    const uint8_t* row = p.dets + (size_t)shot * p.stride;
+    const uint32_t nbytes = (D + 7) / 8;
+    uint32_t my_fired = 0;
+    uint4 root_key = make_uint4(0, 0, 0, 0);
+    for (uint32_t w = lane; w < nwords; w += 32) {
+      uint32_t word = 0;
+      for (uint32_t b = 0; b < 4; ++b) {
+        const uint32_t at = w * 4 + b;
+        if (at < nbytes) word |= (uint32_t)row[at] << (8 * b);
+      }
+      if (w * 32 + 32 > D) word &= (1u << (D - w * 32)) - 1u;
+      sm.rbits[w] = word;
+      my_fired += __popc(word);
+      for (uint32_t m = word; m; m &= m - 1) key_xor(root_key, ldg16(t.zobrist + (w * 32 + (uint32_t)__ffs((int)m) - 1)));
+    }
+    const uint32_t root_dets = __reduce_add_sync(kFull, my_fired);
+    root_key = warp_xor(root_key);
+    if (lane == 0) {
+      c.root_key = root_key;
+      c.root_dets = root_dets;
+      c.min_dets = root_dets;
+      c.max_dets = root_dets + beam;
+      c.root_pending = 1;
+      c.heap_size = c.chain_size = c.pushed = c.n_visited = 0;
+    }
+  }
+  __syncthreads();
+
+  while (true) {
+    // ---- phase 1 (warp 0): next node ----------------------------------------------------------------
+    if (warp == 0) {
+      int action = kActExpand;
+      uint32_t status = kItemOk;
+      const int root_pending = c.root_pending;
+      const unsigned long long heap_size0 = c.heap_size;
+      const uint32_t max_dets0 = c.max_dets;
+      __syncwarp();
+      if (root_pending) {
+        if (lane == 0) {
+          c.cost = 0;
+          c.chain = kNoChain;
+          c.num_dets = c.root_dets;
+          c.depth = 0;
+          c.terms_cached = 0;
+        }
+      } else if (heap_size0 == 0) {
+        action = kActDone;
+        status = kItemLowConfidence;  // tesseract.cc:609-615
+      } else {
+        HeapNode node;
+        node.cost = 0;
+        node.chain = 0;
+        node.num_dets = 0;
+        node.depth = 0;
+        unsigned long long hs = heap_size0;
+        if (lane == 0) node = heap_pop(heap, hs);
+        __syncwarp();
+        const uint32_t nd = __shfl_sync(kFull, (uint32_t)node.num_dets, 0);
+        ++ctr.P;
+        if (lane == 0) {
+          c.heap_size = hs;
+          c.cost = node.cost;
+          c.chain = node.chain;
+          c.num_dets = node.num_dets;
+          c.depth = node.depth;
+          c.terms_cached = node.chain == kNoChain;  // the root's detector terms are still in hc
+        }
+        if (nd > max_dets0) action = kActSkip;  // tesseract.cc:434
+      }
+      if (lane == 0) {
+        c.action = action;
+        c.status = status;
+      }
+    }
+    __syncthreads();
+    if (c.action == kActDone) return c.status;
+    if (c.action == kActSkip) {
+      __syncthreads();
+      continue;
+    }
+
+    // ---- phase 2 (all): the node's state from its chain (tesseract.cc:349-369) ------------------------
+    for (uint32_t i = tid; i < dpad / 2; i += nthr) reinterpret_cast<uint32_t*>(sm.pst)[i] = 0;
+    for (uint32_t w = tid; w < nwords; w += nthr) sm.fbits[w] = sm.rbits[w];
+    __syncthreads();
+    for (uint32_t w = tid; w < nwords; w += nthr)
+      for (uint32_t m = sm.rbits[w]; m; m &= m - 1) sm.pst[w * 32 + (uint32_t)__ffs((int)m) - 1] = (uint16_t)kFired;
+    __syncthreads();
+    if (warp == 0) {
+      uint4 key = make_uint4(0, 0, 0, 0);
+      for (uint32_t at = c.chain; at != kNoChain;) {
+        const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(chain + at));
+        const uint32_t err = raw.x, parent = raw.y, mind_pos = raw.z, off_mask = raw.w;
+        const uint32_t eb = __ldg(t.e_off + err), deg = __ldg(t.e_off + err + 1) - eb;
+        uint32_t dj = 0;
+        if (lane < deg) {
+          dj = (uint32_t)__ldg(t.e_det + eb + lane);
+          sm.pst[dj] ^= (uint16_t)kFired;
+          atomicXor(&sm.fbits[dj >> 5], 1u << (dj & 31));
+          key_xor(key, ldg16(t.zobrist + dj));
+        }
+        __syncwarp();
+        if (p.at_most_two && lane < deg && ((off_mask >> lane) & 1)) sm.pst[dj] = (uint16_t)((sm.pst[dj] & kFired) | kThr);
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t md = mind_pos >> 16, thr = (mind_pos & 0xFFFF) + 1;
+          const uint32_t s = sm.pst[md];
+          if ((s & kThr) < thr) sm.pst[md] = (uint16_t)((s & kFired) | thr);
+        }
+        __syncwarp();
+        at = parent;
+        ++ctr.L;
+      }
+      key = warp_xor(key);
+      key_xor(key, c.root_key);
+
+      // ---- phase 3 (warp 0): goal, visited, beam window ------------------------------------------------
+      int action = kActExpand;
+      uint32_t status = kItemOk;
+      if (!c.root_pending) {
+        if (c.num_dets == 0) {
+          // Goal (tesseract.cc:441-473): chain errors in root -> leaf order.
+          action = kActDone;
+          if (c.depth > p.sol_stride) {
+            status = kItemSolutionOverflow;
+          } else if (lane == 0) {
+            uint32_t* out = p.sol + (size_t)item * p.sol_stride;
+            uint32_t at = c.chain;
+            for (uint32_t i = 0; i < c.depth; ++i) {
+              const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(chain + at));
+              out[c.depth - 1 - i] = raw.x;
+              at = raw.y;
+            }
+            p.sol_len[item] = c.depth;
+            p.fcost[item] = c.cost;
+          }
+        } else {
+          if (p.no_revisit) {  // tesseract.cc:475-476
+            int inserted = 0;
+            if (lane == 0) {
+              if ((c.n_visited + 1) * 2 > p.visit_cap) {
+                inserted = -1;
+              } else {
+                uint64_t where = 0;
+                inserted = visited_insert(vtab, p.visit_cap, key, where);
+                if (inserted == 1 && c.n_visited < p.vlist_cap) vlist[c.n_visited] = (uint32_t)where;
+              }
+            }
+            inserted = __shfl_sync(kFull, inserted, 0);
+            ++ctr.V;
+            if (inserted < 0) {
+              action = kActDone;
+              status = kItemNodeOverflow;
+            } else if (inserted == 0) {
+              action = kActSkip;
+            } else if (lane == 0) {
+              ++c.n_visited;
+            }
+          }
+          if (action == kActExpand && lane == 0 && c.num_dets < c.min_dets) {  // tesseract.cc:503-511
+            c.min_dets = c.num_dets;
+            c.max_dets = min(c.max_dets, c.min_dets + beam);
+          }
+        }
+      }
+      if (lane == 0) {
+        c.key = key;
+        c.action = action;
+        c.status = status;
+      }
+    }
+    __syncthreads();
+    if (c.action == kActDone) return c.status;
+    if (c.action == kActSkip) {
+      __syncthreads();
+      continue;
+    }
+
+    // ---- phase 4 (all): private state copies; detector terms of the node ------------------------------
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(sm.pst);
+      uint4* dst = reinterpret_cast<uint4*>(sm.st);
+      for (uint32_t i = lane; i < dpad / 8; i += 32) dst[i] = src[i];
+      __syncwarp();
+    }
+    if (!c.terms_cached) {
+      // (the reference memoises these lazily in detector_cost_cache, tesseract.cc:531,569-582; same values)
+      for (uint32_t w = warp; w < nwords; w += nwarps) {
+        uint32_t word = sm.fbits[w];
+        while (word) {
+          const uint32_t d = w * 32 + (uint32_t)__ffs((int)word) - 1;
+          word &= word - 1;
+          const double h = __dadd_rn(scan_row<kInstr>(t, sm.st, sm.rank, d, lane, ctr.S), p.det_penalty);
+          if (lane == 0) sm.hc[d] = h;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 5 (warp 0): root push, or min detector and the list of children --------------------------
+    if (warp == 0) {
+      int action = kActExpand;
+      uint32_t status = kItemOk;
+      if (c.root_pending) {
+        // initial cost = in-order sum of the fired detectors' terms (tesseract.cc:411-414)
+        double root_cost = 0;
+        for (uint32_t w = 0; w < nwords; ++w)
+          for (uint32_t m = sm.fbits[w]; m; m &= m - 1) root_cost = __dadd_rn(root_cost, sm.hc[w * 32 + (uint32_t)__ffs((int)m) - 1]);
+        action = kActSkip;
+        if (root_cost == kInf) {  // tesseract.cc:416-419
+          action = kActDone;
+          status = kItemLowConfidence;
+        } else if (p.node_cap < 1) {
+          action = kActDone;
+          status = kItemNodeOverflow;
+        } else {
+          HeapNode hn;
+          hn.cost = root_cost;
+          hn.chain = kNoChain;
+          hn.num_dets = (uint16_t)c.root_dets;
+          hn.depth = 0;
+          heap_push_warp(heap, 0, hn, lane);
+          ++ctr.Q;
+          if (lane == 0) {
+            c.heap_size = 1;
+            c.pushed = 1;
+            c.root_pending = 0;  // the loop now pops it back (tesseract.cc:427-432)
+          }
+        }
+      } else {
+        ++ctr.X;
+        // min_detector: first fired detector in this trial's order (tesseract.cc:522-528)
+        uint32_t best_pos = 0xFFFFFFFFu;
+        for (uint32_t w = lane; w < nwords; w += 32)
+          for (uint32_t m = sm.fbits[w]; m; m &= m - 1)
+            best_pos = min(best_pos, __ldg(order_pos + (w * 32 + (uint32_t)__ffs((int)m) - 1)));
+        best_pos = __reduce_min_sync(kFull, best_pos);
+        const uint32_t mind = __ldg(order_det + best_pos);
+        const uint32_t m_off = __ldg(t.row_off + mind), m_len = __ldg(t.row_off + mind + 1) - m_off;
+        const uint32_t m_thr = sm.st[mind] & kThr;
+        // children: unblocked entries of row[min_detector], in row order (tesseract.cc:533-534)
+        uint32_t n = 0;
+        for (uint32_t base = 0; base < m_len; base += 32) {
+          const uint32_t idx = base + lane;
+          bool open = false;
+          if (idx < m_len) open = !eval_entry(t, sm.st, m_off, idx, m_thr).blocked;
+          const unsigned mo = __ballot_sync(kFull, open);
+          if (open) sm.clist[n + __popc(mo & ((1u << lane) - 1u))] = (uint16_t)idx;
+          n += __popc(mo);
+        }
+        if (lane == 0) {
+          c.mind = mind;
+          c.m_off = m_off;
+          c.m_len = m_len;
+          c.nchild = n;
+        }
+      }
+      if (lane == 0) {
+        c.action = action;
+        c.status = status;
+      }
+    }
+    __syncthreads();
+    if (c.action == kActDone) return c.status;
+    if (c.action == kActSkip) {
+      __syncthreads();
+      continue;
+    }
+
+    // ---- phase 6 (all warps): the children, round-robin ----------------------------------------------------
+    for (uint32_t j = warp; j < c.nchild; j += nwarps) eval_child<kInstr>(p, sm, j, lane, vtab, ctr);
+    __syncthreads();
+
+    // ---- phase 7 (warp 0): pushes, in row order (tesseract.cc:590-605) ----------------------------------------
+    if (warp == 0) {
+      int action = kActSkip;
+      uint32_t status = kItemOk;
+      unsigned long long heap_size = c.heap_size, chain_size = c.chain_size, pushed = c.pushed;
+      const uint32_t n = c.nchild;
+      for (uint32_t j = 0; j < n; ++j) {
+        const uint4 meta = sm.res_meta[j];
+        if (meta.w != kChildOk) continue;
+        if (c.depth == 0xFFFF) {
+          action = kActDone;
+          status = kItemSolutionOverflow;
+          break;
+        }
+        if (heap_size >= p.node_cap || chain_size >= p.node_cap || chain_size >= 0xFFFFFFFEull) {
+          action = kActDone;
+          status = kItemNodeOverflow;
+          break;
+        }
+        if (lane == 0)
+          __stcg(reinterpret_cast<uint4*>(chain + chain_size), make_uint4(meta.x, c.chain, (c.mind << 16) | (meta.z >> 16), meta.y));
+        HeapNode hn;
+        hn.cost = sm.res_cost[j];
+        hn.chain = (uint32_t)chain_size;
+        hn.num_dets = (uint16_t)(meta.z & 0xFFFF);
+        hn.depth = (uint16_t)(c.depth + 1);
+        heap_push_warp(heap, heap_size, hn, lane);
+        ++heap_size;
+        ++chain_size;
+        ++pushed;
+        ++ctr.Q;
+        if (pushed > p.pqlimit) {  // tesseract.cc:599-605
+          action = kActDone;
+          status = kItemLowConfidence;
+          break;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        c.heap_size = heap_size;
+        c.chain_size = chain_size;
+        c.pushed = pushed;
+        c.action = action;
+        c.status = status;
+      }
+    }
+    __syncthreads();
+    if (c.action == kActDone) return c.status;
+    __syncthreads();
+  }
+}
+
+template <bool kInstr>
+__global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams p) {
+  extern __shared__ uint4 smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t slot = blockIdx.x;
+  const uint32_t D = p.t.D;
+  const uint32_t rank_entries = p.t.fn_costs * p.t.fnstride;
+  const Layout L = make_layout(D, p.t.nwords, rank_entries, p.t.max_row_len, nwarps, p.hc_shared != 0);
+  Smem sm;
+  sm.ctl = reinterpret_cast<Ctl*>(base);
+  sm.rank = reinterpret_cast<uint16_t*>(base + L.off_rank);
+  sm.rbits = reinterpret_cast<uint32_t*>(base + L.off_rbits);
+  sm.fbits = reinterpret_cast<uint32_t*>(base + L.off_fbits);
+  sm.pst = reinterpret_cast<uint16_t*>(base + L.off_pst);
+  sm.hc = p.hc_shared ? reinterpret_cast<double*>(base + L.off_hc) : p.hcache + (size_t)slot * D;
+  sm.res_cost = reinterpret_cast<double*>(base + L.off_cost);
+  sm.res_meta = reinterpret_cast<uint4*>(base + L.off_meta);
+  sm.clist = reinterpret_cast<uint16_t*>(base + L.off_clist);
+  sm.st = reinterpret_cast<uint16_t*>(base + L.off_st) + (size_t)warp * dpad_of(D);
+  for (uint32_t i = tid; i < rank_entries; i += blockDim.x) sm.rank[i] = __ldg(p.t.frank + i);
+  __syncthreads();
+
+  Counters ctr;
+  unsigned long long searches = 0;
+  while (true) {
+    if (tid == 0) sm.ctl->work = atomicAdd(p.work_counter, 1u);
+    __syncthreads();
+    const uint32_t work = sm.ctl->work;
+    if (work >= p.n_work) break;
+    const uint32_t item = p.item_ids ? __ldg(p.item_ids + work) : work;
+    const uint32_t status = run_search<kInstr>(p, sm, slot, item, ctr);
+    __syncthreads();
+    ++searches;
+    if (tid == 0) {
+      p.status[item] = (uint8_t)status;
+      if (status != kItemOk) p.sol_len[item] = 0;
+    }
+    // Empty the visited table for the next search of this slot.
+    const unsigned long long n_visited = sm.ctl->n_visited;
+    if (p.no_revisit && n_visited) {
+      uint4* vtab = p.visited + (size_t)slot * p.visit_cap;
+      const uint4 zero = make_uint4(0, 0, 0, 0);
+      if (n_visited <= p.vlist_cap) {
+        const uint32_t* vlist = p.vlist + (size_t)slot * p.vlist_cap;
+        for (unsigned long long i = tid; i < n_visited; i += blockDim.x) __stcg(vtab + __ldcg(vlist + i), zero);
+      } else {
+        for (unsigned long long i = tid; i < p.visit_cap; i += blockDim.x) __stcg(vtab + i, zero);
+      }
+    }
+    __syncthreads();
+  }
+  if (lane == 0 && p.counters) {
+    if (warp == 0) {
+      atomicAdd(p.counters + 0, ctr.Q);
+      atomicAdd(p.counters + 1, ctr.P);
+      atomicAdd(p.counters + 2, ctr.X);
+      atomicAdd(p.counters + 3, ctr.L);
+      atomicAdd(p.counters + 7, searches);
+    }
+    atomicAdd(p.counters + 4, ctr.S);
+    atomicAdd(p.counters + 5, ctr.A);
+    atomicAdd(p.counters + 6, ctr.V);
+  }
+}
+
+template <bool kInstr>
+int configure(size_t smem) {
+  if (smem > 48 * 1024)
+    return (int)cudaFuncSetAttribute(search_fast_kernel<kInstr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return 0;
+}
+
+}  // namespace
+
+uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared) {
+  return make_layout(t.D, t.nwords, t.fn_costs * t.fnstride, t.max_row_len, warps, hc_shared).total;
+}
+
+int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared) {
+  int n = 0;
+  const size_t smem = search_fast_smem_bytes(t, warps, hc_shared);
+  if (smem > 227 * 1024) return 0;
+  if (configure<false>(smem) != 0 || configure<true>(smem) != 0) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false>, (int)(warps * 32), smem) != cudaSuccess) return 0;
+  return n;
+}
+
+int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, void* stream) {
+  if (p.n_work == 0 || blocks == 0) return 0;
+  const size_t smem = search_fast_smem_bytes(p.t, warps, p.hc_shared != 0);
+  if (instrumented) {
+    if (int e = configure<true>(smem)) return e;
+    search_fast_kernel<true><<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+  } else {
+    if (int e = configure<false>(smem)) return e;
+    search_fast_kernel<false><<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace tsr

@@ -160,3 +160,22 @@ def test_decode_without_a_device_fails_loudly():
 def test_circuit_analyzer_reproduces_committed_dems():
     path = "/root/reference/testdata/surfacecodes/r=5,d=5,p=0.002,noise=si1000,c=surface_code_X,q=49,gates=cz.stim"
     assert capi.circuit_to_dem(open(path).read()) == W.load_dem("surface_d5_r5_p0.002_X")
+
+
+def test_fast_path_certificate():
+    """csrc/fast.h: every fixture DEM is certified for the integer-rank kernel; DEMs outside its proof
+    obligations or packing limits fall back to the generic CUDA kernel with a stated reason."""
+    for name in ["surface_d5_r5_p0.002_X", "bb72_r6_p0.001_X", "color_superdense_d5_r5_p0.001_Z", "transcx_d3_p0.001_X"]:
+        dec = capi.Decoder(W.load_dem(name), host_only=True)
+        assert dec.search_path == "fast" and dec.search_path_reason == ""
+    assert capi.Decoder(W.load_dem("bb72_r6_p0.001_X"), host_only=True, force_generic_kernel=True).search_path == "generic"
+    # p > 0.5 gives a negative cost: the sorted-row / early-exit argument does not hold
+    dec = capi.Decoder("error(0.7) D0 D1\nerror(0.1) D0\nerror(0.1) D1", host_only=True)
+    assert dec.search_path == "generic" and "cost" in dec.search_path_reason
+    # more than 128 distinct costs
+    many = "\n".join(f"error({0.001 + 0.0001 * i}) D{i} D{i + 1}" for i in range(200))
+    dec = capi.Decoder(many, host_only=True)
+    assert dec.search_path == "generic" and "128" in dec.search_path_reason
+    # an error on more than 11 detectors
+    dec = capi.Decoder("error(0.01) " + " ".join(f"D{i}" for i in range(13)) + "\nerror(0.02) D0", host_only=True)
+    assert dec.search_path == "generic" and "11" in dec.search_path_reason
