@@ -1,0 +1,221 @@
+// Host-side mirror of the reference's decoder interface (tesseract.h:33-147) over the C ABI
+// (include/tesseract_b200.h).  Same names, argument meaning and error behaviour; the search runs on the GPU.
+// Header-only C++20; used by the pybind11 module (pybind.cc) and the CLI (main.cc).
+#pragma once
+#include <cstdint>
+#include <limits>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "tesseract_b200.h"
+
+namespace tesseract_b200 {
+
+constexpr int INF_DET_BEAM = 65535;       // tesseract.h:33 (std::numeric_limits<uint16_t>::max())
+constexpr int DEFAULT_DET_BEAM = 5;       // tesseract.h:34
+constexpr size_t DEFAULT_PQLIMIT = 200000;  // tesseract.h:36
+
+[[noreturn]] inline void throw_last(int rc) {
+  const std::string msg = tsr_last_error();
+  if (rc == TSR_E_INVALID_ARGUMENT) throw std::invalid_argument(msg);
+  throw std::runtime_error(msg);
+}
+inline void check(int rc) {
+  if (rc != TSR_OK) throw_last(rc);
+}
+
+// tesseract.h:39-58.  The DEM is held as text (what crosses the Python boundary in the reference too,
+// stim_utils.pybind.h:22-26).
+struct TesseractConfig {
+  std::string dem;
+  int det_beam = DEFAULT_DET_BEAM;
+  bool beam_climbing = false;
+  bool no_revisit_dets = true;
+  bool verbose = false;
+  bool merge_errors = true;
+  size_t pqlimit = DEFAULT_PQLIMIT;
+  std::vector<std::vector<size_t>> det_orders;
+  double det_penalty = 0;
+  bool create_visualization = false;
+  bool at_most_two_errors_per_detector = false;  // README.md:59,159 (no code in the reference snapshot)
+  int device = -1;
+
+  std::string str() const {  // tesseract.cc:84-117
+    std::stringstream ss;
+    ss << "TesseractConfig(dem=DetectorErrorModel_Object, det_beam=" << det_beam << ", no_revisit_dets=" << no_revisit_dets
+       << ", verbose=" << verbose << ", merge_errors=" << merge_errors << ", pqlimit=" << pqlimit
+       << ", det_penalty=" << det_penalty << ", create_visualization=" << create_visualization << ")";
+    return ss.str();
+  }
+};
+
+// common::Symptom / common::Error (common.h:29-50), as far as the decoder exposes them.
+struct Symptom {
+  std::vector<int> detectors;
+  std::vector<int> observables;
+};
+struct Error {
+  double likelihood_cost = 0;
+  Symptom symptom;
+};
+
+struct HandleDeleter {
+  void operator()(tsr_decoder* h) const { tsr_destroy(h); }
+};
+
+struct TesseractDecoder {
+  TesseractConfig config;
+  // tesseract.h:112-130
+  bool low_confidence_flag = false;
+  std::vector<size_t> predicted_errors_buffer;
+  std::vector<Error> errors;
+  size_t num_detectors = 0, num_observables = 0, num_errors = 0;
+  std::vector<size_t> dem_error_to_error, error_to_dem_error;
+
+  explicit TesseractDecoder(TesseractConfig cfg, bool host_only = false) : config(std::move(cfg)) {
+    tsr_config c;
+    tsr_config_init(&c);
+    c.det_beam = config.det_beam;
+    c.beam_climbing = config.beam_climbing;
+    c.no_revisit_dets = config.no_revisit_dets;
+    c.merge_errors = config.merge_errors;
+    c.at_most_two_errors_per_detector = config.at_most_two_errors_per_detector;
+    c.device = config.device;
+    c.pqlimit = config.pqlimit;
+    c.det_penalty = config.det_penalty;
+    std::vector<uint64_t> flat;
+    for (const auto& o : config.det_orders) {
+      if (o.size() != config.det_orders[0].size())
+        throw std::invalid_argument("Each detector order list must have a size equal to the number of detectors.");
+      flat.insert(flat.end(), o.begin(), o.end());
+    }
+    c.num_det_orders = config.det_orders.size();
+    c.det_orders = flat.data();
+    c.det_order_len = config.det_orders.empty() ? 0 : config.det_orders[0].size();
+    if (c.num_det_orders && c.det_order_len == 0 && tsr_dem_count_detectors(config.dem.c_str()) != 0)
+      throw std::invalid_argument("Each detector order list must have a size equal to the number of detectors.");
+    tsr_decoder* raw = nullptr;
+    check(tsr_create(config.dem.c_str(), &c, host_only ? TSR_CREATE_HOST_ONLY : 0, &raw));
+    h_.reset(raw);
+    num_detectors = tsr_num_detectors(raw);
+    num_observables = tsr_num_observables(raw);
+    num_errors = tsr_num_errors(raw);
+    if (config.det_orders.empty()) {  // tesseract.cc:175-177
+      config.det_orders.emplace_back(num_detectors);
+      for (size_t i = 0; i < num_detectors; ++i) config.det_orders[0][i] = i;
+    }
+    // errors, maps (tesseract.cc:172-173, 189)
+    std::vector<double> costs(num_errors);
+    check(tsr_error_costs(raw, costs.data()));
+    std::vector<uint64_t> d2e(tsr_num_dem_errors(raw)), e2d(num_errors);
+    check(tsr_maps(raw, d2e.data(), e2d.data()));
+    dem_error_to_error.assign(d2e.begin(), d2e.end());
+    error_to_dem_error.assign(e2d.begin(), e2d.end());
+    errors.resize(num_errors);
+    auto fill = [&](int which, bool dets) {
+      std::vector<uint64_t> off(num_errors + 1);
+      const int64_t nnz = tsr_csr(raw, which, nullptr, nullptr);
+      std::vector<int32_t> idx((size_t)std::max<int64_t>(nnz, 1));
+      tsr_csr(raw, which, off.data(), idx.data());
+      for (size_t e = 0; e < num_errors; ++e) {
+        auto& v = dets ? errors[e].symptom.detectors : errors[e].symptom.observables;
+        v.assign(idx.begin() + (std::ptrdiff_t)off[e], idx.begin() + (std::ptrdiff_t)off[e + 1]);
+      }
+    };
+    fill(1, true);
+    fill(3, false);
+    for (size_t e = 0; e < num_errors; ++e) errors[e].likelihood_cost = costs[e];
+  }
+
+  tsr_decoder* handle() const { return h_.get(); }
+
+  // tesseract.cc:295-347
+  void decode_to_errors(const std::vector<uint64_t>& detections) { run(detections, -1, 0); }
+  // tesseract.cc:371-378
+  void decode_to_errors(const std::vector<uint64_t>& detections, size_t detector_order, size_t detector_beam) {
+    run(detections, (int64_t)detector_order, detector_beam);
+  }
+  // tesseract.cc:660-663
+  std::vector<int> decode(const std::vector<uint64_t>& detections) {
+    decode_to_errors(detections);
+    return get_flipped_observables(predicted_errors_buffer);
+  }
+  // tesseract.cc:618-628
+  double cost_from_errors(const std::vector<size_t>& predicted_errors) const {
+    std::vector<uint64_t> e(predicted_errors.begin(), predicted_errors.end());
+    double out = 0;
+    check(tsr_cost_from_errors(h_.get(), e.data(), e.size(), &out));
+    return out;
+  }
+  // tesseract.cc:630-658
+  std::vector<int> get_flipped_observables(const std::vector<size_t>& predicted_errors) const {
+    std::vector<uint64_t> e(predicted_errors.begin(), predicted_errors.end());
+    std::vector<uint8_t> bits((num_observables + 7) / 8 + 1, 0);
+    check(tsr_flipped_observables(h_.get(), e.data(), e.size(), bits.data()));
+    std::vector<int> out;
+    for (size_t o = 0; o < num_observables; ++o)
+      if ((bits[o >> 3] >> (o & 7)) & 1) out.push_back((int)o);
+    return out;
+  }
+  std::vector<std::vector<int>> get_eneighbors() const { return csr_rows(2, num_errors); }
+  std::vector<std::vector<int>> get_d2e() const { return csr_rows(0, num_detectors); }
+
+  // The batched hot path: decode_shots (tesseract.cc:665-671) / decode_batch / decode_shots_bit_packed on
+  // bit-packed rows (bit k of byte j = detector 8j+k).  Any output may be null.
+  void decode_batch_b8(const uint8_t* dets, size_t stride, size_t shots, uint8_t* obs_out, double* cost_out,
+                       uint8_t* low_conf_out, bool collect_errors = false) {
+    tsr_set_collect_errors(h_.get(), collect_errors ? 1 : 0);
+    const int rc = tsr_decode_batch_b8(h_.get(), dets, stride, shots, obs_out, cost_out, low_conf_out);
+    tsr_set_collect_errors(h_.get(), 1);
+    check(rc);
+  }
+  // predicted_errors_buffer of every shot of the last decode_batch_b8(collect_errors = true), as CSR.
+  void last_batch_errors(size_t shots, std::vector<uint64_t>& offsets, std::vector<uint64_t>& idx) const {
+    const uint64_t nnz = tsr_last_batch_nnz(h_.get());
+    offsets.assign(shots + 1, 0);
+    idx.assign((size_t)nnz + 1, 0);
+    check(tsr_last_batch_errors(h_.get(), offsets.data(), idx.data()));
+    idx.resize((size_t)nnz);
+  }
+
+ private:
+  std::unique_ptr<tsr_decoder, HandleDeleter> h_;
+
+  void run(const std::vector<uint64_t>& detections, int64_t order, uint64_t beam) {
+    uint64_t n = 0;
+    double cost = 0;
+    int32_t low = 0;
+    std::vector<uint64_t> buf(num_errors + 1);
+    check(tsr_decode(h_.get(), detections.data(), detections.size(), order, beam, buf.data(), buf.size(), &n, &cost, &low));
+    predicted_errors_buffer.assign(buf.begin(), buf.begin() + (std::ptrdiff_t)n);
+    low_confidence_flag = low != 0;
+  }
+  std::vector<std::vector<int>> csr_rows(int which, size_t rows) const {
+    std::vector<uint64_t> off(rows + 1);
+    const int64_t nnz = tsr_csr(h_.get(), which, nullptr, nullptr);
+    if (nnz < 0) throw_last((int)nnz);
+    std::vector<int32_t> idx((size_t)std::max<int64_t>(nnz, 1));
+    tsr_csr(h_.get(), which, off.data(), idx.data());
+    std::vector<std::vector<int>> out(rows);
+    for (size_t r = 0; r < rows; ++r) out[r].assign(idx.begin() + (std::ptrdiff_t)off[r], idx.begin() + (std::ptrdiff_t)off[r + 1]);
+    return out;
+  }
+};
+
+// utils.cc:192-205
+enum class DetOrder { DetBFS = 0, DetIndex = 1, DetCoordinate = 2 };
+inline std::vector<std::vector<size_t>> build_det_orders(const std::string& dem, size_t num_det_orders, DetOrder method,
+                                                         uint64_t seed) {
+  const uint64_t D = tsr_dem_count_detectors(dem.c_str());
+  if (D == UINT64_MAX) throw std::invalid_argument(tsr_last_error());
+  std::vector<uint64_t> flat(num_det_orders * D + 1);
+  check(tsr_build_det_orders(dem.c_str(), num_det_orders, (int)method, seed, flat.data()));
+  std::vector<std::vector<size_t>> out(num_det_orders);
+  for (size_t k = 0; k < num_det_orders; ++k) out[k].assign(flat.begin() + (std::ptrdiff_t)(k * D), flat.begin() + (std::ptrdiff_t)((k + 1) * D));
+  return out;
+}
+
+}  // namespace tesseract_b200

@@ -1,0 +1,135 @@
+"""The reference's Python surface (src/tesseract.pybind.h, src/tesseract_sinter_compat.pybind.h) as mirrored by the
+pybind11 module over the C ABI.  Tests read like the reference's own (src/py/tesseract_test.py,
+shared_decoding_tests.py, tesseract_sinter_compat_test.py); a DEM is any object whose str() is DEM text."""
+import math
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+import workloads as W
+import tesseract_decoder_b200 as td
+
+tesseract = td.tesseract
+TesseractSinterDecoder = td.tesseract_sinter_compat.TesseractSinterDecoder
+
+_DETECTOR_ERROR_MODEL = "error(0.125) D0\nerror(0.375) D0 D1\nerror(0.25) D1\ndetector(0, 0, 0) D0\ndetector(1, 0, 0) D1"
+
+
+class Dem:  # stand-in for stim.DetectorErrorModel: only str() crosses the boundary (stim_utils.pybind.h:22-26)
+    def __init__(self, text):
+        self.text = text
+
+    def __str__(self):
+        return self.text
+
+
+# ---- no GPU needed -------------------------------------------------------------------------------------
+
+def test_config_defaults():  # tesseract_test.py:38-55
+    c = tesseract.TesseractConfig(Dem(_DETECTOR_ERROR_MODEL))
+    assert (c.det_beam, c.beam_climbing, c.no_revisit_dets, c.verbose, c.merge_errors, c.pqlimit, c.det_penalty) == \
+        (5, False, True, False, True, 200000, 0.0)
+    assert len(c.det_orders) == 20 and all(len(o) == 2 for o in c.det_orders)  # 20 DetIndex orders, seed 2384753
+    assert c.det_orders == td.utils.build_det_orders(Dem(_DETECTOR_ERROR_MODEL), 20, td.utils.DetOrder.DetIndex, 2384753)
+    assert tesseract.INF_DET_BEAM == 65535
+    assert str(c).startswith("TesseractConfig(dem=DetectorErrorModel_Object, det_beam=5")
+    c.det_beam = 9
+    c.dem = Dem("error(0.1) D0")
+    assert c.det_beam == 9 and c.dem == "error(0.1) D0"
+    assert tesseract.TesseractConfig(det_beam=3, pqlimit=7).pqlimit == 7  # the overload without a DEM
+
+
+def test_det_order_shapes():  # utils_test.py:37-76
+    dem = Dem(W.load_dem("transcx_d3_p0.001_X"))
+    for method in (td.utils.DetOrder.DetBFS, td.utils.DetOrder.DetIndex, td.utils.DetOrder.DetCoordinate):
+        orders = td.utils.build_det_orders(dem, 4, method, 11)
+        assert len(orders) == 4 and all(sorted(o) == list(range(96)) for o in orders)
+
+
+def test_sinter_decoder_object():  # tesseract_sinter_compat_test.py:691-795
+    d = TesseractSinterDecoder()
+    assert (d.det_beam, d.no_revisit_dets, d.pqlimit, d.num_det_orders, d.seed) == (5, True, 200000, 0, 2384753)
+    e = TesseractSinterDecoder(det_beam=20, beam_climbing=True, pqlimit=10**6, num_det_orders=21)
+    assert e != d and pickle.loads(pickle.dumps(e)) == e and pickle.loads(pickle.dumps(e)).num_det_orders == 21
+    presets = td.make_tesseract_sinter_decoders_dict()
+    assert {"tesseract", "tesseract-long-beam", "tesseract-short-beam"} <= set(presets)
+    assert presets["tesseract"] == presets["tesseract-long-beam"] and presets["tesseract-short-beam"].det_beam == 15
+
+
+def test_invalid_inputs_without_decoding():
+    with pytest.raises(ValueError):  # tesseract.cc:178-184
+        tesseract.TesseractConfig(Dem(_DETECTOR_ERROR_MODEL), det_orders=[[0, 1, 2]]).compile_decoder()
+    with pytest.raises(ValueError):
+        tesseract.TesseractConfig(Dem("error(1.5) D0")).compile_decoder()
+
+
+# ---- on the GPU ----------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+def test_decode_single_shot_api():  # shared_decoding_tests.py:37-237, tesseract_test.py:193-201
+    dec = tesseract.TesseractConfig(Dem("error(0.1) D0 D1 L0\nerror(0.2) D0\nerror(0.3) D1")).compile_decoder()
+    assert (dec.num_detectors, dec.num_observables, len(dec.errors)) == (2, 1, 3)
+    errs = dec.decode_to_errors(np.array([True, True]))
+    assert errs == dec.predicted_errors_buffer and not dec.low_confidence_flag
+    assert dec.cost_from_errors(errs) == pytest.approx(min(math.log(9), math.log(4) + math.log(7 / 3)))
+    assert dec.get_observables_from_errors(errs) == [errs == [0]]
+    assert dec.decode(np.array([True, True])).dtype == np.bool_
+    assert dec.decode_from_detection_events([0, 1]).tolist() == dec.decode(np.array([True, True])).tolist()
+    assert dec.decode_to_errors(np.array([True, False]), 0, 5) == [1]
+    assert dec.errors[0].symptom.detectors == [0, 1] and dec.errors[0].likelihood_cost == pytest.approx(math.log(9))
+    with pytest.raises(ValueError, match=r"Syndrome array size \(3\) does not match the number of detectors in the decoder \(2\)\."):
+        dec.decode(np.array([True, False, True]))  # shared_decoding_tests.py:378-382
+    with pytest.raises(RuntimeError, match="Input syndromes must be a 2D NumPy array."):
+        dec.decode_batch(np.array([True, False]))  # :251
+    with pytest.raises(ValueError, match=r"The number of detectors in the input array \(3\) does not match"):
+        dec.decode_batch(np.zeros((2, 3), dtype=bool))  # :399-403
+    dec = tesseract.TesseractConfig(Dem("error(0.1) D0\nerror(0) D1\nerror(0.2) D2\nerror(0.3) D2")).compile_decoder()
+    with pytest.raises(ValueError, match="error index does not map to a retained decoder error"):
+        dec.cost_from_errors([1])
+
+
+@pytest.mark.gpu
+def test_decode_batch_expected_matrices():  # shared_decoding_tests.py:255-329
+    dec = tesseract.TesseractDecoder(tesseract.TesseractConfig(Dem("error(0.1) D0 D1 L0\nerror(0.2) D0 L1\nerror(0.05) D1")))
+    out = dec.decode_batch(np.array([[True, True], [True, False], [False, True]]))
+    assert out.dtype == np.bool_ and out.tolist() == [[True, False], [False, True], [False, False]]
+    cfg = tesseract.TesseractConfig(det_beam=7)
+    dec = cfg.compile_decoder_for_dem(Dem("error(0.1) D0 D1 L0\nerror(0.2) D0 D2 L1\nerror(0.05) D1 D3 L0 L2\nerror(0.15) D2\nerror(0.25) D3"))
+    out = dec.decode_batch(np.array([[1, 1, 0, 0], [1, 0, 1, 0], [0, 1, 0, 1], [0, 0, 1, 1]], dtype=bool))
+    assert out.tolist() == [[True, False, False], [False, True, False], [True, False, True], [False, False, False]]
+    assert dec.config.det_beam == 7
+
+
+@pytest.mark.gpu
+def test_sinter_bit_packed_known_answers(tmp_path):  # tesseract_sinter_compat_test.py:75-162, 165-372
+    dem = Dem("detector(0, 0, 0) D0\ndetector(0, 0, 1) D1\ndetector(0, 0, 2) D2\nerror(0.1) D0 D1 L0\nerror(0.1) D1 D2 L1")
+    compiled = TesseractSinterDecoder().compile_decoder_for_dem(dem=dem)
+    assert (compiled.num_detectors, compiled.num_observables) == (3, 2)
+    assert compiled.decoder.config.det_beam == 5
+    dets = np.array([[0b011], [0b110], [0b101]], dtype=np.uint8)
+    out = compiled.decode_shots_bit_packed(bit_packed_detection_event_data=dets)
+    assert out.dtype == np.uint8 and out.tolist() == [[0b01], [0b10], [0b11]]
+    with pytest.raises(ValueError):
+        compiled.decode_shots_bit_packed(bit_packed_detection_event_data=np.zeros((2, 2), dtype=np.uint8))
+    (tmp_path / "m.dem").write_text(str(dem))
+    dets.tofile(tmp_path / "dets.b8")
+    TesseractSinterDecoder().decode_via_files(num_shots=3, num_dets=3, num_obs=2, dem_path=tmp_path / "m.dem",
+                                              dets_b8_in_path=tmp_path / "dets.b8",
+                                              obs_predictions_b8_out_path=tmp_path / "out.b8", tmp_dir=tmp_path)
+    assert np.fromfile(tmp_path / "out.b8", dtype=np.uint8).tolist() == [0b01, 0b10, 0b11]
+
+
+@pytest.mark.gpu
+def test_bit_packed_equals_decode_batch_on_color_code_shots():  # tesseract_sinter_compat_test.py:578-653
+    dem_text = W.load_dem("color_superdense_d5_r5_p0.001_Z")
+    dets, _ = td.capi.sample_dem_b8(dem_text, 9, 1000, td.capi.dem_count_detectors(dem_text), 1)
+    D = td.capi.dem_count_detectors(dem_text)
+    bits = np.unpackbits(dets, axis=1, bitorder="little")[:, :D].astype(bool)
+    for kw in (dict(), dict(det_beam=2, beam_climbing=True), dict(no_revisit_dets=False), dict(pqlimit=1000, det_penalty=0.1)):
+        sinter = TesseractSinterDecoder(num_det_orders=4, **kw).compile_decoder_for_dem(dem=Dem(dem_text))
+        packed = sinter.decode_shots_bit_packed(bit_packed_detection_event_data=dets)
+        cfg = tesseract.TesseractConfig(Dem(dem_text), det_orders=td.utils.build_det_orders(Dem(dem_text), 4, td.utils.DetOrder.DetIndex, 2384753), **kw)
+        batch = cfg.compile_decoder().decode_batch(bits)
+        assert np.array_equal(np.unpackbits(packed, axis=1, bitorder="little")[:, :1].astype(bool), batch)
