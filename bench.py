@@ -267,7 +267,7 @@ def run_b200(args, wl, rank, world, local):
     n_launch = args.steps * ((S + (1 << 16) - 1) >> 16)  # tier-0 search launches (one per 65536-shot chunk)
     achieved = alg / (a["search_ms"] * 1e-3) / 1e9 if a["search_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "tsr::search_fast_kernel" if dec.search_path == "fast" else "tsr::search_kernel", "algorithmic_bytes_per_launch": alg / n_launch,
+                "peak_source": peak_src, "kernel": "tsr::search_fast_kernel" if dec.search_path.startswith("fast") else "tsr::search_kernel", "algorithmic_bytes_per_launch": alg / n_launch,
                 "algorithmic_bytes_per_shot": alg / (S * args.steps), "kernel_ms_per_launch": a["search_ms"] / n_launch,
                 "launches_timed": n_launch, "scanned_entries_per_shot": ctr1["S"] / S, "search_path": dec.search_path,
                 "counters_per_batch": ctr1}

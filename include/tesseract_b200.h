@@ -54,7 +54,7 @@ typedef struct tsr_config {
   uint64_t node_pool_bytes;    /* HBM set aside for heaps / chains / visited sets */
   uint64_t max_batch_shots;    /* shots staged per kernel launch */
   int32_t force_generic_kernel; /* 1 = always use the event-replay kernel (search.cu), even for certified DEMs */
-  int32_t reserved;
+  int32_t disable_bit_sliced_scan; /* 1 = certified DEMs scan rows one entry per lane instead of 32 entries per lane */
 } tsr_config;
 
 /* Fills the reference's C++ defaults (tesseract.h:39-58). */
@@ -123,9 +123,10 @@ int tsr_decode(tsr_decoder* h, const uint64_t* detections, uint64_t n, int64_t o
 int tsr_cost_from_errors(const tsr_decoder* h, const uint64_t* errs, uint64_t n, double* out);
 int tsr_flipped_observables(const tsr_decoder* h, const uint64_t* errs, uint64_t n, uint8_t* obs_bits_out);
 
-/* Which search kernel this handle decodes with: 1 = the CTA-per-search integer-rank kernel (search_fast.cu),
- * taken when the DEM passes the host-side certificate of csrc/fast.h; 0 = the generic kernel (search.cu) that
- * replays get_detcost's floating-point scan event by event.  Both are CUDA; results are identical.
+/* Which search kernel this handle decodes with: 2 = the CTA-per-search integer-rank kernel with bit-sliced row
+ * scans, 1 = the same kernel scanning one row entry per lane (search_fast.cu; both need the DEM to pass the
+ * host-side certificate of csrc/fast.h); 0 = the generic kernel (search.cu) that replays get_detcost's
+ * floating-point scan event by event.  All are CUDA; results are identical.
  * tsr_search_path_reason says why a DEM was not certified ("" when it was). */
 int tsr_search_path(const tsr_decoder* h);
 const char* tsr_search_path_reason(const tsr_decoder* h);

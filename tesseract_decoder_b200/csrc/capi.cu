@@ -113,6 +113,8 @@ struct tsr_decoder {
   tsr_config cfg{};
   tsr::DemTables T;
   tsr::FastTables F;
+  tsr::BitTables B;
+  bool bits = false;          // fast path: bit-sliced row scans (32 row entries per lane)
   bool fast = false;          // decode with search_fast.cu (CTA per search) instead of search.cu
   bool instrumented = false;  // fast path: also count the reference's scanned row entries (counter S)
   bool hc_shared = false;
@@ -127,7 +129,7 @@ struct tsr_decoder {
 
   // Device tables.
   DevBuf row_off, row_err, rec_a, rec_b, rec_c, e_off, e_det, e_rank, e_cost, e_nnbr, eo_off, eo_obs, e2dem, adj,
-      zobrist, order_det, order_pos, frec_a, frec_b, frank, fquot;
+      zobrist, order_det, order_pos, frec_a, frec_b, frank, fquot, bs_meta, bs_adjpre, bs_masks, bs_cls_cid, bs_pl_off, bs_pl;
   tsr::DeviceTables dt;
   TrialSet ensemble;
 
@@ -300,6 +302,22 @@ void init_device(tsr_decoder& h) {
     dt.fa_slots = h.F.a_slots;
     dt.fnstride = h.F.nstride;
     dt.fn_costs = h.F.n_costs;
+    if (h.bits) {
+      h.bs_meta.upload(h.B.rowmeta);
+      h.bs_adjpre.upload(h.B.adjpre);
+      h.bs_masks.upload(h.B.masks);
+      h.bs_cls_cid.upload(h.B.cls_cid);
+      h.bs_pl_off.upload(h.B.pl_off);
+      h.bs_pl.upload(h.B.pl);
+      dt.bs_meta = h.bs_meta.as<uint4>();
+      dt.bs_adjpre = h.bs_adjpre.as<uint16_t>();
+      dt.bs_masks = h.bs_masks.as<uint32_t>();
+      dt.bs_cls_cid = h.bs_cls_cid.as<uint8_t>();
+      dt.bs_pl_off = h.bs_pl_off.as<uint32_t>();
+      dt.bs_pl = h.bs_pl.as<uint32_t>();
+      dt.bs_group = h.B.group;
+      dt.bs_cap = (h.B.max_nbrs + 7) & ~7u;
+    }
   }
 
   make_ensemble(h, h.ensemble);
@@ -312,11 +330,28 @@ void init_device(tsr_decoder& h) {
     uint32_t w = h.cfg.warps_per_block ? h.cfg.warps_per_block : (T.max_row_len > 96 ? 8 : T.max_row_len > 48 ? 4 : 2);
     w = std::max<uint32_t>(1, std::min<uint32_t>(w, 16));
     h.hc_shared = (size_t)D * 8 <= 32 * 1024;
-    int occ = tsr::search_fast_max_blocks_per_sm(dt, w, h.hc_shared);
-    while (occ == 0 && (w > 1 || h.hc_shared)) {
-      if (h.hc_shared && w <= 2) h.hc_shared = false; else w = std::max<uint32_t>(w / 2, 1);
-      occ = tsr::search_fast_max_blocks_per_sm(dt, w, h.hc_shared);
+    auto fit = [&](uint32_t& w_, bool& hc_, bool bits_) {
+      int o = tsr::search_fast_max_blocks_per_sm(dt, w_, hc_, bits_);
+      while (o == 0 && (w_ > 1 || hc_)) {
+        if (hc_ && w_ <= 2) hc_ = false; else w_ = std::max<uint32_t>(w_ / 2, 1);
+        o = tsr::search_fast_max_blocks_per_sm(dt, w_, hc_, bits_);
+      }
+      return o;
+    };
+    int occ = 0;
+    if (h.bits) {
+      uint32_t wb = w;
+      bool hcb = h.hc_shared;
+      occ = fit(wb, hcb, true);
+      if (occ == 0) {
+        h.bits = false;
+      } else {
+        w = wb;
+        h.hc_shared = hcb;
+        // the entry-per-lane variants (instrumented counters) share the block shape; they need less shared memory
+      }
     }
+    if (!h.bits) occ = fit(w, h.hc_shared, false);
     if (occ == 0) {
       h.fast = false;  // state does not fit in shared memory: generic kernel
       h.F.why_not = "the per-search state does not fit in shared memory";
@@ -492,7 +527,8 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
   // Tier 0 over every item.
   const Tier& t0 = h.tiers[0];
   auto launch = [&](const tsr::SearchParams& sp_, uint32_t tier_slots, uint32_t n_work) {
-    if (h.fast) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, h.instrumented, s);
+    if (h.fast)
+      return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, h.instrumented, h.bits && !h.instrumented, s);
     return tsr::launch_search(sp_, std::min<uint32_t>((tier_slots + h.wpb - 1) / h.wpb, (n_work + h.wpb - 1) / h.wpb), h.wpb, s);
   };
   CUDA_OK(cudaEventRecord(h.ev[1], s));
@@ -677,6 +713,10 @@ int tsr_create(const char* dem_text, const tsr_config* cfg, uint32_t flags, tsr_
     h->n_perms = (uint32_t)perm_ids.size();
     h->F = tsr::build_fast_tables(h->T);
     h->fast = h->F.certified && !cfg->force_generic_kernel;
+    if (h->fast && !cfg->disable_bit_sliced_scan) {
+      h->B = tsr::build_bit_tables(h->T, h->F);
+      h->bits = h->B.ok;
+    }
     if (h->F.certified && cfg->force_generic_kernel) h->F.why_not = "force_generic_kernel is set";
     h->host_only = (flags & TSR_CREATE_HOST_ONLY) != 0;
     if (!h->host_only) init_device(*h);
@@ -769,7 +809,7 @@ int tsr_set_instrumented(tsr_decoder* h, int on) {
 }
 
 int tsr_search_path(const tsr_decoder* h) {
-  return h->fast ? 1 : 0;
+  return h->fast ? (h->bits ? 2 : 1) : 0;
 }
 
 const char* tsr_search_path_reason(const tsr_decoder* h) {

@@ -136,4 +136,93 @@ FastTables build_fast_tables(const DemTables& T) {
   return F;
 }
 
+BitTables build_bit_tables(const DemTables& T, const FastTables& F) {
+  BitTables B;
+  if (!F.certified) {
+    B.why_not = F.why_not;
+    return B;
+  }
+  const uint64_t D = T.num_detectors;
+  const uint32_t aw = T.adj_words;
+  B.rowmeta.resize(D);
+  B.adjpre.assign((size_t)D * aw + 1, 0);
+  uint32_t max_nw = 1;
+  uint64_t mask_words = 0, pairs = 0, classes = 0;
+  std::vector<std::vector<uint32_t>> nbrs(D);
+  std::vector<std::vector<uint8_t>> row_cls(D);
+  for (uint64_t x = 0; x < D; ++x) {
+    uint32_t run = 0;
+    for (uint32_t w = 0; w < aw; ++w) {
+      B.adjpre[(size_t)x * aw + w] = (uint16_t)run;
+      for (uint32_t m = T.adj[(size_t)x * aw + w]; m; m &= m - 1) nbrs[x].push_back(w * 32 + (uint32_t)__builtin_ctz(m));
+      run += (uint32_t)__builtin_popcount(T.adj[(size_t)x * aw + w]);
+    }
+    if (run > 0xFFFF) {
+      B.why_not = "a detector has more than 65535 neighbours";
+      return B;
+    }
+    B.max_nbrs = std::max(B.max_nbrs, run);
+    const uint32_t len = T.row_off[x + 1] - T.row_off[x];
+    const uint32_t nw = std::max<uint32_t>((len + 31) / 32, 1);
+    max_nw = std::max(max_nw, nw);
+    std::vector<uint8_t> cls;
+    for (uint32_t k = T.row_off[x]; k < T.row_off[x + 1]; ++k) cls.push_back(F.cost_id[(size_t)T.row_err[k]]);
+    std::sort(cls.begin(), cls.end());
+    cls.erase(std::unique(cls.begin(), cls.end()), cls.end());  // ascending cost id == ascending cost
+    row_cls[x] = cls;
+    BitRowMeta& m = B.rowmeta[x];
+    m.len = len;
+    m.nw = nw;
+    m.ncls = (uint32_t)cls.size();
+    m.pad = 0;
+    m.mask_off = (uint32_t)mask_words;
+    mask_words += (uint64_t)nbrs[x].size() * nw;
+    m.cmask_off = (uint32_t)mask_words;
+    mask_words += (uint64_t)cls.size() * nw;
+    m.pair_base = (uint32_t)pairs;
+    pairs += nbrs[x].size();
+    m.cls_off = (uint32_t)classes;
+    classes += cls.size();
+    if (mask_words > 0x7FFFFFFFull) {
+      B.why_not = "the bit-sliced row masks exceed 8 GB";
+      return B;
+    }
+  }
+  B.group = 1;
+  while (B.group < max_nw) B.group *= 2;
+  if (B.group > 32) {
+    B.why_not = "a detector row is longer than 1024 errors";
+    return B;
+  }
+  B.masks.assign((size_t)mask_words + 4, 0);
+  B.cls_cid.assign((size_t)classes + 4, 0);
+  std::vector<std::vector<uint32_t>> lists((size_t)pairs);
+  for (uint64_t x = 0; x < D; ++x) {
+    const BitRowMeta& m = B.rowmeta[x];
+    for (uint32_t k = 0; k < m.ncls; ++k) B.cls_cid[m.cls_off + k] = row_cls[x][k];
+    for (uint32_t i = 0; i < m.len; ++i) {
+      const uint64_t e = (uint64_t)T.row_err[T.row_off[x] + i];
+      const uint32_t kc = (uint32_t)(std::lower_bound(row_cls[x].begin(), row_cls[x].end(), F.cost_id[e]) - row_cls[x].begin());
+      B.masks[m.cmask_off + (size_t)kc * m.nw + (i >> 5)] |= 1u << (i & 31);
+      const auto& dets = T.errors[e].detectors;
+      for (size_t q = 0; q < dets.size(); ++q) {
+        const uint32_t y = (uint32_t)dets[q];
+        if (y == x) continue;
+        const uint32_t j = (uint32_t)(std::lower_bound(nbrs[x].begin(), nbrs[x].end(), y) - nbrs[x].begin());
+        B.masks[m.mask_off + (size_t)j * m.nw + (i >> 5)] |= 1u << (i & 31);
+        lists[m.pair_base + j].push_back(((uint32_t)T.e_rank[T.e_off[e] + q] << 16) | i);
+      }
+    }
+  }
+  B.pl_off.assign((size_t)pairs + 1, 0);
+  for (size_t p = 0; p < lists.size(); ++p) {
+    std::sort(lists[p].begin(), lists[p].end());  // by rank in the neighbour's row (ranks are distinct)
+    B.pl_off[p + 1] = B.pl_off[p] + (uint32_t)lists[p].size();
+  }
+  B.pl.assign((size_t)B.pl_off[pairs] + 4, 0);
+  for (size_t p = 0; p < lists.size(); ++p) std::copy(lists[p].begin(), lists[p].end(), B.pl.begin() + B.pl_off[p]);
+  B.ok = true;
+  return B;
+}
+
 }  // namespace tsr

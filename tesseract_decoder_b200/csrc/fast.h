@@ -53,4 +53,33 @@ struct FastTables {
 
 FastTables build_fast_tables(const DemTables& T);
 
+// Bit-sliced row tables (search_fast.cu, "bits" scan): the same rank minimum, evaluated 32 row entries per
+// lane instead of one.  For a detector x with row length L (ceil(L/32) words):
+//   * for each detector y adjacent to x (the set bits of adj[x], in ascending order; index j = number of set
+//     bits of adj[x] below y): the L-bit mask of row[x] entries whose error also contains y.  The fired-count
+//     of every row entry is 1 + the bit-sliced sum of the masks of the FIRED neighbours;
+//   * for each pair (x, y): the entries of row[x] containing y as (rank in row[y], position in row[x]) sorted
+//     by rank — the entries a block threshold on y removes from row[x] are a prefix of that list;
+//   * for each distinct cost in row[x] (ascending): the L-bit mask of entries with that cost.
+struct BitRowMeta {   // 32 bytes, one per detector
+  uint32_t mask_off;  // word offset of the neighbour masks [j][word] in `masks`
+  uint32_t cmask_off; // word offset of the cost-class masks [k][word] in `masks`
+  uint32_t pair_base; // pair index of (x, first neighbour); pair lists are pl[pl_off[p] .. pl_off[p+1])
+  uint32_t cls_off;   // index of the first cost class of the row in cls_cid
+  uint32_t len, nw, ncls, pad;
+};
+struct BitTables {
+  bool ok = false;
+  std::string why_not;
+  uint32_t group = 0;     // lanes per target: smallest power of two >= max words per row
+  uint32_t max_nbrs = 0;  // largest number of set bits in an adjacency row
+  std::vector<BitRowMeta> rowmeta;  // [D]
+  std::vector<uint16_t> adjpre;     // [D * adj_words] set bits of adj[x] before word w
+  std::vector<uint32_t> masks;
+  std::vector<uint8_t> cls_cid;
+  std::vector<uint32_t> pl_off;     // [pairs + 1]
+  std::vector<uint32_t> pl;         // rank << 16 | position
+};
+BitTables build_bit_tables(const DemTables& T, const FastTables& F);
+
 }  // namespace tsr

@@ -36,6 +36,14 @@ struct DeviceTables {
   const double* fquot = nullptr;     // [fn_costs * fnstride] fl(cost / count)
   uint32_t fa_slots = 0, fnstride = 0, fn_costs = 0;
   uint32_t max_row_len = 0;
+  // Bit-sliced row tables (fast.h: BitTables; null / 0 when absent).
+  const uint4* bs_meta = nullptr;       // [D][2] BitRowMeta
+  const uint16_t* bs_adjpre = nullptr;  // [D][nwords]
+  const uint32_t* bs_masks = nullptr;
+  const uint8_t* bs_cls_cid = nullptr;
+  const uint32_t* bs_pl_off = nullptr;
+  const uint32_t* bs_pl = nullptr;
+  uint32_t bs_group = 0, bs_cap = 0;
 };
 
 struct alignas(16) HeapNode {
@@ -135,9 +143,11 @@ int launch_stage(const StageParams& p, void* stream);
 int launch_search(const SearchParams& p, uint32_t blocks, uint32_t warps_per_block, void* stream);
 int launch_resolve(const ResolveParams& p, void* stream);
 // Fast path (search_fast.cu): one CTA of `warps` warps per search.
-int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, void* stream);
-uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared);
-int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared);
+// `bits` selects the bit-sliced row scan (needs the bs_* tables); otherwise rows are scanned entry per lane, and
+// `instrumented` additionally counts the reference's visited row entries.
+int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, bool bits, void* stream);
+uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits);
+int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits);
 // Shared memory bytes one search warp needs for a DEM with D detectors.
 uint32_t search_smem_bytes_per_warp(uint32_t D);
 // Resident blocks per SM of the search kernel for this block shape (0 on failure).

@@ -69,7 +69,18 @@ struct Smem {
   uint4* res_meta;   // [max_row_len] {error, fired_mask, next_dets | pos << 16, status}
   uint16_t* clist;   // [max_row_len]
   uint16_t* st;      // this warp's private state [dpad]
+  // bit-sliced scan (kBits): shared blocking-detector bitset of the node, and this warp's scratch
+  uint32_t* pbb;     // [nwords] detectors with a block threshold in the node's state
+  uint32_t* cf;      // [nwords] fired bitset of this warp's current state (node or child)
+  uint32_t* cb;      // [nwords] blocking-detector bitset of this warp's current state
+  uint16_t* tl;      // [kTL] targets
+  double* hv;        // [kTL] their heuristic terms (without det_penalty)
+  uint16_t* fl;      // [groups][cap] fired-neighbour indices of each group's target
+  uint32_t* bl;      // [groups][cap] blocking neighbours: index | threshold << 16
+  uint32_t* gc;      // [groups][4] list lengths and the target's own threshold
 };
+
+constexpr uint32_t kTL = 128;  // targets evaluated per flush
 
 __host__ __device__ inline uint32_t round16(uint32_t bytes) {
   return (bytes + 15u) & ~15u;
@@ -80,9 +91,10 @@ __host__ __device__ inline uint32_t dpad_of(uint32_t D) {
 
 struct Layout {
   uint32_t off_rank, off_rbits, off_fbits, off_pst, off_hc, off_cost, off_meta, off_clist, off_st, total;
+  uint32_t off_pbb, warp_stride, w_cf, w_cb, w_tl, w_hv, w_fl, w_bl, w_gc;  // w_*: offsets inside a warp's region
 };
 __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint32_t rank_entries, uint32_t max_row_len,
-                                               uint32_t warps, bool hc_shared) {
+                                               uint32_t warps, bool hc_shared, uint32_t bs_group = 0, uint32_t bs_cap = 0) {
   Layout L;
   uint32_t at = round16(sizeof(Ctl));
   L.off_rank = at;
@@ -101,8 +113,30 @@ __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint3
   at += max_row_len * 16;
   L.off_clist = at;
   at += round16(max_row_len * 2);
+  L.off_pbb = at;
+  if (bs_group) at += round16(nwords * 4);
   L.off_st = at;
-  at += warps * dpad_of(D) * 2;
+  uint32_t w = dpad_of(D) * 2;  // this warp's region: st, then the bit-sliced scratch
+  L.w_cf = L.w_cb = L.w_tl = L.w_hv = L.w_fl = L.w_bl = L.w_gc = 0;
+  if (bs_group) {
+    const uint32_t groups = 32 / bs_group;
+    L.w_cf = w;
+    w += round16(nwords * 4);
+    L.w_cb = w;
+    w += round16(nwords * 4);
+    L.w_hv = w;
+    w += kTL * 8;
+    L.w_tl = w;
+    w += round16(kTL * 2);
+    L.w_bl = w;
+    w += round16(groups * bs_cap * 4);
+    L.w_fl = w;
+    w += round16(groups * bs_cap * 2);
+    L.w_gc = w;
+    w += round16(groups * 16);
+  }
+  L.warp_stride = w;
+  at += warps * w;
   L.total = at;
   return L;
 }
@@ -210,6 +244,171 @@ __device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t
   const int winner = __ffs((int)__ballot_sync(kFull, best == m)) - 1;
   const uint32_t cls = __shfl_sync(kFull, best_cls, winner);
   return __ldg(t.fquot + cls);
+}
+
+
+// ---- bit-sliced row scan (fast.h: BitTables) ----------------------------------------------------------
+//
+// A group of G lanes owns one target detector x; lane wl of the group owns entries [32 wl, 32 wl + 32) of
+// row[x] as bit masks.  32/G targets are evaluated per warp pass.
+
+struct BsRow {
+  uint32_t U;               // unblocked entries of this lane's word
+  uint32_t c0, c1, c2, c3;  // bit planes of (fired-detector count - 1) per entry
+  uint32_t nw, cmask_off, cls_off, ncls;
+};
+
+// Phases A-C for the group's target x in the warp's current state (st: thresholds, sm.cf: fired bitset,
+// sm.cb: blocking-detector bitset).  Must be called by all 32 lanes.
+template <bool kCounts>
+__device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, bool active, uint32_t x, uint32_t g, uint32_t wl) {
+  const uint32_t G = t.bs_group, cap = t.bs_cap, nwords = t.nwords;
+  uint32_t* gc = sm.gc + g * 4;
+  if (wl == 0) {
+    gc[0] = 0;
+    gc[1] = 0;
+    gc[2] = 0;
+  }
+  __syncwarp();
+  uint4 ma = make_uint4(0, 0, 0, 0), mb = make_uint4(0, 0, 0, 0);
+  if (active) {
+    ma = ldg16(t.bs_meta + 2 * (size_t)x);
+    mb = ldg16(t.bs_meta + 2 * (size_t)x + 1);
+    // A: the fired neighbours of x (their mask index) and the neighbours that carry a block threshold
+    const uint32_t* arow = t.adj + (size_t)x * nwords;
+    for (uint32_t w = wl; w < nwords; w += G) {
+      const uint32_t a = __ldg(arow + w);
+      uint32_t f = kCounts ? (a & sm.cf[w]) : 0u;
+      uint32_t b = a & sm.cb[w];
+      if ((x >> 5) == w) f &= ~(1u << (x & 31));
+      if (f | b) {
+        const uint32_t pre = __ldg(t.bs_adjpre + (size_t)x * nwords + w);
+        while (f) {
+          const uint32_t bit = (uint32_t)__ffs((int)f) - 1;
+          f &= f - 1;
+          const uint32_t j = pre + (uint32_t)__popc(a & ((1u << bit) - 1u));
+          sm.fl[g * cap + atomicAdd(&gc[0], 1u)] = (uint16_t)j;
+        }
+        while (b) {
+          const uint32_t bit = (uint32_t)__ffs((int)b) - 1;
+          b &= b - 1;
+          const uint32_t det = w * 32 + bit;
+          const uint32_t thr = sm.st[det] & kThr;
+          if (det == x) {
+            gc[2] = thr;
+          } else if (thr) {
+            const uint32_t j = pre + (uint32_t)__popc(a & ((1u << bit) - 1u));
+            sm.bl[g * cap + atomicAdd(&gc[1], 1u)] = j | (thr << 16);
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  BsRow r;
+  r.U = r.c0 = r.c1 = r.c2 = r.c3 = 0;
+  r.nw = mb.y;
+  r.cmask_off = ma.y;
+  r.cls_off = ma.w;
+  r.ncls = mb.z;
+  if (active && wl < mb.y) {
+    const uint32_t nw = mb.y, len = mb.x, lo = wl * 32;
+    const uint32_t nf = gc[0], nb = gc[1], thr0 = gc[2];
+    if (kCounts) {
+      // B: bit-sliced sum of the fired neighbours' masks
+      const uint32_t* mrow = t.bs_masks + ma.x + wl;
+      for (uint32_t q = 0; q < nf; ++q) {
+        const uint32_t m = __ldg(mrow + (size_t)sm.fl[g * cap + q] * nw);
+        const uint32_t t0 = r.c0 & m;
+        r.c0 ^= m;
+        const uint32_t t1 = r.c1 & t0;
+        r.c1 ^= t0;
+        const uint32_t t2 = r.c2 & t1;
+        r.c2 ^= t1;
+        r.c3 ^= t2;
+      }
+    }
+    // C: blocked entries — the row's own prefix, and per blocking neighbour a prefix of the pair list
+    const uint32_t valid = len - lo >= 32 ? 0xFFFFFFFFu : ((1u << (len - lo)) - 1u);
+    uint32_t B = thr0 <= lo ? 0u : (thr0 - lo >= 32 ? 0xFFFFFFFFu : ((1u << (thr0 - lo)) - 1u));
+    for (uint32_t q = 0; q < nb; ++q) {
+      const uint32_t jb = sm.bl[g * cap + q];
+      const uint32_t pi = ma.z + (jb & 0xFFFF), thr = jb >> 16;
+      const uint32_t pe = __ldg(t.bs_pl_off + pi + 1);
+      for (uint32_t at = __ldg(t.bs_pl_off + pi); at < pe; ++at) {
+        const uint32_t v = __ldg(t.bs_pl + at);
+        if ((v >> 16) >= thr) break;
+        if (((v & 0xFFFF) >> 5) == wl) B |= 1u << (v & 31);
+      }
+    }
+    r.U = valid & ~B;
+  }
+  return r;
+}
+
+// get_detcost (without det_penalty) of targets sm.tl[0..n) in the warp's current state -> sm.hv[0..n).
+__device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm, uint32_t n, uint32_t lane) {
+  const uint32_t G = t.bs_group, ng = 32 / G;
+  const uint32_t g = lane / G, wl = lane % G;
+  __syncwarp();
+  for (uint32_t base = 0; base < n; base += ng) {
+    const uint32_t k = base + g;
+    const bool active = k < n;
+    const uint32_t x = active ? sm.tl[k] : 0u;
+    const BsRow r = bs_core<true>(t, sm, active, x, g, wl);
+    uint32_t best = kKeyInf, bcls = 0;
+    if (r.U) {
+      // D: per count value v+1, the cheapest cost class with an unblocked entry wins (classes ascend in cost,
+      // hence in rank); classes of EQUAL rank (costs one ulp apart) compete on row position.
+      const uint32_t c0 = r.c0 & r.U, c1 = r.c1 & r.U, c2 = r.c2 & r.U, c3 = r.c3 & r.U;
+      const uint32_t vmax = c3 ? 15u : c2 ? 7u : c1 ? 3u : c0 ? 1u : 0u;
+      const uint32_t* crow = t.bs_masks + r.cmask_off + wl;
+      for (uint32_t v = 0; v <= vmax; ++v) {
+        const uint32_t E = r.U & ((v & 1) ? c0 : ~c0) & ((v & 2) ? c1 : ~c1) & ((v & 4) ? c2 : ~c2) & ((v & 8) ? c3 : ~c3);
+        if (!E) continue;
+        bool found = false;
+        uint32_t rv = 0, cls_v = 0;
+        for (uint32_t kc = 0; kc < r.ncls; ++kc) {
+          uint32_t cls = 0;
+          if (found) {
+            cls = (uint32_t)__ldg(t.bs_cls_cid + r.cls_off + kc) * t.fnstride + v + 1;
+            if (sm.rank[cls] != rv) break;
+          }
+          const uint32_t cm = __ldg(crow + (size_t)kc * r.nw) & E;
+          if (!cm) continue;
+          if (!found) {
+            cls = (uint32_t)__ldg(t.bs_cls_cid + r.cls_off + kc) * t.fnstride + v + 1;
+            rv = sm.rank[cls];
+            found = true;
+          }
+          cls_v = cls;
+          const uint32_t key = (rv << 12) | (wl * 32 + (uint32_t)__ffs((int)cm) - 1);
+          if (key < best) {
+            best = key;
+            bcls = cls_v;
+          }
+        }
+      }
+    }
+    for (uint32_t off = G >> 1; off >= 1; off >>= 1) {
+      const uint32_t ob = __shfl_xor_sync(kFull, best, (int)off);
+      const uint32_t oc = __shfl_xor_sync(kFull, bcls, (int)off);
+      if (ob < best) {
+        best = ob;
+        bcls = oc;
+      }
+    }
+    if (active && wl == 0) sm.hv[k] = best == kKeyInf ? __longlong_as_double(0x7FF0000000000000LL) : __ldg(t.fquot + bcls);
+  }
+  __syncwarp();
+}
+
+// Appends the set bits of `word` (detectors base_det + bit) to the warp's target list; the caller flushes
+// the list when fewer than 32 free slots remain.
+__device__ __forceinline__ void tl_append(const Smem& sm, uint32_t& nt, uint32_t word, uint32_t base_det, uint32_t lane) {
+  const uint32_t cnt = (uint32_t)__popc(word);
+  if (lane < cnt) sm.tl[nt + lane] = (uint16_t)(base_det + __fns(word, 0, (int)lane + 1));
+  nt += cnt;
 }
 
 // ---- queue: exact libstdc++ std::priority_queue<Node, vector<Node>, std::greater<Node>> -------------
@@ -346,7 +545,7 @@ struct Counters {
 
 // ---- one child (one warp): tesseract.cc:533-606 up to, not including, the push ----------------------
 
-template <bool kInstr>
+template <bool kInstr, bool kBits>
 __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm, uint32_t j, uint32_t lane,
                                            const uint4* vtab, Counters& ctr) {
   const DeviceTables& t = p.t;
@@ -391,17 +590,40 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
       const uint32_t s = st[mind];
       if ((s & kThr) < pos + 1) st[mind] = (uint16_t)((s & kFired) | (pos + 1));
     }
+    if (kBits) {
+      if (lane < deg) {
+        atomicXor(&sm.cf[dj >> 5], 1u << (dj & 31));
+        if (dj == mind || (p.at_most_two && (sj & kFired))) atomicOr(&sm.cb[dj >> 5], 1u << (dj & 31));
+      }
+    }
     __syncwarp();
 
     // The reference's add/sub chain, in its order (tesseract.cc:549-585).
     cost = __dadd_rn(c.cost, __ldg(t.e_cost + ei));
-    for (uint32_t k = 0; k < deg; ++k) {
-      const uint32_t d = __shfl_sync(kFull, dj, (int)k);
-      if ((fired_mask >> k) & 1) {
-        cost = __dsub_rn(cost, sm.hc[d]);
-      } else {
-        const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, d, lane, ctr.S), p.det_penalty);
-        cost = __dadd_rn(cost, h);
+    if (kBits) {
+      uint32_t nt = 0;
+      const unsigned newly = ~fired_mask & ((deg >= 32) ? kFull : ((1u << deg) - 1u));
+      if (lane < deg && !((fired_mask >> lane) & 1)) sm.tl[__popc(newly & ((1u << lane) - 1u))] = (uint16_t)dj;
+      nt = (uint32_t)__popc(newly);
+      bs_targets(t, sm, nt, lane);
+      uint32_t at = 0;
+      for (uint32_t k = 0; k < deg; ++k) {
+        const uint32_t d = __shfl_sync(kFull, dj, (int)k);
+        if ((fired_mask >> k) & 1) {
+          cost = __dsub_rn(cost, sm.hc[d]);
+        } else {
+          cost = __dadd_rn(cost, __dadd_rn(sm.hv[at++], p.det_penalty));
+        }
+      }
+    } else {
+      for (uint32_t k = 0; k < deg; ++k) {
+        const uint32_t d = __shfl_sync(kFull, dj, (int)k);
+        if ((fired_mask >> k) & 1) {
+          cost = __dsub_rn(cost, sm.hc[d]);
+        } else {
+          const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, d, lane, ctr.S), p.det_penalty);
+          cost = __dadd_rn(cost, h);
+        }
       }
     }
     // eneighbors[ei] ∩ fired: detectors adjacent to one of the error's detectors, fired in the parent
@@ -419,21 +641,46 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
       }
       if (w < nwords) mine &= sm.fbits[w];
       unsigned nz = __ballot_sync(kFull, mine != 0);
-      while (nz) {
-        const uint32_t l = (uint32_t)__ffs((int)nz) - 1;
-        nz &= nz - 1;
-        uint32_t word = __shfl_sync(kFull, mine, (int)l);
-        while (word) {
-          const uint32_t od = (wb + l) * 32 + (uint32_t)__ffs((int)word) - 1;
-          word &= word - 1;
-          cost = __dsub_rn(cost, sm.hc[od]);
-          const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, od, lane, ctr.S), p.det_penalty);
-          cost = __dadd_rn(cost, h);
+      if (kBits) {
+        uint32_t nt = 0;
+        while (true) {
+          if (nz) {
+            const uint32_t l = (uint32_t)__ffs((int)nz) - 1;
+            nz &= nz - 1;
+            tl_append(sm, nt, __shfl_sync(kFull, mine, (int)l), (wb + l) * 32, lane);
+          }
+          if (nt == 0) break;
+          if (nz && nt + 32 <= kTL) continue;
+          bs_targets(t, sm, nt, lane);
+          for (uint32_t i = 0; i < nt; ++i) {
+            cost = __dsub_rn(cost, sm.hc[sm.tl[i]]);
+            cost = __dadd_rn(cost, __dadd_rn(sm.hv[i], p.det_penalty));
+          }
+          nt = 0;
+          if (!nz) break;
+        }
+      } else {
+        while (nz) {
+          const uint32_t l = (uint32_t)__ffs((int)nz) - 1;
+          nz &= nz - 1;
+          uint32_t word = __shfl_sync(kFull, mine, (int)l);
+          while (word) {
+            const uint32_t od = (wb + l) * 32 + (uint32_t)__ffs((int)word) - 1;
+            word &= word - 1;
+            cost = __dsub_rn(cost, sm.hc[od]);
+            const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, od, lane, ctr.S), p.det_penalty);
+            cost = __dadd_rn(cost, h);
+          }
         }
       }
     }
     ctr.A += deg + __ldg(t.e_nnbr + ei);
     if (lane < deg) st[dj] = (uint16_t)sj;  // back to the parent state (the min detector is one of them)
+    if (kBits) {
+      if (lane < deg) atomicXor(&sm.cf[dj >> 5], 1u << (dj & 31));
+      __syncwarp();
+      if (lane < deg) sm.cb[dj >> 5] = sm.pbb[dj >> 5];
+    }
     __syncwarp();
     if (cost == __longlong_as_double(0x7FF0000000000000LL)) status = kChildDropped;  // tesseract.cc:587
   }
@@ -445,7 +692,7 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
 
 // ---- one search (whole CTA).  Returns the item status; on kItemOk the solution has been written. ------
 
-template <bool kInstr>
+template <bool kInstr, bool kBits>
 __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t slot, uint32_t item, Counters& ctr) {
   const DeviceTables& t = p.t;
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
@@ -548,7 +795,10 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
 
     // ---- phase 2 (all): the node's state from its chain (tesseract.cc:349-369) ------------------------
     for (uint32_t i = tid; i < dpad / 2; i += nthr) reinterpret_cast<uint32_t*>(sm.pst)[i] = 0;
-    for (uint32_t w = tid; w < nwords; w += nthr) sm.fbits[w] = sm.rbits[w];
+    for (uint32_t w = tid; w < nwords; w += nthr) {
+      sm.fbits[w] = sm.rbits[w];
+      if (kBits) sm.pbb[w] = 0;
+    }
     __syncthreads();
     for (uint32_t w = tid; w < nwords; w += nthr)
       for (uint32_t m = sm.rbits[w]; m; m &= m - 1) sm.pst[w * 32 + (uint32_t)__ffs((int)m) - 1] = (uint16_t)kFired;
@@ -567,12 +817,16 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           key_xor(key, ldg16(t.zobrist + dj));
         }
         __syncwarp();
-        if (p.at_most_two && lane < deg && ((off_mask >> lane) & 1)) sm.pst[dj] = (uint16_t)((sm.pst[dj] & kFired) | kThr);
+        if (p.at_most_two && lane < deg && ((off_mask >> lane) & 1)) {
+          sm.pst[dj] = (uint16_t)((sm.pst[dj] & kFired) | kThr);
+          if (kBits) atomicOr(&sm.pbb[dj >> 5], 1u << (dj & 31));
+        }
         __syncwarp();
         if (lane == 0) {
           const uint32_t md = mind_pos >> 16, thr = (mind_pos & 0xFFFF) + 1;
           const uint32_t s = sm.pst[md];
           if ((s & kThr) < thr) sm.pst[md] = (uint16_t)((s & kFired) | thr);
+          if (kBits) sm.pbb[md >> 5] |= 1u << (md & 31);
         }
         __syncwarp();
         at = parent;
@@ -648,17 +902,41 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       const uint4* src = reinterpret_cast<const uint4*>(sm.pst);
       uint4* dst = reinterpret_cast<uint4*>(sm.st);
       for (uint32_t i = lane; i < dpad / 8; i += 32) dst[i] = src[i];
+      if (kBits)
+        for (uint32_t w = lane; w < nwords; w += 32) {
+          sm.cf[w] = sm.fbits[w];
+          sm.cb[w] = sm.pbb[w];
+        }
       __syncwarp();
     }
     if (!c.terms_cached) {
       // (the reference memoises these lazily in detector_cost_cache, tesseract.cc:531,569-582; same values)
-      for (uint32_t w = warp; w < nwords; w += nwarps) {
-        uint32_t word = sm.fbits[w];
-        while (word) {
-          const uint32_t d = w * 32 + (uint32_t)__ffs((int)word) - 1;
-          word &= word - 1;
-          const double h = __dadd_rn(scan_row<kInstr>(t, sm.st, sm.rank, d, lane, ctr.S), p.det_penalty);
-          if (lane == 0) sm.hc[d] = h;
+      if (kBits) {
+        uint32_t nt = 0;
+        uint32_t w = warp;
+        while (true) {
+          if (w < nwords) {
+            tl_append(sm, nt, sm.fbits[w], w * 32, lane);
+            w += nwarps;
+          }
+          if (nt == 0 && w >= nwords) break;
+          if (w < nwords && nt + 32 <= kTL) continue;
+          bs_targets(t, sm, nt, lane);
+          if (lane < nt) sm.hc[sm.tl[lane]] = __dadd_rn(sm.hv[lane], p.det_penalty);
+          for (uint32_t i = lane + 32; i < nt; i += 32) sm.hc[sm.tl[i]] = __dadd_rn(sm.hv[i], p.det_penalty);
+          __syncwarp();
+          nt = 0;
+          if (w >= nwords) break;
+        }
+      } else {
+        for (uint32_t w = warp; w < nwords; w += nwarps) {
+          uint32_t word = sm.fbits[w];
+          while (word) {
+            const uint32_t d = w * 32 + (uint32_t)__ffs((int)word) - 1;
+            word &= word - 1;
+            const double h = __dadd_rn(scan_row<kInstr>(t, sm.st, sm.rank, d, lane, ctr.S), p.det_penalty);
+            if (lane == 0) sm.hc[d] = h;
+          }
         }
       }
     }
@@ -707,13 +985,25 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
         const uint32_t m_thr = sm.st[mind] & kThr;
         // children: unblocked entries of row[min_detector], in row order (tesseract.cc:533-534)
         uint32_t n = 0;
-        for (uint32_t base = 0; base < m_len; base += 32) {
-          const uint32_t idx = base + lane;
-          bool open = false;
-          if (idx < m_len) open = !eval_entry(t, sm.st, m_off, idx, m_thr).blocked;
-          const unsigned mo = __ballot_sync(kFull, open);
-          if (open) sm.clist[n + __popc(mo & ((1u << lane) - 1u))] = (uint16_t)idx;
-          n += __popc(mo);
+        if (kBits) {
+          const uint32_t G = t.bs_group;
+          const BsRow r = bs_core<false>(t, sm, lane < G, mind, lane / G, lane % G);
+          uint32_t mine = lane < G ? r.U : 0u, before = 0;
+          for (uint32_t l = 0; l < G; ++l) {
+            const uint32_t cnt = (uint32_t)__popc(__shfl_sync(kFull, mine, (int)l));
+            if (l < lane) before += cnt;
+            n += cnt;
+          }
+          for (uint32_t m = mine; m; m &= m - 1) sm.clist[before++] = (uint16_t)(lane * 32 + (uint32_t)__ffs((int)m) - 1);
+        } else {
+          for (uint32_t base = 0; base < m_len; base += 32) {
+            const uint32_t idx = base + lane;
+            bool open = false;
+            if (idx < m_len) open = !eval_entry(t, sm.st, m_off, idx, m_thr).blocked;
+            const unsigned mo = __ballot_sync(kFull, open);
+            if (open) sm.clist[n + __popc(mo & ((1u << lane) - 1u))] = (uint16_t)idx;
+            n += __popc(mo);
+          }
         }
         if (lane == 0) {
           c.mind = mind;
@@ -735,7 +1025,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
     }
 
     // ---- phase 6 (all warps): the children, round-robin ----------------------------------------------------
-    for (uint32_t j = warp; j < c.nchild; j += nwarps) eval_child<kInstr>(p, sm, j, lane, vtab, ctr);
+    for (uint32_t j = warp; j < c.nchild; j += nwarps) eval_child<kInstr, kBits>(p, sm, j, lane, vtab, ctr);
     __syncthreads();
 
     // ---- phase 7 (warp 0): pushes, in row order (tesseract.cc:590-605) ----------------------------------------
@@ -790,7 +1080,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
   }
 }
 
-template <bool kInstr>
+template <bool kInstr, bool kBits>
 __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams p) {
   extern __shared__ uint4 smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
@@ -798,7 +1088,8 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
   const uint32_t slot = blockIdx.x;
   const uint32_t D = p.t.D;
   const uint32_t rank_entries = p.t.fn_costs * p.t.fnstride;
-  const Layout L = make_layout(D, p.t.nwords, rank_entries, p.t.max_row_len, nwarps, p.hc_shared != 0);
+  const Layout L = make_layout(D, p.t.nwords, rank_entries, p.t.max_row_len, nwarps, p.hc_shared != 0,
+                               kBits ? p.t.bs_group : 0, kBits ? p.t.bs_cap : 0);
   Smem sm;
   sm.ctl = reinterpret_cast<Ctl*>(base);
   sm.rank = reinterpret_cast<uint16_t*>(base + L.off_rank);
@@ -809,7 +1100,16 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
   sm.res_cost = reinterpret_cast<double*>(base + L.off_cost);
   sm.res_meta = reinterpret_cast<uint4*>(base + L.off_meta);
   sm.clist = reinterpret_cast<uint16_t*>(base + L.off_clist);
-  sm.st = reinterpret_cast<uint16_t*>(base + L.off_st) + (size_t)warp * dpad_of(D);
+  uint8_t* wbase = base + L.off_st + (size_t)warp * L.warp_stride;
+  sm.st = reinterpret_cast<uint16_t*>(wbase);
+  sm.pbb = reinterpret_cast<uint32_t*>(base + L.off_pbb);
+  sm.cf = reinterpret_cast<uint32_t*>(wbase + L.w_cf);
+  sm.cb = reinterpret_cast<uint32_t*>(wbase + L.w_cb);
+  sm.tl = reinterpret_cast<uint16_t*>(wbase + L.w_tl);
+  sm.hv = reinterpret_cast<double*>(wbase + L.w_hv);
+  sm.fl = reinterpret_cast<uint16_t*>(wbase + L.w_fl);
+  sm.bl = reinterpret_cast<uint32_t*>(wbase + L.w_bl);
+  sm.gc = reinterpret_cast<uint32_t*>(wbase + L.w_gc);
   for (uint32_t i = tid; i < rank_entries; i += blockDim.x) sm.rank[i] = __ldg(p.t.frank + i);
   __syncthreads();
 
@@ -821,7 +1121,7 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
     const uint32_t work = sm.ctl->work;
     if (work >= p.n_work) break;
     const uint32_t item = p.item_ids ? __ldg(p.item_ids + work) : work;
-    const uint32_t status = run_search<kInstr>(p, sm, slot, item, ctr);
+    const uint32_t status = run_search<kInstr, kBits>(p, sm, slot, item, ctr);
     __syncthreads();
     ++searches;
     if (tid == 0) {
@@ -856,37 +1156,46 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
   }
 }
 
-template <bool kInstr>
+template <bool kInstr, bool kBits>
 int configure(size_t smem) {
   if (smem > 48 * 1024)
-    return (int)cudaFuncSetAttribute(search_fast_kernel<kInstr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return (int)cudaFuncSetAttribute(search_fast_kernel<kInstr, kBits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   return 0;
 }
 
 }  // namespace
 
-uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared) {
-  return make_layout(t.D, t.nwords, t.fn_costs * t.fnstride, t.max_row_len, warps, hc_shared).total;
+uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits) {
+  return make_layout(t.D, t.nwords, t.fn_costs * t.fnstride, t.max_row_len, warps, hc_shared, bits ? t.bs_group : 0,
+                     bits ? t.bs_cap : 0).total;
 }
 
-int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared) {
+int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits) {
   int n = 0;
-  const size_t smem = search_fast_smem_bytes(t, warps, hc_shared);
+  const size_t smem = search_fast_smem_bytes(t, warps, hc_shared, bits);
   if (smem > 227 * 1024) return 0;
-  if (configure<false>(smem) != 0 || configure<true>(smem) != 0) return 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false>, (int)(warps * 32), smem) != cudaSuccess) return 0;
+  if (bits) {
+    if (configure<false, true>(smem) != 0) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, true>, (int)(warps * 32), smem) != cudaSuccess) return 0;
+  } else {
+    if (configure<false, false>(smem) != 0 || configure<true, false>(smem) != 0) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, false>, (int)(warps * 32), smem) != cudaSuccess) return 0;
+  }
   return n;
 }
 
-int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, void* stream) {
+int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, bool bits, void* stream) {
   if (p.n_work == 0 || blocks == 0) return 0;
-  const size_t smem = search_fast_smem_bytes(p.t, warps, p.hc_shared != 0);
-  if (instrumented) {
-    if (int e = configure<true>(smem)) return e;
-    search_fast_kernel<true><<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+  const size_t smem = search_fast_smem_bytes(p.t, warps, p.hc_shared != 0, bits);
+  if (bits) {
+    if (int e = configure<false, true>(smem)) return e;
+    search_fast_kernel<false, true><<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+  } else if (instrumented) {
+    if (int e = configure<true, false>(smem)) return e;
+    search_fast_kernel<true, false><<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
   } else {
-    if (int e = configure<false>(smem)) return e;
-    search_fast_kernel<false><<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+    if (int e = configure<false, false>(smem)) return e;
+    search_fast_kernel<false, false><<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
   }
   return (int)cudaGetLastError();
 }

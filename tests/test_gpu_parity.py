@@ -68,14 +68,15 @@ def check_solutions_are_consistent(dec, dets, out):
 
 # ---- golden vectors of the reference build ---------------------------------------------------------
 
-@pytest.mark.parametrize("path", ["fast", "generic"])
+@pytest.mark.parametrize("path", ["fast-bits", "fast", "generic"])
 @pytest.mark.parametrize("name", W.golden_names())
 def test_golden_vectors(name, path):
-    """Both CUDA search kernels — the CTA-per-search integer-rank kernel every fixture DEM is certified for
-    (csrc/fast.h) and the generic event-replay kernel — reproduce the reference build's outputs."""
+    """All three CUDA search variants — the CTA-per-search integer-rank kernel every fixture DEM is certified for
+    (csrc/fast.h) with bit-sliced and with entry-per-lane row scans, and the generic event-replay kernel —
+    reproduce the reference build's outputs."""
     g = W.load_golden(name)
     dem, kw = W.decoder_kwargs(g["config"], capi.build_det_orders)
-    dec = capi.Decoder(dem, force_generic_kernel=(path == "generic"), **kw)
+    dec = capi.Decoder(dem, force_generic_kernel=(path == "generic"), disable_bit_sliced_scan=(path == "fast"), **kw)
     assert dec.search_path == path, dec.search_path_reason
     out = dec.decode_batch_b8(g["dets"])
     assert_same(out, g)
@@ -233,6 +234,8 @@ def test_fresh_shots_against_the_cpu_checker(case):
     check_solutions_are_consistent(dec, dets, out)
     if case % 2 == 0:  # the generic kernel, on the same shots
         assert_same(capi.Decoder(dem, force_generic_kernel=True, **kw).decode_batch_b8(dets), ref)
+    else:  # the entry-per-lane scan of the fast kernel (the default is the bit-sliced scan)
+        assert_same(capi.Decoder(dem, disable_bit_sliced_scan=True, **kw).decode_batch_b8(dets), ref)
     if oracle.available("port") and shots <= 1000:
         # The search itself is the same search: pushes, pops, expansions, chain steps and visited probes
         # agree exactly with the instrumented CPU port.  Scanned heuristic entries (S) only

@@ -95,7 +95,8 @@ def test_decode_batch_expected_matrices():  # shared_decoding_tests.py:255-329
     dec = tesseract.TesseractDecoder(tesseract.TesseractConfig(Dem("error(0.1) D0 D1 L0\nerror(0.2) D0 L1\nerror(0.05) D1")))
     out = dec.decode_batch(np.array([[True, True], [True, False], [False, True]]))
     assert out.dtype == np.bool_ and out.tolist() == [[True, False], [False, True], [False, False]]
-    cfg = tesseract.TesseractConfig(det_beam=7)
+    cfg = tesseract.TesseractConfig()  # no detector orders yet: the decoder falls back to the identity order
+    cfg.det_beam = 7
     dec = cfg.compile_decoder_for_dem(Dem("error(0.1) D0 D1 L0\nerror(0.2) D0 D2 L1\nerror(0.05) D1 D3 L0 L2\nerror(0.15) D2\nerror(0.25) D3"))
     out = dec.decode_batch(np.array([[1, 1, 0, 0], [1, 0, 1, 0], [0, 1, 0, 1], [0, 0, 1, 1]], dtype=bool))
     assert out.tolist() == [[True, False, False], [False, True, False], [True, False, True], [False, False, False]]
