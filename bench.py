@@ -172,7 +172,8 @@ def run_b200(args, wl, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     dem, kw = W.decoder_kwargs(wl["cfg"], capi.build_det_orders)
-    dec = capi.Decoder(dem, device=local, **kw)
+    dec = capi.Decoder(dem, device=local, warps_per_block=args.warps, force_generic_kernel=args.scan == "generic",
+                       disable_bit_sliced_scan=args.scan == "lanes", **kw)
     dec.set_collect_errors(False)
     D, O = dec.num_detectors, dec.num_observables
     S = args.shots or wl["shots"]
@@ -318,6 +319,9 @@ def main():
     ap.add_argument("--shots", type=int, default=0, help="shots per GPU per step (default: per workload)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="wall-time target of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--warps", type=int, default=0, help="warps per search CTA (0 = automatic)")
+    ap.add_argument("--scan", default="auto", choices=["auto", "bits", "lanes", "generic"],
+                    help="search kernel variant (auto = the decoder's choice)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     wl = WORKLOADS[args.workload]

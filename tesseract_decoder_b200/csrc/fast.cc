@@ -173,16 +173,16 @@ BitTables build_bit_tables(const DemTables& T, const FastTables& F) {
     BitRowMeta& m = B.rowmeta[x];
     m.len = len;
     m.nw = nw;
-    m.ncls = (uint32_t)cls.size();
+    m.ncls = ((uint32_t)cls.size() + 3) & ~3u;  // padded to 4 with empty classes (the kernel reads 4 at a time)
     m.pad = 0;
     m.mask_off = (uint32_t)mask_words;
     mask_words += (uint64_t)nbrs[x].size() * nw;
     m.cmask_off = (uint32_t)mask_words;
-    mask_words += (uint64_t)cls.size() * nw;
+    mask_words += (uint64_t)m.ncls * nw;
     m.pair_base = (uint32_t)pairs;
     pairs += nbrs[x].size();
     m.cls_off = (uint32_t)classes;
-    classes += cls.size();
+    classes += m.ncls;
     if (mask_words > 0x7FFFFFFFull) {
       B.why_not = "the bit-sliced row masks exceed 8 GB";
       return B;
@@ -199,7 +199,7 @@ BitTables build_bit_tables(const DemTables& T, const FastTables& F) {
   std::vector<std::vector<uint32_t>> lists((size_t)pairs);
   for (uint64_t x = 0; x < D; ++x) {
     const BitRowMeta& m = B.rowmeta[x];
-    for (uint32_t k = 0; k < m.ncls; ++k) B.cls_cid[m.cls_off + k] = row_cls[x][k];
+    for (uint32_t k = 0; k < row_cls[x].size(); ++k) B.cls_cid[m.cls_off + k] = row_cls[x][k];
     for (uint32_t i = 0; i < m.len; ++i) {
       const uint64_t e = (uint64_t)T.row_err[T.row_off[x] + i];
       const uint32_t kc = (uint32_t)(std::lower_bound(row_cls[x].begin(), row_cls[x].end(), F.cost_id[e]) - row_cls[x].begin());

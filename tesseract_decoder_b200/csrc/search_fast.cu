@@ -72,7 +72,6 @@ struct Smem {
   // bit-sliced scan (kBits): shared blocking-detector bitset of the node, and this warp's scratch
   uint32_t* pbb;     // [nwords] detectors with a block threshold in the node's state
   uint32_t* cf;      // [nwords] fired bitset of this warp's current state (node or child)
-  uint32_t* cb;      // [nwords] blocking-detector bitset of this warp's current state
   uint16_t* tl;      // [kTL] targets
   double* hv;        // [kTL] their heuristic terms (without det_penalty)
   uint16_t* fl;      // [groups][cap] fired-neighbour indices of each group's target
@@ -80,7 +79,7 @@ struct Smem {
   uint32_t* gc;      // [groups][4] list lengths and the target's own threshold
 };
 
-constexpr uint32_t kTL = 128;  // targets evaluated per flush
+constexpr uint32_t kTL = 64;  // targets evaluated per flush
 
 __host__ __device__ inline uint32_t round16(uint32_t bytes) {
   return (bytes + 15u) & ~15u;
@@ -91,7 +90,7 @@ __host__ __device__ inline uint32_t dpad_of(uint32_t D) {
 
 struct Layout {
   uint32_t off_rank, off_rbits, off_fbits, off_pst, off_hc, off_cost, off_meta, off_clist, off_st, total;
-  uint32_t off_pbb, warp_stride, w_cf, w_cb, w_tl, w_hv, w_fl, w_bl, w_gc;  // w_*: offsets inside a warp's region
+  uint32_t off_pbb, warp_stride, w_cf, w_tl, w_hv, w_fl, w_bl, w_gc;  // w_*: offsets inside a warp's region
 };
 __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint32_t rank_entries, uint32_t max_row_len,
                                                uint32_t warps, bool hc_shared, uint32_t bs_group = 0, uint32_t bs_cap = 0) {
@@ -116,13 +115,12 @@ __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint3
   L.off_pbb = at;
   if (bs_group) at += round16(nwords * 4);
   L.off_st = at;
-  uint32_t w = dpad_of(D) * 2;  // this warp's region: st, then the bit-sliced scratch
-  L.w_cf = L.w_cb = L.w_tl = L.w_hv = L.w_fl = L.w_bl = L.w_gc = 0;
+  // this warp's region: the private state copy (entry-per-lane scans) or the bit-sliced scratch
+  uint32_t w = bs_group ? 0 : dpad_of(D) * 2;
+  L.w_cf = L.w_tl = L.w_hv = L.w_fl = L.w_bl = L.w_gc = 0;
   if (bs_group) {
     const uint32_t groups = 32 / bs_group;
     L.w_cf = w;
-    w += round16(nwords * 4);
-    L.w_cb = w;
     w += round16(nwords * 4);
     L.w_hv = w;
     w += kTL * 8;
@@ -258,10 +256,18 @@ struct BsRow {
   uint32_t nw, cmask_off, cls_off, ncls;
 };
 
-// Phases A-C for the group's target x in the warp's current state (st: thresholds, sm.cf: fired bitset,
-// sm.cb: blocking-detector bitset).  Must be called by all 32 lanes.
+// The warp's current state is the node's (sm.pst thresholds, sm.fbits fired, sm.pbb detectors with a threshold)
+// or one of its children: fired bitset sm.cf, the min detector's threshold raised to c_thr, and with
+// at-most-two the detectors the child's error switched off (fired in the node, not in the child) fully blocked.
+struct BsState {
+  uint32_t c_mind, c_thr;  // c_mind = 0xFFFFFFFF: the node's own state
+  bool amt;
+};
+
+// Phases A-C for the group's target x.  Must be called by all 32 lanes.
 template <bool kCounts>
-__device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, bool active, uint32_t x, uint32_t g, uint32_t wl) {
+__device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, const BsState& bs, bool active, uint32_t x,
+                                         uint32_t g, uint32_t wl) {
   const uint32_t G = t.bs_group, cap = t.bs_cap, nwords = t.nwords;
   uint32_t* gc = sm.gc + g * 4;
   if (wl == 0) {
@@ -276,10 +282,13 @@ __device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, 
     mb = ldg16(t.bs_meta + 2 * (size_t)x + 1);
     // A: the fired neighbours of x (their mask index) and the neighbours that carry a block threshold
     const uint32_t* arow = t.adj + (size_t)x * nwords;
-    for (uint32_t w = wl; w < nwords; w += G) {
-      const uint32_t a = __ldg(arow + w);
-      uint32_t f = kCounts ? (a & sm.cf[w]) : 0u;
-      uint32_t b = a & sm.cb[w];
+    auto scan_word = [&](uint32_t w, uint32_t a) {
+      const uint32_t cfw = sm.cf[w];
+      uint32_t f = kCounts ? (a & cfw) : 0u;
+      uint32_t bsrc = sm.pbb[w];
+      if (bs.amt) bsrc |= sm.fbits[w] & ~cfw;
+      if ((bs.c_mind >> 5) == w) bsrc |= 1u << (bs.c_mind & 31);
+      uint32_t b = a & bsrc;
       if ((x >> 5) == w) f &= ~(1u << (x & 31));
       if (f | b) {
         const uint32_t pre = __ldg(t.bs_adjpre + (size_t)x * nwords + w);
@@ -293,7 +302,9 @@ __device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, 
           const uint32_t bit = (uint32_t)__ffs((int)b) - 1;
           b &= b - 1;
           const uint32_t det = w * 32 + bit;
-          const uint32_t thr = sm.st[det] & kThr;
+          uint32_t thr = sm.pst[det] & kThr;
+          if (det == bs.c_mind) thr = max(thr, bs.c_thr);
+          if (bs.amt && (((sm.fbits[w] & ~cfw) >> bit) & 1)) thr = kThr;
           if (det == x) {
             gc[2] = thr;
           } else if (thr) {
@@ -302,6 +313,17 @@ __device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, 
           }
         }
       }
+    };
+    for (uint32_t w0 = wl; w0 < nwords; w0 += 4 * G) {  // four independent loads in flight per lane
+      const uint32_t w1 = w0 + G, w2 = w0 + 2 * G, w3 = w0 + 3 * G;
+      const uint32_t a0 = __ldg(arow + w0);
+      const uint32_t a1 = w1 < nwords ? __ldg(arow + w1) : 0u;
+      const uint32_t a2 = w2 < nwords ? __ldg(arow + w2) : 0u;
+      const uint32_t a3 = w3 < nwords ? __ldg(arow + w3) : 0u;
+      if (a0) scan_word(w0, a0);
+      if (a1) scan_word(w1, a1);
+      if (a2) scan_word(w2, a2);
+      if (a3) scan_word(w3, a3);
     }
   }
   __syncwarp();
@@ -317,8 +339,7 @@ __device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, 
     if (kCounts) {
       // B: bit-sliced sum of the fired neighbours' masks
       const uint32_t* mrow = t.bs_masks + ma.x + wl;
-      for (uint32_t q = 0; q < nf; ++q) {
-        const uint32_t m = __ldg(mrow + (size_t)sm.fl[g * cap + q] * nw);
+      auto add = [&](uint32_t m) {
         const uint32_t t0 = r.c0 & m;
         r.c0 ^= m;
         const uint32_t t1 = r.c1 & t0;
@@ -326,7 +347,18 @@ __device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, 
         const uint32_t t2 = r.c2 & t1;
         r.c2 ^= t1;
         r.c3 ^= t2;
+      };
+      const uint16_t* fl = sm.fl + g * cap;
+      uint32_t q = 0;
+      for (; q + 4 <= nf; q += 4) {
+        const uint32_t m0 = __ldg(mrow + (size_t)fl[q] * nw), m1 = __ldg(mrow + (size_t)fl[q + 1] * nw);
+        const uint32_t m2 = __ldg(mrow + (size_t)fl[q + 2] * nw), m3 = __ldg(mrow + (size_t)fl[q + 3] * nw);
+        add(m0);
+        add(m1);
+        add(m2);
+        add(m3);
       }
+      for (; q < nf; ++q) add(__ldg(mrow + (size_t)fl[q] * nw));
     }
     // C: blocked entries — the row's own prefix, and per blocking neighbour a prefix of the pair list
     const uint32_t valid = len - lo >= 32 ? 0xFFFFFFFFu : ((1u << (len - lo)) - 1u);
@@ -347,7 +379,7 @@ __device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, 
 }
 
 // get_detcost (without det_penalty) of targets sm.tl[0..n) in the warp's current state -> sm.hv[0..n).
-__device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm, uint32_t n, uint32_t lane) {
+__device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm, const BsState& bs, uint32_t n, uint32_t lane) {
   const uint32_t G = t.bs_group, ng = 32 / G;
   const uint32_t g = lane / G, wl = lane % G;
   __syncwarp();
@@ -355,39 +387,42 @@ __device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm
     const uint32_t k = base + g;
     const bool active = k < n;
     const uint32_t x = active ? sm.tl[k] : 0u;
-    const BsRow r = bs_core<true>(t, sm, active, x, g, wl);
+    const BsRow r = bs_core<true>(t, sm, bs, active, x, g, wl);
     uint32_t best = kKeyInf, bcls = 0;
+    // D: within a cost class the entry with the most fired detectors has the lowest rank (rank(c, n) falls
+    // strictly with n), ties going to the lowest position; the classes then compete on (rank, position).
+    // Straight-line per class, so the lanes of a warp stay converged.
     if (r.U) {
-      // D: per count value v+1, the cheapest cost class with an unblocked entry wins (classes ascend in cost,
-      // hence in rank); classes of EQUAL rank (costs one ulp apart) compete on row position.
-      const uint32_t c0 = r.c0 & r.U, c1 = r.c1 & r.U, c2 = r.c2 & r.U, c3 = r.c3 & r.U;
-      const uint32_t vmax = c3 ? 15u : c2 ? 7u : c1 ? 3u : c0 ? 1u : 0u;
       const uint32_t* crow = t.bs_masks + r.cmask_off + wl;
-      for (uint32_t v = 0; v <= vmax; ++v) {
-        const uint32_t E = r.U & ((v & 1) ? c0 : ~c0) & ((v & 2) ? c1 : ~c1) & ((v & 4) ? c2 : ~c2) & ((v & 8) ? c3 : ~c3);
-        if (!E) continue;
-        bool found = false;
-        uint32_t rv = 0, cls_v = 0;
-        for (uint32_t kc = 0; kc < r.ncls; ++kc) {
-          uint32_t cls = 0;
-          if (found) {
-            cls = (uint32_t)__ldg(t.bs_cls_cid + r.cls_off + kc) * t.fnstride + v + 1;
-            if (sm.rank[cls] != rv) break;
-          }
-          const uint32_t cm = __ldg(crow + (size_t)kc * r.nw) & E;
-          if (!cm) continue;
-          if (!found) {
-            cls = (uint32_t)__ldg(t.bs_cls_cid + r.cls_off + kc) * t.fnstride + v + 1;
-            rv = sm.rank[cls];
-            found = true;
-          }
-          cls_v = cls;
-          const uint32_t key = (rv << 12) | (wl * 32 + (uint32_t)__ffs((int)cm) - 1);
+      const uint32_t* cid4 = reinterpret_cast<const uint32_t*>(t.bs_cls_cid + r.cls_off);  // 4 class ids per word
+      auto consider = [&](uint32_t cm, uint32_t cid) {
+        if (cm) {
+          uint32_t m = cm, q;
+          q = m & r.c3;
+          m = q ? q : m;
+          q = m & r.c2;
+          m = q ? q : m;
+          q = m & r.c1;
+          m = q ? q : m;
+          q = m & r.c0;
+          m = q ? q : m;
+          const uint32_t v = ((m & r.c3) ? 8u : 0u) | ((m & r.c2) ? 4u : 0u) | ((m & r.c1) ? 2u : 0u) | ((m & r.c0) ? 1u : 0u);
+          const uint32_t cls = cid * t.fnstride + v + 1;
+          const uint32_t key = ((uint32_t)sm.rank[cls] << 12) | (wl * 32 + (uint32_t)__ffs((int)m) - 1);
           if (key < best) {
             best = key;
-            bcls = cls_v;
+            bcls = cls;
           }
         }
+      };
+      for (uint32_t kc = 0; kc < r.ncls; kc += 4) {  // ncls is padded to a multiple of 4 with empty classes
+        const uint32_t ids = __ldg(cid4 + (kc >> 2));
+        const uint32_t m0 = __ldg(crow + (size_t)(kc + 0) * r.nw), m1 = __ldg(crow + (size_t)(kc + 1) * r.nw);
+        const uint32_t m2 = __ldg(crow + (size_t)(kc + 2) * r.nw), m3 = __ldg(crow + (size_t)(kc + 3) * r.nw);
+        consider(m0 & r.U, ids & 0xFF);
+        consider(m1 & r.U, (ids >> 8) & 0xFF);
+        consider(m2 & r.U, (ids >> 16) & 0xFF);
+        consider(m3 & r.U, ids >> 24);
       }
     }
     for (uint32_t off = G >> 1; off >= 1; off >>= 1) {
@@ -550,7 +585,7 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
                                            const uint4* vtab, Counters& ctr) {
   const DeviceTables& t = p.t;
   const Ctl& c = *sm.ctl;
-  uint16_t* st = sm.st;
+  uint16_t* st = kBits ? sm.pst : sm.st;  // kBits: the node's state, read only
   const uint32_t D = t.D, nwords = t.nwords;
   const uint32_t pos = sm.clist[j];
   const uint32_t mind = c.mind;
@@ -580,41 +615,35 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
   }
   if (status == kChildOk) {
     // The child's state: toggle the error's detectors, block the min-detector row up to this entry.
-    if (lane < deg) {
-      uint32_t nv = sj ^ kFired;
-      if (p.at_most_two && (sj & kFired)) nv = (nv & kFired) | kThr;
-      st[dj] = (uint16_t)nv;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      const uint32_t s = st[mind];
-      if ((s & kThr) < pos + 1) st[mind] = (uint16_t)((s & kFired) | (pos + 1));
-    }
     if (kBits) {
+      if (lane < deg) atomicXor(&sm.cf[dj >> 5], 1u << (dj & 31));
+    } else {
       if (lane < deg) {
-        atomicXor(&sm.cf[dj >> 5], 1u << (dj & 31));
-        if (dj == mind || (p.at_most_two && (sj & kFired))) atomicOr(&sm.cb[dj >> 5], 1u << (dj & 31));
+        uint32_t nv = sj ^ kFired;
+        if (p.at_most_two && (sj & kFired)) nv = (nv & kFired) | kThr;
+        st[dj] = (uint16_t)nv;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t s = st[mind];
+        if ((s & kThr) < pos + 1) st[mind] = (uint16_t)((s & kFired) | (pos + 1));
       }
     }
     __syncwarp();
+    BsState bs;
+    bs.c_mind = mind;
+    bs.c_thr = pos + 1;
+    bs.amt = p.at_most_two != 0;
 
     // The reference's add/sub chain, in its order (tesseract.cc:549-585).
     cost = __dadd_rn(c.cost, __ldg(t.e_cost + ei));
+    uint32_t nt = 0, nt0 = 0;  // kBits: targets collected so far; how many of them are the error's own detectors
     if (kBits) {
-      uint32_t nt = 0;
+      // targets: first the error's detectors that become fired, then (below) the fired neighbours; they are
+      // evaluated together, 32/G per warp pass, and the chain is applied afterwards in the reference's order
       const unsigned newly = ~fired_mask & ((deg >= 32) ? kFull : ((1u << deg) - 1u));
       if (lane < deg && !((fired_mask >> lane) & 1)) sm.tl[__popc(newly & ((1u << lane) - 1u))] = (uint16_t)dj;
-      nt = (uint32_t)__popc(newly);
-      bs_targets(t, sm, nt, lane);
-      uint32_t at = 0;
-      for (uint32_t k = 0; k < deg; ++k) {
-        const uint32_t d = __shfl_sync(kFull, dj, (int)k);
-        if ((fired_mask >> k) & 1) {
-          cost = __dsub_rn(cost, sm.hc[d]);
-        } else {
-          cost = __dadd_rn(cost, __dadd_rn(sm.hv[at++], p.det_penalty));
-        }
-      }
+      nt = nt0 = (uint32_t)__popc(newly);
     } else {
       for (uint32_t k = 0; k < deg; ++k) {
         const uint32_t d = __shfl_sync(kFull, dj, (int)k);
@@ -626,6 +655,28 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
         }
       }
     }
+    bool own_applied = false;
+    auto flush = [&]() {
+      bs_targets(t, sm, bs, nt, lane);
+      uint32_t at = 0;
+      if (!own_applied) {
+        for (uint32_t k = 0; k < deg; ++k) {
+          const uint32_t d = __shfl_sync(kFull, dj, (int)k);
+          if ((fired_mask >> k) & 1) {
+            cost = __dsub_rn(cost, sm.hc[d]);
+          } else {
+            cost = __dadd_rn(cost, __dadd_rn(sm.hv[at++], p.det_penalty));
+          }
+        }
+        own_applied = true;
+      }
+      for (; at < nt; ++at) {
+        cost = __dsub_rn(cost, sm.hc[sm.tl[at]]);
+        cost = __dadd_rn(cost, __dadd_rn(sm.hv[at], p.det_penalty));
+      }
+      nt = 0;
+      __syncwarp();
+    };
     // eneighbors[ei] ∩ fired: detectors adjacent to one of the error's detectors, fired in the parent
     // (hence in the child), not in the error itself; ascending.
     for (uint32_t wb = 0; wb < nwords; wb += 32) {
@@ -642,22 +693,11 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
       if (w < nwords) mine &= sm.fbits[w];
       unsigned nz = __ballot_sync(kFull, mine != 0);
       if (kBits) {
-        uint32_t nt = 0;
-        while (true) {
-          if (nz) {
-            const uint32_t l = (uint32_t)__ffs((int)nz) - 1;
-            nz &= nz - 1;
-            tl_append(sm, nt, __shfl_sync(kFull, mine, (int)l), (wb + l) * 32, lane);
-          }
-          if (nt == 0) break;
-          if (nz && nt + 32 <= kTL) continue;
-          bs_targets(t, sm, nt, lane);
-          for (uint32_t i = 0; i < nt; ++i) {
-            cost = __dsub_rn(cost, sm.hc[sm.tl[i]]);
-            cost = __dadd_rn(cost, __dadd_rn(sm.hv[i], p.det_penalty));
-          }
-          nt = 0;
-          if (!nz) break;
+        while (nz) {
+          if (nt + 32 > kTL) flush();
+          const uint32_t l = (uint32_t)__ffs((int)nz) - 1;
+          nz &= nz - 1;
+          tl_append(sm, nt, __shfl_sync(kFull, mine, (int)l), (wb + l) * 32, lane);
         }
       } else {
         while (nz) {
@@ -674,12 +714,13 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
         }
       }
     }
+    if (kBits) flush();
+    (void)nt0;
     ctr.A += deg + __ldg(t.e_nnbr + ei);
-    if (lane < deg) st[dj] = (uint16_t)sj;  // back to the parent state (the min detector is one of them)
     if (kBits) {
-      if (lane < deg) atomicXor(&sm.cf[dj >> 5], 1u << (dj & 31));
-      __syncwarp();
-      if (lane < deg) sm.cb[dj >> 5] = sm.pbb[dj >> 5];
+      if (lane < deg) atomicXor(&sm.cf[dj >> 5], 1u << (dj & 31));  // back to the node's fired set
+    } else {
+      if (lane < deg) st[dj] = (uint16_t)sj;  // back to the parent state (the min detector is one of them)
     }
     __syncwarp();
     if (cost == __longlong_as_double(0x7FF0000000000000LL)) status = kChildDropped;  // tesseract.cc:587
@@ -898,17 +939,19 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
     }
 
     // ---- phase 4 (all): private state copies; detector terms of the node ------------------------------
-    {
+    if (kBits) {
+      for (uint32_t w = lane; w < nwords; w += 32) sm.cf[w] = sm.fbits[w];
+      __syncwarp();
+    } else {
       const uint4* src = reinterpret_cast<const uint4*>(sm.pst);
       uint4* dst = reinterpret_cast<uint4*>(sm.st);
       for (uint32_t i = lane; i < dpad / 8; i += 32) dst[i] = src[i];
-      if (kBits)
-        for (uint32_t w = lane; w < nwords; w += 32) {
-          sm.cf[w] = sm.fbits[w];
-          sm.cb[w] = sm.pbb[w];
-        }
       __syncwarp();
     }
+    BsState node_state;
+    node_state.c_mind = 0xFFFFFFFFu;
+    node_state.c_thr = 0;
+    node_state.amt = false;
     if (!c.terms_cached) {
       // (the reference memoises these lazily in detector_cost_cache, tesseract.cc:531,569-582; same values)
       if (kBits) {
@@ -921,7 +964,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           }
           if (nt == 0 && w >= nwords) break;
           if (w < nwords && nt + 32 <= kTL) continue;
-          bs_targets(t, sm, nt, lane);
+          bs_targets(t, sm, node_state, nt, lane);
           if (lane < nt) sm.hc[sm.tl[lane]] = __dadd_rn(sm.hv[lane], p.det_penalty);
           for (uint32_t i = lane + 32; i < nt; i += 32) sm.hc[sm.tl[i]] = __dadd_rn(sm.hv[i], p.det_penalty);
           __syncwarp();
@@ -982,12 +1025,12 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
         best_pos = __reduce_min_sync(kFull, best_pos);
         const uint32_t mind = __ldg(order_det + best_pos);
         const uint32_t m_off = __ldg(t.row_off + mind), m_len = __ldg(t.row_off + mind + 1) - m_off;
-        const uint32_t m_thr = sm.st[mind] & kThr;
+        const uint32_t m_thr = (kBits ? sm.pst : sm.st)[mind] & kThr;
         // children: unblocked entries of row[min_detector], in row order (tesseract.cc:533-534)
         uint32_t n = 0;
         if (kBits) {
           const uint32_t G = t.bs_group;
-          const BsRow r = bs_core<false>(t, sm, lane < G, mind, lane / G, lane % G);
+          const BsRow r = bs_core<false>(t, sm, node_state, lane < G, mind, lane / G, lane % G);
           uint32_t mine = lane < G ? r.U : 0u, before = 0;
           for (uint32_t l = 0; l < G; ++l) {
             const uint32_t cnt = (uint32_t)__popc(__shfl_sync(kFull, mine, (int)l));
@@ -1104,7 +1147,6 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
   sm.st = reinterpret_cast<uint16_t*>(wbase);
   sm.pbb = reinterpret_cast<uint32_t*>(base + L.off_pbb);
   sm.cf = reinterpret_cast<uint32_t*>(wbase + L.w_cf);
-  sm.cb = reinterpret_cast<uint32_t*>(wbase + L.w_cb);
   sm.tl = reinterpret_cast<uint16_t*>(wbase + L.w_tl);
   sm.hv = reinterpret_cast<double*>(wbase + L.w_hv);
   sm.fl = reinterpret_cast<uint16_t*>(wbase + L.w_fl);
