@@ -40,7 +40,7 @@ import workloads as W  # noqa: E402
 # bivariate-bicycle [[144,12,12]] code (configs[3]); the config leaves p open — p=1e-4 is the noise level at
 # which the literal flags (unbounded beam and queue) are a million-shot workload at all.
 WORKLOADS = {
-    "bb144": dict(cfg=W.CONFIGS["C4"], shots=65536,
+    "bb144": dict(cfg=W.CONFIGS["C4"], shots=262144,
                   name="bivariate-bicycle [[144,12,12]] r=12 si1000 p=1e-4 X, --num-det-orders 24 --no-revisit-dets "
                        "(DetIndex, seed 518278944), beam/pqlimit unbounded (CLI defaults)"),
     "bb144_p5e-4": dict(cfg=dict(W.CONFIGS["C4"], dem="bb144_r12_p0.0005_X"), shots=4096,
@@ -196,7 +196,7 @@ def run_b200(args, wl, rank, world, local):
 
     def note_timing():
         t = dec.last_batch_timing()
-        chunks = (S + (1 << 16) - 1) >> 16
+        chunks = (S + (1 << 18) - 1) >> 18
         acc["search_ms"] += t["search_ms"]
         acc["pipeline_ms"] += t["pipeline_ms"]
         acc["launches"] += chunks + 2 * t["search_launches"]
@@ -265,7 +265,7 @@ def run_b200(args, wl, rank, world, local):
     peak, peak_src = measured_peak_gbs()
     alg = algorithmic_bytes(ctr1, S, D, O) * args.steps  # rank 0's launches: the same batch every step
     assert all(ctr[k] == ctr1[k] * args.steps for k in ("Q", "P", "X", "L", "V")), (ctr, ctr1)
-    n_launch = args.steps * ((S + (1 << 16) - 1) >> 16)  # tier-0 search launches (one per 65536-shot chunk)
+    n_launch = args.steps * ((S + (1 << 18) - 1) >> 18)  # tier-0 search launches (one per 262144-shot chunk)
     achieved = alg / (a["search_ms"] * 1e-3) / 1e9 if a["search_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "kernel": "tsr::search_fast_kernel" if dec.search_path.startswith("fast") else "tsr::search_kernel", "algorithmic_bytes_per_launch": alg / n_launch,

@@ -410,7 +410,7 @@ void init_device(tsr_decoder& h) {
   h.d_counters.ensure(8 * sizeof(unsigned long long));
   CUDA_OK(cudaMemsetAsync(h.d_counters.p, 0, 64, h.stream));
   CUDA_OK(cudaStreamSynchronize(h.stream));
-  h.max_batch = h.cfg.max_batch_shots ? h.cfg.max_batch_shots : (uint64_t{1} << 16);
+  h.max_batch = h.cfg.max_batch_shots ? h.cfg.max_batch_shots : (uint64_t{1} << 18);
 }
 
 void require_device(const tsr_decoder& h) {
@@ -452,6 +452,15 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
   CUDA_OK(cudaStreamSynchronize(s));
   const uint32_t stride_need =
       (uint32_t)std::min<uint64_t>(std::max<uint64_t>(T.num_errors, 1), 4ull * hs.max_fired + 32);
+  // Bound the per-chunk solution buffer (items x stride x 4 B) to 2 GiB: split the chunk when it would not fit.
+  if ((uint64_t)items * stride_need * 4 > (uint64_t{2} << 30) && shots > 1024) {
+    const uint32_t half = shots / 2;
+    const uint64_t ob = (T.num_observables + 7) / 8;
+    run_chunk(h, d_dets, stride, half, ts, d_obs, d_cost, d_low);
+    run_chunk(h, d_dets + (size_t)half * stride, stride, shots - half, ts, d_obs ? d_obs + (size_t)half * ob : nullptr,
+              d_cost ? d_cost + half : nullptr, d_low ? d_low + half : nullptr);
+    return;
+  }
   h.sol_stride = stride_need;
 
   h.d_status.ensure(items);
@@ -461,7 +470,7 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
   h.d_err_off.ensure((size_t)shots * 8);
   h.d_err_len.ensure((size_t)shots * 4);
   const uint64_t err_cap = (uint64_t)shots * h.sol_stride;
-  h.d_err.ensure(err_cap * 8);
+  if (h.collect_errors) h.d_err.ensure(err_cap * 8);
   h.d_retry.ensure((size_t)shots * 4 * 2);
 
   auto search_params = [&](const Tier& tier, const uint32_t* item_ids, uint32_t n_work) {
