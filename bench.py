@@ -173,7 +173,7 @@ def run_b200(args, wl, rank, world, local):
 
     dem, kw = W.decoder_kwargs(wl["cfg"], capi.build_det_orders)
     dec = capi.Decoder(dem, device=local, warps_per_block=args.warps, force_generic_kernel=args.scan == "generic",
-                       disable_bit_sliced_scan=args.scan == "lanes", **kw)
+                       row_scan={"lanes": 1, "bits": 2}.get(args.scan, 0), **kw)
     dec.set_collect_errors(False)
     D, O = dec.num_detectors, dec.num_observables
     S = args.shots or wl["shots"]

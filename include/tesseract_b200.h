@@ -54,7 +54,7 @@ typedef struct tsr_config {
   uint64_t node_pool_bytes;    /* HBM set aside for heaps / chains / visited sets */
   uint64_t max_batch_shots;    /* shots staged per kernel launch */
   int32_t force_generic_kernel; /* 1 = always use the event-replay kernel (search.cu), even for certified DEMs */
-  int32_t disable_bit_sliced_scan; /* 1 = certified DEMs scan rows one entry per lane instead of 32 entries per lane */
+  int32_t row_scan; /* certified DEMs: 0 = choose by DEM shape, 1 = one row entry per lane, 2 = bit-sliced (32 entries per lane) */
 } tsr_config;
 
 /* Fills the reference's C++ defaults (tesseract.h:39-58). */

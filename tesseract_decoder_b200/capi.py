@@ -48,7 +48,7 @@ class TsrConfig(C.Structure):
         ("node_pool_bytes", C.c_uint64),
         ("max_batch_shots", C.c_uint64),
         ("force_generic_kernel", C.c_int32),
-        ("disable_bit_sliced_scan", C.c_int32),
+        ("row_scan", C.c_int32),
     ]
 
 
@@ -186,7 +186,7 @@ class Decoder:
                  det_penalty: float = 0.0, det_orders=None, at_most_two_errors_per_detector: bool = False,
                  device: int = -1, host_only: bool = False, search_slots: int = 0, warps_per_block: int = 0,
                  node_pool_bytes: int = 0, max_batch_shots: int = 0, force_generic_kernel: bool = False,
-                 disable_bit_sliced_scan: bool = False):
+                 row_scan: int = 0):
         L = lib()
         cfg = TsrConfig()
         L.tsr_config_init(C.byref(cfg))
@@ -211,7 +211,7 @@ class Decoder:
         cfg.node_pool_bytes = node_pool_bytes
         cfg.max_batch_shots = max_batch_shots
         cfg.force_generic_kernel = int(force_generic_kernel)
-        cfg.disable_bit_sliced_scan = int(disable_bit_sliced_scan)
+        cfg.row_scan = int(row_scan)  # 0 auto, 1 entry per lane, 2 bit-sliced
         h = C.c_void_p()
         self.h = None
         _check(L.tsr_create(dem_text.encode(), C.byref(cfg), CREATE_HOST_ONLY if host_only else 0, C.byref(h)))

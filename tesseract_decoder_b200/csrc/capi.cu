@@ -722,9 +722,17 @@ int tsr_create(const char* dem_text, const tsr_config* cfg, uint32_t flags, tsr_
     h->n_perms = (uint32_t)perm_ids.size();
     h->F = tsr::build_fast_tables(h->T);
     h->fast = h->F.certified && !cfg->force_generic_kernel;
-    if (h->fast && !cfg->disable_bit_sliced_scan) {
-      h->B = tsr::build_bit_tables(h->T, h->F);
-      h->bits = h->B.ok;
+    if (h->fast && cfg->row_scan != 1) {
+      // Bit-sliced scans pay a fixed cost per scanned row and win when rows are long and errors touch many
+      // detectors (measured: BB [[144,12,12]] 1.7x, colour / surface codes 0.65-0.8x); sum(deg^2)/D is the
+      // entry-per-lane work per row scan.
+      double work = 0;
+      for (const auto& e : h->T.errors) work += (double)e.detectors.size() * (double)e.detectors.size();
+      work /= (double)std::max<uint64_t>(D, 1);
+      if (cfg->row_scan == 2 || work > 1200.0) {
+        h->B = tsr::build_bit_tables(h->T, h->F);
+        h->bits = h->B.ok;
+      }
     }
     if (h->F.certified && cfg->force_generic_kernel) h->F.why_not = "force_generic_kernel is set";
     h->host_only = (flags & TSR_CREATE_HOST_ONLY) != 0;

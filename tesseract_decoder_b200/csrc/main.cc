@@ -1,0 +1,304 @@
+// `tesseract` CLI over the C ABI: the decode-path flags of the reference CLI (tesseract_main.cc:350-538) with the
+// same names and defaults, the same accounting (tesseract_main.cc:592-616: a low-confidence shot is not a logical
+// error) and the same final line / --stats-out keys (tesseract_main.cc:657-699).  Shots are decoded in batches on
+// the GPU(s) instead of per-thread on the CPU; --threads is accepted and ignored, --gpus N shards batches over N
+// devices (one handle each).  stim is not available here, so --circuit goes through the built-in circuit->DEM
+// analyzer and --sample-num-shots through the i.i.d. DEM sampler; shot files are b8 or 01.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <random>
+#include <sstream>
+#include <thread>
+
+#include "decoder.h"
+
+using namespace tesseract_b200;
+
+namespace {
+
+struct Args {
+  std::string circuit_path, dem_path, in_fname, in_format = "b8", obs_in_fname, obs_in_format = "b8", out_fname,
+      out_format = "b8", stats_out_fname;
+  bool in_includes_appended_observables = false;
+  size_t num_det_orders = 1;              // tesseract_main.cc:358
+  int det_order_method = 1;               // DetIndex (tesseract_main.cc:230-237)
+  uint64_t det_order_seed = 518278944;    // tesseract_main.cc:379
+  uint64_t sample_num_shots = 0, sample_seed = std::random_device{}();
+  uint64_t max_errors = UINT64_MAX, shot_range_begin = 0, shot_range_end = 0;
+  int det_beam = INF_DET_BEAM;            // tesseract_main.cc:482
+  double det_penalty = 0;
+  bool beam_climbing = false, no_revisit_dets = false, at_most_two = false, no_merge_errors = false, verbose = false,
+       print_stats = false;
+  size_t pqlimit = std::numeric_limits<size_t>::max();  // tesseract_main.cc:503
+  int num_threads = (int)std::thread::hardware_concurrency();
+  int gpus = 1;
+  uint64_t batch = 1 << 18;
+};
+
+[[noreturn]] void usage(const std::string& why) {
+  std::cerr << why << "\n"
+            << "usage: tesseract (--dem FILE | --circuit FILE) (--sample-num-shots N [--sample-seed S] | --in FILE [--in-format b8|01]\n"
+               "       [--in-includes-appended-observables] [--obs_in FILE [--obs-in-format b8|01]]) [--out FILE [--out-format b8|01]]\n"
+               "       [--beam N] [--det-penalty X] [--beam-climbing] [--no-revisit-dets] [--at-most-two-errors-per-detector]\n"
+               "       [--pqlimit N] [--num-det-orders N] [--det-order-seed S] [--det-order-bfs|--det-order-index|--det-order-coordinate]\n"
+               "       [--no-merge-errors] [--max-errors N] [--shot-range-begin A --shot-range-end B] [--stats-out FILE] [--print-stats]\n"
+               "       [--gpus N] [--threads N (ignored)] [--verbose]\n";
+  std::exit(EXIT_FAILURE);
+}
+
+std::string read_file(const std::string& path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw std::invalid_argument("Failed to open " + path);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return ss.str();
+}
+
+// Reads shots as rows of `bits` bits into a [shots][ceil(bits/8)] b8 matrix.
+std::vector<uint8_t> read_shots(const std::string& path, const std::string& format, uint64_t bits, uint64_t& shots_out) {
+  const std::string raw = read_file(path);
+  const uint64_t nb = (bits + 7) / 8;
+  std::vector<uint8_t> out;
+  if (format == "b8") {
+    if (nb == 0 || raw.size() % nb) throw std::invalid_argument(path + ": size is not a multiple of the b8 shot size");
+    out.assign(raw.begin(), raw.end());
+    shots_out = raw.size() / nb;
+  } else if (format == "01") {
+    shots_out = 0;
+    std::istringstream ss(raw);
+    std::string line;
+    while (std::getline(ss, line)) {
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      if (line.empty()) continue;
+      if (line.size() != bits) throw std::invalid_argument(path + ": a 01 line does not have " + std::to_string(bits) + " bits");
+      out.resize(out.size() + nb, 0);
+      uint8_t* row = out.data() + out.size() - nb;
+      for (uint64_t i = 0; i < bits; ++i) {
+        if (line[i] == '1') row[i / 8] |= (uint8_t)(1u << (i % 8));
+        else if (line[i] != '0') throw std::invalid_argument(path + ": unexpected character in 01 data");
+      }
+      ++shots_out;
+    }
+  } else {
+    throw std::invalid_argument("unsupported shot format '" + format + "' (b8 and 01 are supported)");
+  }
+  return out;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Args a;
+  std::map<std::string, std::string*> str_opts = {
+      {"--circuit", &a.circuit_path}, {"--dem", &a.dem_path}, {"--in", &a.in_fname}, {"--in-format", &a.in_format},
+      {"--in_format", &a.in_format}, {"--obs_in", &a.obs_in_fname}, {"--obs-in", &a.obs_in_fname},
+      {"--obs-in-format", &a.obs_in_format}, {"--obs_in_format", &a.obs_in_format}, {"--out", &a.out_fname},
+      {"--out-format", &a.out_format}, {"--stats-out", &a.stats_out_fname}};
+  std::map<std::string, bool*> flag_opts = {
+      {"--beam-climbing", &a.beam_climbing}, {"--no-revisit-dets", &a.no_revisit_dets},
+      {"--at-most-two-errors-per-detector", &a.at_most_two}, {"--no-merge-errors", &a.no_merge_errors},
+      {"--verbose", &a.verbose}, {"--print-stats", &a.print_stats},
+      {"--in-includes-appended-observables", &a.in_includes_appended_observables},
+      {"--in_includes_appended_observables", &a.in_includes_appended_observables}};
+  try {
+    for (int i = 1; i < argc; ++i) {
+      const std::string k = argv[i];
+      auto need = [&]() -> std::string {
+        if (i + 1 >= argc) usage(k + " needs a value");
+        return argv[++i];
+      };
+      if (str_opts.count(k)) *str_opts[k] = need();
+      else if (flag_opts.count(k)) *flag_opts[k] = true;
+      else if (k == "--num-det-orders") a.num_det_orders = std::stoull(need());
+      else if (k == "--det-order-bfs") a.det_order_method = 0;
+      else if (k == "--det-order-index") a.det_order_method = 1;
+      else if (k == "--det-order-coordinate") a.det_order_method = 2;
+      else if (k == "--det-order-seed") a.det_order_seed = std::stoull(need());
+      else if (k == "--sample-num-shots") a.sample_num_shots = std::stoull(need());
+      else if (k == "--sample-seed") a.sample_seed = std::stoull(need());
+      else if (k == "--max-errors") a.max_errors = std::stoull(need());
+      else if (k == "--shot-range-begin") a.shot_range_begin = std::stoull(need());
+      else if (k == "--shot-range-end") a.shot_range_end = std::stoull(need());
+      else if (k == "--beam") a.det_beam = std::stoi(need());
+      else if (k == "--det-penalty") a.det_penalty = std::stod(need());
+      else if (k == "--pqlimit") a.pqlimit = std::stoull(need());
+      else if (k == "--threads") a.num_threads = std::stoi(need());
+      else if (k == "--gpus") a.gpus = std::stoi(need());
+      else if (k == "--batch") a.batch = std::stoull(need());
+      else if (k == "-h" || k == "--help") usage("tesseract (B200): A* most-likely-error decoder");
+      else usage("unknown argument " + k);
+    }
+    // Args::validate (tesseract_main.cc:98-180)
+    if (a.circuit_path.empty() == a.dem_path.empty()) usage("Must provide exactly one of --circuit or --dem");
+    if ((a.sample_num_shots != 0) == !a.in_fname.empty()) usage("Must provide exactly one of --sample-num-shots or --in");
+    if (a.beam_climbing && a.det_beam == INF_DET_BEAM) usage("Beam climbing requires a finite beam");
+    if (a.gpus < 1) usage("--gpus must be >= 1");
+
+    std::string dem_text;
+    if (!a.circuit_path.empty()) {
+      char* out = nullptr;
+      check(tsr_circuit_to_dem(read_file(a.circuit_path).c_str(), &out));
+      dem_text = out;
+      tsr_free(out);
+    } else {
+      dem_text = read_file(a.dem_path);
+    }
+
+    TesseractConfig config;
+    config.dem = dem_text;
+    config.det_beam = a.det_beam;
+    config.det_penalty = a.det_penalty;
+    config.beam_climbing = a.beam_climbing;
+    config.no_revisit_dets = a.no_revisit_dets;
+    config.at_most_two_errors_per_detector = a.at_most_two;
+    config.merge_errors = !a.no_merge_errors;
+    config.pqlimit = a.pqlimit;
+    config.verbose = a.verbose;
+    config.det_orders = build_det_orders(dem_text, a.num_det_orders, (DetOrder)a.det_order_method, a.det_order_seed);
+
+    std::vector<std::unique_ptr<TesseractDecoder>> decoders;
+    for (int g = 0; g < a.gpus; ++g) {
+      TesseractConfig c = config;
+      c.device = a.gpus == 1 ? -1 : g;
+      decoders.push_back(std::make_unique<TesseractDecoder>(c));
+    }
+    const uint64_t D = decoders[0]->num_detectors, O = decoders[0]->num_observables;
+    const uint64_t nb = std::max<uint64_t>((D + 7) / 8, 1), ob = (O + 7) / 8;
+
+    // Shots.
+    uint64_t shots = 0;
+    std::vector<uint8_t> dets, obs_true;
+    bool has_obs = false;
+    if (a.sample_num_shots) {
+      shots = a.sample_num_shots;
+      dets.assign((size_t)(shots * nb), 0);
+      obs_true.assign((size_t)(shots * ob) + 1, 0);
+      check(tsr_sample_dem_b8(dem_text.c_str(), a.sample_seed, shots, dets.data(), obs_true.data()));
+      has_obs = true;
+    } else {
+      if (a.in_includes_appended_observables) {
+        uint64_t n = 0;
+        std::vector<uint8_t> both = read_shots(a.in_fname, a.in_format, D + O, n);
+        const uint64_t bb = (D + O + 7) / 8;
+        shots = n;
+        dets.assign((size_t)(shots * nb), 0);
+        obs_true.assign((size_t)(shots * ob) + 1, 0);
+        for (uint64_t s = 0; s < shots; ++s)
+          for (uint64_t i = 0; i < D + O; ++i)
+            if ((both[s * bb + i / 8] >> (i % 8)) & 1) {
+              if (i < D) dets[s * nb + i / 8] |= (uint8_t)(1u << (i % 8));
+              else obs_true[s * ob + (i - D) / 8] |= (uint8_t)(1u << ((i - D) % 8));
+            }
+        has_obs = true;
+      } else {
+        dets = read_shots(a.in_fname, a.in_format, D, shots);
+        if (!a.obs_in_fname.empty()) {
+          uint64_t n = 0;
+          obs_true = read_shots(a.obs_in_fname, a.obs_in_format, O, n);
+          if (n != shots) throw std::invalid_argument("--obs_in has a different number of shots than --in");
+          obs_true.push_back(0);
+          has_obs = true;
+        }
+      }
+    }
+    // --shot-range-begin/--shot-range-end (tesseract_main.cc:307-316)
+    if (a.shot_range_begin || a.shot_range_end) {
+      if (a.shot_range_end < a.shot_range_begin || a.shot_range_end > shots) throw std::invalid_argument("Invalid shot range");
+      dets.assign(dets.begin() + (std::ptrdiff_t)(a.shot_range_begin * nb), dets.begin() + (std::ptrdiff_t)(a.shot_range_end * nb));
+      if (has_obs)
+        obs_true.assign(obs_true.begin() + (std::ptrdiff_t)(a.shot_range_begin * ob), obs_true.begin() + (std::ptrdiff_t)(a.shot_range_end * ob));
+      obs_true.push_back(0);
+      shots = a.shot_range_end - a.shot_range_begin;
+    }
+
+    std::vector<uint8_t> obs_pred((size_t)(shots * ob) + 1, 0), low(shots, 0);
+    std::vector<double> cost(shots, 0);
+    std::ofstream out_file;
+    if (!a.out_fname.empty() && a.out_fname != "-") {
+      out_file.open(a.out_fname, std::ios::binary);
+      if (!out_file) throw std::invalid_argument("Failed to open " + a.out_fname);
+    }
+    std::ostream& out = a.out_fname == "-" ? std::cout : static_cast<std::ostream&>(out_file);
+
+    uint64_t num_errors = 0, num_low_confidence = 0, done = 0;
+    double total_time_seconds = 0;
+    // Batches in shot order (so --max-errors stops where the reference's in-order consumer would, up to a batch);
+    // each batch is split over the GPUs.
+    for (uint64_t at = 0; at < shots && num_errors < a.max_errors; at += a.batch) {
+      const uint64_t n = std::min<uint64_t>(a.batch, shots - at);
+      const auto t0 = std::chrono::steady_clock::now();
+      std::vector<std::thread> workers;
+      std::vector<std::string> errors((size_t)a.gpus);
+      for (int g = 0; g < a.gpus; ++g) {
+        const uint64_t b = at + n * (uint64_t)g / (uint64_t)a.gpus, e = at + n * (uint64_t)(g + 1) / (uint64_t)a.gpus;
+        workers.emplace_back([&, g, b, e] {
+          try {
+            decoders[(size_t)g]->decode_batch_b8(dets.data() + b * nb, nb, e - b, obs_pred.data() + b * ob, cost.data() + b, low.data() + b);
+          } catch (const std::exception& ex) {
+            errors[(size_t)g] = ex.what();
+          }
+        });
+      }
+      for (auto& w : workers) w.join();
+      for (const auto& e : errors)
+        if (!e.empty()) throw std::runtime_error(e);
+      total_time_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      for (uint64_t s = at; s < at + n; ++s) {  // consume(shot), tesseract_main.cc:592-616
+        if (!a.out_fname.empty()) {
+          if (a.out_format == "b8") {
+            out.write(reinterpret_cast<const char*>(obs_pred.data() + s * ob), (std::streamsize)ob);
+          } else if (a.out_format == "01") {
+            for (uint64_t o = 0; o < O; ++o) out.put(((obs_pred[s * ob + o / 8] >> (o % 8)) & 1) ? '1' : '0');
+            out.put('\n');
+          } else {
+            throw std::invalid_argument("unsupported --out-format '" + a.out_format + "'");
+          }
+        }
+        if (low[s]) ++num_low_confidence;
+        else if (has_obs && std::memcmp(obs_pred.data() + s * ob, obs_true.data() + s * ob, (size_t)ob) != 0) ++num_errors;
+        ++done;
+        if (a.print_stats) {
+          std::cout << "num_shots = " << done << " num_low_confidence = " << num_low_confidence;
+          if (has_obs) std::cout << " num_errors = " << num_errors;
+          std::cout << " total_time_seconds = " << total_time_seconds << std::endl;
+          std::cout << "cost = " << cost[s] << std::endl;
+        }
+        if (has_obs && num_errors >= a.max_errors) break;
+      }
+    }
+
+    bool print_final_stats = true;
+    if (!a.stats_out_fname.empty()) {  // tesseract_main.cc:657-690
+      std::ostringstream js;
+      auto q = [](const std::string& s) { return "\"" + s + "\""; };
+      js << "{\"circuit_path\":" << q(a.circuit_path) << ",\"dem_path\":" << q(a.dem_path) << ",\"max_errors\":" << a.max_errors
+         << ",\"sample_seed\":" << a.sample_seed << ",\"det_beam\":" << a.det_beam << ",\"det_penalty\":" << a.det_penalty
+         << ",\"beam_climbing\":" << (a.beam_climbing ? "true" : "false") << ",\"no_revisit_dets\":" << (a.no_revisit_dets ? "true" : "false")
+         << ",\"at_most_two_errors_per_detector\":" << (a.at_most_two ? "true" : "false") << ",\"pqlimit\":" << a.pqlimit
+         << ",\"num_det_orders\":" << a.num_det_orders << ",\"det_order_seed\":" << a.det_order_seed
+         << ",\"total_time_seconds\":" << total_time_seconds << ",\"num_errors\":" << (has_obs ? std::to_string(num_errors) : "null")
+         << ",\"num_low_confidence\":" << num_low_confidence << ",\"num_shots\":" << done << ",\"num_threads\":" << a.num_threads
+         << ",\"num_gpus\":" << a.gpus << ",\"sample_num_shots\":" << a.sample_num_shots << "}";
+      if (a.stats_out_fname == "-") {
+        std::cout << js.str() << std::endl;
+        print_final_stats = false;
+      } else {
+        std::ofstream f(a.stats_out_fname);
+        f << js.str() << std::endl;
+      }
+    }
+    if (print_final_stats) {  // tesseract_main.cc:691-699
+      std::cout << "num_shots = " << done << " num_low_confidence = " << num_low_confidence;
+      if (has_obs) std::cout << " num_errors = " << num_errors;
+      std::cout << " total_time_seconds = " << total_time_seconds << std::endl;
+    }
+  } catch (const std::exception& e) {
+    std::cerr << "tesseract: " << e.what() << std::endl;
+    return EXIT_FAILURE;
+  }
+  return EXIT_SUCCESS;
+}

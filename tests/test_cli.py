@@ -1,0 +1,66 @@
+"""The `tesseract` CLI (csrc/main.cc): the reference CLI's decode flags, validation and accounting
+(tesseract_main.cc:98-180, 350-538, 592-616, 657-699)."""
+import gzip
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import workloads as W
+from tesseract_decoder_b200 import capi
+
+CLI = os.path.join(W.ROOT, "tesseract_decoder_b200", "tesseract")
+
+
+def run(*args):
+    return subprocess.run([CLI, *map(str, args)], capture_output=True, text=True, timeout=600)
+
+
+def test_argument_validation():
+    assert os.path.exists(CLI), "build the CLI with `make -C tesseract_decoder_b200/csrc cli`"
+    r = run("--sample-num-shots", 5)
+    assert r.returncode != 0 and "exactly one of --circuit or --dem" in r.stderr
+    r = run("--dem", "x.dem")
+    assert r.returncode != 0 and "exactly one of --sample-num-shots or --in" in r.stderr
+    r = run("--dem", "x.dem", "--sample-num-shots", 5, "--beam-climbing")  # tesseract_main.cc:151-153
+    assert r.returncode != 0 and "Beam climbing requires a finite beam" in r.stderr
+    r = run("--dem", "x.dem", "--sample-num-shots", 5, "--bogus")
+    assert r.returncode != 0 and "unknown argument" in r.stderr
+    r = run("--dem", "/nonexistent.dem", "--sample-num-shots", 5)
+    assert r.returncode != 0 and "Failed to open" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_matches_the_library(tmp_path):
+    dem = W.load_dem("surface_d5_r5_p0.002_X")
+    (tmp_path / "m.dem").write_text(dem)
+    # sampled shots: counts equal the library's on the same sampler seed
+    r = run("--dem", tmp_path / "m.dem", "--sample-num-shots", 3000, "--sample-seed", 7, "--beam", 5, "--pqlimit", 200000,
+            "--stats-out", tmp_path / "stats.json")
+    assert r.returncode == 0, r.stderr
+    dec = capi.Decoder(dem, det_beam=5, pqlimit=200000, no_revisit_dets=False, det_orders=capi.build_det_orders(dem, 1, 1, W.CLI_ORDER_SEED))
+    dets, obs = capi.sample_dem_b8(dem, 7, 3000, 120, 1)
+    out = dec.decode_batch_b8(dets)
+    wrong = int(((out["obs"] != obs).any(axis=1) & (out["low_confidence"] == 0)).sum())
+    low = int(out["low_confidence"].sum())
+    assert r.stdout.startswith(f"num_shots = 3000 num_low_confidence = {low} num_errors = {wrong} total_time_seconds = ")
+    stats = json.loads((tmp_path / "stats.json").read_text())
+    assert (stats["num_shots"], stats["num_errors"], stats["num_low_confidence"], stats["det_beam"], stats["pqlimit"]) == \
+        (3000, wrong, low, 5, 200000)
+    # shots from files, predictions to a file, in both formats
+    dets.tofile(tmp_path / "dets.b8")
+    obs.tofile(tmp_path / "obs.b8")
+    r = run("--dem", tmp_path / "m.dem", "--in", tmp_path / "dets.b8", "--obs_in", tmp_path / "obs.b8", "--beam", 5,
+            "--pqlimit", 200000, "--out", tmp_path / "pred.01", "--out-format", "01", "--shot-range-begin", 100, "--shot-range-end", 600)
+    assert r.returncode == 0, r.stderr
+    lines = (tmp_path / "pred.01").read_text().split()
+    assert len(lines) == 500 and [int(x) for x in lines] == out["obs"][100:600, 0].tolist()
+    bits01 = "\n".join("".join(str(b) for b in row) for row in np.unpackbits(dets[:50], axis=1, bitorder="little")[:, :120]) + "\n"
+    (tmp_path / "dets.01").write_text(bits01)
+    r = run("--dem", tmp_path / "m.dem", "--in", tmp_path / "dets.01", "--in-format", "01", "--beam", 5, "--pqlimit", 200000,
+            "--out", tmp_path / "pred.b8")
+    assert r.returncode == 0, r.stderr
+    assert np.fromfile(tmp_path / "pred.b8", dtype=np.uint8).tolist() == out["obs"][:50, 0].tolist()
+    assert "num_errors" not in r.stdout  # no observables given (tesseract_main.cc:693-695)

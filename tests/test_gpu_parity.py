@@ -76,7 +76,7 @@ def test_golden_vectors(name, path):
     reproduce the reference build's outputs."""
     g = W.load_golden(name)
     dem, kw = W.decoder_kwargs(g["config"], capi.build_det_orders)
-    dec = capi.Decoder(dem, force_generic_kernel=(path == "generic"), disable_bit_sliced_scan=(path == "fast"), **kw)
+    dec = capi.Decoder(dem, force_generic_kernel=(path == "generic"), row_scan={"fast": 1, "fast-bits": 2}.get(path, 0), **kw)
     assert dec.search_path == path, dec.search_path_reason
     out = dec.decode_batch_b8(g["dets"])
     assert_same(out, g)
@@ -234,8 +234,10 @@ def test_fresh_shots_against_the_cpu_checker(case):
     check_solutions_are_consistent(dec, dets, out)
     if case % 2 == 0:  # the generic kernel, on the same shots
         assert_same(capi.Decoder(dem, force_generic_kernel=True, **kw).decode_batch_b8(dets), ref)
-    else:  # the entry-per-lane scan of the fast kernel (the default is the bit-sliced scan)
-        assert_same(capi.Decoder(dem, disable_bit_sliced_scan=True, **kw).decode_batch_b8(dets), ref)
+    else:  # the other row-scan variant of the fast kernel
+        other = capi.Decoder(dem, row_scan=1 if dec.search_path == "fast-bits" else 2, **kw)
+        assert other.search_path != dec.search_path
+        assert_same(other.decode_batch_b8(dets), ref)
     if oracle.available("port") and shots <= 1000:
         # The search itself is the same search: pushes, pops, expansions, chain steps and visited probes
         # agree exactly with the instrumented CPU port.  Scanned heuristic entries (S) only

@@ -167,8 +167,11 @@ def test_fast_path_certificate():
     obligations or packing limits fall back to the generic CUDA kernel with a stated reason."""
     for name in ["surface_d5_r5_p0.002_X", "bb72_r6_p0.001_X", "color_superdense_d5_r5_p0.001_Z", "transcx_d3_p0.001_X"]:
         dec = capi.Decoder(W.load_dem(name), host_only=True)
-        assert dec.search_path == "fast-bits" and dec.search_path_reason == ""
-        assert capi.Decoder(W.load_dem(name), host_only=True, disable_bit_sliced_scan=True).search_path == "fast"
+        assert dec.search_path.startswith("fast") and dec.search_path_reason == ""
+        assert capi.Decoder(W.load_dem(name), host_only=True, row_scan=1).search_path == "fast"
+        assert capi.Decoder(W.load_dem(name), host_only=True, row_scan=2).search_path == "fast-bits"
+    assert capi.Decoder(W.load_dem("bb72_r6_p0.001_X"), host_only=True).search_path == "fast-bits"  # long rows, degree 9
+    assert capi.Decoder(W.load_dem("surface_d5_r5_p0.002_X"), host_only=True).search_path == "fast"
     assert capi.Decoder(W.load_dem("bb72_r6_p0.001_X"), host_only=True, force_generic_kernel=True).search_path == "generic"
     # p > 0.5 gives a negative cost: the sorted-row / early-exit argument does not hold
     dec = capi.Decoder("error(0.7) D0 D1\nerror(0.1) D0\nerror(0.1) D1", host_only=True)
