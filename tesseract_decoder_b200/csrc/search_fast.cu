@@ -51,6 +51,7 @@ struct alignas(16) Ctl {
   uint4 key, root_key;
   // expansion
   uint32_t mind, m_off, m_len, nchild;
+  uint32_t next_child;  // children are claimed one at a time by the warps
   // control
   int action;
   uint32_t status;
@@ -1053,6 +1054,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           c.m_off = m_off;
           c.m_len = m_len;
           c.nchild = n;
+          c.next_child = 0;
         }
       }
       if (lane == 0) {
@@ -1068,7 +1070,13 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
     }
 
     // ---- phase 6 (all warps): the children, round-robin ----------------------------------------------------
-    for (uint32_t j = warp; j < c.nchild; j += nwarps) eval_child<kInstr, kBits>(p, sm, j, lane, vtab, ctr);
+    while (true) {
+      uint32_t j = 0;
+      if (lane == 0) j = atomicAdd(&c.next_child, 1u);
+      j = __shfl_sync(kFull, j, 0);
+      if (j >= c.nchild) break;
+      eval_child<kInstr, kBits>(p, sm, j, lane, vtab, ctr);
+    }
     __syncthreads();
 
     // ---- phase 7 (warp 0): pushes, in row order (tesseract.cc:590-605) ----------------------------------------
@@ -1077,35 +1085,87 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       uint32_t status = kItemOk;
       unsigned long long heap_size = c.heap_size, chain_size = c.chain_size, pushed = c.pushed;
       const uint32_t n = c.nchild;
-      for (uint32_t j = 0; j < n; ++j) {
-        const uint4 meta = sm.res_meta[j];
-        if (meta.w != kChildOk) continue;
+      // Windows of 32 children.  A push whose value is not smaller than its heap parent leaves the rest of the
+      // heap alone, so the leading run of such pushes in a window commits in ONE memory round trip (each lane
+      // checks its own parent); the first push that has to sift is replayed with the warp-wide sift, and the
+      // window restarts behind it.  Same heap contents as one-at-a-time std::push_heap.
+      uint32_t j0 = 0;
+      while (j0 < n) {
+        const uint32_t idx = j0 + lane;
+        uint4 meta = make_uint4(0, 0, 0, kChildDropped);
+        if (idx < n) meta = sm.res_meta[idx];
+        const bool ok = meta.w == kChildOk;
+        const unsigned okmask = __ballot_sync(kFull, ok);
+        const uint32_t cnt = (uint32_t)__popc(okmask);
+        if (cnt == 0) {
+          j0 += 32;
+          continue;
+        }
         if (c.depth == 0xFFFF) {
           action = kActDone;
           status = kItemSolutionOverflow;
           break;
         }
-        if (heap_size >= p.node_cap || chain_size >= p.node_cap || chain_size >= 0xFFFFFFFEull) {
+        if (pushed + cnt > p.pqlimit) {  // the limit falls inside this window (tesseract.cc:599-605): nothing
+          action = kActDone;             // pushed before it is observable once the search is abandoned
+          status = kItemLowConfidence;
+          ctr.Q += p.pqlimit + 1 - pushed;
+          break;
+        }
+        if (heap_size + cnt > p.node_cap || chain_size + cnt > p.node_cap || chain_size + cnt >= 0xFFFFFFFEull) {
           action = kActDone;
           status = kItemNodeOverflow;
           break;
         }
-        if (lane == 0)
-          __stcg(reinterpret_cast<uint4*>(chain + chain_size), make_uint4(meta.x, c.chain, (c.mind << 16) | (meta.z >> 16), meta.y));
+        const uint32_t rank = (uint32_t)__popc(okmask & ((1u << lane) - 1u));
         HeapNode hn;
-        hn.cost = sm.res_cost[j];
-        hn.chain = (uint32_t)chain_size;
+        hn.cost = idx < n ? sm.res_cost[idx] : 0.0;
+        hn.chain = (uint32_t)(chain_size + rank);
         hn.num_dets = (uint16_t)(meta.z & 0xFFFF);
         hn.depth = (uint16_t)(c.depth + 1);
-        heap_push_warp(heap, heap_size, hn, lane);
-        ++heap_size;
-        ++chain_size;
-        ++pushed;
-        ++ctr.Q;
+        bool sift = false;
+        if (ok) {
+          __stcg(reinterpret_cast<uint4*>(chain + chain_size + rank), make_uint4(meta.x, c.chain, (c.mind << 16) | (meta.z >> 16), meta.y));
+          const unsigned long long leaf1 = heap_size + rank + 1;  // 1-based
+          if (leaf1 > 1) {
+            const unsigned long long parent1 = leaf1 >> 1;
+            sift = parent1 > heap_size || node_greater(heap_ld(heap + (parent1 - 1)), hn);
+          }
+        }
+        const unsigned siftmask = __ballot_sync(kFull, sift);
+        const uint32_t first = siftmask ? (uint32_t)__ffs((int)siftmask) - 1 : 32u;
+        if (ok && lane < first) heap_st(heap + heap_size + rank, hn);
+        const uint32_t committed = (uint32_t)__popc(okmask & (first >= 32 ? kFull : ((1u << first) - 1u)));
+        heap_size += committed;
+        chain_size += committed;
+        pushed += committed;
+        ctr.Q += committed;
+        __syncwarp();
         if (pushed > p.pqlimit) {  // tesseract.cc:599-605
           action = kActDone;
           status = kItemLowConfidence;
           break;
+        }
+        if (first < 32) {
+          HeapNode hb;
+          hb.cost = __shfl_sync(kFull, hn.cost, (int)first);
+          hb.chain = __shfl_sync(kFull, hn.chain, (int)first);
+          const uint32_t packed = __shfl_sync(kFull, (uint32_t)hn.num_dets | ((uint32_t)hn.depth << 16), (int)first);
+          hb.num_dets = (uint16_t)(packed & 0xFFFF);
+          hb.depth = (uint16_t)(packed >> 16);
+          heap_push_warp(heap, heap_size, hb, lane);
+          ++heap_size;
+          ++chain_size;
+          ++pushed;
+          ++ctr.Q;
+          if (pushed > p.pqlimit) {
+            action = kActDone;
+            status = kItemLowConfidence;
+            break;
+          }
+          j0 += first + 1;
+        } else {
+          j0 += 32;
         }
       }
       __syncwarp();
