@@ -78,6 +78,9 @@ struct Smem {
   uint16_t* fl;      // [groups][cap] fired-neighbour indices of each group's target
   uint32_t* bl;      // [groups][cap] blocking neighbours: index | threshold << 16
   uint32_t* gc;      // [groups][4] list lengths and the target's own threshold
+  // push staging (phase 7): the other warps' regions, idle while warp 0 pushes
+  uint4* stage;
+  uint32_t stage_cap;  // in 16-byte nodes
 };
 
 constexpr uint32_t kTL = 64;  // targets evaluated per flush
@@ -1085,11 +1088,105 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       uint32_t status = kItemOk;
       unsigned long long heap_size = c.heap_size, chain_size = c.chain_size, pushed = c.pushed;
       const uint32_t n = c.nchild;
-      // Windows of 32 children.  A push whose value is not smaller than its heap parent leaves the rest of the
-      // heap alone, so the leading run of such pushes in a window commits in ONE memory round trip (each lane
-      // checks its own parent); the first push that has to sift is replayed with the warp-wide sift, and the
-      // window restarts behind it.  Same heap contents as one-at-a-time std::push_heap.
-      uint32_t j0 = 0;
+      // Staged pushes: the heap nodes K consecutive pushes can touch are the ancestors of leaves [size, size+K),
+      // one contiguous index range per level.  They are copied to shared memory (the other warps' scratch, idle
+      // in this phase) in one round trip, the K std::push_heap sifts run there (warp-wide: lane s-1 holds the
+      // ancestor s levels up), and the ranges are written back.  Needs size >= K so that the ranges of
+      // different levels are disjoint; otherwise the windowed path below pushes straight to global memory.
+      uint32_t K = 0;
+      for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+        const uint32_t idx = b0 + lane;
+        const bool ok = idx < n && sm.res_meta[idx].w == kChildOk;
+        const unsigned m = __ballot_sync(kFull, ok);
+        if (ok) sm.clist[K + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
+        K += (uint32_t)__popc(m);
+      }
+      __syncwarp();
+      uint32_t i0 = 0;  // children (of the compact list) pushed so far
+      if (K >= 96 && c.depth != 0xFFFF && pushed + K <= p.pqlimit && heap_size + K <= p.node_cap && chain_size + K <= p.node_cap &&
+          chain_size + K < 0xFFFFFFFEull) {
+        for (uint32_t i = lane; i < K; i += 32) {  // chain nodes
+          const uint4 meta = sm.res_meta[sm.clist[i]];
+          __stcg(reinterpret_cast<uint4*>(chain + chain_size + i), make_uint4(meta.x, c.chain, (c.mind << 16) | (meta.z >> 16), meta.y));
+        }
+        while (i0 < K) {
+          // one sub-batch = new leaves on ONE tree level, so that "s levels up" names a distinct level for every s
+          const unsigned long long lo1 = heap_size + 1;  // 1-based index of the first new leaf
+          const uint32_t lvl = 63u - (uint32_t)__clzll((long long)lo1);
+          const unsigned long long level_end1 = (2ull << lvl) - 1;
+          const uint32_t Kb = (uint32_t)min((unsigned long long)(K - i0), level_end1 - lo1 + 1);
+          const unsigned long long hi1 = lo1 + Kb - 1;
+          uint32_t lo_s = 0, width_s = 0;  // this lane's level: s = lane + 1 levels above the leaves
+          if (lane + 1 <= lvl) {
+            lo_s = (uint32_t)(lo1 >> (lane + 1));
+            width_s = (uint32_t)(hi1 >> (lane + 1)) - lo_s + 1;
+          }
+          uint32_t incl = width_s;
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFull, incl, o);
+            if ((int)lane >= o) incl += v;
+          }
+          const uint32_t off_s = Kb + incl - width_s;
+          if (Kb + __shfl_sync(kFull, incl, 31) > sm.stage_cap) break;  // does not fit: windowed path for the rest
+          for (uint32_t sft = 0; sft < lvl && sft < 32; ++sft) {  // load the ancestor ranges
+            const uint32_t w_ = __shfl_sync(kFull, width_s, (int)sft);
+            const uint32_t lo_ = __shfl_sync(kFull, lo_s, (int)sft), off_ = __shfl_sync(kFull, off_s, (int)sft);
+            for (uint32_t q = lane; q < w_; q += 32) sm.stage[off_ + q] = __ldcg(reinterpret_cast<const uint4*>(heap + (lo_ - 1 + q)));
+          }
+          __syncwarp();
+          for (uint32_t i = 0; i < Kb; ++i) {
+            const uint32_t ci = sm.clist[i0 + i];
+            const uint4 meta = sm.res_meta[ci];
+            HeapNode value;
+            value.cost = sm.res_cost[ci];
+            value.chain = (uint32_t)(chain_size + i);
+            value.num_dets = (uint16_t)(meta.z & 0xFFFF);
+            value.depth = (uint16_t)(c.depth + 1);
+            const bool valid = lane + 1 <= lvl;
+            const uint32_t slot = valid ? off_s + (uint32_t)((lo1 + i) >> (lane + 1)) - lo_s : 0u;
+            uint4 pv = make_uint4(0, 0, 0, 0);
+            if (valid) pv = sm.stage[slot];
+            HeapNode pn;
+            pn.cost = __hiloint2double((int)pv.y, (int)pv.x);
+            pn.chain = pv.z;
+            pn.num_dets = (uint16_t)(pv.w & 0xFFFF);
+            pn.depth = (uint16_t)(pv.w >> 16);
+            const bool up = valid && node_greater(pn, value);
+            const unsigned not_up = ~__ballot_sync(kFull, up);
+            const uint32_t stop = not_up ? (uint32_t)__ffs((int)not_up) - 1 : 32u;
+            uint32_t below = __shfl_up_sync(kFull, slot, 1);  // slot one level closer to the leaf
+            if (lane == 0) below = i;
+            if (lane < stop) sm.stage[below] = pv;
+            const uint32_t vslot = stop == 0 ? i : __shfl_sync(kFull, slot, (int)stop - 1);
+            if (lane == 0) {
+              uint4 vv;
+              vv.x = (uint32_t)__double2loint(value.cost);
+              vv.y = (uint32_t)__double2hiint(value.cost);
+              vv.z = value.chain;
+              vv.w = (uint32_t)value.num_dets | ((uint32_t)value.depth << 16);
+              sm.stage[vslot] = vv;
+            }
+            __syncwarp();
+          }
+          for (uint32_t i = lane; i < Kb; i += 32) __stcg(reinterpret_cast<uint4*>(heap + heap_size + i), sm.stage[i]);
+          for (uint32_t sft = 0; sft < lvl && sft < 32; ++sft) {  // write the ancestor ranges back
+            const uint32_t w_ = __shfl_sync(kFull, width_s, (int)sft);
+            const uint32_t lo_ = __shfl_sync(kFull, lo_s, (int)sft), off_ = __shfl_sync(kFull, off_s, (int)sft);
+            for (uint32_t q = lane; q < w_; q += 32) __stcg(reinterpret_cast<uint4*>(heap + (lo_ - 1 + q)), sm.stage[off_ + q]);
+          }
+          __syncwarp();
+          heap_size += Kb;
+          chain_size += Kb;
+          pushed += Kb;
+          ctr.Q += Kb;
+          i0 += Kb;
+        }
+      }
+      // Otherwise: windows of 32 children.  A push whose value is not smaller than its heap parent leaves the rest
+      // of the heap alone, so the leading run of such pushes in a window commits in one round trip (each lane
+      // checks its own parent); the first push that has to sift is replayed with the warp-wide sift and the
+      // window restarts behind it.
+      uint32_t j0 = i0 >= K ? n : sm.clist[i0];
       while (j0 < n) {
         const uint32_t idx = j0 + lane;
         uint4 meta = make_uint4(0, 0, 0, kChildDropped);
@@ -1212,6 +1309,8 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
   sm.fl = reinterpret_cast<uint16_t*>(wbase + L.w_fl);
   sm.bl = reinterpret_cast<uint32_t*>(wbase + L.w_bl);
   sm.gc = reinterpret_cast<uint32_t*>(wbase + L.w_gc);
+  sm.stage = reinterpret_cast<uint4*>(base + L.off_st + L.warp_stride);
+  sm.stage_cap = (nwarps - 1) * (L.warp_stride / 16);
   for (uint32_t i = tid; i < rank_entries; i += blockDim.x) sm.rank[i] = __ldg(p.t.frank + i);
   __syncthreads();
 
