@@ -275,7 +275,9 @@ def run_b200(args, wl, rank, world, local):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(args.workload)
+            per_shot = json.load(open(prof)).get(args.workload, {}).get("dram_bytes_per_shot")
+            if per_shot:
+                roofline["traffic"] = per_shot * min(S, 1 << 18)  # DRAM bytes per launch, from the committed ncu capture
         except Exception:
             pass
 
