@@ -255,6 +255,28 @@ def test_fresh_shots_against_the_cpu_checker(case):
             assert abs(gc["S"] - pc["S"]) <= 0.15 * pc["S"], (gc, pc)
 
 
+def test_uncertified_dems_take_the_generic_kernel_and_still_match():
+    """DEMs outside the fast path's certificate (csrc/fast.h) — p > 0.5 (negative costs), more than 128 distinct
+    costs, an error on more than 11 detectors — are decoded by the event-replay kernel, with the same answers as
+    the CPU checker."""
+    rng = np.random.default_rng(5)
+    ring = "\n".join(f"error({0.01 + 0.002 * i}) D{i} D{(i + 1) % 150}" for i in range(150)) + "\n" + \
+           "\n".join(f"error({0.02 + 0.001 * i}) D{i} L{i % 3}" for i in range(150))
+    wide = "error(0.01) " + " ".join(f"D{i}" for i in range(13)) + " L0\n" + "\n".join(f"error(0.03) D{i} D{i + 1}" for i in range(13)) + \
+           "\nerror(0.02) D0\nerror(0.02) D13 L1"
+    neg = "error(0.7) D0 D1 L0\nerror(0.1) D0\nerror(0.1) D1\nerror(0.6) D1 D2\nerror(0.2) D2 L1"
+    for dem, shots in ((ring, 400), (wide, 200), (neg, 8)):
+        dec = capi.Decoder(dem, det_beam=W.INF_BEAM, pqlimit=100000)
+        assert dec.search_path == "generic" and dec.search_path_reason
+        D = dec.num_detectors
+        bits = (rng.random((shots, D)) < 0.06).astype(np.uint8)
+        if shots == 8:
+            bits = ((np.arange(8)[:, None] >> np.arange(D)[None, :]) & 1).astype(np.uint8)
+        dets = np.packbits(bits, axis=1, bitorder="little")
+        ref = OracleDecoder(dem, det_beam=W.INF_BEAM, pqlimit=100000, kind=KIND, num_threads=4).decode_batch_b8(dets)
+        assert_same(dec.decode_batch_b8(dets), ref)
+
+
 # ---- invariances at larger sizes --------------------------------------------------------------------
 
 def test_results_do_not_depend_on_batching_slots_or_pool_tiers():
