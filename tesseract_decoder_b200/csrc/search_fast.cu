@@ -52,6 +52,11 @@ struct alignas(16) Ctl {
   // expansion
   uint32_t mind, m_off, m_len, nchild;
   uint32_t next_child;  // children are claimed one at a time by the warps
+  // which node's state pst / fbits / pbb / key currently hold, and how phase 2 gets to the popped node's
+  uint32_t state_chain, state_depth;
+  int state_valid;
+  int rebuild;     // 0 = from the root along the chain, 1 = one step from state_chain, 2 = already there
+  uint4 last_raw;  // the popped node's chain entry (rebuild == 1)
   // control
   int action;
   uint32_t status;
@@ -780,6 +785,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       c.min_dets = root_dets;
       c.max_dets = root_dets + beam;
       c.root_pending = 1;
+      c.state_valid = 0;
       c.heap_size = c.chain_size = c.pushed = c.n_visited = 0;
     }
   }
@@ -801,6 +807,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           c.num_dets = c.root_dets;
           c.depth = 0;
           c.terms_cached = 0;
+          c.rebuild = 0;
         }
       } else if (heap_size0 == 0) {
         action = kActDone;
@@ -823,6 +830,18 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           c.num_dets = node.num_dets;
           c.depth = node.depth;
           c.terms_cached = node.chain == kNoChain;  // the root's detector terms are still in hc
+          // Most pops continue from the node expanded last (a descent): one chain step instead of a walk.
+          int mode = 0;
+          if (c.state_valid && node.chain == c.state_chain) {
+            mode = 2;
+          } else if (c.state_valid && node.chain != kNoChain && nd <= max_dets0 && node.depth == c.state_depth + 1) {
+            const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(chain + node.chain));
+            if (raw.y == c.state_chain) {
+              mode = 1;
+              c.last_raw = raw;
+            }
+          }
+          c.rebuild = mode;
         }
         if (nd > max_dets0) action = kActSkip;  // tesseract.cc:434
       }
@@ -839,20 +858,22 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
     }
 
     // ---- phase 2 (all): the node's state from its chain (tesseract.cc:349-369) ------------------------
-    for (uint32_t i = tid; i < dpad / 2; i += nthr) reinterpret_cast<uint32_t*>(sm.pst)[i] = 0;
-    for (uint32_t w = tid; w < nwords; w += nthr) {
-      sm.fbits[w] = sm.rbits[w];
-      if (kBits) sm.pbb[w] = 0;
+    const int rebuild = c.rebuild;
+    if (rebuild == 0) {
+      for (uint32_t i = tid; i < dpad / 2; i += nthr) reinterpret_cast<uint32_t*>(sm.pst)[i] = 0;
+      for (uint32_t w = tid; w < nwords; w += nthr) {
+        sm.fbits[w] = sm.rbits[w];
+        if (kBits) sm.pbb[w] = 0;
+      }
+      __syncthreads();
+      for (uint32_t w = tid; w < nwords; w += nthr)
+        for (uint32_t m = sm.rbits[w]; m; m &= m - 1) sm.pst[w * 32 + (uint32_t)__ffs((int)m) - 1] = (uint16_t)kFired;
+      __syncthreads();
     }
-    __syncthreads();
-    for (uint32_t w = tid; w < nwords; w += nthr)
-      for (uint32_t m = sm.rbits[w]; m; m &= m - 1) sm.pst[w * 32 + (uint32_t)__ffs((int)m) - 1] = (uint16_t)kFired;
-    __syncthreads();
     if (warp == 0) {
       uint4 key = make_uint4(0, 0, 0, 0);
-      for (uint32_t at = c.chain; at != kNoChain;) {
-        const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(chain + at));
-        const uint32_t err = raw.x, parent = raw.y, mind_pos = raw.z, off_mask = raw.w;
+      auto apply = [&](const uint4& raw) {  // one chain entry: flip the error's detectors, block its row prefix
+        const uint32_t err = raw.x, mind_pos = raw.z, off_mask = raw.w;
         const uint32_t eb = __ldg(t.e_off + err), deg = __ldg(t.e_off + err + 1) - eb;
         uint32_t dj = 0;
         if (lane < deg) {
@@ -874,11 +895,26 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           if (kBits) sm.pbb[md >> 5] |= 1u << (md & 31);
         }
         __syncwarp();
-        at = parent;
-        ++ctr.L;
+      };
+      if (rebuild == 0) {
+        for (uint32_t at = c.chain; at != kNoChain;) {
+          const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(chain + at));
+          apply(raw);
+          at = raw.y;
+        }
+        key = warp_xor(key);
+        key_xor(key, c.root_key);
+      } else {
+        if (rebuild == 1) apply(c.last_raw);
+        key = warp_xor(key);
+        key_xor(key, c.key);  // the key of the state this step started from
       }
-      key = warp_xor(key);
-      key_xor(key, c.root_key);
+      ctr.L += c.depth;  // the reference walks the whole chain at every pop
+      if (lane == 0) {
+        c.state_chain = c.chain;
+        c.state_depth = c.depth;
+        c.state_valid = 1;
+      }
 
       // ---- phase 3 (warp 0): goal, visited, beam window ------------------------------------------------
       int action = kActExpand;
@@ -1103,7 +1139,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
       __syncwarp();
       uint32_t i0 = 0;  // children (of the compact list) pushed so far
-      if (K >= 96 && c.depth != 0xFFFF && pushed + K <= p.pqlimit && heap_size + K <= p.node_cap && chain_size + K <= p.node_cap &&
+      if ((K >= 96 || (K >= 8 && heap_size >= 4096)) && c.depth != 0xFFFF && pushed + K <= p.pqlimit && heap_size + K <= p.node_cap && chain_size + K <= p.node_cap &&
           chain_size + K < 0xFFFFFFFEull) {
         for (uint32_t i = lane; i < K; i += 32) {  // chain nodes
           const uint4 meta = sm.res_meta[sm.clist[i]];
