@@ -652,13 +652,13 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
 
     // The reference's add/sub chain, in its order (tesseract.cc:549-585).
     cost = __dadd_rn(c.cost, __ldg(t.e_cost + ei));
-    uint32_t nt = 0, nt0 = 0;  // kBits: targets collected so far; how many of them are the error's own detectors
+    uint32_t nt = 0;  // kBits: targets collected so far (the error's own detectors first)
     if (kBits) {
       // targets: first the error's detectors that become fired, then (below) the fired neighbours; they are
       // evaluated together, 32/G per warp pass, and the chain is applied afterwards in the reference's order
       const unsigned newly = ~fired_mask & ((deg >= 32) ? kFull : ((1u << deg) - 1u));
       if (lane < deg && !((fired_mask >> lane) & 1)) sm.tl[__popc(newly & ((1u << lane) - 1u))] = (uint16_t)dj;
-      nt = nt0 = (uint32_t)__popc(newly);
+      nt = (uint32_t)__popc(newly);
     } else {
       for (uint32_t k = 0; k < deg; ++k) {
         const uint32_t d = __shfl_sync(kFull, dj, (int)k);
@@ -730,7 +730,6 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
       }
     }
     if (kBits) flush();
-    (void)nt0;
     ctr.A += deg + __ldg(t.e_nnbr + ei);
     if (kBits) {
       if (lane < deg) atomicXor(&sm.cf[dj >> 5], 1u << (dj & 31));  // back to the node's fired set
