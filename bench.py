@@ -199,7 +199,7 @@ def run_b200(args, wl, rank, world, local):
         chunks = (S + (1 << 18) - 1) >> 18
         acc["search_ms"] += t["search_ms"]
         acc["pipeline_ms"] += t["pipeline_ms"]
-        acc["launches"] += chunks + 2 * t["search_launches"]
+        acc["launches"] += 4 * chunks + 2 * t["search_launches"]  # stage + 3 ordering kernels per chunk, search + resolve per tier
         acc["rerun"] += t["rerun_items"]
 
     def reduce_counts(wrong, low):

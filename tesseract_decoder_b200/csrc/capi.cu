@@ -142,7 +142,7 @@ struct tsr_decoder {
   // Per-batch buffers.
   uint64_t max_batch = 0;
   DevBuf d_dets, d_status, d_sol_len, d_fcost, d_sol, d_obs, d_cost, d_low, d_err_off, d_err_len, d_err, d_retry,
-      d_items, d_scalars, d_counters;
+      d_items, d_scalars, d_counters, d_fired, d_order, d_bins;
   uint32_t sol_stride = 0;
   bool collect_errors = true;
 
@@ -447,6 +447,8 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
   sp.D = (uint32_t)T.num_detectors;
   sp.max_fired = &sc->max_fired;
   sp.total_fired = &sc->total_fired;
+  h.d_fired.ensure((size_t)shots * 4);
+  sp.fired = h.d_fired.as<uint32_t>();
   CUDA_OK((cudaError_t)tsr::launch_stage(sp, s));
   Scalars hs{};
   CUDA_OK(cudaMemcpyAsync(&hs, sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
@@ -463,6 +465,22 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     return;
   }
   h.sol_stride = stride_need;
+
+  // Longest searches first: shots in decreasing order of fired detectors (counting sort on the device).
+  const uint32_t* d_shot_order = nullptr;
+  if (shots > 1) {
+    tsr::OrderParams op;
+    op.fired = h.d_fired.as<uint32_t>();
+    op.shots = shots;
+    op.bins = hs.max_fired + 1;
+    h.d_bins.ensure((size_t)op.bins * 4);
+    h.d_order.ensure((size_t)shots * 4);
+    CUDA_OK(cudaMemsetAsync(h.d_bins.p, 0, (size_t)op.bins * 4, s));
+    op.bin_cursor = h.d_bins.as<uint32_t>();
+    op.order = h.d_order.as<uint32_t>();
+    CUDA_OK((cudaError_t)tsr::launch_order(op, s));
+    d_shot_order = op.order;
+  }
 
   h.d_status.ensure(items);
   h.d_sol_len.ensure((size_t)items * 4);
@@ -481,6 +499,7 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     p.stride = stride;
     p.n_work = n_work;
     p.item_ids = item_ids;
+    p.shot_order = item_ids ? nullptr : d_shot_order;
     p.n_trials = U;
     p.trial_perm = ts.d_perm.as<uint32_t>();
     p.trial_beam = ts.d_beam.as<uint32_t>();

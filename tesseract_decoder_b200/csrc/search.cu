@@ -581,7 +581,8 @@ __global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
     if (lane == 0) work = atomicAdd(p.work_counter, 1u);
     work = __shfl_sync(kFull, work, 0);
     if (work >= p.n_work) break;
-    const uint32_t item = p.item_ids ? __ldg(p.item_ids + work) : work;
+    uint32_t item = p.item_ids ? __ldg(p.item_ids + work) : work;
+    if (p.shot_order) item = __ldg(p.shot_order + work / p.n_trials) * p.n_trials + work % p.n_trials;
     uint64_t n_visited = 0;
     const uint8_t status = run_search(p, slot, item, lane, fbits, rbits, st, ctr, n_visited);
     __syncwarp();
@@ -629,12 +630,32 @@ __global__ void stage_kernel(const StageParams p) {
       fired += __popc(v);
     }
   }
+  if (p.fired && shot < p.shots) p.fired[shot] = fired;
   const uint32_t wmax = __reduce_max_sync(kFull, fired);
   const uint32_t wsum = __reduce_add_sync(kFull, fired);
   if ((threadIdx.x & 31) == 0) {
     atomicMax(p.max_fired, wmax);
     atomicAdd(p.total_fired, (unsigned long long)wsum);
   }
+}
+
+// ---- order: shots by decreasing syndrome weight (counting sort) ------------------------------------
+
+__global__ void order_hist_kernel(const OrderParams p) {
+  const uint32_t shot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (shot < p.shots) atomicAdd(p.bin_cursor + p.fired[shot], 1u);
+}
+__global__ void order_scan_kernel(const OrderParams p) {  // one thread: bins is at most num_detectors + 1
+  uint32_t run = 0;
+  for (uint32_t b = p.bins; b-- > 0;) {
+    const uint32_t n = p.bin_cursor[b];
+    p.bin_cursor[b] = run;
+    run += n;
+  }
+}
+__global__ void order_scatter_kernel(const OrderParams p) {
+  const uint32_t shot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (shot < p.shots) p.order[atomicAdd(p.bin_cursor + p.fired[shot], 1u)] = shot;
 }
 
 // ---- resolve: ensemble minimum + per-shot outputs (tesseract.cc:295-347, 618-658) --------------
@@ -710,6 +731,15 @@ int search_max_blocks_per_sm(uint32_t warps_per_block, uint32_t D) {
 int launch_stage(const StageParams& p, void* stream) {
   if (p.shots == 0) return 0;
   stage_kernel<<<(p.shots + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int launch_order(const OrderParams& p, void* stream) {
+  if (p.shots == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  order_hist_kernel<<<(p.shots + 255) / 256, 256, 0, s>>>(p);
+  order_scan_kernel<<<1, 1, 0, s>>>(p);
+  order_scatter_kernel<<<(p.shots + 255) / 256, 256, 0, s>>>(p);
   return (int)cudaGetLastError();
 }
 

@@ -75,6 +75,10 @@ struct SearchParams {
   uint64_t stride = 0;
   uint32_t n_work = 0;
   const uint32_t* item_ids = nullptr;
+  // Tier 0 only (nullable): shots in decreasing order of fired detectors — the k-th claimed work unit is
+  // (shot_order[k / n_trials], k % n_trials).  Search cost grows with the syndrome weight and is heavy-tailed, so the
+  // longest searches start first instead of setting the tail of the batch.
+  const uint32_t* shot_order = nullptr;
   uint32_t n_trials = 1;
   const uint32_t* trial_perm = nullptr;  // [n_trials] distinct order id
   const uint32_t* trial_beam = nullptr;  // [n_trials]
@@ -136,10 +140,20 @@ struct StageParams {
   uint32_t D = 0;
   unsigned int* max_fired = nullptr;  // out: largest number of fired detectors in the batch
   unsigned long long* total_fired = nullptr;
+  uint32_t* fired = nullptr;          // out (nullable): fired detectors per shot
+};
+
+struct OrderParams {
+  const uint32_t* fired = nullptr;  // [shots]
+  uint32_t shots = 0;
+  uint32_t bins = 0;                // max fired + 1
+  uint32_t* bin_cursor = nullptr;   // [bins], zeroed by the caller; scratch
+  uint32_t* order = nullptr;        // out [shots]: shots by decreasing fired count
 };
 
 // Launchers (search.cu).  All enqueue on `stream` and return the cudaError_t of the launch.
 int launch_stage(const StageParams& p, void* stream);
+int launch_order(const OrderParams& p, void* stream);  // counting sort: three small kernels
 int launch_search(const SearchParams& p, uint32_t blocks, uint32_t warps_per_block, void* stream);
 int launch_resolve(const ResolveParams& p, void* stream);
 // Fast path (search_fast.cu): one CTA of `warps` warps per search.

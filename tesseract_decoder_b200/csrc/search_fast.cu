@@ -1362,7 +1362,8 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
     __syncthreads();
     const uint32_t work = sm.ctl->work;
     if (work >= p.n_work) break;
-    const uint32_t item = p.item_ids ? __ldg(p.item_ids + work) : work;
+    uint32_t item = p.item_ids ? __ldg(p.item_ids + work) : work;
+    if (p.shot_order) item = __ldg(p.shot_order + work / p.n_trials) * p.n_trials + work % p.n_trials;
     const uint32_t status = run_search<kInstr, kBits>(p, sm, slot, item, ctr);
     __syncthreads();
     ++searches;
