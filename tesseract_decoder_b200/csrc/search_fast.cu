@@ -82,6 +82,7 @@ struct Smem {
   double* hv;        // [kTL] their heuristic terms (without det_penalty)
   uint16_t* fl;      // [groups][cap] fired-neighbour indices of each group's target
   uint32_t* bl;      // [groups][cap] blocking neighbours: index | threshold << 16
+  uint16_t* nzw;     // [nwords] indices of the bitset words that hold a fired or blocking detector in this state
   uint32_t* gc;      // [groups][4] list lengths and the target's own threshold
   // push staging (phase 7): the other warps' regions, idle while warp 0 pushes
   uint4* stage;
@@ -99,7 +100,7 @@ __host__ __device__ inline uint32_t dpad_of(uint32_t D) {
 
 struct Layout {
   uint32_t off_rank, off_rbits, off_fbits, off_pst, off_hc, off_cost, off_meta, off_clist, off_st, total;
-  uint32_t off_pbb, warp_stride, w_cf, w_tl, w_hv, w_fl, w_bl, w_gc;  // w_*: offsets inside a warp's region
+  uint32_t off_pbb, warp_stride, w_cf, w_tl, w_hv, w_fl, w_bl, w_gc, w_nzw;  // w_*: offsets inside a warp's region
 };
 __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint32_t rank_entries, uint32_t max_row_len,
                                                uint32_t warps, bool hc_shared, uint32_t bs_group = 0, uint32_t bs_cap = 0) {
@@ -126,7 +127,7 @@ __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint3
   L.off_st = at;
   // this warp's region: the private state copy (entry-per-lane scans) or the bit-sliced scratch
   uint32_t w = bs_group ? 0 : dpad_of(D) * 2;
-  L.w_cf = L.w_tl = L.w_hv = L.w_fl = L.w_bl = L.w_gc = 0;
+  L.w_cf = L.w_tl = L.w_hv = L.w_fl = L.w_bl = L.w_gc = L.w_nzw = 0;
   if (bs_group) {
     const uint32_t groups = 32 / bs_group;
     L.w_cf = w;
@@ -141,6 +142,8 @@ __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint3
     w += round16(groups * bs_cap * 2);
     L.w_gc = w;
     w += round16(groups * 16);
+    L.w_nzw = w;
+    w += round16(nwords * 2);
   }
   L.warp_stride = w;
   at += warps * w;
@@ -271,7 +274,27 @@ struct BsRow {
 struct BsState {
   uint32_t c_mind, c_thr;  // c_mind = 0xFFFFFFFF: the node's own state
   bool amt;
+  uint32_t n_nz;           // entries of sm.nzw (bs_list_words)
 };
+
+// Lists the bitset words that can contribute a fired or a blocking detector in this state, so that a row scan
+// visits those (a dozen) instead of every word of the adjacency row.
+__device__ __forceinline__ void bs_list_words(const Smem& sm, BsState& bs, uint32_t nwords, uint32_t lane) {
+  uint32_t n = 0;
+  for (uint32_t wb = 0; wb < nwords; wb += 32) {
+    const uint32_t w = wb + lane;
+    bool nz = false;
+    if (w < nwords) {
+      const uint32_t cfw = sm.cf[w];
+      nz = (cfw | sm.pbb[w] | (bs.amt ? (sm.fbits[w] & ~cfw) : 0u)) != 0 || (bs.c_mind >> 5) == w;
+    }
+    const unsigned m = __ballot_sync(kFull, nz);
+    if (nz) sm.nzw[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)w;
+    n += (uint32_t)__popc(m);
+  }
+  bs.n_nz = n;
+  __syncwarp();
+}
 
 // Phases A-C for the group's target x.  Must be called by all 32 lanes.
 template <bool kCounts>
@@ -323,12 +346,14 @@ __device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, 
         }
       }
     };
-    for (uint32_t w0 = wl; w0 < nwords; w0 += 4 * G) {  // four independent loads in flight per lane
-      const uint32_t w1 = w0 + G, w2 = w0 + 2 * G, w3 = w0 + 3 * G;
+    for (uint32_t i0 = wl; i0 < bs.n_nz; i0 += 4 * G) {  // four independent loads in flight per lane
+      const uint32_t i1 = i0 + G, i2 = i0 + 2 * G, i3 = i0 + 3 * G;
+      const uint32_t w0 = sm.nzw[i0];
+      const uint32_t w1 = i1 < bs.n_nz ? sm.nzw[i1] : 0u, w2 = i2 < bs.n_nz ? sm.nzw[i2] : 0u, w3 = i3 < bs.n_nz ? sm.nzw[i3] : 0u;
       const uint32_t a0 = __ldg(arow + w0);
-      const uint32_t a1 = w1 < nwords ? __ldg(arow + w1) : 0u;
-      const uint32_t a2 = w2 < nwords ? __ldg(arow + w2) : 0u;
-      const uint32_t a3 = w3 < nwords ? __ldg(arow + w3) : 0u;
+      const uint32_t a1 = i1 < bs.n_nz ? __ldg(arow + w1) : 0u;
+      const uint32_t a2 = i2 < bs.n_nz ? __ldg(arow + w2) : 0u;
+      const uint32_t a3 = i3 < bs.n_nz ? __ldg(arow + w3) : 0u;
       if (a0) scan_word(w0, a0);
       if (a1) scan_word(w1, a1);
       if (a2) scan_word(w2, a2);
@@ -649,6 +674,8 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
     bs.c_mind = mind;
     bs.c_thr = pos + 1;
     bs.amt = p.at_most_two != 0;
+    bs.n_nz = 0;
+    if (kBits) bs_list_words(sm, bs, nwords, lane);
 
     // The reference's add/sub chain, in its order (tesseract.cc:549-585).
     cost = __dadd_rn(c.cost, __ldg(t.e_cost + ei));
@@ -997,6 +1024,8 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
     node_state.c_mind = 0xFFFFFFFFu;
     node_state.c_thr = 0;
     node_state.amt = false;
+    node_state.n_nz = 0;
+    if (kBits) bs_list_words(sm, node_state, nwords, lane);
     if (!c.terms_cached) {
       // (the reference memoises these lazily in detector_cost_cache, tesseract.cc:531,569-582; same values)
       if (kBits) {
@@ -1350,6 +1379,7 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
   sm.fl = reinterpret_cast<uint16_t*>(wbase + L.w_fl);
   sm.bl = reinterpret_cast<uint32_t*>(wbase + L.w_bl);
   sm.gc = reinterpret_cast<uint32_t*>(wbase + L.w_gc);
+  sm.nzw = reinterpret_cast<uint16_t*>(wbase + L.w_nzw);
   sm.stage = reinterpret_cast<uint4*>(base + L.off_st + L.warp_stride);
   sm.stage_cap = (nwarps - 1) * (L.warp_stride / 16);
   for (uint32_t i = tid; i < rank_entries; i += blockDim.x) sm.rank[i] = __ldg(p.t.frank + i);
