@@ -52,6 +52,7 @@ struct alignas(16) Ctl {
   // expansion
   uint32_t mind, m_off, m_len, nchild;
   uint32_t next_child;  // children are claimed one at a time by the warps
+  uint32_t n_fz;        // non-zero words of the node's fired bitset (sm.fz)
   // which node's state pst / fbits / pbb / key currently hold, and how phase 2 gets to the popped node's
   uint32_t state_chain, state_depth;
   int state_valid;
@@ -77,6 +78,7 @@ struct Smem {
   uint16_t* st;      // this warp's private state [dpad]
   // bit-sliced scan (kBits): shared blocking-detector bitset of the node, and this warp's scratch
   uint32_t* pbb;     // [nwords] detectors with a block threshold in the node's state
+  uint16_t* fz;      // [nwords] indices of the non-zero words of fbits (ctl->n_fz of them)
   uint32_t* cf;      // [nwords] fired bitset of this warp's current state (node or child)
   uint16_t* tl;      // [kTL] targets
   double* hv;        // [kTL] their heuristic terms (without det_penalty)
@@ -100,7 +102,7 @@ __host__ __device__ inline uint32_t dpad_of(uint32_t D) {
 
 struct Layout {
   uint32_t off_rank, off_rbits, off_fbits, off_pst, off_hc, off_cost, off_meta, off_clist, off_st, total;
-  uint32_t off_pbb, warp_stride, w_cf, w_tl, w_hv, w_fl, w_bl, w_gc, w_nzw;  // w_*: offsets inside a warp's region
+  uint32_t off_pbb, off_fz, warp_stride, w_cf, w_tl, w_hv, w_fl, w_bl, w_gc, w_nzw;  // w_*: offsets inside a warp's region
 };
 __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint32_t rank_entries, uint32_t max_row_len,
                                                uint32_t warps, bool hc_shared, uint32_t bs_group = 0, uint32_t bs_cap = 0) {
@@ -124,6 +126,8 @@ __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint3
   at += round16(max_row_len * 2);
   L.off_pbb = at;
   if (bs_group) at += round16(nwords * 4);
+  L.off_fz = at;
+  at += round16(nwords * 2);
   L.off_st = at;
   // this warp's region: the private state copy (entry-per-lane scans) or the bit-sliced scratch
   uint32_t w = bs_group ? 0 : dpad_of(D) * 2;
@@ -721,25 +725,27 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
     };
     // eneighbors[ei] ∩ fired: detectors adjacent to one of the error's detectors, fired in the parent
     // (hence in the child), not in the error itself; ascending.
-    for (uint32_t wb = 0; wb < nwords; wb += 32) {
-      const uint32_t w = wb + lane;
+    const uint32_t n_fz = c.n_fz;
+    for (uint32_t wb = 0; wb < n_fz; wb += 32) {  // only bitset words that hold a fired detector
+      const uint32_t wi = wb + lane;
+      const uint32_t w = wi < n_fz ? sm.fz[wi] : 0xFFFFFFFFu;
       uint32_t mine = 0;
       for (uint32_t k = 0; k < deg; ++k) {
         const uint32_t d = __shfl_sync(kFull, dj, (int)k);
-        if (w < nwords) mine |= __ldg(t.adj + (size_t)d * nwords + w);
+        if (wi < n_fz) mine |= __ldg(t.adj + (size_t)d * nwords + w);
       }
       for (uint32_t k = 0; k < deg; ++k) {
         const uint32_t d = __shfl_sync(kFull, dj, (int)k);
         if ((d >> 5) == w) mine &= ~(1u << (d & 31));
       }
-      if (w < nwords) mine &= sm.fbits[w];
+      if (wi < n_fz) mine &= sm.fbits[w];
       unsigned nz = __ballot_sync(kFull, mine != 0);
       if (kBits) {
         while (nz) {
           if (nt + 32 > kTL) flush();
           const uint32_t l = (uint32_t)__ffs((int)nz) - 1;
           nz &= nz - 1;
-          tl_append(sm, nt, __shfl_sync(kFull, mine, (int)l), (wb + l) * 32, lane);
+          tl_append(sm, nt, __shfl_sync(kFull, mine, (int)l), __shfl_sync(kFull, w, (int)l) * 32, lane);
         }
       } else {
         while (nz) {
@@ -747,7 +753,7 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
           nz &= nz - 1;
           uint32_t word = __shfl_sync(kFull, mine, (int)l);
           while (word) {
-            const uint32_t od = (wb + l) * 32 + (uint32_t)__ffs((int)word) - 1;
+            const uint32_t od = __shfl_sync(kFull, w, (int)l) * 32 + (uint32_t)__ffs((int)word) - 1;
             word &= word - 1;
             cost = __dsub_rn(cost, sm.hc[od]);
             const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, od, lane, ctr.S), p.det_penalty);
@@ -1019,6 +1025,17 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       uint4* dst = reinterpret_cast<uint4*>(sm.st);
       for (uint32_t i = lane; i < dpad / 8; i += 32) dst[i] = src[i];
       __syncwarp();
+    }
+    if (warp == 0) {  // the non-zero words of the fired bitset, for the children's neighbour enumeration
+      uint32_t n = 0;
+      for (uint32_t wb = 0; wb < nwords; wb += 32) {
+        const uint32_t w = wb + lane;
+        const bool nz = w < nwords && sm.fbits[w] != 0;
+        const unsigned m = __ballot_sync(kFull, nz);
+        if (nz) sm.fz[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)w;
+        n += (uint32_t)__popc(m);
+      }
+      if (lane == 0) c.n_fz = n;
     }
     BsState node_state;
     node_state.c_mind = 0xFFFFFFFFu;
@@ -1373,6 +1390,7 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
   uint8_t* wbase = base + L.off_st + (size_t)warp * L.warp_stride;
   sm.st = reinterpret_cast<uint16_t*>(wbase);
   sm.pbb = reinterpret_cast<uint32_t*>(base + L.off_pbb);
+  sm.fz = reinterpret_cast<uint16_t*>(base + L.off_fz);
   sm.cf = reinterpret_cast<uint32_t*>(wbase + L.w_cf);
   sm.tl = reinterpret_cast<uint16_t*>(wbase + L.w_tl);
   sm.hv = reinterpret_cast<double*>(wbase + L.w_hv);
