@@ -214,13 +214,34 @@ BitTables build_bit_tables(const DemTables& T, const FastTables& F) {
       }
     }
   }
-  B.pl_off.assign((size_t)pairs + 1, 0);
-  for (size_t p = 0; p < lists.size(); ++p) {
-    std::sort(lists[p].begin(), lists[p].end());  // by rank in the neighbour's row (ranks are distinct)
-    B.pl_off[p + 1] = B.pl_off[p] + (uint32_t)lists[p].size();
+  // Pair lists, split by row word: pl_off is indexed like the neighbour masks (mask_off + j * nw + word) and bounds
+  // the entries of pair (x, neighbour j) that fall into that word of row[x], sorted by rank in the neighbour's row.
+  B.pl_off.assign(B.masks.size() + 1, 0);
+  size_t total = 0;
+  for (const auto& l : lists) total += l.size();
+  B.pl.assign(total + 4, 0);
+  uint32_t run = 0;
+  size_t next_index = 0;  // pl_off entries below this are final
+  for (uint64_t x = 0; x < D; ++x) {
+    const BitRowMeta& m = B.rowmeta[x];
+    for (size_t j = 0; j < nbrs[x].size(); ++j) {
+      std::vector<uint32_t>& l = lists[m.pair_base + j];
+      std::sort(l.begin(), l.end(), [](uint32_t a, uint32_t b) {  // by word of row[x], then by rank (ranks are distinct)
+        const uint32_t wa = (a & 0xFFFF) >> 5, wb = (b & 0xFFFF) >> 5;
+        return wa != wb ? wa < wb : a < b;
+      });
+      size_t at = 0;
+      for (uint32_t w = 0; w < m.nw; ++w) {
+        const size_t index = (size_t)m.mask_off + j * m.nw + w;
+        for (; next_index <= index; ++next_index) B.pl_off[next_index] = run;
+        while (at < l.size() && ((l[at] & 0xFFFF) >> 5) == w) {
+          B.pl[run++] = (l[at] & 0xFFFF0000u) | (l[at] & 31);  // rank << 16 | bit within the word
+          ++at;
+        }
+      }
+    }
   }
-  B.pl.assign((size_t)B.pl_off[pairs] + 4, 0);
-  for (size_t p = 0; p < lists.size(); ++p) std::copy(lists[p].begin(), lists[p].end(), B.pl.begin() + B.pl_off[p]);
+  for (; next_index < B.pl_off.size(); ++next_index) B.pl_off[next_index] = run;
   B.ok = true;
   return B;
 }

@@ -58,8 +58,8 @@ FastTables build_fast_tables(const DemTables& T);
 //   * for each detector y adjacent to x (the set bits of adj[x], in ascending order; index j = number of set
 //     bits of adj[x] below y): the L-bit mask of row[x] entries whose error also contains y.  The fired-count
 //     of every row entry is 1 + the bit-sliced sum of the masks of the FIRED neighbours;
-//   * for each pair (x, y): the entries of row[x] containing y as (rank in row[y], position in row[x]) sorted
-//     by rank — the entries a block threshold on y removes from row[x] are a prefix of that list;
+//   * for each pair (x, y) and each 32-entry word of row[x]: the entries of that word containing y as
+//     (rank in row[y], bit) sorted by rank — the entries a block threshold on y removes are a prefix of that list;
 //   * for each distinct cost in row[x] (ascending): the L-bit mask of entries with that cost.
 struct BitRowMeta {   // 32 bytes, one per detector
   uint32_t mask_off;  // word offset of the neighbour masks [j][word] in `masks`
@@ -77,8 +77,8 @@ struct BitTables {
   std::vector<uint16_t> adjpre;     // [D * adj_words] set bits of adj[x] before word w
   std::vector<uint32_t> masks;
   std::vector<uint8_t> cls_cid;
-  std::vector<uint32_t> pl_off;     // [pairs + 1]
-  std::vector<uint32_t> pl;         // rank << 16 | position
+  std::vector<uint32_t> pl_off;     // [masks.size() + 1], indexed like the neighbour masks: per (pair, row word)
+  std::vector<uint32_t> pl;         // rank in the neighbour's row << 16 | bit within the row word
 };
 BitTables build_bit_tables(const DemTables& T, const FastTables& F);
 

@@ -403,18 +403,13 @@ __device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, 
     uint32_t B = thr0 <= lo ? 0u : (thr0 - lo >= 32 ? 0xFFFFFFFFu : ((1u << (thr0 - lo)) - 1u));
     for (uint32_t q = 0; q < nb; ++q) {
       const uint32_t jb = sm.bl[g * cap + q];
-      const uint32_t pi = ma.z + (jb & 0xFFFF), thr = jb >> 16;
-      const uint32_t pe = __ldg(t.bs_pl_off + pi + 1);
-      for (uint32_t at = __ldg(t.bs_pl_off + pi); at < pe; at += 4) {  // four entries in flight; the list is rank-sorted
-        const uint32_t v0 = __ldg(t.bs_pl + at);
-        const uint32_t v1 = at + 1 < pe ? __ldg(t.bs_pl + at + 1) : 0xFFFFFFFFu;
-        const uint32_t v2 = at + 2 < pe ? __ldg(t.bs_pl + at + 2) : 0xFFFFFFFFu;
-        const uint32_t v3 = at + 3 < pe ? __ldg(t.bs_pl + at + 3) : 0xFFFFFFFFu;
-        if ((v0 >> 16) < thr && ((v0 & 0xFFFF) >> 5) == wl) B |= 1u << (v0 & 31);
-        if ((v1 >> 16) < thr && ((v1 & 0xFFFF) >> 5) == wl) B |= 1u << (v1 & 31);
-        if ((v2 >> 16) < thr && ((v2 & 0xFFFF) >> 5) == wl) B |= 1u << (v2 & 31);
-        if ((v3 >> 16) < thr && ((v3 & 0xFFFF) >> 5) == wl) B |= 1u << (v3 & 31);
-        if ((v3 >> 16) >= thr) break;
+      const uint32_t thr = jb >> 16;
+      const uint32_t* po = t.bs_pl_off + ma.x + (size_t)(jb & 0xFFFF) * nw + wl;  // this pair, this lane's word
+      const uint32_t pe = __ldg(po + 1);
+      for (uint32_t at = __ldg(po); at < pe; ++at) {
+        const uint32_t v = __ldg(t.bs_pl + at);
+        if ((v >> 16) >= thr) break;
+        B |= 1u << (v & 31);
       }
     }
     r.U = valid & ~B;
