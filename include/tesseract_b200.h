@@ -151,6 +151,11 @@ int tsr_device(const tsr_decoder* h);
 int tsr_build_det_orders(const char* dem_text, uint64_t num_det_orders, int method, uint64_t seed, uint64_t* out);
 uint64_t tsr_dem_count_detectors(const char* dem_text); /* UINT64_MAX on parse failure */
 double tsr_merge_weights(double a, double b);           /* common.cc:118-123 */
+/* common::dem_from_counts (common.cc:241-263): the flattened DEM with error k's probability replaced by
+ * counts[k] / num_shots; n_counts must equal the number of error instructions (TSR_E_INVALID_ARGUMENT otherwise).
+ * Used by the CLI's --dem-out (tesseract_main.cc:625-639).  Caller frees *dem_text_out with tsr_free. */
+int tsr_dem_from_counts(const char* dem_text, const uint64_t* counts, uint64_t n_counts, uint64_t num_shots,
+                        char** dem_text_out);
 /* Stand-ins for the stim services the reference CLI uses (tesseract_main.cc:191-211, utils.cc:207-251):
  * circuit text -> DEM text (caller frees with tsr_free) and an i.i.d. DEM shot sampler into bit-packed
  * rows ([shots][ceil(D/8)], [shots][ceil(O/8)]; obs_out may be NULL). */

@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
     L.tsr_merge_weights.restype = C.c_double
     L.tsr_merge_weights.argtypes = [C.c_double, C.c_double]
     L.tsr_circuit_to_dem.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.tsr_dem_from_counts.argtypes = [C.c_char_p, u64p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
     L.tsr_sample_dem_b8.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, u8p, u8p]
     _lib = L
     return L
@@ -114,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "tsr_decode_batch_b8_device", "tsr_set_collect_errors", "tsr_set_instrumented", "tsr_search_path",
     "tsr_search_path_reason", "tsr_last_batch_nnz", "tsr_last_batch_errors", "tsr_decode",
     "tsr_cost_from_errors", "tsr_flipped_observables", "tsr_counters", "tsr_last_batch_timing", "tsr_stream",
-    "tsr_device", "tsr_build_det_orders", "tsr_dem_count_detectors", "tsr_merge_weights", "tsr_circuit_to_dem",
+    "tsr_device", "tsr_build_det_orders", "tsr_dem_count_detectors", "tsr_merge_weights", "tsr_dem_from_counts", "tsr_circuit_to_dem",
     "tsr_sample_dem_b8",
 ]
 
@@ -149,6 +150,14 @@ def _take_text(ptr: C.c_void_p) -> str:
 def circuit_to_dem(circuit_text: str) -> str:
     out = C.c_void_p()
     _check(lib().tsr_circuit_to_dem(circuit_text.encode(), C.byref(out)))
+    return _take_text(out)
+
+
+def dem_from_counts(dem_text: str, counts, num_shots: int) -> str:
+    """common::dem_from_counts (common.cc:241-263)."""
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    out = C.c_void_p()
+    _check(lib().tsr_dem_from_counts(dem_text.encode(), _p(counts, C.c_uint64), len(counts), num_shots, C.byref(out)))
     return _take_text(out)
 
 

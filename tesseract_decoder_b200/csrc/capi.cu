@@ -962,6 +962,26 @@ double tsr_merge_weights(double a, double b) {
   return tsr::merge_weights(a, b);
 }
 
+int tsr_dem_from_counts(const char* dem_text, const uint64_t* counts, uint64_t n_counts, uint64_t num_shots,
+                        char** dem_text_out) {
+  return guarded([&] {
+    DemModel dem = DemModel::parse(dem_text);  // parsed models are already flat
+    if (dem.count_errors() != n_counts)
+      throw std::invalid_argument("Error hits array must be the same size as the number of errors in the original DEM.");
+    DemModel out;
+    uint64_t k = 0;
+    for (const tsr::DemInstruction& inst : dem.instructions) {
+      if (inst.kind == tsr::DemKind::Error) {
+        out.append_error((double)counts[k] / (double)num_shots, inst.targets, inst.tag);
+        ++k;
+      } else {
+        out.instructions.push_back(inst);
+      }
+    }
+    *dem_text_out = dup_text(out.str());
+  });
+}
+
 int tsr_circuit_to_dem(const char* circuit_text, char** dem_text_out) {
   return guarded([&] { *dem_text_out = dup_text(tsr::circuit_to_dem_text(circuit_text)); });
 }

@@ -22,7 +22,7 @@ namespace {
 
 struct Args {
   std::string circuit_path, dem_path, in_fname, in_format = "b8", obs_in_fname, obs_in_format = "b8", out_fname,
-      out_format = "b8", stats_out_fname;
+      out_format = "b8", stats_out_fname, dem_out_fname;
   bool in_includes_appended_observables = false;
   size_t num_det_orders = 1;              // tesseract_main.cc:358
   int det_order_method = 1;               // DetIndex (tesseract_main.cc:230-237)
@@ -45,7 +45,8 @@ struct Args {
                "       [--in-includes-appended-observables] [--obs_in FILE [--obs-in-format b8|01]]) [--out FILE [--out-format b8|01]]\n"
                "       [--beam N] [--det-penalty X] [--beam-climbing] [--no-revisit-dets] [--at-most-two-errors-per-detector]\n"
                "       [--pqlimit N] [--num-det-orders N] [--det-order-seed S] [--det-order-bfs|--det-order-index|--det-order-coordinate]\n"
-               "       [--no-merge-errors] [--max-errors N] [--shot-range-begin A --shot-range-end B] [--stats-out FILE] [--print-stats]\n"
+               "       [--no-merge-errors] [--max-errors N] [--shot-range-begin A --shot-range-end B] [--stats-out FILE] [--dem-out FILE]\n"
+               "       [--print-stats]\n"
                "       [--gpus N] [--threads N (ignored)] [--verbose]\n";
   std::exit(EXIT_FAILURE);
 }
@@ -97,7 +98,7 @@ int main(int argc, char** argv) {
       {"--circuit", &a.circuit_path}, {"--dem", &a.dem_path}, {"--in", &a.in_fname}, {"--in-format", &a.in_format},
       {"--in_format", &a.in_format}, {"--obs_in", &a.obs_in_fname}, {"--obs-in", &a.obs_in_fname},
       {"--obs-in-format", &a.obs_in_format}, {"--obs_in_format", &a.obs_in_format}, {"--out", &a.out_fname},
-      {"--out-format", &a.out_format}, {"--stats-out", &a.stats_out_fname}};
+      {"--out-format", &a.out_format}, {"--stats-out", &a.stats_out_fname}, {"--dem-out", &a.dem_out_fname}};
   std::map<std::string, bool*> flag_opts = {
       {"--beam-climbing", &a.beam_climbing}, {"--no-revisit-dets", &a.no_revisit_dets},
       {"--at-most-two-errors-per-detector", &a.at_most_two}, {"--no-merge-errors", &a.no_merge_errors},
@@ -226,6 +227,9 @@ int main(int argc, char** argv) {
 
     uint64_t num_errors = 0, num_low_confidence = 0, done = 0;
     double total_time_seconds = 0;
+    const bool want_use = !a.dem_out_fname.empty();
+    std::vector<uint64_t> error_use(want_use ? (size_t)tsr_num_dem_errors(decoders[0]->handle()) : 0, 0);
+    std::vector<std::vector<uint64_t>> batch_off((size_t)a.gpus), batch_idx((size_t)a.gpus);
     // Batches in shot order (so --max-errors stops where the reference's in-order consumer would, up to a batch);
     // each batch is split over the GPUs.
     for (uint64_t at = 0; at < shots && num_errors < a.max_errors; at += a.batch) {
@@ -237,7 +241,9 @@ int main(int argc, char** argv) {
         const uint64_t b = at + n * (uint64_t)g / (uint64_t)a.gpus, e = at + n * (uint64_t)(g + 1) / (uint64_t)a.gpus;
         workers.emplace_back([&, g, b, e] {
           try {
-            decoders[(size_t)g]->decode_batch_b8(dets.data() + b * nb, nb, e - b, obs_pred.data() + b * ob, cost.data() + b, low.data() + b);
+            decoders[(size_t)g]->decode_batch_b8(dets.data() + b * nb, nb, e - b, obs_pred.data() + b * ob, cost.data() + b,
+                                                 low.data() + b, want_use);
+            if (want_use) decoders[(size_t)g]->last_batch_errors(e - b, batch_off[(size_t)g], batch_idx[(size_t)g]);
           } catch (const std::exception& ex) {
             errors[(size_t)g] = ex.what();
           }
@@ -258,8 +264,16 @@ int main(int argc, char** argv) {
             throw std::invalid_argument("unsupported --out-format '" + a.out_format + "'");
           }
         }
+        const bool match = !has_obs || std::memcmp(obs_pred.data() + s * ob, obs_true.data() + s * ob, (size_t)ob) == 0;
         if (low[s]) ++num_low_confidence;
-        else if (has_obs && std::memcmp(obs_pred.data() + s * ob, obs_true.data() + s * ob, (size_t)ob) != 0) ++num_errors;
+        else if (!match) ++num_errors;
+        if (want_use && match) {  // error_use: errors of the shots whose prediction matches (tesseract_main.cc:586-590)
+          const uint64_t k = s - at;
+          int g = 0;
+          while (g + 1 < a.gpus && k >= n * (uint64_t)(g + 1) / (uint64_t)a.gpus) ++g;
+          const uint64_t local = k - n * (uint64_t)g / (uint64_t)a.gpus;
+          for (uint64_t q = batch_off[(size_t)g][local]; q < batch_off[(size_t)g][local + 1]; ++q) ++error_use[batch_idx[(size_t)g][q]];
+        }
         ++done;
         if (a.print_stats) {
           std::cout << "num_shots = " << done << " num_low_confidence = " << num_low_confidence;
@@ -269,6 +283,16 @@ int main(int argc, char** argv) {
         }
         if (has_obs && num_errors >= a.max_errors) break;
       }
+    }
+
+    if (want_use) {  // tesseract_main.cc:625-639
+      const uint64_t usage_shots = has_obs ? done - num_errors : done;
+      char* text = nullptr;
+      check(tsr_dem_from_counts(dem_text.c_str(), error_use.data(), error_use.size(), usage_shots, &text));
+      std::ofstream f(a.dem_out_fname);
+      if (!f) throw std::invalid_argument("Failed to open " + a.dem_out_fname);
+      f << text << '\n';
+      tsr_free(text);
     }
 
     bool print_final_stats = true;

@@ -202,6 +202,16 @@ PYBIND11_MODULE(_tesseract_b200, root) {
       .def_readwrite("likelihood_cost", &Error::likelihood_cost)
       .def_readwrite("symptom", &Error::symptom);
   cm.def("merge_weights", &tsr_merge_weights, py::arg("a"), py::arg("b"));
+  cm.def(
+      "dem_from_counts",
+      [](const py::object& dem, const std::vector<uint64_t>& error_counts, uint64_t num_shots) {
+        char* out = nullptr;
+        check(tsr_dem_from_counts(dem_text(dem).c_str(), error_counts.data(), error_counts.size(), num_shots, &out));
+        std::string text(out);
+        tsr_free(out);
+        return text;
+      },
+      py::arg("orig_dem"), py::arg("error_counts"), py::arg("num_shots"));
 
   // ---- tesseract (tesseract.pybind.h) --------------------------------------------------------------
   auto m = root.def_submodule("tesseract", "Module containing the tesseract algorithm");

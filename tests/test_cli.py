@@ -64,3 +64,14 @@ def test_cli_matches_the_library(tmp_path):
     assert r.returncode == 0, r.stderr
     assert np.fromfile(tmp_path / "pred.b8", dtype=np.uint8).tolist() == out["obs"][:50, 0].tolist()
     assert "num_errors" not in r.stdout  # no observables given (tesseract_main.cc:693-695)
+    # --dem-out: usage-frequency DEM over the shots whose prediction matched (tesseract_main.cc:586-590, 625-639)
+    r = run("--dem", tmp_path / "m.dem", "--in", tmp_path / "dets.b8", "--obs_in", tmp_path / "obs.b8", "--beam", 5,
+            "--pqlimit", 200000, "--dem-out", tmp_path / "use.dem")
+    assert r.returncode == 0, r.stderr
+    use = np.zeros(dec.num_dem_errors, dtype=np.int64)
+    lists = W.split_lists(out["err_offsets"], out["err_idx"])
+    good = (out["obs"] == obs).all(axis=1)
+    for s_, errs in enumerate(lists):
+        if good[s_]:
+            use[errs] += 1
+    assert (tmp_path / "use.dem").read_text().strip() == capi.dem_from_counts(dem, use, 3000 - wrong).strip()

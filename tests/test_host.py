@@ -183,3 +183,15 @@ def test_fast_path_certificate():
     # an error on more than 11 detectors
     dec = capi.Decoder("error(0.01) " + " ".join(f"D{i}" for i in range(13)) + "\nerror(0.02) D0", host_only=True)
     assert dec.search_path == "generic" and "11" in dec.search_path_reason
+
+
+def test_dem_from_counts():  # common.test.cc:31-92
+    dem = "error(0.25) D0\nerror(0.35) D1\ndetector(0, 0, 0) D0\ndetector(0, 0, 0) D1"
+    out = capi.dem_from_counts(dem, [5, 7], 20)
+    assert out.splitlines()[:2] == ["error(0.25) D0", "error(0.35) D1"] and "detector" in out
+    dem = "error(0.1) D0\nerror(0) D1\nerror(0.2) D2\ndetector(0,0,0) D0\ndetector(0,0,0) D1\ndetector(0,0,0) D2"
+    out = capi.Decoder(capi.dem_from_counts(dem, [1, 7, 4], 10), merge_errors=False, host_only=True)
+    p = 1 / (1 + np.exp(out.error_costs()))
+    assert np.allclose(p, [0.1, 0.7, 0.4], atol=1e-12)
+    with pytest.raises(ValueError, match="Error hits array must be the same size"):
+        capi.dem_from_counts(dem, [1, 2], 10)
