@@ -134,6 +134,13 @@ const char* tsr_search_path_reason(const tsr_decoder* h);
  * off by default because it costs a warp scan per 32 entries.  The generic kernel always counts. */
 int tsr_set_instrumented(tsr_decoder* h, int on);
 
+/* Host-only self check (no GPU): evaluates get_detcost (tesseract.cc:128-154) on `trials` random search states
+ * three ways — the reference's floating-point loop, the rank minimum over the packed row records, and the
+ * bit-sliced evaluation the sm_100a kernel performs — and returns the number of evaluations that are not
+ * bit-identical (0 is the only acceptable answer), or a negative code.  *checked receives how many were compared
+ * (0 when the DEM is not certified for the fast path). */
+int64_t tsr_cross_check_detcost(const tsr_decoder* h, uint64_t trials, uint64_t seed, uint64_t* checked);
+
 /* Search counters since the last reset, summed over every search this handle ran:
  * [0]=Q pushes [1]=P pops [2]=X expanded nodes [3]=L chain-walk steps [4]=S scanned row entries
  * [5]=A sum(|edets|+|fired neighbours|) over evaluated children [6]=V visited inserts+probes

@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
     L.tsr_last_batch_errors.argtypes = [C.c_void_p, u64p, u64p]
     L.tsr_set_collect_errors.argtypes = [C.c_void_p, C.c_int]
     L.tsr_set_instrumented.argtypes = [C.c_void_p, C.c_int]
+    L.tsr_cross_check_detcost.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, u64p]
+    L.tsr_cross_check_detcost.restype = C.c_int64
     L.tsr_search_path.argtypes = [C.c_void_p]
     L.tsr_search_path_reason.argtypes = [C.c_void_p]
     L.tsr_search_path_reason.restype = C.c_char_p
@@ -112,7 +114,7 @@ EXPORTED_SYMBOLS = [
     "tsr_config_init", "tsr_last_error", "tsr_version", "tsr_create", "tsr_destroy", "tsr_num_detectors",
     "tsr_num_observables", "tsr_num_errors", "tsr_num_dem_errors", "tsr_num_det_orders", "tsr_error_costs",
     "tsr_maps", "tsr_csr", "tsr_compiled_dem_text", "tsr_free", "tsr_decode_batch_b8",
-    "tsr_decode_batch_b8_device", "tsr_set_collect_errors", "tsr_set_instrumented", "tsr_search_path",
+    "tsr_decode_batch_b8_device", "tsr_set_collect_errors", "tsr_cross_check_detcost", "tsr_set_instrumented", "tsr_search_path",
     "tsr_search_path_reason", "tsr_last_batch_nnz", "tsr_last_batch_errors", "tsr_decode",
     "tsr_cost_from_errors", "tsr_flipped_observables", "tsr_counters", "tsr_last_batch_timing", "tsr_stream",
     "tsr_device", "tsr_build_det_orders", "tsr_dem_count_detectors", "tsr_merge_weights", "tsr_dem_from_counts", "tsr_circuit_to_dem",
@@ -291,6 +293,14 @@ class Decoder:
     @property
     def search_path_reason(self) -> str:
         return lib().tsr_search_path_reason(self.h).decode()
+
+    def cross_check_detcost(self, trials: int, seed: int = 1):
+        """(mismatches, evaluations compared) of the host cross-check of the three get_detcost formulations."""
+        n = C.c_uint64()
+        bad = lib().tsr_cross_check_detcost(self.h, trials, seed, C.byref(n))
+        if bad < 0:
+            _raise(int(bad))
+        return int(bad), n.value
 
     def set_instrumented(self, on: bool):
         _check(lib().tsr_set_instrumented(self.h, int(on)))

@@ -840,6 +840,20 @@ int tsr_set_collect_errors(tsr_decoder* h, int on) {
   return TSR_OK;
 }
 
+int64_t tsr_cross_check_detcost(const tsr_decoder* h, uint64_t trials, uint64_t seed, uint64_t* checked) {
+  int64_t bad = 0;
+  const int rc = guarded([&] {
+    tsr::BitTables local;
+    const tsr::BitTables* B = &h->B;
+    if (h->F.certified && !h->B.ok) {  // the handle chose the entry-per-lane scan: build the tables for the check
+      local = tsr::build_bit_tables(h->T, h->F);
+      B = &local;
+    }
+    bad = (int64_t)tsr::cross_check_detcost(h->T, h->F, *B, trials, seed, checked);
+  });
+  return rc == TSR_OK ? bad : rc;
+}
+
 int tsr_set_instrumented(tsr_decoder* h, int on) {
   h->instrumented = on != 0;
   return TSR_OK;

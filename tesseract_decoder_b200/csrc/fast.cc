@@ -246,4 +246,169 @@ BitTables build_bit_tables(const DemTables& T, const FastTables& F) {
   return B;
 }
 
+namespace {
+
+uint64_t mix64(uint64_t& s) {
+  s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+}  // namespace
+
+uint64_t cross_check_detcost(const DemTables& T, const FastTables& F, const BitTables& B, uint64_t trials, uint64_t seed,
+                             uint64_t* checked) {
+  const uint64_t D = T.num_detectors;
+  uint64_t bad = 0, n_checked = 0;
+  if (!F.certified || D == 0) {
+    if (checked) *checked = 0;
+    return 0;
+  }
+  std::vector<uint8_t> fired(D);
+  std::vector<uint32_t> thr(D);
+  const uint32_t aw = T.adj_words;
+  for (uint64_t trial = 0; trial < trials; ++trial) {
+    // a random state: a cluster of fired detectors around a random error neighbourhood, a few thresholds
+    std::fill(fired.begin(), fired.end(), 0);
+    std::fill(thr.begin(), thr.end(), 0u);
+    const uint64_t n_seed_errors = 1 + mix64(seed) % 6;
+    for (uint64_t k = 0; k < n_seed_errors && T.num_errors; ++k)
+      for (int d : T.errors[mix64(seed) % T.num_errors].detectors) fired[(size_t)d] ^= 1;
+    for (uint64_t k = 0; k < 3; ++k) fired[mix64(seed) % D] = 1;
+    for (uint64_t k = 0; k < 1 + mix64(seed) % 4; ++k) {
+      const uint64_t d = mix64(seed) % D;
+      const uint32_t len = T.row_off[d + 1] - T.row_off[d];
+      thr[d] = len ? (uint32_t)(mix64(seed) % (len + 1)) : 0;
+      if (mix64(seed) % 8 == 0) thr[d] = 0x7FF;  // "block the whole row" (at-most-two)
+    }
+    for (uint64_t x = 0; x < D; ++x) {
+      if (!fired[x]) continue;
+      const uint32_t roff = T.row_off[x], len = T.row_off[x + 1] - roff;
+      auto count_of = [&](uint64_t e) {
+        uint32_t c = 0;
+        for (int d : T.errors[e].detectors) c += fired[(size_t)d];
+        return c;
+      };
+      auto blocked_of = [&](uint64_t e) {
+        const auto& dets = T.errors[e].detectors;
+        for (size_t j = 0; j < dets.size(); ++j)
+          if ((uint32_t)T.e_rank[T.e_off[e] + j] < thr[(size_t)dets[j]]) return true;
+        return false;
+      };
+      // (1) the reference loop
+      double min_cost = INFINITY;
+      uint32_t min_count = 0xFFFFFFFFu;
+      for (uint32_t i = 0; i < len; ++i) {
+        const uint64_t e = (uint64_t)T.row_err[roff + i];
+        volatile double lhs = T.e_cost[e] * (double)min_count, rhs = min_cost * (double)T.errors[e].detectors.size();
+        if (lhs >= rhs) break;
+        if (!blocked_of(e)) {
+          const uint32_t cnt = count_of(e);
+          volatile double l2 = T.e_cost[e] * (double)min_count, r2 = min_cost * (double)cnt;
+          if (l2 < r2) {
+            min_cost = T.e_cost[e];
+            min_count = cnt;
+          }
+        }
+      }
+      volatile double ref = min_cost / (double)min_count;
+      // (2) rank minimum over the packed records
+      uint32_t best = 0xFFFFFFFFu, best_cls = 0;
+      for (uint32_t i = 0; i < len; ++i) {
+        const uint8_t* a = &F.rec_a[(size_t)(roff + i) * 16];
+        const uint8_t* b = &F.rec_b[(size_t)(roff + i) * 16];
+        uint32_t cnt = 1;
+        bool blk = i < (thr[x] & 0x7FF);
+        auto slot = [&](const uint8_t* q) {
+          const uint32_t v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
+          const uint32_t det = v & 0x3FFF, rk = v >> 14;
+          if (det < D) {
+            cnt += fired[det];
+            blk |= rk < thr[det];
+          }
+        };
+        for (int k = 0; k < 5; ++k) slot(a + 1 + 3 * k);
+        if (a[0] & 0x80)
+          for (int k = 0; k < 5; ++k) slot(b + 3 * k);
+        if (blk) continue;
+        const uint32_t cls = (uint32_t)(a[0] & 0x7F) * F.nstride + cnt;
+        const uint32_t key = ((uint32_t)F.rank[cls] << 12) | i;
+        if (key < best) {
+          best = key;
+          best_cls = cls;
+        }
+      }
+      const double lanes = best == 0xFFFFFFFFu ? INFINITY : F.quotient[best_cls];
+      // (3) bit-sliced
+      double bits = lanes;
+      if (B.ok) {
+        const BitRowMeta& m = B.rowmeta[x];
+        uint32_t bbest = 0xFFFFFFFFu, bcls = 0;
+        for (uint32_t wl = 0; wl < m.nw; ++wl) {
+          uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+          const uint32_t lo = wl * 32;
+          const uint32_t valid = m.len - lo >= 32 ? 0xFFFFFFFFu : ((1u << (m.len - lo)) - 1u);
+          const uint32_t t0 = thr[x];
+          uint32_t Bm = t0 <= lo ? 0u : (t0 - lo >= 32 ? 0xFFFFFFFFu : ((1u << (t0 - lo)) - 1u));
+          for (uint32_t w = 0; w < aw; ++w) {
+            const uint32_t arow = T.adj[(size_t)x * aw + w];
+            for (uint32_t mm = arow; mm; mm &= mm - 1) {
+              const uint32_t bit = (uint32_t)__builtin_ctz(mm), y = w * 32 + bit;
+              if (y == x) continue;
+              const uint32_t j = B.adjpre[(size_t)x * aw + w] + (uint32_t)__builtin_popcount(arow & ((1u << bit) - 1u));
+              if (fired[y]) {
+                const uint32_t msk = B.masks[m.mask_off + (size_t)j * m.nw + wl];
+                const uint32_t a0 = c0 & msk;
+                c0 ^= msk;
+                const uint32_t a1 = c1 & a0;
+                c1 ^= a0;
+                const uint32_t a2 = c2 & a1;
+                c2 ^= a1;
+                c3 ^= a2;
+              }
+              if (thr[y]) {
+                const size_t idx = m.mask_off + (size_t)j * m.nw + wl;
+                for (uint32_t at = B.pl_off[idx]; at < B.pl_off[idx + 1]; ++at) {
+                  if ((B.pl[at] >> 16) >= thr[y]) break;
+                  Bm |= 1u << (B.pl[at] & 31);
+                }
+              }
+            }
+          }
+          const uint32_t U = valid & ~Bm;
+          if (!U) continue;
+          for (uint32_t kc = 0; kc < m.ncls; ++kc) {
+            uint32_t cm = B.masks[m.cmask_off + (size_t)kc * m.nw + wl] & U;
+            if (!cm) continue;
+            uint32_t q;
+            q = cm & c3;
+            cm = q ? q : cm;
+            q = cm & c2;
+            cm = q ? q : cm;
+            q = cm & c1;
+            cm = q ? q : cm;
+            q = cm & c0;
+            cm = q ? q : cm;
+            const uint32_t v = ((cm & c3) ? 8u : 0u) | ((cm & c2) ? 4u : 0u) | ((cm & c1) ? 2u : 0u) | ((cm & c0) ? 1u : 0u);
+            const uint32_t cls = (uint32_t)B.cls_cid[m.cls_off + kc] * F.nstride + v + 1;
+            const uint32_t key = ((uint32_t)F.rank[cls] << 12) | (lo + (uint32_t)__builtin_ctz(cm));
+            if (key < bbest) {
+              bbest = key;
+              bcls = cls;
+            }
+          }
+        }
+        bits = bbest == 0xFFFFFFFFu ? INFINITY : F.quotient[bcls];
+      }
+      ++n_checked;
+      const double r = ref;
+      if (std::memcmp(&r, &lanes, 8) != 0 || std::memcmp(&r, &bits, 8) != 0) ++bad;
+    }
+  }
+  if (checked) *checked = n_checked;
+  return bad;
+}
+
 }  // namespace tsr

@@ -82,4 +82,13 @@ struct BitTables {
 };
 BitTables build_bit_tables(const DemTables& T, const FastTables& F);
 
+// Host cross-check of the three formulations of get_detcost on `trials` random search states (random fired
+// sets and block thresholds): (1) the reference's floating-point loop with its early exit (tesseract.cc:128-154)
+// on the plain tables, (2) the rank minimum over packed row records (entry-per-lane kernel), (3) the bit-sliced
+// evaluation over BitTables (masks, pair lists, cost classes) exactly as search_fast.cu performs it.  Returns
+// the number of (state, detector) evaluations whose three values are not bit-identical doubles; `checked`
+// receives how many were compared.  B may be !ok (then (3) is skipped).
+uint64_t cross_check_detcost(const DemTables& T, const FastTables& F, const BitTables& B, uint64_t trials, uint64_t seed,
+                             uint64_t* checked);
+
 }  // namespace tsr

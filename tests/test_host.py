@@ -195,3 +195,15 @@ def test_dem_from_counts():  # common.test.cc:31-92
     assert np.allclose(p, [0.1, 0.7, 0.4], atol=1e-12)
     with pytest.raises(ValueError, match="Error hits array must be the same size"):
         capi.dem_from_counts(dem, [1, 2], 10)
+
+
+@pytest.mark.parametrize("name", ["surface_d5_r5_p0.002_X", "color_superdense_d5_r5_p0.001_Z", "color_superdense_d7_r7_p0.001_X",
+                                  "transcx_d5_p0.001_X", "bb72_r6_p0.001_X", "bb144_r12_p0.0001_X", "surface_d11_r11_p0.001_X"])
+def test_detcost_formulations_agree_on_the_host(name):
+    """csrc/fast.h: on random search states the reference's floating-point get_detcost loop (with its early exit),
+    the rank minimum over the packed row records and the bit-sliced evaluation the kernel performs give
+    bit-identical doubles — the certificate and the derived tables, checked without a GPU."""
+    dec = capi.Decoder(W.load_dem(name), host_only=True)
+    bad, checked = dec.cross_check_detcost(400, seed=11)
+    assert checked > 2000 and bad == 0
+    assert capi.Decoder("error(0.7) D0 D1\nerror(0.1) D0\nerror(0.1) D1", host_only=True).cross_check_detcost(10) == (0, 0)
