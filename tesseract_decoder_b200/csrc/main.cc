@@ -32,7 +32,7 @@ struct Args {
   int det_beam = INF_DET_BEAM;            // tesseract_main.cc:482
   double det_penalty = 0;
   bool beam_climbing = false, no_revisit_dets = false, at_most_two = false, no_merge_errors = false, verbose = false,
-       print_stats = false;
+       print_stats = false, convert_only = false;
   size_t pqlimit = std::numeric_limits<size_t>::max();  // tesseract_main.cc:503
   int num_threads = (int)std::thread::hardware_concurrency();
   int gpus = 1;
@@ -60,7 +60,9 @@ std::string read_file(const std::string& path) {
 }
 
 // Reads shots as rows of `bits` bits into a [shots][ceil(bits/8)] b8 matrix.
-std::vector<uint8_t> read_shots(const std::string& path, const std::string& format, uint64_t bits, uint64_t& shots_out) {
+// (`dets_prefix`: in the dets format, L# tokens index bits after the first dets_prefix bits.)
+std::vector<uint8_t> read_shots(const std::string& path, const std::string& format, uint64_t bits, uint64_t& shots_out,
+                                uint64_t dets_prefix = 0) {
   const std::string raw = read_file(path);
   const uint64_t nb = (bits + 7) / 8;
   std::vector<uint8_t> out;
@@ -84,10 +86,108 @@ std::vector<uint8_t> read_shots(const std::string& path, const std::string& form
       }
       ++shots_out;
     }
+  } else if (format == "hits") {  // one line per shot: comma-separated indices of the set bits
+    shots_out = 0;
+    std::istringstream ss(raw);
+    std::string line;
+    while (std::getline(ss, line)) {
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      out.resize(out.size() + nb, 0);
+      uint8_t* row = out.data() + out.size() - nb;
+      std::istringstream ls(line);
+      std::string tok;
+      while (std::getline(ls, tok, ',')) {
+        if (tok.empty()) continue;
+        const uint64_t i = std::stoull(tok);
+        if (i >= bits) throw std::invalid_argument(path + ": hit index " + tok + " is out of range");
+        row[i / 8] ^= (uint8_t)(1u << (i % 8));
+      }
+      ++shots_out;
+    }
+  } else if (format == "dets") {  // "shot D3 D7 L0": D# are the first num_detectors bits, L# follow them
+    shots_out = 0;
+    std::istringstream ss(raw);
+    std::string line;
+    while (std::getline(ss, line)) {
+      std::istringstream ls(line);
+      std::string tok;
+      if (!(ls >> tok)) continue;
+      if (tok != "shot") throw std::invalid_argument(path + ": a dets line must start with 'shot'");
+      out.resize(out.size() + nb, 0);
+      uint8_t* row = out.data() + out.size() - nb;
+      while (ls >> tok) {
+        if (tok.size() < 2 || (tok[0] != 'D' && tok[0] != 'L' && tok[0] != 'M')) throw std::invalid_argument(path + ": bad dets token " + tok);
+        uint64_t i = std::stoull(tok.substr(1));
+        if (tok[0] == 'L') i += dets_prefix;
+        if (i >= bits) throw std::invalid_argument(path + ": dets token " + tok + " is out of range");
+        row[i / 8] ^= (uint8_t)(1u << (i % 8));
+      }
+      ++shots_out;
+    }
+  } else if (format == "r8") {  // run lengths of zeros before each one; 0xFF = 255 zeros, no one; a one is appended per shot
+    shots_out = 0;
+    size_t at = 0;
+    while (at < raw.size()) {
+      out.resize(out.size() + nb, 0);
+      uint8_t* row = out.data() + out.size() - nb;
+      uint64_t pos = 0;
+      while (true) {
+        if (at >= raw.size()) throw std::invalid_argument(path + ": r8 data ends inside a shot");
+        const uint8_t run = (uint8_t)raw[at++];
+        pos += run;
+        if (run == 0xFF) continue;
+        if (pos == bits) break;  // the terminating one
+        if (pos > bits) throw std::invalid_argument(path + ": r8 run passes the end of a shot");
+        row[pos / 8] |= (uint8_t)(1u << (pos % 8));
+        ++pos;
+      }
+      ++shots_out;
+    }
   } else {
-    throw std::invalid_argument("unsupported shot format '" + format + "' (b8 and 01 are supported)");
+    throw std::invalid_argument("unsupported shot format '" + format + "' (b8, 01, hits, dets and r8 are supported)");
   }
   return out;
+}
+
+// Writes one shot of `bits` bits (stim result formats b8, 01, hits, dets with the given token letter, r8).
+void write_shot(std::ostream& out, const std::string& format, const uint8_t* row, uint64_t bits, char letter) {
+  auto bit = [&](uint64_t i) { return (row[i / 8] >> (i % 8)) & 1; };
+  if (format == "b8") {
+    out.write(reinterpret_cast<const char*>(row), (std::streamsize)((bits + 7) / 8));
+  } else if (format == "01") {
+    for (uint64_t i = 0; i < bits; ++i) out.put(bit(i) ? '1' : '0');
+    out.put('\n');
+  } else if (format == "hits") {
+    bool first = true;
+    for (uint64_t i = 0; i < bits; ++i)
+      if (bit(i)) {
+        if (!first) out.put(',');
+        out << i;
+        first = false;
+      }
+    out.put('\n');
+  } else if (format == "dets") {
+    out << "shot";
+    for (uint64_t i = 0; i < bits; ++i)
+      if (bit(i)) out << ' ' << letter << i;
+    out.put('\n');
+  } else if (format == "r8") {
+    uint64_t run = 0;
+    for (uint64_t i = 0; i <= bits; ++i) {
+      if (i == bits || bit(i)) {
+        while (run >= 255) {
+          out.put((char)0xFF);
+          run -= 255;
+        }
+        out.put((char)run);
+        run = 0;
+      } else {
+        ++run;
+      }
+    }
+  } else {
+    throw std::invalid_argument("unsupported --out-format '" + format + "' (b8, 01, hits, dets and r8 are supported)");
+  }
 }
 
 }  // namespace
@@ -102,7 +202,7 @@ int main(int argc, char** argv) {
   std::map<std::string, bool*> flag_opts = {
       {"--beam-climbing", &a.beam_climbing}, {"--no-revisit-dets", &a.no_revisit_dets},
       {"--at-most-two-errors-per-detector", &a.at_most_two}, {"--no-merge-errors", &a.no_merge_errors},
-      {"--verbose", &a.verbose}, {"--print-stats", &a.print_stats},
+      {"--verbose", &a.verbose}, {"--print-stats", &a.print_stats}, {"--convert-only", &a.convert_only},
       {"--in-includes-appended-observables", &a.in_includes_appended_observables},
       {"--in_includes_appended_observables", &a.in_includes_appended_observables}};
   try {
@@ -139,6 +239,18 @@ int main(int argc, char** argv) {
     if (a.beam_climbing && a.det_beam == INF_DET_BEAM) usage("Beam climbing requires a finite beam");
     if (a.gpus < 1) usage("--gpus must be >= 1");
 
+    if (a.convert_only) {
+      // Host-only helper: re-encode the detection-event file given by --in into --out / --out-format (no decoding).
+      if (a.in_fname.empty() || a.out_fname.empty() || a.dem_path.empty()) usage("--convert-only needs --dem, --in and --out");
+      const uint64_t bits = tsr_dem_count_detectors(read_file(a.dem_path).c_str());
+      if (bits == UINT64_MAX) throw std::invalid_argument(tsr_last_error());
+      uint64_t n = 0;
+      const std::vector<uint8_t> rows = read_shots(a.in_fname, a.in_format, bits, n);
+      std::ofstream f(a.out_fname, std::ios::binary);
+      if (!f) throw std::invalid_argument("Failed to open " + a.out_fname);
+      for (uint64_t k = 0; k < n; ++k) write_shot(f, a.out_format, rows.data() + k * ((bits + 7) / 8), bits, 'D');
+      return EXIT_SUCCESS;
+    }
     std::string dem_text;
     if (!a.circuit_path.empty()) {
       char* out = nullptr;
@@ -183,7 +295,7 @@ int main(int argc, char** argv) {
     } else {
       if (a.in_includes_appended_observables) {
         uint64_t n = 0;
-        std::vector<uint8_t> both = read_shots(a.in_fname, a.in_format, D + O, n);
+        std::vector<uint8_t> both = read_shots(a.in_fname, a.in_format, D + O, n, D);
         const uint64_t bb = (D + O + 7) / 8;
         shots = n;
         dets.assign((size_t)(shots * nb), 0);
@@ -254,16 +366,7 @@ int main(int argc, char** argv) {
         if (!e.empty()) throw std::runtime_error(e);
       total_time_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       for (uint64_t s = at; s < at + n; ++s) {  // consume(shot), tesseract_main.cc:592-616
-        if (!a.out_fname.empty()) {
-          if (a.out_format == "b8") {
-            out.write(reinterpret_cast<const char*>(obs_pred.data() + s * ob), (std::streamsize)ob);
-          } else if (a.out_format == "01") {
-            for (uint64_t o = 0; o < O; ++o) out.put(((obs_pred[s * ob + o / 8] >> (o % 8)) & 1) ? '1' : '0');
-            out.put('\n');
-          } else {
-            throw std::invalid_argument("unsupported --out-format '" + a.out_format + "'");
-          }
-        }
+        if (!a.out_fname.empty()) write_shot(out, a.out_format, obs_pred.data() + s * ob, O, 'L');
         const bool match = !has_obs || std::memcmp(obs_pred.data() + s * ob, obs_true.data() + s * ob, (size_t)ob) == 0;
         if (low[s]) ++num_low_confidence;
         else if (!match) ++num_errors;

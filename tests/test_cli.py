@@ -75,3 +75,29 @@ def test_cli_matches_the_library(tmp_path):
         if good[s_]:
             use[errs] += 1
     assert (tmp_path / "use.dem").read_text().strip() == capi.dem_from_counts(dem, use, 3000 - wrong).strip()
+
+
+def test_shot_file_formats_round_trip(tmp_path):
+    """stim result formats the CLI reads and writes (--in-format / --out-format): b8, 01, hits, dets, r8.
+    Host-only (--convert-only): every format re-encodes to the same b8 bytes."""
+    dem = W.load_dem("surface_d5_r5_p0.002_X")
+    (tmp_path / "m.dem").write_text(dem)
+    dets, _ = capi.sample_dem_b8(dem, 3, 200, 120, 1)
+    dets[5] = 0       # an empty shot
+    dets[6] = 0xFF    # a full one (120 ones: the last byte is entirely detector bits)
+    dets.tofile(tmp_path / "a.b8")
+    for fmt in ("01", "hits", "dets", "r8"):
+        r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / "a.b8", "--out", tmp_path / f"a.{fmt}", "--out-format", fmt)
+        assert r.returncode == 0, r.stderr
+        r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / f"a.{fmt}", "--in-format", fmt, "--out",
+                tmp_path / f"back_{fmt}.b8", "--out-format", "b8")
+        assert r.returncode == 0, r.stderr
+        assert np.array_equal(np.fromfile(tmp_path / f"back_{fmt}.b8", dtype=np.uint8).reshape(200, 15), dets), fmt
+    assert (tmp_path / "a.hits").read_text().splitlines()[5] == ""
+    assert (tmp_path / "a.dets").read_text().splitlines()[5] == "shot"
+    first = np.nonzero(np.unpackbits(dets[0], bitorder="little")[:120])[0]
+    assert (tmp_path / "a.dets").read_text().splitlines()[0] == "shot" + "".join(f" D{i}" for i in first)
+    raw = (tmp_path / "a.r8").read_bytes()
+    assert raw[0] == first[0]  # run of zeros before the first one
+    r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / "a.b8", "--out", tmp_path / "x", "--out-format", "ptb64")
+    assert r.returncode != 0 and "unsupported" in r.stderr

@@ -217,6 +217,10 @@ FRESH = [
     (dict(dem="bb144_r12_p0.0001_X", det_beam=W.INF_BEAM, pqlimit=None, no_revisit_dets=True, num_det_orders=24), 40, 28),
     (dict(dem="surface_d11_r11_p0.001_X", det_beam=3, beam_climbing=True, pqlimit=20000, no_revisit_dets=True,
           num_det_orders=0), 60, 29),
+    # real ensembles: BFS and coordinate detector orders (utils.cc:89-171) are distinct permutations
+    (dict(dem="transcx_d3_p0.001_X", det_beam=4, pqlimit=50000, no_revisit_dets=True, num_det_orders=6, det_order_method=0), 500, 30),
+    (dict(dem="color_superdense_d5_r5_p0.001_Z", det_beam=3, beam_climbing=True, pqlimit=20000, no_revisit_dets=True,
+          num_det_orders=5, det_order_method=2), 400, 31),
 ]
 
 

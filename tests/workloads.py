@@ -43,11 +43,12 @@ def decoder_kwargs(cfg: dict, build_det_orders) -> tuple[str, dict]:
     dem = load_dem(cfg.pop("dem"))
     n_orders = cfg.pop("num_det_orders", 0)
     seed = cfg.pop("det_order_seed", CLI_ORDER_SEED)
+    method = cfg.pop("det_order_method", 1)  # 0 = DetBFS, 1 = DetIndex, 2 = DetCoordinate (utils.h:43)
     kw = dict(det_beam=cfg.pop("det_beam", 5), beam_climbing=cfg.pop("beam_climbing", False),
               no_revisit_dets=cfg.pop("no_revisit_dets", True), merge_errors=cfg.pop("merge_errors", True),
               pqlimit=cfg.pop("pqlimit", 200000), det_penalty=cfg.pop("det_penalty", 0.0))
     assert not cfg, f"unknown config keys {cfg}"
-    kw["det_orders"] = build_det_orders(dem, n_orders, 1, seed) if n_orders else None
+    kw["det_orders"] = build_det_orders(dem, n_orders, method, seed) if n_orders else None
     return dem, kw
 
 
