@@ -141,7 +141,7 @@ def run_reference(args, wl, rank):
     D, O = dec.num_detectors, dec.num_observables
     shots = args.shots or wl["shots"]
     dets, _ = capi.sample_dem_b8(dem, 1000, shots, D, O)
-    budget = 150.0 / (args.steps + args.warmup)  # seconds of CPU wall per step
+    budget = args.ref_seconds / (args.steps + args.warmup)  # seconds of CPU wall per step
     n, _, _ = cpu_sample(dec, dets, budget, threads)
     for _ in range(args.warmup):
         dec.decode_batch_b8(dets[:n])
@@ -320,6 +320,7 @@ def main():
     ap.add_argument("--workload", default="bb144", choices=sorted(WORKLOADS))
     ap.add_argument("--shots", type=int, default=0, help="shots per GPU per step (default: per workload)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="wall-time target of the cpu_baseline sample")
+    ap.add_argument("--ref-seconds", type=float, default=150.0, help="--impl reference: wall-time budget of the whole run")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--warps", type=int, default=0, help="warps per search CTA (0 = automatic)")
     ap.add_argument("--scan", default="auto", choices=["auto", "bits", "lanes", "generic"],
