@@ -332,19 +332,28 @@ def test_device_resident_entry_point_matches_host_entry_point():
 
 def test_at_most_two_errors_per_detector_is_a_valid_restriction():
     """No reference code exists for this flag (parity unpinned).  What can be pinned: answers
-    stay valid, no detector is touched by more than two chosen errors, and switching the flag off
-    restores reference parity."""
-    dem = W.load_dem("transcx_d5_p0.001_X")
-    dec = capi.Decoder(dem, det_beam=W.INF_BEAM, pqlimit=200000, no_revisit_dets=True, det_penalty=0.5,
-                       at_most_two_errors_per_detector=True)
-    dets, _ = capi.sample_dem_b8(dem, 31, 400, dec.num_detectors, dec.num_observables)
-    out = dec.decode_batch_b8(dets)
-    check_solutions_are_consistent(dec, dets, out)
-    d2e, _ = dec.maps()
-    off, edets = dec.csr(1)
-    for errs in W.split_lists(out["err_offsets"], out["err_idx"]):
-        touched = np.zeros(dec.num_detectors, dtype=np.int32)
-        for e in errs:
-            ce = int(d2e[e])
-            touched[edets[int(off[ce]):int(off[ce + 1])]] += 1
-        assert touched.max(initial=0) <= 2
+    stay valid, no detector is touched by more than two chosen errors, and the three independent CUDA
+    implementations (generic event replay, entry-per-lane, bit-sliced) agree shot for shot."""
+    for name, shots, extra in (("transcx_d5_p0.001_X", 400, dict(det_penalty=0.5)), ("bb72_r6_p0.001_X", 120, dict(num_orders=2))):
+        dem = W.load_dem(name)
+        kw = dict(det_beam=W.INF_BEAM, pqlimit=20000, no_revisit_dets=True, det_penalty=extra.get("det_penalty", 0.0),
+                  at_most_two_errors_per_detector=True)
+        if extra.get("num_orders"):
+            kw["det_orders"] = capi.build_det_orders(dem, extra["num_orders"], 1, W.CLI_ORDER_SEED)
+        outs = {}
+        for variant, opts in (("generic", dict(force_generic_kernel=True)), ("lanes", dict(row_scan=1)), ("bits", dict(row_scan=2))):
+            dec = capi.Decoder(dem, **opts, **kw)
+            dets, _ = capi.sample_dem_b8(dem, 31, shots, dec.num_detectors, dec.num_observables)
+            outs[variant] = dec.decode_batch_b8(dets)
+        assert_same(outs["lanes"], outs["generic"])
+        assert_same(outs["bits"], outs["generic"])
+        out = outs["bits"]
+        check_solutions_are_consistent(dec, dets, out)
+        d2e, _ = dec.maps()
+        off, edets = dec.csr(1)
+        for errs in W.split_lists(out["err_offsets"], out["err_idx"]):
+            touched = np.zeros(dec.num_detectors, dtype=np.int32)
+            for e in errs:
+                ce = int(d2e[e])
+                touched[edets[int(off[ce]):int(off[ce + 1])]] += 1
+            assert touched.max(initial=0) <= 2
