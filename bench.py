@@ -45,6 +45,12 @@ WORKLOADS = {
                        "(DetIndex, seed 518278944), beam/pqlimit unbounded (CLI defaults)"),
     "bb144_p5e-4": dict(cfg=dict(W.CONFIGS["C4"], dem="bb144_r12_p0.0005_X"), shots=4096,
                         name="bivariate-bicycle [[144,12,12]] r=12 si1000 p=5e-4 X, --num-det-orders 24 --no-revisit-dets"),
+    # the reference's own published sweep point (benchmarking/sparsify_errors/aggregated_results.jsonl:195, submit.sh:223):
+    # 4.105 CPU-seconds per shot on their hardware
+    "bb144_p1e-3_longbeam": dict(cfg=dict(dem="bb144_r12_p0.001_X", det_beam=20, beam_climbing=True, pqlimit=1000000,
+                                          no_revisit_dets=True, num_det_orders=21), shots=1024,
+                                 name="bivariate-bicycle [[144,12,12]] r=12 si1000 p=1e-3 X, --beam 20 --beam-climbing --num-det-orders 21 "
+                                      "--pqlimit 1000000 --no-revisit-dets (the reference's long-beam sweep point)"),
     "surface_d5": dict(cfg=W.CONFIGS["C1"], shots=1 << 20, name="surface code d=5 r=5 p=0.002 X, --beam 5 --pqlimit 200000"),
     "color_d7": dict(cfg=dict(W.CONFIGS["C2"], det_beam=5, pqlimit=200000, no_revisit_dets=True), shots=65536,
                      name="superdense color code d=7 r=7 p=0.001 X, --num-det-orders 1 --beam 5 --pqlimit 200000 --no-revisit-dets"),
