@@ -7,19 +7,28 @@
 //
 //   * a search owns a CTA.  The children of an expanded node are independent (each is the parent state
 //     with the error's detectors toggled and a longer blocked prefix of the min-detector's row), so the
-//     W warps evaluate them round-robin, each on a private copy of the 16-bit-per-detector state, and
-//     warp 0 then pushes the results in row order — which keeps the reference's queue order.  All W
-//     warps scan the same few detector rows, so the row records become L1 hits, and a batch needs 8-16x
-//     fewer concurrent searches to fill the machine (smaller tail, larger node pool per search).
-//   * a row scan is integer-only.  Under the host-checked certificate (fast.h) get_detcost is "the first
-//     unblocked row entry of minimal rank(cost, count)", so a lane keeps min(rank << 12 | position) over
-//     its entries, the warp takes one REDUX.MIN, and the winner's host-computed quotient fl(cost/count)
-//     is looked up.  No per-chunk ballots, no FP64 in the loop, and chunk loads are independent.
-//   * row records are 16 bytes (5 neighbours) + 16 bytes (5 more, only for errors of degree > 6) with
-//     24-bit (detector, rank) slots instead of 16 + 16 + 16 bytes with an 8-byte cost.
+//     warps claim them one at a time and warp 0 then pushes the results in row order — which keeps the
+//     reference's queue order.  A batch needs 8-16x fewer concurrent searches to fill the machine
+//     (smaller tail, larger node pool per search).
+//   * get_detcost is integer-only.  Under the host-checked certificate (fast.h) it is "the first unblocked
+//     row entry of minimal rank(cost, count)", and the value is the host-computed quotient fl(cost/count).
+//     Two scans compute that minimum:
+//       - entry per lane (scan_row): lanes stride over 16-byte row records (5 neighbours, +16 bytes with 5
+//         more for errors of degree > 6; 24-bit (detector, rank) slots), look the neighbours up in the
+//         warp's private copy of the 16-bit-per-detector state, keep min(rank << 12 | position), one
+//         REDUX.MIN per row.  kInstr additionally counts the row entries the reference's early-exit loop
+//         visits (counter S).
+//       - bit-sliced (bs_core / bs_targets, kBits): a group of G lanes owns a target row, a lane 32 row
+//         entries as bit masks; fired counts are a carry-save sum of precomputed neighbour masks, blocked
+//         entries come from rank-sorted pair lists, and each cost class yields one candidate.  No private
+//         state copy: a child is (fired bitset, min detector's threshold) on top of the node's state.
+//   * the queue is the libstdc++ binary heap in global memory; the pushes of an expansion are staged in
+//     shared memory (one tree level per sub-batch) or committed in windows of 32.
+//   * a popped node that is a child of the state already materialised (a descent) costs one chain step
+//     instead of a walk from the root.
 //
 // Exactness: the child cost is still node.cost + cost(e) then -= / += detector terms in the reference's
-// order with round-to-nearest adds; pushes happen in row order; the queue is the same libstdc++ heap.
+// order with round-to-nearest adds; pushes happen in row order; the heap performs the same moves.
 #include <cuda_runtime.h>
 
 #include <cstdint>
