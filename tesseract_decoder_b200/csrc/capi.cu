@@ -1,10 +1,11 @@
 // C ABI (include/tesseract_b200.h): host-side decoder object, device memory and the launch pipeline.
 //
-// Per batch:  stage_kernel (syndrome statistics)  ->  search_kernel (one warp per (shot, trial),
-// persistent warps claiming work from an atomic counter, like utils.h:88-92)  ->  resolve_kernel
-// (ensemble minimum, observables, costs, pooled error lists).  Searches that outgrow their slot's
-// heap/chain/visited capacity are re-run in the next "tier": fewer slots over the same node pool,
-// each proportionally larger — never on the CPU.
+// Per batch chunk:  stage_kernel (fired detectors per shot)  ->  counting sort of the shots by decreasing
+// syndrome weight  ->  search kernel (search_fast.cu: one CTA per (shot, trial) for DEMs certified by fast.h;
+// search.cu: one warp per (shot, trial) otherwise; persistent CTAs / warps claiming work from an atomic
+// counter, like utils.h:88-92)  ->  resolve_kernel (ensemble minimum, observables, costs, pooled error
+// lists).  Searches that outgrow their slot's heap/chain/visited capacity are re-run in the next "tier":
+// fewer slots over the same node pool, each proportionally larger — never on the CPU.
 #include <cuda_runtime.h>
 
 #include <algorithm>

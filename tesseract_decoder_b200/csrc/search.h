@@ -1,10 +1,10 @@
-// Device-side data layout and launch interface of the A* search kernels (search.cu).
+// Device-side data layout and launch interface of the A* search kernels (search.cu, search_fast.cu).
 #pragma once
 #include <cstdint>
 
 namespace tsr {
 
-// ---- device-resident DEM tables (read-only during decoding, L2-resident: <= ~20 MB) --------------
+// ---- device-resident DEM tables (read-only during decoding, L2-resident: tens of MB) --------------
 struct DeviceTables {
   uint32_t D = 0, E = 0, O = 0;
   uint32_t nwords = 0;  // ceil(D/32): words per detector bitset and per adjacency row
