@@ -156,7 +156,8 @@ int tsr_device(const tsr_decoder* h);
 /* ---- helpers either side of the path -------------------------------------------------------------*/
 /* build_det_orders (utils.cc:192-205); method 0=DetBFS 1=DetIndex 2=DetCoordinate; out [n][D]. */
 int tsr_build_det_orders(const char* dem_text, uint64_t num_det_orders, int method, uint64_t seed, uint64_t* out);
-uint64_t tsr_dem_count_detectors(const char* dem_text); /* UINT64_MAX on parse failure */
+uint64_t tsr_dem_count_detectors(const char* dem_text);   /* UINT64_MAX on parse failure */
+uint64_t tsr_dem_count_observables(const char* dem_text); /* UINT64_MAX on parse failure */
 double tsr_merge_weights(double a, double b);           /* common.cc:118-123 */
 /* common::dem_from_counts (common.cc:241-263): the flattened DEM with error k's probability replaced by
  * counts[k] / num_shots; n_counts must equal the number of error instructions (TSR_E_INVALID_ARGUMENT otherwise).

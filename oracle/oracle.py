@@ -35,7 +35,10 @@ class OrcConfig(C.Structure):
         ("num_det_orders", C.c_uint64),
         ("det_orders", C.POINTER(C.c_uint64)),
         ("num_threads", C.c_int32),
-        ("reserved", C.c_int32),
+        ("sparsify_errors", C.c_int32),
+        ("sparsify_base_degree", C.c_int32),
+        ("sparsify_max_degree", C.c_int32),
+        ("sparsify_reactivate_limit", C.c_int32),
     ]
 
 
@@ -114,7 +117,9 @@ class OracleDecoder:
 
     def __init__(self, dem_text: str, *, det_beam: int = 5, beam_climbing: bool = False,
                  no_revisit_dets: bool = True, merge_errors: bool = True, pqlimit: int = 200000,
-                 det_penalty: float = 0.0, det_orders=None, num_threads: int = 1, kind: str = "reference"):
+                 det_penalty: float = 0.0, det_orders=None, num_threads: int = 1, kind: str = "reference",
+                 sparsify_errors: bool = False, sparsify_base_degree: int = -1, sparsify_max_degree: int = -1,
+                 sparsify_reactivate_limit: int = -1):
         self.lib = _lib(kind)
         self.kind = kind
         cfg = OrcConfig()
@@ -130,6 +135,10 @@ class OracleDecoder:
             cfg.num_det_orders = self._orders.shape[0]
             cfg.det_orders = _p(self._orders, C.c_uint64)
         cfg.num_threads = num_threads
+        cfg.sparsify_errors = int(sparsify_errors)
+        cfg.sparsify_base_degree = sparsify_base_degree
+        cfg.sparsify_max_degree = sparsify_max_degree
+        cfg.sparsify_reactivate_limit = sparsify_reactivate_limit
         self.h = self.lib.orc_create(dem_text.encode(), C.byref(cfg))
         if not self.h:
             raise OracleError(self.lib.orc_last_error().decode())

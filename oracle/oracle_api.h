@@ -32,7 +32,10 @@ typedef struct orc_config {
   uint64_t num_det_orders; /* 0 -> the decoder's default single identity order (tesseract.cc:175-177) */
   const uint64_t* det_orders; /* [num_det_orders][num_detectors], row-major */
   int32_t num_threads;     /* decoders in the pool; one per worker like tesseract_main.cc:559-571 */
-  int32_t reserved;
+  int32_t sparsify_errors; /* tesseract.h:52-55, tesseract.cc:256-292, 673-737 */
+  int32_t sparsify_base_degree;
+  int32_t sparsify_max_degree;
+  int32_t sparsify_reactivate_limit;
 } orc_config;
 
 const char* orc_last_error(void);

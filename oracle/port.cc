@@ -70,6 +70,9 @@ struct Config {
   uint64_t pqlimit = 200000;
   double det_penalty = 0;
   std::vector<std::vector<uint64_t>> orders;
+  // tesseract.h:52-55
+  bool sparsify = false;
+  int sparsify_base_degree = -1, sparsify_max_degree = -1, sparsify_reactivate_limit = -1;
 };
 
 struct Counters {
@@ -148,6 +151,11 @@ struct Decoder {
   // scratch
   std::vector<ChainLink> chain;
   std::vector<uint32_t> blocked, count, child_blocked, child_count;
+  // Rows the search walks: the full detector rows, or the shot's sparse rows (tesseract.cc:296-298).
+  std::vector<uint32_t> aoff;
+  std::vector<int> arow;
+  std::vector<int> mandatory, optional;  // tesseract.cc:279-289
+  std::vector<uint8_t> active;
 
   Decoder(const stim::DetectorErrorModel& input, Config c) : cfg(std::move(c)) {
     // tesseract.cc:156-205
@@ -269,14 +277,17 @@ struct Decoder {
     }
     blocked.resize(E);
     count.resize(E);
+    aoff = row_off;  // the search walks the full rows unless sparsification narrows them per shot
+    arow = row;
+    init_sparsify();
   }
 
   // tesseract.cc:128-154
   double detcost(uint64_t d, const std::vector<uint32_t>& blk, const std::vector<uint32_t>& cnt) {
     double best = kInf;
     uint32_t best_n = std::numeric_limits<uint32_t>::max();
-    for (uint32_t k = row_off[d]; k < row_off[d + 1]; ++k) {
-      const int e = row[k];
+    for (uint32_t k = aoff[d]; k < aoff[d + 1]; ++k) {
+      const int e = arow[k];
       ++ctr.S;
       if (cost[(size_t)e] * best_n >= best * (e_off[(size_t)e + 1] - e_off[(size_t)e])) break;
       if (!blk[(size_t)e] && cost[(size_t)e] * best_n < best * cnt[(size_t)e]) {
@@ -303,7 +314,7 @@ struct Decoder {
         throw std::runtime_error("Symptom " + std::to_string(d) + " references a detector >= num_detectors (= " +
                                  std::to_string(D) + ").");
       root[d] = true;
-      for (uint32_t k = row_off[d]; k < row_off[d + 1]; ++k) ++count[(size_t)row[k]];
+      for (uint32_t k = aoff[d]; k < aoff[d + 1]; ++k) ++count[(size_t)arow[k]];
     }
     double f0 = 0;
     for (uint64_t d : hits) f0 += detcost(d, blocked, count);
@@ -330,9 +341,9 @@ struct Decoder {
       for (int64_t at = node.chain; at != -1; at = chain[(size_t)at].parent) {
         const ChainLink& link = chain[(size_t)at];
         ++ctr.L;
-        for (uint32_t k = row_off[link.min_det]; k < row_off[link.min_det + 1]; ++k) {
-          blocked[(size_t)row[k]] = 1;
-          if ((uint32_t)row[k] == link.error) break;
+        for (uint32_t k = aoff[link.min_det]; k < aoff[link.min_det + 1]; ++k) {
+          blocked[(size_t)arow[k]] = 1;
+          if ((uint32_t)arow[k] == link.error) break;
         }
         for (uint32_t k = e_off[link.error]; k < e_off[link.error + 1]; ++k) fired[(size_t)edet[k]] = !fired[(size_t)edet[k]];
       }
@@ -358,7 +369,7 @@ struct Decoder {
       }
       for (uint64_t d = 0; d < D; ++d)
         if (fired[d])
-          for (uint32_t k = row_off[d]; k < row_off[d + 1]; ++k) ++count[(size_t)row[k]];
+          for (uint32_t k = aoff[d]; k < aoff[d + 1]; ++k) ++count[(size_t)arow[k]];
       child_blocked = blocked;
       child_count = count;
       uint64_t min_det = kGone;
@@ -369,13 +380,13 @@ struct Decoder {
         }
       std::fill(memo.begin(), memo.end(), -1.0);
       int64_t prev = -1;
-      for (uint32_t k = row_off[min_det]; k < row_off[min_det + 1]; ++k) {
-        const int e = row[k];
+      for (uint32_t k = aoff[min_det]; k < aoff[min_det + 1]; ++k) {
+        const int e = arow[k];
         if (blocked[(size_t)e]) continue;
         if (prev >= 0)  // undo the previous sibling's count deltas (tesseract.cc:536-543)
           for (uint32_t j = e_off[(size_t)prev]; j < e_off[(size_t)prev + 1]; ++j) {
             const int d = edet[j], delta = fired[(size_t)d] ? 1 : -1;
-            for (uint32_t q = row_off[(size_t)d]; q < row_off[(size_t)d + 1]; ++q) child_count[(size_t)row[q]] += (uint32_t)delta;
+            for (uint32_t q = aoff[(size_t)d]; q < aoff[(size_t)d + 1]; ++q) child_count[(size_t)arow[q]] += (uint32_t)delta;
           }
         prev = e;
         next_fired = fired;
@@ -387,7 +398,7 @@ struct Decoder {
           next_fired[(size_t)d] = !next_fired[(size_t)d];
           const int delta = next_fired[(size_t)d] ? 1 : -1;
           nd += (uint64_t)(int64_t)delta;
-          for (uint32_t q = row_off[(size_t)d]; q < row_off[(size_t)d + 1]; ++q) child_count[(size_t)row[q]] += (uint32_t)delta;
+          for (uint32_t q = aoff[(size_t)d]; q < aoff[(size_t)d + 1]; ++q) child_count[(size_t)arow[q]] += (uint32_t)delta;
         }
         if (nd > hi) continue;
         if (cfg.no_revisit) {
@@ -444,7 +455,73 @@ struct Decoder {
     return std::vector<int>(on.begin(), on.end());
   }
 
+  // tesseract.cc:45-69
+  static int suggest_limit_capped(size_t num_detectors, int base_degree, int max_limit) {
+    if (base_degree < 0) throw std::invalid_argument("sparsify_base_degree must be >= 0.");
+    if (num_detectors == 0 || max_limit <= 0) return 0;
+    const double exponent = (double)base_degree - 2.0, max_result = (double)max_limit;
+    const double log_result = exponent * std::log(4.5) - std::log(3.0) + std::log((double)num_detectors);
+    if (!std::isfinite(log_result) || log_result >= std::log(max_result)) return max_limit;
+    const double result = std::exp(log_result);
+    if (!std::isfinite(result)) return max_limit;
+    const double rounded = std::round(result);
+    if (rounded >= max_result) return max_limit;
+    return (int)rounded;
+  }
+
+  void init_sparsify() {  // tesseract.cc:256-292
+    if (!cfg.sparsify) return;
+    if (cfg.sparsify_base_degree <= 0) throw std::invalid_argument("sparsify_base_degree must be > 0 when sparsify_errors is enabled.");
+    if (cfg.sparsify_max_degree < -1) throw std::invalid_argument("sparsify_max_degree must be >= -1.");
+    if (cfg.sparsify_reactivate_limit < -1) throw std::invalid_argument("sparsify_reactivate_limit must be >= -1.");
+    if (cfg.sparsify_max_degree >= 0 && cfg.sparsify_max_degree < cfg.sparsify_base_degree)
+      throw std::invalid_argument("sparsify_max_degree must be >= sparsify_base_degree.");
+    if (cfg.sparsify_reactivate_limit == -1)
+      cfg.sparsify_reactivate_limit =
+          suggest_limit_capped(D, cfg.sparsify_base_degree, (int)std::min<uint64_t>(E, (uint64_t)std::numeric_limits<int>::max()));
+    for (uint64_t e = 0; e < E; ++e) {
+      const int degree = (int)(e_off[e + 1] - e_off[e]);
+      if (degree <= cfg.sparsify_base_degree) mandatory.push_back((int)e);
+      else if (cfg.sparsify_max_degree == -1 || degree <= cfg.sparsify_max_degree) optional.push_back((int)e);
+    }
+    active.assign(E, 0);
+  }
+
+  void build_sparse_rows(const std::vector<uint64_t>& hits) {  // tesseract.cc:673-737
+    std::vector<uint8_t> shot(D, 0);
+    for (uint64_t d : hits)
+      if (d < D) shot[d] = 1;
+    std::fill(active.begin(), active.end(), 0);
+    for (int e : mandatory) active[(size_t)e] = 1;
+    struct Cand {
+      int e, overlap, degree;
+      double cost;
+    };
+    std::vector<Cand> cands;
+    for (int e : optional) {
+      int overlap = 0;
+      for (uint32_t k = e_off[(size_t)e]; k < e_off[(size_t)e + 1]; ++k) overlap += shot[(size_t)edet[k]];
+      if (overlap > 0) cands.push_back({e, overlap, (int)(e_off[(size_t)e + 1] - e_off[(size_t)e]), cost[(size_t)e]});
+    }
+    std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) {
+      if (a.overlap != b.overlap) return a.overlap > b.overlap;
+      if (a.degree != b.degree) return a.degree < b.degree;
+      if (a.cost != b.cost) return a.cost < b.cost;
+      return a.e < b.e;
+    });
+    const size_t limit = std::min<size_t>((size_t)cfg.sparsify_reactivate_limit, cands.size());
+    for (size_t i = 0; i < limit; ++i) active[(size_t)cands[i].e] = 1;
+    aoff.assign(D + 1, 0);
+    arow.clear();
+    for (uint64_t d = 0; d < D; ++d) {
+      for (uint32_t k = row_off[d]; k < row_off[d + 1]; ++k)
+        if (active[(size_t)row[k]]) arow.push_back(row[k]);
+      aoff[d + 1] = (uint32_t)arow.size();
+    }
+  }
+
   void decode(const std::vector<uint64_t>& hits) {  // tesseract.cc:295-347
+    if (cfg.sparsify) build_sparse_rows(hits);
     std::vector<uint64_t> best;
     double best_cost = std::numeric_limits<double>::max();
     auto consider = [&] {
@@ -509,6 +586,10 @@ orc_handle* orc_create(const char* dem_text, const orc_config* cfg) {
     c.merge = cfg->merge_errors != 0;
     c.pqlimit = cfg->pqlimit;
     c.det_penalty = cfg->det_penalty;
+    c.sparsify = cfg->sparsify_errors != 0;
+    c.sparsify_base_degree = cfg->sparsify_base_degree;
+    c.sparsify_max_degree = cfg->sparsify_max_degree;
+    c.sparsify_reactivate_limit = cfg->sparsify_reactivate_limit;
     uint64_t D = dem.flattened().count_detectors();
     for (uint64_t k = 0; k < cfg->num_det_orders; ++k)
       c.orders.emplace_back(cfg->det_orders + k * D, cfg->det_orders + (k + 1) * D);

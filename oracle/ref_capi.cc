@@ -56,6 +56,10 @@ orc_handle* orc_create(const char* dem_text, const orc_config* cfg) {
     c.merge_errors = cfg->merge_errors != 0;
     c.pqlimit = cfg->pqlimit == UINT64_MAX ? std::numeric_limits<size_t>::max() : (size_t)cfg->pqlimit;
     c.det_penalty = cfg->det_penalty;
+    c.sparsify_errors = cfg->sparsify_errors != 0;
+    c.sparsify_base_degree = cfg->sparsify_base_degree;
+    c.sparsify_max_degree = cfg->sparsify_max_degree;
+    c.sparsify_reactivate_limit = cfg->sparsify_reactivate_limit;
     uint64_t D = tesseract_decoder::common::flatten(dem).count_detectors();
     for (uint64_t k = 0; k < cfg->num_det_orders; ++k)
       c.det_orders.emplace_back(cfg->det_orders + k * D, cfg->det_orders + (k + 1) * D);

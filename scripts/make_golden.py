@@ -35,10 +35,21 @@ SETS = {
     "g_c5_transcx_d5_penalty": (W.CONFIGS["C5"], 200, 1005),
     "g_transcx_d3_nomerge": (dict(dem="transcx_d3_p0.001_X", det_beam=5, pqlimit=200000, no_revisit_dets=True, merge_errors=False,
                                   num_det_orders=0, det_penalty=0.25), 300, 9),
+    # --sparsify-errors (tesseract.cc:256-292, 673-737): reference outputs for the next hot-path row
+    "s_color_d5_base3": (dict(dem="color_superdense_d5_r5_p0.001_Z", det_beam=5, pqlimit=200000, no_revisit_dets=True,
+                              num_det_orders=3, sparsify_errors=True, sparsify_base_degree=3), 200, 41),
+    "s_surface_d5_base2_limit8": (dict(dem="surface_d5_r5_p0.002_X", det_beam=5, pqlimit=200000, no_revisit_dets=True,
+                                       num_det_orders=0, sparsify_errors=True, sparsify_base_degree=2, sparsify_max_degree=4,
+                                       sparsify_reactivate_limit=8), 300, 42),
+    "s_bb72_base3_climb": (dict(dem="bb72_r6_p0.001_X", det_beam=3, beam_climbing=True, pqlimit=20000, no_revisit_dets=True,
+                                num_det_orders=4, sparsify_errors=True, sparsify_base_degree=3), 64, 43),
 }
+only = sys.argv[1:]
 for name, (cfg, shots, seed) in SETS.items():
+    if only and name not in only:
+        continue
     dem, kw = W.decoder_kwargs(cfg, capi.build_det_orders)
-    host = capi.Decoder(dem, host_only=True, **kw)
+    host = capi.Decoder(dem, host_only=True, **{k: v for k, v in kw.items() if not k.startswith("sparsify")})
     dets, obs = capi.sample_dem_b8(dem, seed, shots, host.num_detectors, host.num_observables)
     ref = oracle.OracleDecoder(dem, kind="reference", num_threads=8, **kw)
     out = ref.decode_batch_b8(dets)

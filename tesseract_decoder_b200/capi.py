@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
     L.tsr_build_det_orders.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64, u64p]
     L.tsr_dem_count_detectors.restype = C.c_uint64
     L.tsr_dem_count_detectors.argtypes = [C.c_char_p]
+    L.tsr_dem_count_observables.restype = C.c_uint64
+    L.tsr_dem_count_observables.argtypes = [C.c_char_p]
     L.tsr_merge_weights.restype = C.c_double
     L.tsr_merge_weights.argtypes = [C.c_double, C.c_double]
     L.tsr_circuit_to_dem.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
@@ -117,7 +119,7 @@ EXPORTED_SYMBOLS = [
     "tsr_decode_batch_b8_device", "tsr_set_collect_errors", "tsr_cross_check_detcost", "tsr_set_instrumented", "tsr_search_path",
     "tsr_search_path_reason", "tsr_last_batch_nnz", "tsr_last_batch_errors", "tsr_decode",
     "tsr_cost_from_errors", "tsr_flipped_observables", "tsr_counters", "tsr_last_batch_timing", "tsr_stream",
-    "tsr_device", "tsr_build_det_orders", "tsr_dem_count_detectors", "tsr_merge_weights", "tsr_dem_from_counts", "tsr_circuit_to_dem",
+    "tsr_device", "tsr_build_det_orders", "tsr_dem_count_detectors", "tsr_dem_count_observables", "tsr_merge_weights", "tsr_dem_from_counts", "tsr_circuit_to_dem",
     "tsr_sample_dem_b8",
 ]
 
@@ -182,7 +184,20 @@ def merge_weights(a: float, b: float) -> float:
     return lib().tsr_merge_weights(a, b)
 
 
-def sample_dem_b8(dem_text: str, seed: int, shots: int, num_detectors: int, num_observables: int):
+def dem_count_observables(dem_text: str) -> int:
+    n = lib().tsr_dem_count_observables(dem_text.encode())
+    if n == (1 << 64) - 1:
+        raise ValueError(lib().tsr_last_error().decode())
+    return n
+
+
+def sample_dem_b8(dem_text: str, seed: int, shots: int, num_detectors: int | None = None, num_observables: int | None = None):
+    """i.i.d. DEM sampler -> (dets_b8 [shots, ceil(D/8)], obs_b8 [shots, ceil(O/8)]).  The counts are the DEM's own;
+    the optional arguments are only cross-checked (the C side writes ceil(D/8) / ceil(O/8) bytes per shot)."""
+    D, O = dem_count_detectors(dem_text), dem_count_observables(dem_text)
+    if (num_detectors is not None and num_detectors != D) or (num_observables is not None and num_observables != O):
+        raise ValueError(f"the DEM has {D} detectors and {O} observables, not {num_detectors} / {num_observables}")
+    num_detectors, num_observables = D, O
     dets = np.zeros((shots, (num_detectors + 7) // 8), dtype=np.uint8)
     obs = np.zeros((shots, max((num_observables + 7) // 8, 1)), dtype=np.uint8)
     _check(lib().tsr_sample_dem_b8(dem_text.encode(), seed, shots, _p(dets, C.c_uint8), _p(obs, C.c_uint8)))

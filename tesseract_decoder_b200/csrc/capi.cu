@@ -973,6 +973,12 @@ uint64_t tsr_dem_count_detectors(const char* dem_text) {
   return n;
 }
 
+uint64_t tsr_dem_count_observables(const char* dem_text) {
+  uint64_t n = UINT64_MAX;
+  guarded([&] { n = DemModel::parse(dem_text).count_observables(); });
+  return n;
+}
+
 double tsr_merge_weights(double a, double b) {
   return tsr::merge_weights(a, b);
 }

@@ -244,7 +244,21 @@ def test_det_index_orders(kind):  # utils.cc:173-190 (same mt19937_64 draws in b
         assert np.array_equal(got, oracle.build_det_orders(dem, 24, 1, W.CLI_ORDER_SEED, kind="reference"))
 
 
-@pytest.mark.parametrize("name", W.golden_names())
+def test_sparsify_known_answers(kind):  # tesseract.test.cc:478-540 (HighDegreeErrorRemoved), tesseract.cc:257-270
+    dem = "error(0.1) D0\nerror(0.1) D1\nerror(0.1) D2\nerror(0.1) D3\nerror(0.01) D0 D1 D2 D3"
+    assert OracleDecoder(dem, merge_errors=False, kind=kind).decode_to_errors([0, 1, 2, 3])[0] == [4]
+    sp = dict(merge_errors=False, kind=kind, sparsify_errors=True, sparsify_base_degree=2, sparsify_max_degree=4)
+    assert sorted(OracleDecoder(dem, sparsify_reactivate_limit=0, **sp).decode_to_errors([0, 1, 2, 3])[0]) == [0, 1, 2, 3]
+    assert OracleDecoder(dem, sparsify_reactivate_limit=1, **sp).decode_to_errors([0, 1, 2, 3])[0] == [4]
+    for bad, msg in ((dict(sparsify_base_degree=0), "sparsify_base_degree must be > 0"),
+                     (dict(sparsify_base_degree=2, sparsify_max_degree=-2), "sparsify_max_degree must be >= -1"),
+                     (dict(sparsify_base_degree=2, sparsify_reactivate_limit=-2), "sparsify_reactivate_limit must be >= -1"),
+                     (dict(sparsify_base_degree=3, sparsify_max_degree=2), "sparsify_max_degree must be >= sparsify_base_degree")):
+        with pytest.raises(oracle.OracleError, match=msg):
+            OracleDecoder(dem, kind=kind, sparsify_errors=True, **bad)
+
+
+@pytest.mark.parametrize("name", W.golden_names() + W.golden_names(sparsify=True))
 def test_golden_vectors(kind, name):
     """Committed outputs of the reference build: the checker in use must reproduce them bit for bit."""
     g = W.load_golden(name)

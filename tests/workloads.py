@@ -47,6 +47,9 @@ def decoder_kwargs(cfg: dict, build_det_orders) -> tuple[str, dict]:
     kw = dict(det_beam=cfg.pop("det_beam", 5), beam_climbing=cfg.pop("beam_climbing", False),
               no_revisit_dets=cfg.pop("no_revisit_dets", True), merge_errors=cfg.pop("merge_errors", True),
               pqlimit=cfg.pop("pqlimit", 200000), det_penalty=cfg.pop("det_penalty", 0.0))
+    for k in ("sparsify_errors", "sparsify_base_degree", "sparsify_max_degree", "sparsify_reactivate_limit"):
+        if k in cfg:  # understood by the CPU checkers only, so far
+            kw[k] = cfg.pop(k)
     assert not cfg, f"unknown config keys {cfg}"
     kw["det_orders"] = build_det_orders(dem, n_orders, method, seed) if n_orders else None
     return dem, kw
@@ -59,8 +62,11 @@ def load_golden(name: str) -> dict:
     return out
 
 
-def golden_names() -> list[str]:
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+def golden_names(sparsify: bool = False) -> list[str]:
+    """Committed golden sets; names starting with "s_" use --sparsify-errors (reference outputs pinned for the next
+    hot-path row; the CUDA path does not implement it yet)."""
+    names = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    return [n for n in names if n.startswith("s_") == sparsify]
 
 
 def split_lists(offsets, idx):
