@@ -41,6 +41,12 @@ struct TesseractConfig {
   double det_penalty = 0;
   bool create_visualization = false;
   bool at_most_two_errors_per_detector = false;  // README.md:59,159 (no code in the reference snapshot)
+  // tesseract.h:52-55.  Accepted and validated like the reference (tesseract.cc:256-270); decoding with
+  // sparsify_errors = true is not implemented on the device yet and fails loudly (never a silent fallback).
+  bool sparsify_errors = false;
+  int sparsify_base_degree = -1;
+  int sparsify_max_degree = -1;
+  int sparsify_reactivate_limit = -1;
   int device = -1;
 
   std::string str() const {  // tesseract.cc:84-117
@@ -76,6 +82,17 @@ struct TesseractDecoder {
   std::vector<size_t> dem_error_to_error, error_to_dem_error;
 
   explicit TesseractDecoder(TesseractConfig cfg, bool host_only = false) : config(std::move(cfg)) {
+    if (config.sparsify_errors) {  // tesseract.cc:256-270
+      if (config.sparsify_base_degree <= 0)
+        throw std::invalid_argument("sparsify_base_degree must be > 0 when sparsify_errors is enabled.");
+      if (config.sparsify_max_degree < -1) throw std::invalid_argument("sparsify_max_degree must be >= -1.");
+      if (config.sparsify_reactivate_limit < -1) throw std::invalid_argument("sparsify_reactivate_limit must be >= -1.");
+      if (config.sparsify_max_degree >= 0 && config.sparsify_max_degree < config.sparsify_base_degree)
+        throw std::invalid_argument("sparsify_max_degree must be >= sparsify_base_degree.");
+      throw std::runtime_error(
+          "tesseract_b200: sparsify_errors is not implemented on the GPU decode path yet (DESIGN.md, next hot-path row); "
+          "decode with sparsify_errors = false");
+    }
     tsr_config c;
     tsr_config_init(&c);
     c.det_beam = config.det_beam;

@@ -205,6 +205,7 @@ int main(int argc, char** argv) {
       {"--verbose", &a.verbose}, {"--print-stats", &a.print_stats}, {"--convert-only", &a.convert_only},
       {"--in-includes-appended-observables", &a.in_includes_appended_observables},
       {"--in_includes_appended_observables", &a.in_includes_appended_observables}};
+  TesseractConfig config_sparsify;  // carries the --sparsify-* flags (validated, then refused: not on the device yet)
   try {
     for (int i = 1; i < argc; ++i) {
       const std::string k = argv[i];
@@ -230,6 +231,10 @@ int main(int argc, char** argv) {
       else if (k == "--threads") a.num_threads = std::stoi(need());
       else if (k == "--gpus") a.gpus = std::stoi(need());
       else if (k == "--batch") a.batch = std::stoull(need());
+      else if (k == "--sparsify-errors") config_sparsify.sparsify_errors = true;
+      else if (k == "--sparsify-base-degree") config_sparsify.sparsify_base_degree = std::stoi(need());
+      else if (k == "--sparsify-max-degree") config_sparsify.sparsify_max_degree = std::stoi(need());
+      else if (k == "--sparsify-reactivate-limit") config_sparsify.sparsify_reactivate_limit = std::stoi(need());
       else if (k == "-h" || k == "--help") usage("tesseract (B200): A* most-likely-error decoder");
       else usage("unknown argument " + k);
     }
@@ -272,6 +277,10 @@ int main(int argc, char** argv) {
     config.pqlimit = a.pqlimit;
     config.verbose = a.verbose;
     config.det_orders = build_det_orders(dem_text, a.num_det_orders, (DetOrder)a.det_order_method, a.det_order_seed);
+    config.sparsify_errors = config_sparsify.sparsify_errors;
+    config.sparsify_base_degree = config_sparsify.sparsify_base_degree;
+    config.sparsify_max_degree = config_sparsify.sparsify_max_degree;
+    config.sparsify_reactivate_limit = config_sparsify.sparsify_reactivate_limit;
 
     std::vector<std::unique_ptr<TesseractDecoder>> decoders;
     for (int g = 0; g < a.gpus; ++g) {

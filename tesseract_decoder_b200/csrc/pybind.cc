@@ -24,7 +24,8 @@ std::string dem_text(const py::object& dem) {
 // tesseract.pybind.h:38-73: an empty det_orders argument means 20 DetIndex orders, seed 2384753.
 TesseractConfig make_config(const std::string& dem, int det_beam, bool beam_climbing, bool no_revisit_dets, bool verbose,
                             bool merge_errors, size_t pqlimit, std::vector<std::vector<size_t>> det_orders, double det_penalty,
-                            bool create_visualization, bool at_most_two) {
+                            bool create_visualization, bool at_most_two, bool sparsify_errors = false, int sparsify_base_degree = -1,
+                            int sparsify_max_degree = -1, int sparsify_reactivate_limit = -1) {
   if (det_orders.empty()) det_orders = build_det_orders(dem, 20, DetOrder::DetIndex, 2384753);
   TesseractConfig c;
   c.dem = dem;
@@ -38,6 +39,10 @@ TesseractConfig make_config(const std::string& dem, int det_beam, bool beam_clim
   c.det_penalty = det_penalty;
   c.create_visualization = create_visualization;
   c.at_most_two_errors_per_detector = at_most_two;
+  c.sparsify_errors = sparsify_errors;
+  c.sparsify_base_degree = sparsify_base_degree;
+  c.sparsify_max_degree = sparsify_max_degree;
+  c.sparsify_reactivate_limit = sparsify_reactivate_limit;
   return c;
 }
 
@@ -220,24 +225,31 @@ PYBIND11_MODULE(_tesseract_b200, root) {
   py::class_<TesseractConfig>(m, "TesseractConfig")
       .def(py::init<>())
       .def(py::init([](int det_beam, bool beam_climbing, bool no_revisit_dets, bool verbose, bool merge_errors, size_t pqlimit,
-                       std::vector<std::vector<size_t>> det_orders, double det_penalty, bool create_visualization, bool at_most_two) {
+                       std::vector<std::vector<size_t>> det_orders, double det_penalty, bool create_visualization, bool sparsify_errors,
+                       int sparsify_base_degree, int sparsify_max_degree, int sparsify_reactivate_limit, bool at_most_two) {
              return make_config("", det_beam, beam_climbing, no_revisit_dets, verbose, merge_errors, pqlimit, std::move(det_orders),
-                                det_penalty, create_visualization, at_most_two);
+                                det_penalty, create_visualization, at_most_two, sparsify_errors, sparsify_base_degree,
+                                sparsify_max_degree, sparsify_reactivate_limit);
            }),
            py::arg("det_beam") = 5, py::arg("beam_climbing") = false, py::arg("no_revisit_dets") = true, py::arg("verbose") = false,
            py::arg("merge_errors") = true, py::arg("pqlimit") = 200000, py::arg("det_orders") = std::vector<std::vector<size_t>>(),
-           py::arg("det_penalty") = 0.0, py::arg("create_visualization") = false,
+           py::arg("det_penalty") = 0.0, py::arg("create_visualization") = false, py::arg("sparsify_errors") = false,
+           py::arg("sparsify_base_degree") = -1, py::arg("sparsify_max_degree") = -1, py::arg("sparsify_reactivate_limit") = -1,
            py::arg("at_most_two_errors_per_detector") = false)
       .def(py::init([](const py::object& dem, int det_beam, bool beam_climbing, bool no_revisit_dets, bool verbose, bool merge_errors,
                        size_t pqlimit, std::vector<std::vector<size_t>> det_orders, double det_penalty, bool create_visualization,
+                       bool sparsify_errors, int sparsify_base_degree, int sparsify_max_degree, int sparsify_reactivate_limit,
                        bool at_most_two) {
              return make_config(dem_text(dem), det_beam, beam_climbing, no_revisit_dets, verbose, merge_errors, pqlimit,
-                                std::move(det_orders), det_penalty, create_visualization, at_most_two);
+                                std::move(det_orders), det_penalty, create_visualization, at_most_two, sparsify_errors,
+                                sparsify_base_degree, sparsify_max_degree, sparsify_reactivate_limit);
            }),
            py::arg("dem"), py::arg("det_beam") = 5, py::arg("beam_climbing") = false, py::arg("no_revisit_dets") = true,
            py::arg("verbose") = false, py::arg("merge_errors") = true, py::arg("pqlimit") = 200000,
            py::arg("det_orders") = std::vector<std::vector<size_t>>(), py::arg("det_penalty") = 0.0,
-           py::arg("create_visualization") = false, py::arg("at_most_two_errors_per_detector") = false)
+           py::arg("create_visualization") = false, py::arg("sparsify_errors") = false, py::arg("sparsify_base_degree") = -1,
+           py::arg("sparsify_max_degree") = -1, py::arg("sparsify_reactivate_limit") = -1,
+           py::arg("at_most_two_errors_per_detector") = false)
       .def_property(
           "dem", [](const TesseractConfig& c) { return c.dem; },
           [](TesseractConfig& c, const py::object& dem) { c.dem = dem_text(dem); },
@@ -252,6 +264,10 @@ PYBIND11_MODULE(_tesseract_b200, root) {
       .def_readwrite("det_penalty", &TesseractConfig::det_penalty)
       .def_readwrite("create_visualization", &TesseractConfig::create_visualization)
       .def_readwrite("at_most_two_errors_per_detector", &TesseractConfig::at_most_two_errors_per_detector)
+      .def_readwrite("sparsify_errors", &TesseractConfig::sparsify_errors)
+      .def_readwrite("sparsify_base_degree", &TesseractConfig::sparsify_base_degree)
+      .def_readwrite("sparsify_max_degree", &TesseractConfig::sparsify_max_degree)
+      .def_readwrite("sparsify_reactivate_limit", &TesseractConfig::sparsify_reactivate_limit)
       .def_readwrite("device", &TesseractConfig::device, "CUDA device ordinal (-1 = current device)")
       .def("__str__", &TesseractConfig::str)
       .def("compile_decoder", [](const TesseractConfig& self) { return std::make_unique<TesseractDecoder>(self); })

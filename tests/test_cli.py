@@ -30,6 +30,14 @@ def test_argument_validation():
     assert r.returncode != 0 and "unknown argument" in r.stderr
     r = run("--dem", "/nonexistent.dem", "--sample-num-shots", 5)
     assert r.returncode != 0 and "Failed to open" in r.stderr
+    dem = os.path.join(W.GOLDEN, "..", "..", "gpurun_out", "_cli_test.dem")
+    os.makedirs(os.path.dirname(dem), exist_ok=True)
+    with open(dem, "w") as f:
+        f.write("error(0.1) D0 L0\nerror(0.1) D0 D1")
+    r = run("--dem", dem, "--sample-num-shots", 5, "--sparsify-errors", "--sparsify-base-degree", 0)
+    assert r.returncode != 0 and "sparsify_base_degree must be > 0" in r.stderr  # tesseract.cc:257-260
+    r = run("--dem", dem, "--sample-num-shots", 5, "--sparsify-errors", "--sparsify-base-degree", 2)
+    assert r.returncode != 0 and "not implemented on the GPU decode path yet" in r.stderr
 
 
 @pytest.mark.gpu

@@ -65,6 +65,21 @@ def test_invalid_inputs_without_decoding():
         tesseract.TesseractConfig(Dem("error(1.5) D0")).compile_decoder()
 
 
+def test_sparsify_options_are_validated_and_refused_loudly():  # tesseract_test.py:295-465, tesseract.cc:256-270
+    dem = Dem(_DETECTOR_ERROR_MODEL)
+    c = tesseract.TesseractConfig(dem, sparsify_errors=True, sparsify_base_degree=2, sparsify_max_degree=4, sparsify_reactivate_limit=3)
+    assert (c.sparsify_errors, c.sparsify_base_degree, c.sparsify_max_degree, c.sparsify_reactivate_limit) == (True, 2, 4, 3)
+    assert tesseract.TesseractConfig(dem).sparsify_errors is False and tesseract.TesseractConfig(dem).sparsify_base_degree == -1
+    for kw, msg in ((dict(sparsify_base_degree=0), "sparsify_base_degree must be > 0 when sparsify_errors is enabled."),
+                    (dict(sparsify_base_degree=2, sparsify_max_degree=-2), "sparsify_max_degree must be >= -1."),
+                    (dict(sparsify_base_degree=2, sparsify_reactivate_limit=-2), "sparsify_reactivate_limit must be >= -1."),
+                    (dict(sparsify_base_degree=3, sparsify_max_degree=2), "sparsify_max_degree must be >= sparsify_base_degree.")):
+        with pytest.raises(ValueError, match=msg.replace(".", r"\.")):
+            tesseract.TesseractConfig(dem, sparsify_errors=True, **kw).compile_decoder()
+    with pytest.raises(RuntimeError, match="not implemented on the GPU decode path yet"):  # no silent fallback
+        c.compile_decoder()
+
+
 # ---- on the GPU ----------------------------------------------------------------------------------------
 
 @pytest.mark.gpu
