@@ -12,13 +12,19 @@ collective); per step one all-reduce sums {shots, logical errors, low confidence
   value   shots/s with the syndromes already resident in HBM (tsr_decode_batch_b8_device), whole job.
   e2e     the same through the host-buffer entry point (tsr_decode_batch_b8) with pinned host buffers:
           H2D of the bit-packed syndromes and D2H of observables / costs / flags inside the timed region.
-  roofline  algorithmic bytes (B_shot from the search's own counters Q,P,L,S,A,V) over the
-          search kernel's CUDA-event time, against the measured HBM copy bandwidth.
+  roofline  the task's HBM-class figure: algorithmic bytes (B_shot from the search's own counters
+          Q,P,L,S,A,V — the bytes the REFERENCE's loops touch for the same search) over the search kernel's
+          CUDA-event time, against the measured HBM copy bandwidth.  The tables are L2-resident, so this is a
+          work rate, not DRAM use; `issue` beside it is what actually bounds the kernel (warp instructions
+          per second against the SM issue peak, from the committed ncu capture).
   cpu_baseline  the reference's own decoder (oracle/_ref, built from the unmodified reference sources) or the
           CPU port, shot-parallel on all host cores, on a bounded prefix of the same shots; every shot it
-          decodes is also compared with the GPU's answer.
+          decodes is compared with the GPU's answer (observables, costs, flags and error lists).
+  workloads  (N=1, default workload only) the other BASELINE.json configs at their literal flags, each with
+          value / e2e / roofline frac / cpu / mismatches, on batches sized to a few seconds.
 
---impl reference times that CPU decoder alone (rank 0 only), on the same workload.
+Any mismatch against the CPU decoder makes the run exit non-zero (after printing the line).
+--impl reference times that CPU decoder alone (rank 0 only), on the same workload; it loads only oracle/.
 """
 import argparse
 import json
@@ -36,36 +42,51 @@ import numpy as np  # noqa: E402
 
 import workloads as W  # noqa: E402
 
-# Bench workloads: BASELINE.json configs, SURVEY.md §8d flags.  The headline metric is quoted on the
-# bivariate-bicycle [[144,12,12]] code (configs[3]); the config leaves p open — p=1e-4 is the noise level at
+# Bench workloads: BASELINE.json configs at their literal flags.  The headline metric is quoted on
+# the bivariate-bicycle [[144,12,12]] code (configs[3]); the config leaves p open — p=1e-4 is the noise level at
 # which the literal flags (unbounded beam and queue) are a million-shot workload at all.
+# `side`: (shots, steps, warmup, cpu_seconds) when the workload runs as an entry of the headline's `workloads` array.
 WORKLOADS = {
-    "bb144": dict(cfg=W.CONFIGS["C4"], shots=262144,
+    "bb144": dict(cfg=W.CONFIGS["C4"], shots=262144, tag="C4 bb144 p=1e-4",
                   name="bivariate-bicycle [[144,12,12]] r=12 si1000 p=1e-4 X, --num-det-orders 24 --no-revisit-dets "
                        "(DetIndex, seed 518278944), beam/pqlimit unbounded (CLI defaults)"),
-    "bb144_p5e-4": dict(cfg=dict(W.CONFIGS["C4"], dem="bb144_r12_p0.0005_X"), shots=4096,
-                        name="bivariate-bicycle [[144,12,12]] r=12 si1000 p=5e-4 X, --num-det-orders 24 --no-revisit-dets"),
+    "surface_d5": dict(cfg=W.CONFIGS["C1"], shots=1 << 20, tag="C1 surface d5", side=(262144, 3, 1, 2.0),
+                       name="surface code d=5 r=5 p=0.002 X, --beam 5 --pqlimit 200000"),
+    "color_d7": dict(cfg=W.CONFIGS["C2"], shots=4096, tag="C2 color d7 literal", side=(2048, 2, 1, 3.0),
+                     name="superdense color code d=7 r=7 p=0.001 X, --num-det-orders 1, CLI defaults otherwise "
+                          "(beam and pqlimit unbounded, revisits allowed)"),
+    "surface_d11": dict(cfg=W.CONFIGS["C3"], shots=8192, tag="C3 surface d11 climb", side=(2048, 2, 1, 3.0),
+                        name="surface code d=11 r=11 p=0.001 X, --beam 23 --beam-climbing"),
+    "transcx_d5": dict(cfg=W.CONFIGS["C5"], shots=262144, tag="C5 transcx d5 penalty", side=(131072, 3, 1, 2.0),
+                       name="transversal-CNOT surface code d=5 p=0.001 X, --det-penalty 1"),
+    "transcx_d5_amt": dict(cfg=dict(W.CONFIGS["C5"], at_most_two_errors_per_detector=True), shots=262144,
+                           tag="C5 transcx d5 penalty at-most-two", side=(131072, 3, 1, 2.0), cpu_kind="port",
+                           name="transversal-CNOT surface code d=5 p=0.001 X, --det-penalty 1 --at-most-two-errors-per-detector "
+                                "(no reference code for this flag: checked against the CPU port)"),
     # the reference's own published sweep point (benchmarking/sparsify_errors/aggregated_results.jsonl:195, submit.sh:223):
     # 4.105 CPU-seconds per shot on their hardware
     "bb144_p1e-3_longbeam": dict(cfg=dict(dem="bb144_r12_p0.001_X", det_beam=20, beam_climbing=True, pqlimit=1000000,
-                                          no_revisit_dets=True, num_det_orders=21), shots=1024,
+                                          no_revisit_dets=True, num_det_orders=21), shots=1024, tag="bb144 p=1e-3 long-beam",
+                                 side=(256, 1, 1, 4.0), counters_from="port",
                                  name="bivariate-bicycle [[144,12,12]] r=12 si1000 p=1e-3 X, --beam 20 --beam-climbing --num-det-orders 21 "
                                       "--pqlimit 1000000 --no-revisit-dets (the reference's long-beam sweep point)"),
-    "surface_d5": dict(cfg=W.CONFIGS["C1"], shots=1 << 20, name="surface code d=5 r=5 p=0.002 X, --beam 5 --pqlimit 200000"),
-    "color_d7": dict(cfg=dict(W.CONFIGS["C2"], det_beam=5, pqlimit=200000, no_revisit_dets=True), shots=65536,
-                     name="superdense color code d=7 r=7 p=0.001 X, --num-det-orders 1 --beam 5 --pqlimit 200000 --no-revisit-dets"),
-    "surface_d11": dict(cfg=W.CONFIGS["C3"], shots=8192, name="surface code d=11 r=11 p=0.001 X, --beam 23 --beam-climbing"),
-    "transcx_d5": dict(cfg=W.CONFIGS["C5"], shots=262144, name="transversal-CNOT surface code d=5 p=0.001 X, --det-penalty 1"),
+    "bb144_p5e-4": dict(cfg=dict(W.CONFIGS["C4"], dem="bb144_r12_p0.0005_X"), shots=4096, tag="C4 bb144 p=5e-4",
+                        name="bivariate-bicycle [[144,12,12]] r=12 si1000 p=5e-4 X, --num-det-orders 24 --no-revisit-dets"),
 }
+SIDE_ORDER = ["surface_d5", "color_d7", "surface_d11", "transcx_d5", "transcx_d5_amt", "bb144_p1e-3_longbeam"]
 L2_FLUSH_BYTES = 256 << 20
+MAX_CHUNK = 1 << 18  # tsr_config.max_batch_shots default: shots per search launch
+# Issue-slot peak of one B200: 148 SMs x 4 schedulers x 1 warp instruction per cycle at the measured max SM clock.
+ISSUE_PEAK_PER_CLOCK = 148 * 4
 
 
-def measured_peak_gbs():
+def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            j = json.load(f)
+            return float(j["hbm_gbs"]), float(j.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -121,9 +142,18 @@ def algorithmic_bytes(c, shots, D, O):
             + 16 * c["S"] + 4 * c["A"] + Wv * c["V"])
 
 
-def cpu_decoder(dem, kw, threads):
+def oracle_kwargs(kw):
+    """Decoder keywords the CPU checkers understand (the device-resource knobs are the product's own)."""
+    return dict(kw)
+
+
+def cpu_decoder(dem, kw, threads, kind=None):
     from oracle import oracle
-    kind = "reference" if oracle.available("reference") else "port"
+    if kind is None:
+        kind = "reference" if oracle.available("reference") else "port"
+    if kw.get("at_most_two_errors_per_detector") and kind == "reference":
+        kind = "port"  # the reference snapshot has no code for this flag (SURVEY.md F4)
+    kw = {k: v for k, v in kw.items() if not (k == "at_most_two_errors_per_detector" and not v)}
     return oracle.OracleDecoder(dem, kind=kind, num_threads=threads, **kw), kind
 
 
@@ -131,6 +161,8 @@ def cpu_sample(dec, dets, target_seconds, threads):
     """Decode a prefix of `dets` sized for about target_seconds of wall time; returns (n, wall, result)."""
     n0 = min(len(dets), max(2 * threads, 16))
     r0 = dec.decode_batch_b8(dets[:n0])
+    if r0["wall_seconds"] >= target_seconds or n0 == len(dets):
+        return n0, r0["wall_seconds"], r0
     rate = n0 / max(r0["wall_seconds"], 1e-6)
     n = int(min(len(dets), max(n0, rate * target_seconds)))
     r = dec.decode_batch_b8(dets[:n])
@@ -138,15 +170,18 @@ def cpu_sample(dec, dets, target_seconds, threads):
 
 
 def run_reference(args, wl, rank):
+    """The reference's own CPU decoder on this workload.  Loads oracle/ only: det orders and the synthetic shots come
+    from the checker side (oracle.build_det_orders, oracle.sample_dem_b8), not from the product library."""
     if rank != 0:
         return
-    from tesseract_decoder_b200 import capi  # host-side helpers only (DEM sampler, det orders): no GPU use
-    dem, kw = W.decoder_kwargs(wl["cfg"], capi.build_det_orders)
+    from oracle import oracle
+    kind = "reference" if oracle.available("reference") else "port"
+    dem, kw = W.decoder_kwargs(wl["cfg"], lambda d, n, m, s: oracle.build_det_orders(d, n, m, s, kind=kind))
     threads = os.cpu_count() or 1
-    dec, kind = cpu_decoder(dem, kw, threads)
+    dec, kind = cpu_decoder(dem, kw, threads, kind)
     D, O = dec.num_detectors, dec.num_observables
     shots = args.shots or wl["shots"]
-    dets, _ = capi.sample_dem_b8(dem, 1000, shots, D, O)
+    dets, _ = oracle.sample_dem_b8(dem, 1000, shots, kind=kind)
     budget = args.ref_seconds / (args.steps + args.warmup)  # seconds of CPU wall per step
     n, _, _ = cpu_sample(dec, dets, budget, threads)
     for _ in range(args.warmup):
@@ -167,9 +202,162 @@ def run_reference(args, wl, rank):
     }))
 
 
+class Bench:
+    """One workload on this rank's GPU: buffers, the two timed legs, counters and the CPU comparison."""
+
+    def __init__(self, args, wl, S, rank, world, local, dist):
+        import torch
+        from tesseract_decoder_b200 import capi
+        self.torch, self.capi, self.args, self.wl, self.S = torch, capi, args, wl, S
+        self.rank, self.world, self.local, self.dist = rank, world, local, dist
+        self.dem, self.kw = W.decoder_kwargs(wl["cfg"], capi.build_det_orders)
+        self.dec = capi.Decoder(self.dem, device=local, warps_per_block=args.warps, force_generic_kernel=args.scan == "generic",
+                                row_scan={"lanes": 1, "bits": 2}.get(args.scan, 0), **self.kw)
+        self.dec.set_collect_errors(False)
+        self.D, self.O = self.dec.num_detectors, self.dec.num_observables
+        self.stride, self.ostride = (self.D + 7) // 8, (self.O + 7) // 8
+        self.dets, self.true_obs = capi.sample_dem_b8(self.dem, 1000 + rank, S, self.D, self.O)
+        # Device-resident buffers (value leg) and pinned host buffers (e2e leg).
+        self.d_dets = torch.from_numpy(self.dets).cuda()
+        self.d_true = torch.from_numpy(np.ascontiguousarray(self.true_obs)).cuda()
+        self.d_obs = torch.zeros((S, self.ostride), dtype=torch.uint8, device="cuda")
+        self.d_cost = torch.zeros(S, dtype=torch.float64, device="cuda")
+        self.d_low = torch.zeros(S, dtype=torch.uint8, device="cuda")
+        self.h_dets = torch.from_numpy(self.dets).pin_memory()
+        self.h_obs = torch.zeros((S, self.ostride), dtype=torch.uint8).pin_memory()
+        self.h_cost = torch.zeros(S, dtype=torch.float64).pin_memory()
+        self.h_low = torch.zeros(S, dtype=torch.uint8).pin_memory()
+        self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        self.tally = torch.zeros(3, dtype=torch.int64, device="cuda")
+        self.acc = {"search_ms": 0.0, "pipeline_ms": 0.0, "launches": 0, "rerun": 0}
+
+    def note_timing(self):
+        t = self.dec.last_batch_timing()
+        chunks = (self.S + MAX_CHUNK - 1) // MAX_CHUNK
+        self.acc["search_ms"] += t["search_ms"]
+        self.acc["pipeline_ms"] += t["pipeline_ms"]
+        self.acc["launches"] += 4 * chunks + 2 * t["search_launches"]  # stage + 3 ordering kernels per chunk, search + resolve per tier
+        self.acc["rerun"] += t["rerun_items"]
+
+    def reduce_counts(self, wrong, low):
+        self.tally[0], self.tally[1], self.tally[2] = self.S, wrong, low
+        if self.dist is not None:
+            self.dist.all_reduce(self.tally)  # the path's only collective: {shots, logical errors, low confidence}
+        return self.tally.tolist()
+
+    def step_device(self):
+        self.flush.zero_()  # evict L2 between steps (256 MB > 126 MB)
+        self.torch.cuda.synchronize()
+        self.dec.decode_batch_b8_device(self.d_dets.data_ptr(), self.stride, self.S, self.d_obs.data_ptr(), self.d_cost.data_ptr(),
+                                        self.d_low.data_ptr())
+        self.note_timing()
+        bad = ((self.d_obs != self.d_true).any(dim=1) & (self.d_low == 0)).sum()
+        return self.reduce_counts(bad, self.d_low.sum())
+
+    def step_e2e(self):
+        self.flush.zero_()
+        self.torch.cuda.synchronize()
+        self.dec.decode_batch_b8_raw(self.h_dets.data_ptr(), self.stride, self.S, self.h_obs.data_ptr(), self.h_cost.data_ptr(),
+                                     self.h_low.data_ptr())
+        self.note_timing()
+        low = self.h_low.numpy()
+        bad = int(((self.h_obs.numpy() != self.true_obs).any(axis=1) & (low == 0)).sum())
+        return self.reduce_counts(bad, int(low.sum()))
+
+    def timed(self, step, steps, warmup):
+        torch, dist = self.torch, self.dist
+        for _ in range(warmup):
+            step()
+        for k in self.acc:
+            self.acc[k] = 0
+        self.dec.counters(reset=True)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        sampler = ClockSampler(self.local) if self.rank == 0 else None
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            counts = step()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        dt = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([dt, self.acc["pipeline_ms"], self.acc["search_ms"]], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+        return t.tolist(), counts, clocks, dict(self.acc), self.dec.counters()
+
+    def instrumented_counters(self):
+        """Counters of one batch, S included (the instrumented kernel variant: one untimed pass over the same batch)."""
+        self.dec.set_instrumented(True)
+        self.dec.counters(reset=True)
+        self.step_device()
+        c = self.dec.counters(reset=True)
+        self.dec.set_instrumented(False)
+        return c
+
+    def compare_with_cpu(self, seconds, kind=None, want_counters=False):
+        """Times the CPU decoder on a prefix of this batch and compares every shot it decoded with the GPU's answers
+        (observables, cost, low-confidence flag and the error lists)."""
+        threads = os.cpu_count() or 1
+        cpu, kind = cpu_decoder(self.dem, self.kw, threads, kind)
+        n, wall, ref = cpu_sample(cpu, self.dets, seconds, threads)
+        self.dec.set_collect_errors(True)
+        out = self.dec.decode_batch_b8(self.dets[:n])
+        self.dec.set_collect_errors(False)
+        lists_g = W.split_lists(out["err_offsets"], out["err_idx"])
+        lists_c = W.split_lists(ref["err_offsets"], ref["err_idx"])
+        bad = ((ref["obs"] != out["obs"]).any(axis=1) | (ref["low_confidence"] != out["low_confidence"]) | (ref["cost"] != out["cost"])
+               | np.array([a != b for a, b in zip(lists_g, lists_c)], dtype=bool))
+        # the timed e2e leg wrote the same answers for these shots
+        bad |= (self.h_obs.numpy()[:n] != ref["obs"]).any(axis=1) | (self.h_low.numpy()[:n] != ref["low_confidence"]) \
+            | (self.h_cost.numpy()[:n] != ref["cost"])
+        mism = int(bad.sum())
+        rec = {"value": n / wall, "unit": "shots/s", "cores": threads, "kind": kind,
+               "sample": f"first {n} shots of the same batch, {wall:.1f} s wall, {mism} mismatches vs the GPU "
+                         "(obs, cost, low_conf, error lists)",
+               "cpu_seconds_per_shot": ref["sum_shot_seconds"] / n, "mismatches": mism, "shots_compared": n}
+        ctr = None
+        if want_counters:
+            from oracle import oracle
+            port = oracle.OracleDecoder(self.dem, kind="port", num_threads=threads,
+                                        **{k: v for k, v in self.kw.items() if not (k == "at_most_two_errors_per_detector" and not v)})
+            port.decode_batch_b8(self.dets[:n])
+            ctr = port.counters()
+        return rec, n, ctr
+
+
+def run_side_workload(args, key, rank, world, local):
+    """One entry of the `workloads` array: a BASELINE config at its literal flags on a batch sized to a few seconds."""
+    wl = WORKLOADS[key]
+    S, steps, warmup, cpu_s = wl["side"]
+    peak, _, _ = measured_peaks()
+    t_start = time.perf_counter()
+    b = Bench(args, wl, S, rank, world, local, None)
+    (dt, _, search_ms), counts, _, a, ctr = b.timed(b.step_device, steps, warmup)
+    (dt2, _, _), counts2, _, _, _ = b.timed(b.step_e2e, steps, warmup)
+    cpu, n_cpu, port_ctr = b.compare_with_cpu(cpu_s, wl.get("cpu_kind"), want_counters=wl.get("counters_from") == "port")
+    if port_ctr is not None:  # counters of the CPU port on its prefix, scaled to the batch (distinct trials == literal trials here)
+        b_shot = algorithmic_bytes(port_ctr, n_cpu, b.D, b.O) / n_cpu
+        src = f"CPU port on {n_cpu} shots"
+    else:
+        c1 = b.instrumented_counters()
+        assert all(ctr[k] == c1[k] * steps for k in ("Q", "P", "X", "L", "V")), (ctr, c1)
+        b_shot = algorithmic_bytes(c1, S, b.D, b.O) / S
+        src = "instrumented pass"
+    achieved = b_shot * S * steps / (a["search_ms"] * 1e-3) / 1e9 if a["search_ms"] > 0 else 0.0
+    rec = {"w": wl["tag"], "shots": S, "steps": steps, "value": round(S * steps / dt, 1), "e2e": round(S * steps / dt2, 1),
+           "frac": round(achieved / peak, 4), "MB_per_shot": round(b_shot / 1e6, 3), "cpu": round(cpu["value"], 1), "cpu_kind": cpu["kind"],
+           "cpu_shots": n_cpu, "mism": cpu["mismatches"], "low_conf": counts[2], "errors": counts[1],
+           "path": b.dec.search_path, "rerun": a["rerun"]}
+    print(f"[bench] {wl['tag']}: {json.dumps(rec)} (B_shot from the {src}; {time.perf_counter() - t_start:.1f} s)", file=sys.stderr, flush=True)
+    del b
+    return rec
+
+
 def run_b200(args, wl, rank, world, local):
     import torch
-    from tesseract_decoder_b200 import capi
 
     torch.cuda.set_device(local)
     dist = None
@@ -177,113 +365,46 @@ def run_b200(args, wl, rank, world, local):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    dem, kw = W.decoder_kwargs(wl["cfg"], capi.build_det_orders)
-    dec = capi.Decoder(dem, device=local, warps_per_block=args.warps, force_generic_kernel=args.scan == "generic",
-                       row_scan={"lanes": 1, "bits": 2}.get(args.scan, 0), **kw)
-    dec.set_collect_errors(False)
-    D, O = dec.num_detectors, dec.num_observables
     S = args.shots or wl["shots"]
-    stride, ostride = (D + 7) // 8, (O + 7) // 8
-    dets, true_obs = capi.sample_dem_b8(dem, 1000 + rank, S, D, O)
-
-    # Device-resident buffers (value leg) and pinned host buffers (e2e leg).
-    d_dets = torch.from_numpy(dets).cuda()
-    d_true = torch.from_numpy(np.ascontiguousarray(true_obs)).cuda()
-    d_obs = torch.zeros((S, ostride), dtype=torch.uint8, device="cuda")
-    d_cost = torch.zeros(S, dtype=torch.float64, device="cuda")
-    d_low = torch.zeros(S, dtype=torch.uint8, device="cuda")
-    h_dets = torch.from_numpy(dets).pin_memory()
-    h_obs = torch.zeros((S, ostride), dtype=torch.uint8).pin_memory()
-    h_cost = torch.zeros(S, dtype=torch.float64).pin_memory()
-    h_low = torch.zeros(S, dtype=torch.uint8).pin_memory()
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-    tally = torch.zeros(3, dtype=torch.int64, device="cuda")
-    acc = {"search_ms": 0.0, "pipeline_ms": 0.0, "launches": 0, "rerun": 0}
-
-    def note_timing():
-        t = dec.last_batch_timing()
-        chunks = (S + (1 << 18) - 1) >> 18
-        acc["search_ms"] += t["search_ms"]
-        acc["pipeline_ms"] += t["pipeline_ms"]
-        acc["launches"] += 4 * chunks + 2 * t["search_launches"]  # stage + 3 ordering kernels per chunk, search + resolve per tier
-        acc["rerun"] += t["rerun_items"]
-
-    def reduce_counts(wrong, low):
-        tally[0], tally[1], tally[2] = S, wrong, low
-        if dist is not None:
-            dist.all_reduce(tally)  # the path's only collective: {shots, logical errors, low confidence}
-        return tally.tolist()
-
-    def step_device():
-        flush.zero_()  # evict L2 between steps (256 MB > 126 MB)
-        torch.cuda.synchronize()
-        dec.decode_batch_b8_device(d_dets.data_ptr(), stride, S, d_obs.data_ptr(), d_cost.data_ptr(), d_low.data_ptr())
-        note_timing()
-        bad = ((d_obs != d_true).any(dim=1) & (d_low == 0)).sum()
-        return reduce_counts(bad, d_low.sum())
-
-    def step_e2e():
-        flush.zero_()
-        torch.cuda.synchronize()
-        dec.decode_batch_b8_raw(h_dets.data_ptr(), stride, S, h_obs.data_ptr(), h_cost.data_ptr(), h_low.data_ptr())
-        note_timing()
-        low = h_low.numpy()
-        bad = int(((h_obs.numpy() != true_obs).any(axis=1) & (low == 0)).sum())
-        return reduce_counts(bad, int(low.sum()))
+    b = Bench(args, wl, S, rank, world, local, dist)
+    dec, D, O = b.dec, b.D, b.O
 
     # Algorithmic bytes of one batch, from the search's own operation counters.  Counter S
     # (row entries the reference's early-exit loop visits) needs the instrumented kernel variant, so it is
     # taken from one untimed pass over the same batch; the timed steps run the production variant.
-    dec.set_instrumented(True)
-    dec.counters(reset=True)
-    step_device()
-    ctr1 = dec.counters(reset=True)
-    dec.set_instrumented(False)
-
-    def timed(step):
-        for _ in range(args.warmup):
-            step()
-        for k in acc:
-            acc[k] = 0
-        dec.counters(reset=True)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            counts = step()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        dt = time.perf_counter() - t0
-        clocks = sampler.stop() if sampler else None
-        t = torch.tensor([dt, acc["pipeline_ms"], acc["search_ms"]], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
-        return t.tolist(), counts, clocks, dict(acc), dec.counters()
-
-    (dt, pipe_ms, search_ms), counts, clocks, a, ctr = timed(step_device)
-    (dt2, _, _), counts2, _, _, _ = timed(step_e2e)
+    ctr1 = b.instrumented_counters()
+    (dt, pipe_ms, search_ms), counts, clocks, a, ctr = b.timed(b.step_device, args.steps, args.warmup)
+    (dt2, _, _), counts2, _, _, _ = b.timed(b.step_e2e, args.steps, args.warmup)
     total = S * world * args.steps
     value, e2e = total / dt, total / dt2
 
-    peak, peak_src = measured_peak_gbs()
+    peak, sm_max_mhz, peak_src = measured_peaks()
     alg = algorithmic_bytes(ctr1, S, D, O) * args.steps  # rank 0's launches: the same batch every step
     assert all(ctr[k] == ctr1[k] * args.steps for k in ("Q", "P", "X", "L", "V")), (ctr, ctr1)
-    n_launch = args.steps * ((S + (1 << 18) - 1) >> 18)  # tier-0 search launches (one per 262144-shot chunk)
+    n_launch = args.steps * ((S + MAX_CHUNK - 1) // MAX_CHUNK)  # tier-0 search launches (one per 262144-shot chunk)
     achieved = alg / (a["search_ms"] * 1e-3) / 1e9 if a["search_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "tsr::search_fast_kernel" if dec.search_path.startswith("fast") else "tsr::search_kernel", "algorithmic_bytes_per_launch": alg / n_launch,
-                "algorithmic_bytes_per_shot": alg / (S * args.steps), "kernel_ms_per_launch": a["search_ms"] / n_launch,
-                "launches_timed": n_launch, "scanned_entries_per_shot": ctr1["S"] / S, "search_path": dec.search_path,
-                "counters_per_batch": ctr1}
+                "peak_source": peak_src, "kernel": "tsr::search_fast_kernel" if dec.search_path.startswith("fast") else "tsr::search_kernel",
+                "what": "reference-equivalent algorithmic bytes (SURVEY.md 8d) / search-kernel time; tables are L2-resident, see `issue`",
+                "algorithmic_bytes_per_launch": alg / n_launch, "algorithmic_bytes_per_shot": alg / (S * args.steps),
+                "kernel_ms_per_launch": a["search_ms"] / n_launch, "launches_timed": n_launch,
+                "scanned_entries_per_shot": ctr1["S"] / S, "search_path": dec.search_path}
+    issue = None
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            per_shot = json.load(open(prof)).get(args.workload, {}).get("dram_bytes_per_shot")
-            if per_shot:
-                roofline["traffic"] = per_shot * min(S, 1 << 18)  # DRAM bytes per launch, from the committed ncu capture
+            rec = json.load(open(prof)).get(args.workload, {})
+            if rec.get("dram_bytes_per_shot"):
+                roofline["traffic"] = rec["dram_bytes_per_shot"] * min(S, MAX_CHUNK)  # DRAM bytes per launch, from the committed ncu capture
+            if rec.get("warp_instructions_per_shot"):
+                # what bounds the kernel: warp instructions issued per second against 148 SMs x 4 schedulers x SM clock
+                wi = rec["warp_instructions_per_shot"] * S * args.steps / (a["search_ms"] * 1e-3)
+                pk = ISSUE_PEAK_PER_CLOCK * sm_max_mhz * 1e6
+                issue = {"bound": "issue", "achieved": wi / 1e9, "peak": pk / 1e9, "unit": "G warp-instr/s", "frac": wi / pk,
+                         "warp_instructions_per_shot": rec["warp_instructions_per_shot"], "source": rec.get("source", "profiles/")}
+                for k in ("l2_hit_pct", "l2_throughput_pct", "achieved_occupancy_pct", "dram_pct_of_peak"):
+                    if k in rec:
+                        issue[k] = rec[k]
         except Exception:
             pass
 
@@ -294,27 +415,41 @@ def run_b200(args, wl, rank, world, local):
         "config": {"workload": wl["name"], "shots_per_gpu_per_step": S, "detectors": D, "errors": dec.num_errors, "observables": O,
                    "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MB write)", "sharding": f"shots x{world}, tables replicated"},
         "device_ms_per_step": pipe_ms / args.steps, "search_kernel_ms_per_step": search_ms / args.steps,
-        "e2e": {"value": e2e, "unit": "shots/s", "h2d_bytes_per_step": S * stride, "d2h_bytes_per_step": S * (ostride + 9),
+        "e2e": {"value": e2e, "unit": "shots/s", "h2d_bytes_per_step": S * b.stride, "d2h_bytes_per_step": S * (b.ostride + 9),
                 "ms_per_step": 1e3 * dt2 / args.steps},
         "gpu_launches": a["launches"], "rerun_items": a["rerun"],
         "tally": {"shots": counts[0], "logical_errors": counts[1], "low_confidence": counts[2], "e2e_equal": counts == counts2},
         "roofline": roofline, "clocks": clocks,
     }
+    if issue:
+        line["issue"] = issue
 
+    mismatches = 0
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        cpu, kind = cpu_decoder(dem, kw, threads)
-        n, wall, ref = cpu_sample(cpu, dets, args.cpu_seconds, threads)
-        mism = int((ref["obs"] != h_obs.numpy()[:n]).any(axis=1).sum() + (ref["low_confidence"] != h_low.numpy()[:n]).sum()
-                   + (ref["cost"] != h_cost.numpy()[:n]).sum())
-        line["cpu_baseline"] = {"value": n / wall, "unit": "shots/s", "cores": threads, "kind": kind,
-                                "sample": f"first {n} shots of the same batch, {wall:.1f} s wall",
-                                "cpu_seconds_per_shot": ref["sum_shot_seconds"] / n,
-                                "parity": {"shots": n, "mismatches_obs_cost_lowconf": mism}}
+        cpu, n_cpu, _ = b.compare_with_cpu(args.cpu_seconds)
+        mismatches += cpu["mismatches"]
+        line["cpu_baseline"] = cpu
+        line["config"]["parity"] = f"{cpu['mismatches']} mismatches / {n_cpu} shots vs the {cpu['kind']} CPU decoder"
+        line["tally"]["mismatches"] = cpu["mismatches"]
+    if rank == 0 and world == 1 and not args.no_side and args.workload == "bb144" and not args.shots:
+        del b
+        side = []
+        for key in SIDE_ORDER:
+            try:
+                side.append(run_side_workload(args, key, rank, world, local))
+            except Exception as e:  # a workload that cannot run is a failure of the run, reported in place
+                side.append({"w": WORKLOADS[key]["tag"], "error": f"{type(e).__name__}: {e}"[:200], "mism": -1})
+        line["workloads"] = side
+        mismatches += sum(abs(r["mism"]) for r in side)
+        line["config"]["parity"] += f"; side workloads: {sum(max(r['mism'], 0) for r in side)} mismatches, " \
+                                    f"{sum(1 for r in side if 'error' in r)} failed"
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    if mismatches:
+        print(f"[bench] FAILED: {mismatches} parity mismatches / failed workloads against the CPU decoder", file=sys.stderr)
+        sys.exit(1)
 
 
 def main():
@@ -328,6 +463,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="wall-time target of the cpu_baseline sample")
     ap.add_argument("--ref-seconds", type=float, default=150.0, help="--impl reference: wall-time budget of the whole run")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the `workloads` array (the other BASELINE configs)")
     ap.add_argument("--warps", type=int, default=0, help="warps per search CTA (0 = automatic)")
     ap.add_argument("--scan", default="auto", choices=["auto", "bits", "lanes", "generic"],
                     help="search kernel variant (auto = the decoder's choice)")

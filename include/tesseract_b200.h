@@ -49,7 +49,7 @@ typedef struct tsr_config {
   const uint64_t* det_orders; /* [num_det_orders][num_detectors] row-major, position -> detector */
   uint64_t det_order_len;  /* entries per order; must equal num_detectors (tesseract.cc:178-184); 0 = unchecked */
   /* Device resources; 0 = choose automatically. */
-  uint32_t search_slots;       /* concurrent searches (one warp each) */
+  uint32_t search_slots;       /* concurrent searches (fast path: one CTA each; generic kernel: one warp each) */
   uint32_t warps_per_block;
   uint64_t node_pool_bytes;    /* HBM set aside for heaps / chains / visited sets */
   uint64_t max_batch_shots;    /* shots staged per kernel launch */
@@ -146,6 +146,13 @@ int64_t tsr_cross_check_detcost(const tsr_decoder* h, uint64_t trials, uint64_t 
  * [5]=A sum(|edets|+|fired neighbours|) over evaluated children [6]=V visited inserts+probes
  * [7]=searches run (distinct (order, beam) trials only). */
 int tsr_counters(tsr_decoder* h, uint64_t out[8], int reset);
+/* Phase profile of the CTA-per-search kernel (diagnostic; off by default, a few clock reads per expansion when on).
+ * Ticks of the SM clock summed over every search CTA since the last reset, by phase of an expansion
+ * (csrc/search_fast.cu): [0]=pop [1]=state rebuild + goal / visited test [2]=detector terms of the node
+ * [3]=min detector + child list [4]=children (all warps) [5]=pushes [6]=shot staging, work claiming, table
+ * cleanup [7]=expansions (a count, not ticks). */
+int tsr_set_profile(tsr_decoder* h, int on);
+int tsr_profile(tsr_decoder* h, uint64_t out[8], int reset);
 /* Timing of the last batch, measured with CUDA events on tsr_stream(h): [0]=search kernel ms,
  * [1]=whole device pipeline ms (stage + search + resolve), [2]=search kernel launches,
  * [3]=items rerun in a larger node-pool tier. */

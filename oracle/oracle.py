@@ -39,6 +39,7 @@ class OrcConfig(C.Structure):
         ("sparsify_base_degree", C.c_int32),
         ("sparsify_max_degree", C.c_int32),
         ("sparsify_reactivate_limit", C.c_int32),
+        ("at_most_two_errors_per_detector", C.c_int32),
     ]
 
 
@@ -83,6 +84,7 @@ def _lib(kind: str) -> C.CDLL:
     lib.orc_merge_weights.restype = C.c_double
     lib.orc_merge_weights.argtypes = [C.c_double, C.c_double]
     lib.orc_counters.argtypes = [C.c_void_p, u64p, C.c_int]
+    lib.orc_sample_dem_b8.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, u8p, u8p]
     _libs[kind] = lib
     return lib
 
@@ -108,6 +110,19 @@ def build_det_orders(dem_text: str, num_det_orders: int, method: int = 1, seed: 
     return out
 
 
+def sample_dem_b8(dem_text: str, seed: int, shots: int, kind: str = "reference"):
+    """Synthetic i.i.d. shots of the DEM (oracle/sampler.inc): (dets [shots, ceil(D/8)], obs [shots, ceil(O/8)])."""
+    lib = _lib(kind)
+    tmp = OracleDecoder(dem_text, kind=kind)
+    D, O = tmp.num_detectors, tmp.num_observables
+    tmp.close()
+    dets = np.zeros((shots, (D + 7) // 8), dtype=np.uint8)
+    obs = np.zeros((shots, (O + 7) // 8), dtype=np.uint8)
+    if lib.orc_sample_dem_b8(dem_text.encode(), seed, shots, _p(dets, C.c_uint8), _p(obs, C.c_uint8)) != 0:
+        raise OracleError(lib.orc_last_error().decode())
+    return dets, obs
+
+
 def merge_weights(a: float, b: float, kind: str = "reference") -> float:
     return _lib(kind).orc_merge_weights(a, b)
 
@@ -119,7 +134,7 @@ class OracleDecoder:
                  no_revisit_dets: bool = True, merge_errors: bool = True, pqlimit: int = 200000,
                  det_penalty: float = 0.0, det_orders=None, num_threads: int = 1, kind: str = "reference",
                  sparsify_errors: bool = False, sparsify_base_degree: int = -1, sparsify_max_degree: int = -1,
-                 sparsify_reactivate_limit: int = -1):
+                 sparsify_reactivate_limit: int = -1, at_most_two_errors_per_detector: bool = False):
         self.lib = _lib(kind)
         self.kind = kind
         cfg = OrcConfig()
@@ -139,6 +154,7 @@ class OracleDecoder:
         cfg.sparsify_base_degree = sparsify_base_degree
         cfg.sparsify_max_degree = sparsify_max_degree
         cfg.sparsify_reactivate_limit = sparsify_reactivate_limit
+        cfg.at_most_two_errors_per_detector = int(at_most_two_errors_per_detector)
         self.h = self.lib.orc_create(dem_text.encode(), C.byref(cfg))
         if not self.h:
             raise OracleError(self.lib.orc_last_error().decode())

@@ -36,6 +36,8 @@ typedef struct orc_config {
   int32_t sparsify_base_degree;
   int32_t sparsify_max_degree;
   int32_t sparsify_reactivate_limit;
+  int32_t at_most_two_errors_per_detector; /* README.md:59 only — no reference code: the port implements it (port.cc: Config),
+                                              the reference build refuses it */
 } orc_config;
 
 const char* orc_last_error(void);
@@ -87,6 +89,11 @@ double orc_merge_weights(double a, double b); /* common.cc:118-123 */
  * [4]=S get_detcost loop iterations, [5]=A sum(|edets|+|eneighbors|) over evaluated children,
  * [6]=V visited inserts+probes, [7]=searches.  The reference build reports zeros. */
 int orc_counters(orc_handle* h, uint64_t out[8], int reset);
+
+/* Synthetic i.i.d. shots of a DEM (oracle/sampler.inc): the bench / test workload generator restated on the
+ * checker side; bit-identical to the product's tsr_sample_dem_b8.  dets_out [shots][ceil(D/8)],
+ * obs_out [shots][ceil(O/8)] or NULL. */
+int orc_sample_dem_b8(const char* dem_text, uint64_t seed, uint64_t shots, uint8_t* dets_out, uint8_t* obs_out);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,14 @@ struct Config {
   // tesseract.h:52-55
   bool sparsify = false;
   int sparsify_base_degree = -1, sparsify_max_degree = -1, sparsify_reactivate_limit = -1;
+  // --at-most-two-errors-per-detector.  The reference snapshot names the flag (README.md:59,159) but holds no code for
+  // it, so there is nothing to follow line by line: PARITY UNPINNED against the reference.  The meaning restated here
+  // (and implemented independently by the CUDA kernels): once a chosen error switches a fired detector OFF, no
+  // further error may touch that detector — every error of its row is blocked for the node's descendants.  A
+  // detector that starts fired is then touched exactly once and one that starts quiet zero or two times (on, off),
+  // so the search returns the cheapest explanation among those that use at most two errors per detector
+  // (tests/test_oracle.py checks that against brute force on the reference's four literal DEMs).
+  bool at_most_two = false;
 };
 
 struct Counters {
@@ -133,6 +141,7 @@ struct MinQueue {
 struct ChainLink {  // common.h:52-56
   uint32_t error, min_det;
   int64_t parent;
+  uint32_t switched_off;  // at-most-two: bit j = detector j of `error` was fired when the error was chosen
 };
 
 struct Decoder {
@@ -151,6 +160,7 @@ struct Decoder {
   // scratch
   std::vector<ChainLink> chain;
   std::vector<uint32_t> blocked, count, child_blocked, child_count;
+  std::vector<int> amt_undo;  // at-most-two: errors blocked for the current child only
   // Rows the search walks: the full detector rows, or the shot's sparse rows (tesseract.cc:296-298).
   std::vector<uint32_t> aoff;
   std::vector<int> arow;
@@ -346,6 +356,10 @@ struct Decoder {
           if ((uint32_t)arow[k] == link.error) break;
         }
         for (uint32_t k = e_off[link.error]; k < e_off[link.error + 1]; ++k) fired[(size_t)edet[k]] = !fired[(size_t)edet[k]];
+        if (cfg.at_most_two)  // a detector an ancestor switched off takes no further error (see Config::at_most_two)
+          for (uint32_t k = e_off[link.error]; k < e_off[link.error + 1]; ++k)
+            if ((link.switched_off >> (k - e_off[link.error])) & 1)
+              for (uint32_t q = aoff[(size_t)edet[k]]; q < aoff[(size_t)edet[k] + 1]; ++q) blocked[(size_t)arow[q]] = 1;
       }
       if (node.num_dets == 0) {  // tesseract.cc:441-473
         predicted.resize(node.depth);
@@ -380,6 +394,7 @@ struct Decoder {
         }
       std::fill(memo.begin(), memo.end(), -1.0);
       int64_t prev = -1;
+      amt_undo.clear();
       for (uint32_t k = aoff[min_det]; k < aoff[min_det + 1]; ++k) {
         const int e = arow[k];
         if (blocked[(size_t)e]) continue;
@@ -388,17 +403,27 @@ struct Decoder {
             const int d = edet[j], delta = fired[(size_t)d] ? 1 : -1;
             for (uint32_t q = aoff[(size_t)d]; q < aoff[(size_t)d + 1]; ++q) child_count[(size_t)arow[q]] += (uint32_t)delta;
           }
+        for (int b : amt_undo) child_blocked[(size_t)b] = 0;  // ... and the rows its switched-off detectors blocked
+        amt_undo.clear();
         prev = e;
         next_fired = fired;
         child_blocked[(size_t)e] = 1;  // persists for later siblings
         double f = node.f + cost[(size_t)e];
         uint64_t nd = node.num_dets;
+        uint32_t switched_off = 0;
         for (uint32_t j = e_off[(size_t)e]; j < e_off[(size_t)e + 1]; ++j) {
           const int d = edet[j];
           next_fired[(size_t)d] = !next_fired[(size_t)d];
           const int delta = next_fired[(size_t)d] ? 1 : -1;
           nd += (uint64_t)(int64_t)delta;
           for (uint32_t q = aoff[(size_t)d]; q < aoff[(size_t)d + 1]; ++q) child_count[(size_t)arow[q]] += (uint32_t)delta;
+          if (fired[(size_t)d]) switched_off |= 1u << (j - e_off[(size_t)e]);
+          if (cfg.at_most_two && fired[(size_t)d])
+            for (uint32_t q = aoff[(size_t)d]; q < aoff[(size_t)d + 1]; ++q)
+              if (!child_blocked[(size_t)arow[q]]) {
+                child_blocked[(size_t)arow[q]] = 1;
+                amt_undo.push_back(arow[q]);
+              }
         }
         if (nd > hi) continue;
         if (cfg.no_revisit) {
@@ -423,7 +448,7 @@ struct Decoder {
           f += detcost(od, child_blocked, child_count);
         }
         if (f == kInf) continue;
-        chain.push_back({(uint32_t)e, (uint32_t)min_det, node.chain});
+        chain.push_back({(uint32_t)e, (uint32_t)min_det, node.chain, switched_off});
         pq.push({f, nd, node.depth + 1, (int64_t)chain.size() - 1});
         ++ctr.Q;
         if (++pushed > cfg.pqlimit) {  // tesseract.cc:597-605
@@ -590,6 +615,7 @@ orc_handle* orc_create(const char* dem_text, const orc_config* cfg) {
     c.sparsify_base_degree = cfg->sparsify_base_degree;
     c.sparsify_max_degree = cfg->sparsify_max_degree;
     c.sparsify_reactivate_limit = cfg->sparsify_reactivate_limit;
+    c.at_most_two = cfg->at_most_two_errors_per_detector != 0;
     uint64_t D = dem.flattened().count_detectors();
     for (uint64_t k = 0; k < cfg->num_det_orders; ++k)
       c.orders.emplace_back(cfg->det_orders + k * D, cfg->det_orders + (k + 1) * D);
@@ -765,3 +791,5 @@ int orc_counters(orc_handle* h, uint64_t out[8], int reset) {
 }
 
 }  // extern "C"
+
+#include "sampler.inc"

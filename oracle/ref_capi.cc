@@ -47,6 +47,8 @@ const char* orc_kind(void) {
 orc_handle* orc_create(const char* dem_text, const orc_config* cfg) {
   orc_handle* h = nullptr;
   int rc = guarded([&] {
+    if (cfg->at_most_two_errors_per_detector)
+      throw std::invalid_argument("the reference has no at_most_two_errors_per_detector (README.md:59 only); use the port checker");
     stim::DetectorErrorModel dem(dem_text);
     TesseractConfig c;
     c.dem = dem;
@@ -270,3 +272,5 @@ int orc_counters(orc_handle*, uint64_t out[8], int) {
 }
 
 }  // extern "C"
+
+#include "sampler.inc"

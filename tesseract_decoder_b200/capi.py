@@ -95,6 +95,8 @@ def lib() -> C.CDLL:
     L.tsr_flipped_observables.argtypes = [C.c_void_p, u64p, C.c_uint64, u8p]
     L.tsr_counters.argtypes = [C.c_void_p, u64p, C.c_int]
     L.tsr_last_batch_timing.argtypes = [C.c_void_p, f64p]
+    L.tsr_set_profile.argtypes = [C.c_void_p, C.c_int]
+    L.tsr_profile.argtypes = [C.c_void_p, u64p, C.c_int]
     L.tsr_stream.restype = C.c_void_p
     L.tsr_stream.argtypes = [C.c_void_p]
     L.tsr_device.argtypes = [C.c_void_p]
@@ -120,7 +122,7 @@ EXPORTED_SYMBOLS = [
     "tsr_search_path_reason", "tsr_last_batch_nnz", "tsr_last_batch_errors", "tsr_decode",
     "tsr_cost_from_errors", "tsr_flipped_observables", "tsr_counters", "tsr_last_batch_timing", "tsr_stream",
     "tsr_device", "tsr_build_det_orders", "tsr_dem_count_detectors", "tsr_dem_count_observables", "tsr_merge_weights", "tsr_dem_from_counts", "tsr_circuit_to_dem",
-    "tsr_sample_dem_b8",
+    "tsr_sample_dem_b8", "tsr_set_profile", "tsr_profile",
 ]
 
 
@@ -377,6 +379,19 @@ class Decoder:
         out = np.zeros(8, dtype=np.uint64)
         _check(lib().tsr_counters(self.h, _p(out, C.c_uint64), int(reset)))
         return dict(zip(["Q", "P", "X", "L", "S", "A", "V", "searches"], out.tolist()))
+
+    def set_profile(self, on: bool):
+        _check(lib().tsr_set_profile(self.h, int(on)))
+
+    PROFILE_PHASES = ["pop", "rebuild_goal_visited", "node_terms", "min_detector_child_list", "children", "push", "staging_cleanup"]
+
+    def profile(self, reset: bool = False):
+        """SM clock ticks per expansion phase summed over search CTAs, plus the expansion count (tsr_profile)."""
+        out = np.zeros(8, dtype=np.uint64)
+        _check(lib().tsr_profile(self.h, _p(out, C.c_uint64), int(reset)))
+        d = dict(zip(self.PROFILE_PHASES, out[:7].tolist()))
+        d["expansions"] = int(out[7])
+        return d
 
     def last_batch_timing(self):
         out = np.zeros(4, dtype=np.float64)

@@ -83,11 +83,15 @@ struct DevBuf {
   T* as() const {
     return static_cast<T*>(p);
   }
+  // Pageable H2D copy on the legacy stream.  The decoder's own stream is non-blocking, so it is NOT ordered after this
+  // copy (and cudaMemcpy may return before the DMA of a small pageable buffer has landed): callers finish a group
+  // of uploads with uploads_done() before anything is launched on another stream.
   template <typename T>
   void upload(const std::vector<T>& v) {
     ensure(std::max<size_t>(v.size() * sizeof(T), 16));
     if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   }
+  static void uploads_done() { CUDA_OK(cudaStreamSynchronize(cudaStreamLegacy)); }
 };
 
 struct Tier {
@@ -105,6 +109,7 @@ struct TrialSet {
     d_perm.upload(perm);
     d_beam.upload(beam);
     d_literal.upload(literal_to_trial);
+    DevBuf::uploads_done();
   }
 };
 
@@ -118,6 +123,7 @@ struct tsr_decoder {
   bool bits = false;          // fast path: bit-sliced row scans (32 row entries per lane)
   bool fast = false;          // decode with search_fast.cu (CTA per search) instead of search.cu
   bool instrumented = false;  // fast path: also count the reference's scanned row entries (counter S)
+  bool profile = false;       // fast path: per-phase clock ticks (tsr_profile)
   bool hc_shared = false;
   std::vector<std::vector<uint64_t>> det_orders;
   std::vector<uint32_t> order_to_perm;  // det order index -> distinct permutation id
@@ -143,7 +149,7 @@ struct tsr_decoder {
   // Per-batch buffers.
   uint64_t max_batch = 0;
   DevBuf d_dets, d_status, d_sol_len, d_fcost, d_sol, d_obs, d_cost, d_low, d_err_off, d_err_len, d_err, d_retry,
-      d_items, d_scalars, d_counters, d_fired, d_order, d_bins;
+      d_items, d_scalars, d_counters, d_prof, d_fired, d_order, d_bins;
   uint32_t sol_stride = 0;
   bool collect_errors = true;
 
@@ -411,7 +417,10 @@ void init_device(tsr_decoder& h) {
   h.d_scalars.ensure(64);
   h.d_counters.ensure(8 * sizeof(unsigned long long));
   CUDA_OK(cudaMemsetAsync(h.d_counters.p, 0, 64, h.stream));
+  h.d_prof.ensure(8 * sizeof(unsigned long long));
+  CUDA_OK(cudaMemsetAsync(h.d_prof.p, 0, 64, h.stream));
   CUDA_OK(cudaStreamSynchronize(h.stream));
+  DevBuf::uploads_done();  // the table uploads above went through the legacy stream
   h.max_batch = h.cfg.max_batch_shots ? h.cfg.max_batch_shots : (uint64_t{1} << 18);
 }
 
@@ -526,6 +535,7 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     p.fcost = h.d_fcost.as<double>();
     p.work_counter = &sc->work;
     p.counters = h.d_counters.as<unsigned long long>();
+    p.prof = h.profile ? h.d_prof.as<unsigned long long>() : nullptr;
     return p;
   };
   auto resolve_params = [&](const uint32_t* shot_ids, uint32_t n, uint32_t* retry_out) {
@@ -940,8 +950,24 @@ int tsr_counters(tsr_decoder* h, uint64_t out[8], int reset) {
     require_device(*h);
     CUDA_OK(cudaSetDevice(h->device));
     CUDA_OK(cudaStreamSynchronize(h->stream));
-    CUDA_OK(cudaMemcpy(out, h->d_counters.p, 64, cudaMemcpyDeviceToHost));
-    if (reset) CUDA_OK(cudaMemset(h->d_counters.p, 0, 64));
+    CUDA_OK(cudaMemcpyAsync(out, h->d_counters.p, 64, cudaMemcpyDeviceToHost, h->stream));
+    if (reset) CUDA_OK(cudaMemsetAsync(h->d_counters.p, 0, 64, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int tsr_set_profile(tsr_decoder* h, int on) {
+  h->profile = on != 0;
+  return TSR_OK;
+}
+
+int tsr_profile(tsr_decoder* h, uint64_t out[8], int reset) {
+  return guarded([&] {
+    require_device(*h);
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaMemcpyAsync(out, h->d_prof.p, 64, cudaMemcpyDeviceToHost, h->stream));
+    if (reset) CUDA_OK(cudaMemsetAsync(h->d_prof.p, 0, 64, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
   });
 }
 

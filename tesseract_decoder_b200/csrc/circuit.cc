@@ -193,7 +193,7 @@ SymSet xor_of(const SymSet& a, const SymSet& b) {
 }
 
 bool is_measure(const std::string& n) {
-  return n == "M" || n == "MZ" || n == "MX" || n == "MPP" || n == "MR" || n == "MRX";
+  return n == "M" || n == "MZ" || n == "MX" || n == "MPP" || n == "MR" || n == "MRZ" || n == "MRX";
 }
 
 }  // namespace
@@ -265,16 +265,33 @@ std::string circuit_to_dem_text(std::string_view circuit_text) {
       it->second = it->second * (1 - p) + p * (1 - it->second);
     }
   };
+  // A reset into the Z (X) basis absorbs a Z (X) error placed right after it.  Detectors or observables that such an
+  // error would still flip do not have a deterministic value ("gauge" detectors; stim reports them as error(0.5)
+  // mechanisms when asked to allow them, tesseract_main.cc:206-211).  This analyzer does not model them: refuse
+  // instead of emitting a DEM that silently lacks them.
+  auto require_deterministic = [&](const SymSet& absorbed, const std::string& at) {
+    if (!absorbed.empty())
+      throw std::invalid_argument("the circuit has a non-deterministic detector or observable (sensitive to the basis of a '" + at +
+                                  "'); gauge detectors are not supported by this analyzer");
+  };
   for (size_t k = ops.size(); k-- > 0;) {
     const Op& o = ops[k];
     const std::string& n = o.name;
     double arg = o.args.empty() ? 0.0 : o.args[0];
-    if (n == "M" || n == "MZ" || n == "MX") {
+    if (n == "M" || n == "MZ" || n == "MX" || n == "MR" || n == "MRZ" || n == "MRX") {
+      // MR / MRX = the measurement followed by a reset of the same qubit: walking backwards the reset comes
+      // first (nothing after it depends on the qubit's earlier frame), then the measurement's readers.
+      const bool resets = n[1] == 'R', x_basis = n.back() == 'X';
       for (size_t i = o.targets.size(); i-- > 0;) {
         const SymSet& r = readers[meas_begin[k] + i];
         uint32_t q = o.targets[i].qubit;
+        if (resets) {
+          require_deterministic(x_basis ? xs[q] : zs[q], n);
+          xs[q].clear();
+          zs[q].clear();
+        }
         emit(r, arg);
-        xor_into(n == "MX" ? zs[q] : xs[q], r);
+        xor_into(x_basis ? zs[q] : xs[q], r);
       }
     } else if (n == "MPP") {
       // Walk products from the last to the first; factors of one product share a record.
@@ -292,6 +309,7 @@ std::string circuit_to_dem_text(std::string_view circuit_text) {
       }
     } else if (n == "R" || n == "RZ" || n == "RX") {
       for (const Target& t : o.targets) {
+        require_deterministic(n == "RX" ? xs[t.qubit] : zs[t.qubit], n);
         xs[t.qubit].clear();
         zs[t.qubit].clear();
       }
@@ -343,6 +361,8 @@ std::string circuit_to_dem_text(std::string_view circuit_text) {
       throw std::invalid_argument("circuit instruction '" + n + "' is not supported by this analyzer");
     }
   }
+
+  for (uint32_t q = 0; q < num_qubits; ++q) require_deterministic(zs[q], "start of the circuit (|0>)");
 
   std::string text;
   for (size_t k = first_seen.size(); k-- > 0;) {

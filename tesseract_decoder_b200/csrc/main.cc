@@ -330,9 +330,12 @@ int main(int argc, char** argv) {
     // --shot-range-begin/--shot-range-end (tesseract_main.cc:307-316)
     if (a.shot_range_begin || a.shot_range_end) {
       if (a.shot_range_end < a.shot_range_begin || a.shot_range_end > shots) throw std::invalid_argument("Invalid shot range");
-      dets.assign(dets.begin() + (std::ptrdiff_t)(a.shot_range_begin * nb), dets.begin() + (std::ptrdiff_t)(a.shot_range_end * nb));
-      if (has_obs)
-        obs_true.assign(obs_true.begin() + (std::ptrdiff_t)(a.shot_range_begin * ob), obs_true.begin() + (std::ptrdiff_t)(a.shot_range_end * ob));
+      auto keep = [](std::vector<uint8_t>& v, uint64_t b, uint64_t e) {  // v = v[b:e), without aliasing assign()
+        v.erase(v.begin() + (std::ptrdiff_t)e, v.end());
+        v.erase(v.begin(), v.begin() + (std::ptrdiff_t)b);
+      };
+      keep(dets, a.shot_range_begin * nb, a.shot_range_end * nb);
+      if (has_obs) keep(obs_true, a.shot_range_begin * ob, a.shot_range_end * ob);
       obs_true.push_back(0);
       shots = a.shot_range_end - a.shot_range_begin;
     }

@@ -106,6 +106,7 @@ struct SearchParams {
   double* fcost = nullptr;      // [items] f of the goal node (diagnostic)
   unsigned int* work_counter = nullptr;
   unsigned long long* counters = nullptr;  // [8], see tsr_counters
+  unsigned long long* prof = nullptr;      // [8] nullable, fast path only: per-phase ticks, see tsr_profile
 };
 
 struct ResolveParams {

@@ -72,6 +72,9 @@ struct alignas(16) Ctl {
   uint32_t status;
   uint32_t work;
   uint32_t item;
+  // phase profile (SearchParams::prof): clock64 ticks of thread 0 per phase, see tsr_profile
+  long long prof_last;
+  unsigned long long prof[8];
 };
 
 struct Smem {
@@ -626,6 +629,16 @@ struct Counters {
   unsigned long long Q = 0, P = 0, X = 0, L = 0, S = 0, A = 0, V = 0;
 };
 
+// Phase profile: thread 0 charges the ticks since the previous mark to `phase`.  Called right after a CTA barrier, so a
+// phase's ticks are its critical path including the wait for the slowest warp.
+__device__ __forceinline__ void prof_mark(const SearchParams& p, Ctl& c, uint32_t phase) {
+  if (p.prof && threadIdx.x == 0) {
+    const long long now = clock64();
+    c.prof[phase] += (unsigned long long)(now - c.prof_last);
+    c.prof_last = now;
+  }
+}
+
 // ---- one child (one warp): tesseract.cc:533-606 up to, not including, the push ----------------------
 
 template <bool kInstr, bool kBits>
@@ -832,6 +845,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
     }
   }
   __syncthreads();
+  prof_mark(p, c, 6);
 
   while (true) {
     // ---- phase 1 (warp 0): next node ----------------------------------------------------------------
@@ -893,6 +907,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
     }
     __syncthreads();
+    prof_mark(p, c, 0);
     if (c.action == kActDone) return c.status;
     if (c.action == kActSkip) {
       __syncthreads();
@@ -1014,6 +1029,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
     }
     __syncthreads();
+    prof_mark(p, c, 1);
     if (c.action == kActDone) return c.status;
     if (c.action == kActSkip) {
       __syncthreads();
@@ -1079,6 +1095,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
     }
     __syncthreads();
+    prof_mark(p, c, 2);
 
     // ---- phase 5 (warp 0): root push, or min detector and the list of children --------------------------
     if (warp == 0) {
@@ -1157,6 +1174,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
     }
     __syncthreads();
+    prof_mark(p, c, 3);
     if (c.action == kActDone) return c.status;
     if (c.action == kActSkip) {
       __syncthreads();
@@ -1172,6 +1190,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       eval_child<kInstr, kBits>(p, sm, j, lane, vtab, ctr);
     }
     __syncthreads();
+    prof_mark(p, c, 4);
 
     // ---- phase 7 (warp 0): pushes, in row order (tesseract.cc:590-605) ----------------------------------------
     if (warp == 0) {
@@ -1366,6 +1385,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
     }
     __syncthreads();
+    prof_mark(p, c, 5);
     if (c.action == kActDone) return c.status;
     __syncthreads();
   }
@@ -1405,6 +1425,10 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
   sm.stage = reinterpret_cast<uint4*>(base + L.off_st + L.warp_stride);
   sm.stage_cap = (nwarps - 1) * (L.warp_stride / 16);
   for (uint32_t i = tid; i < rank_entries; i += blockDim.x) sm.rank[i] = __ldg(p.t.frank + i);
+  if (tid == 0) {
+    for (auto& v : sm.ctl->prof) v = 0;
+    sm.ctl->prof_last = clock64();
+  }
   __syncthreads();
 
   Counters ctr;
@@ -1436,6 +1460,10 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
       }
     }
     __syncthreads();
+  }
+  if (tid == 0 && p.prof) {
+    sm.ctl->prof[7] = ctr.X;
+    for (int i = 0; i < 8; ++i) atomicAdd(p.prof + i, sm.ctl->prof[i]);
   }
   if (lane == 0 && p.counters) {
     if (warp == 0) {

@@ -207,3 +207,16 @@ def test_detcost_formulations_agree_on_the_host(name):
     bad, checked = dec.cross_check_detcost(400, seed=11)
     assert checked > 2000 and bad == 0
     assert capi.Decoder("error(0.7) D0 D1\nerror(0.1) D0\nerror(0.1) D1", host_only=True).cross_check_detcost(10) == (0, 0)
+
+
+def test_the_checker_side_sampler_draws_the_same_shots():
+    """bench.py --impl reference samples its synthetic shots with oracle/sampler.inc so that it need not load the
+    product library; both samplers must produce the same bytes."""
+    from oracle import oracle
+    for name, seed, shots in (("surface_d5_r5_p0.002_X", 1000, 4096), ("bb72_r6_p0.001_X", 7, 513)):
+        dem = W.load_dem(name)
+        a = capi.sample_dem_b8(dem, seed, shots)
+        for kind in ("reference", "port"):
+            if oracle.available(kind):
+                b = oracle.sample_dem_b8(dem, seed, shots, kind=kind)
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (name, kind)

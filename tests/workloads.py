@@ -47,8 +47,9 @@ def decoder_kwargs(cfg: dict, build_det_orders) -> tuple[str, dict]:
     kw = dict(det_beam=cfg.pop("det_beam", 5), beam_climbing=cfg.pop("beam_climbing", False),
               no_revisit_dets=cfg.pop("no_revisit_dets", True), merge_errors=cfg.pop("merge_errors", True),
               pqlimit=cfg.pop("pqlimit", 200000), det_penalty=cfg.pop("det_penalty", 0.0))
-    for k in ("sparsify_errors", "sparsify_base_degree", "sparsify_max_degree", "sparsify_reactivate_limit"):
-        if k in cfg:  # understood by the CPU checkers only, so far
+    for k in ("sparsify_errors", "sparsify_base_degree", "sparsify_max_degree", "sparsify_reactivate_limit",
+              "at_most_two_errors_per_detector"):
+        if k in cfg:
             kw[k] = cfg.pop(k)
     assert not cfg, f"unknown config keys {cfg}"
     kw["det_orders"] = build_det_orders(dem, n_orders, method, seed) if n_orders else None
