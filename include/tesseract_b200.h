@@ -55,6 +55,12 @@ typedef struct tsr_config {
   uint64_t max_batch_shots;    /* shots staged per kernel launch */
   int32_t force_generic_kernel; /* 1 = always use the event-replay kernel (search.cu), even for certified DEMs */
   int32_t row_scan; /* certified DEMs: 0 = choose by DEM shape, 1 = one row entry per lane, 2 = bit-sliced (32 entries per lane) */
+  /* --sparsify-errors (tesseract.h:52-55; validated like tesseract.cc:256-277, same messages): per shot only the errors of
+   * degree <= base plus the `limit` best-overlapping errors of degree <= max take part (tesseract.cc:673-737). */
+  int32_t sparsify_errors;
+  int32_t sparsify_base_degree;      /* must be > 0 when sparsify_errors */
+  int32_t sparsify_max_degree;       /* -1 = no upper bound */
+  int32_t sparsify_reactivate_limit; /* -1 = suggest_sparsify_reactivate_limit (tesseract.cc:45-69) capped at num_errors */
 } tsr_config;
 
 /* Fills the reference's C++ defaults (tesseract.h:39-58). */
@@ -78,6 +84,10 @@ uint64_t tsr_num_observables(const tsr_decoder* h);
 uint64_t tsr_num_errors(const tsr_decoder* h);     /* errors.size() */
 uint64_t tsr_num_dem_errors(const tsr_decoder* h); /* dem_error_to_error.size() */
 uint64_t tsr_num_det_orders(const tsr_decoder* h); /* config.det_orders.size() */
+/* config.sparsify_reactivate_limit after construction (the suggested value when -1 was passed, tesseract.cc:272-277);
+ * -1 when sparsify_errors is off.  tsr_suggest_sparsify_reactivate_limit is the free function of tesseract.h:37. */
+int64_t tsr_sparsify_reactivate_limit(const tsr_decoder* h);
+int64_t tsr_suggest_sparsify_reactivate_limit(uint64_t num_detectors, int32_t sparsify_base_degree);
 int tsr_error_costs(const tsr_decoder* h, double* out /* [num_errors] */);
 int tsr_maps(const tsr_decoder* h, uint64_t* dem_error_to_error /* [num_dem_errors] or NULL */,
              uint64_t* error_to_dem_error /* [num_errors] or NULL */);

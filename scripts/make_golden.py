@@ -28,8 +28,12 @@ SETS = {
                                  num_det_orders=1), 150, 1002),
     "g_color_d5_climb": (dict(dem="color_superdense_d5_r5_p0.001_Z", det_beam=3, beam_climbing=True, pqlimit=1000,
                               no_revisit_dets=True, num_det_orders=5), 200, 5),
-    "g_c3_surface_d11_climb": (W.CONFIGS["C3"], 24, 1003),
-    "g_c4_bb144_p1e-4": (W.CONFIGS["C4"], 48, 1004),
+    # BASELINE config 2 at its literal flags (CLI defaults: beam 65535, pqlimit unbounded, revisits allowed;
+    # tesseract_main.cc:482, 495-503).  Heavy-tailed: median 837 pushes per shot, but this batch holds searches of
+    # 35.6 M (shot 631), 11.0 M (1296), 4.4 M (1395) ... pushes; the reference needs 226 s for shot 631 alone.
+    "g_c2_color_d7_literal": (W.CONFIGS["C2"], 2000, 1002),
+    "g_c3_surface_d11_climb": (W.CONFIGS["C3"], 256, 1003),
+    "g_c4_bb144_p1e-4": (W.CONFIGS["C4"], 256, 1004),
     "g_bb72_pqlimit2000": (dict(dem="bb72_r6_p0.001_X", det_beam=65535, pqlimit=2000,
                                 no_revisit_dets=True, num_det_orders=2), 64, 77),
     "g_c5_transcx_d5_penalty": (W.CONFIGS["C5"], 200, 1005),

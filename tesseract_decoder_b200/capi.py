@@ -49,6 +49,10 @@ class TsrConfig(C.Structure):
         ("max_batch_shots", C.c_uint64),
         ("force_generic_kernel", C.c_int32),
         ("row_scan", C.c_int32),
+        ("sparsify_errors", C.c_int32),
+        ("sparsify_base_degree", C.c_int32),
+        ("sparsify_max_degree", C.c_int32),
+        ("sparsify_reactivate_limit", C.c_int32),
     ]
 
 
@@ -95,6 +99,10 @@ def lib() -> C.CDLL:
     L.tsr_flipped_observables.argtypes = [C.c_void_p, u64p, C.c_uint64, u8p]
     L.tsr_counters.argtypes = [C.c_void_p, u64p, C.c_int]
     L.tsr_last_batch_timing.argtypes = [C.c_void_p, f64p]
+    L.tsr_sparsify_reactivate_limit.restype = C.c_int64
+    L.tsr_sparsify_reactivate_limit.argtypes = [C.c_void_p]
+    L.tsr_suggest_sparsify_reactivate_limit.restype = C.c_int64
+    L.tsr_suggest_sparsify_reactivate_limit.argtypes = [C.c_uint64, C.c_int32]
     L.tsr_set_profile.argtypes = [C.c_void_p, C.c_int]
     L.tsr_profile.argtypes = [C.c_void_p, u64p, C.c_int]
     L.tsr_stream.restype = C.c_void_p
@@ -122,7 +130,8 @@ EXPORTED_SYMBOLS = [
     "tsr_search_path_reason", "tsr_last_batch_nnz", "tsr_last_batch_errors", "tsr_decode",
     "tsr_cost_from_errors", "tsr_flipped_observables", "tsr_counters", "tsr_last_batch_timing", "tsr_stream",
     "tsr_device", "tsr_build_det_orders", "tsr_dem_count_detectors", "tsr_dem_count_observables", "tsr_merge_weights", "tsr_dem_from_counts", "tsr_circuit_to_dem",
-    "tsr_sample_dem_b8", "tsr_set_profile", "tsr_profile",
+    "tsr_sample_dem_b8", "tsr_set_profile", "tsr_profile", "tsr_sparsify_reactivate_limit",
+    "tsr_suggest_sparsify_reactivate_limit",
 ]
 
 
@@ -214,7 +223,8 @@ class Decoder:
                  det_penalty: float = 0.0, det_orders=None, at_most_two_errors_per_detector: bool = False,
                  device: int = -1, host_only: bool = False, search_slots: int = 0, warps_per_block: int = 0,
                  node_pool_bytes: int = 0, max_batch_shots: int = 0, force_generic_kernel: bool = False,
-                 row_scan: int = 0):
+                 row_scan: int = 0, sparsify_errors: bool = False, sparsify_base_degree: int = -1,
+                 sparsify_max_degree: int = -1, sparsify_reactivate_limit: int = -1):
         L = lib()
         cfg = TsrConfig()
         L.tsr_config_init(C.byref(cfg))
@@ -240,6 +250,10 @@ class Decoder:
         cfg.max_batch_shots = max_batch_shots
         cfg.force_generic_kernel = int(force_generic_kernel)
         cfg.row_scan = int(row_scan)  # 0 auto, 1 entry per lane, 2 bit-sliced
+        cfg.sparsify_errors = int(sparsify_errors)
+        cfg.sparsify_base_degree = sparsify_base_degree
+        cfg.sparsify_max_degree = sparsify_max_degree
+        cfg.sparsify_reactivate_limit = sparsify_reactivate_limit
         h = C.c_void_p()
         self.h = None
         _check(L.tsr_create(dem_text.encode(), C.byref(cfg), CREATE_HOST_ONLY if host_only else 0, C.byref(h)))
@@ -249,6 +263,7 @@ class Decoder:
         self.num_errors = L.tsr_num_errors(h)
         self.num_dem_errors = L.tsr_num_dem_errors(h)
         self.num_det_orders = L.tsr_num_det_orders(h)
+        self.sparsify_reactivate_limit = L.tsr_sparsify_reactivate_limit(h)  # effective value; -1 when sparsify is off
 
     def close(self):
         if getattr(self, "h", None):

@@ -9,8 +9,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -136,7 +138,9 @@ struct tsr_decoder {
 
   // Device tables.
   DevBuf row_off, row_err, rec_a, rec_b, rec_c, e_off, e_det, e_rank, e_cost, e_nnbr, eo_off, eo_obs, e2dem, adj,
-      zobrist, order_det, order_pos, frec_a, frec_b, frank, fquot, bs_meta, bs_adjpre, bs_masks, bs_cls_cid, bs_pl_off, bs_pl;
+      zobrist, order_det, order_pos, frec_a, frec_b, frank, fquot, bs_meta, bs_adjpre, bs_masks, bs_cls_cid, bs_pl_off, bs_pl,
+      sp_mand, sp_opt, sp_crank, sp_act;
+  int64_t sparsify_limit = -1;  // effective sparsify_reactivate_limit (tesseract.cc:272-277); -1 = sparsify off
   tsr::DeviceTables dt;
   TrialSet ensemble;
 
@@ -175,6 +179,20 @@ uint64_t splitmix(uint64_t& s) {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
+}
+
+// suggest_sparsify_reactivate_limit_capped (tesseract.cc:45-69): round(4.5^(base-2) * D / 3), capped.
+int suggest_limit_capped(uint64_t num_detectors, int base_degree, int max_limit) {
+  if (base_degree < 0) throw std::invalid_argument("sparsify_base_degree must be >= 0.");
+  if (num_detectors == 0 || max_limit <= 0) return 0;
+  const double exponent = (double)base_degree - 2.0, max_result = (double)max_limit;
+  const double log_result = exponent * std::log(4.5) - std::log(3.0) + std::log((double)num_detectors);
+  if (!std::isfinite(log_result) || log_result >= std::log(max_result)) return max_limit;
+  const double result = std::exp(log_result);
+  if (!std::isfinite(result)) return max_limit;
+  const double rounded = std::round(result);
+  if (rounded >= max_result) return max_limit;
+  return (int)rounded;
 }
 
 void make_ensemble(const tsr_decoder& h, TrialSet& ts) {
@@ -327,6 +345,35 @@ void init_device(tsr_decoder& h) {
     }
   }
 
+  if (h.cfg.sparsify_errors) {
+    // sparsify.cuh: per row word, which entries are mandatory / optional (tesseract.cc:279-289), and dense cost ranks.
+    const uint32_t rw = (dt.max_row_len + 31) / 32;
+    std::vector<uint32_t> mand((size_t)D * rw + 1, 0u), opt((size_t)D * rw + 1, 0u);
+    for (uint32_t d = 0; d < D; ++d)
+      for (uint32_t k = T.row_off[d]; k < T.row_off[d + 1]; ++k) {
+        const int degree = (int)T.errors[(size_t)T.row_err[k]].detectors.size();
+        const uint32_t idx = k - T.row_off[d];
+        if (degree <= h.cfg.sparsify_base_degree) mand[(size_t)d * rw + (idx >> 5)] |= 1u << (idx & 31);
+        else if (h.cfg.sparsify_max_degree == -1 || degree <= h.cfg.sparsify_max_degree) opt[(size_t)d * rw + (idx >> 5)] |= 1u << (idx & 31);
+      }
+    std::vector<double> distinct(T.e_cost);
+    std::sort(distinct.begin(), distinct.end());
+    distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
+    if (distinct.size() >= (size_t{1} << 24)) throw std::invalid_argument("tesseract_b200: sparsify_errors supports fewer than 2^24 distinct costs");
+    std::vector<uint32_t> crank(E + 1, 0u);
+    for (uint32_t e = 0; e < E; ++e)
+      crank[e] = (uint32_t)(std::lower_bound(distinct.begin(), distinct.end(), T.e_cost[e]) - distinct.begin());
+    h.sp_mand.upload(mand);
+    h.sp_opt.upload(opt);
+    h.sp_crank.upload(crank);
+    dt.sp_mand = h.sp_mand.as<uint32_t>();
+    dt.sp_opt = h.sp_opt.as<uint32_t>();
+    dt.sp_crank = h.sp_crank.as<uint32_t>();
+    dt.sp_rw = rw;
+    dt.sp_limit = (uint32_t)std::min<int64_t>(h.sparsify_limit, (int64_t)E);
+    dt.sp_on = 1;
+  }
+
   make_ensemble(h, h.ensemble);
   h.ensemble.upload();
 
@@ -372,10 +419,10 @@ void init_device(tsr_decoder& h) {
   }
   if (!h.fast) {
     h.wpb = h.cfg.warps_per_block ? std::min<uint32_t>(h.cfg.warps_per_block, 8) : 4;
-    int occ = tsr::search_max_blocks_per_sm(h.wpb, D);
+    int occ = tsr::search_max_blocks_per_sm(h.wpb, D, dt.sp_on != 0);
     while (occ == 0 && h.wpb > 1) {
       h.wpb /= 2;
-      occ = tsr::search_max_blocks_per_sm(h.wpb, D);
+      occ = tsr::search_max_blocks_per_sm(h.wpb, D, dt.sp_on != 0);
     }
     if (occ == 0) throw CudaError("the search kernel does not fit on this device for this many detectors");
     h.blocks = (uint32_t)(h.sm_count * occ);
@@ -413,6 +460,13 @@ void init_device(tsr_decoder& h) {
   h.pool.ensure(pool_bytes + 256);
   h.hcache.ensure((size_t)slots * std::max<uint32_t>(D, 1) * sizeof(double));
   h.vlist.ensure((size_t)slots * h.vlist_cap * sizeof(uint32_t));
+  if (dt.sp_on) {  // every slot's active-entry masks start as (and are restored to) the mandatory masks
+    const size_t per_slot = (size_t)D * dt.sp_rw * 4;
+    h.sp_act.ensure(std::max<size_t>((size_t)slots * per_slot, 16));
+    DevBuf::uploads_done();  // sp_mand was uploaded through the legacy stream
+    for (uint32_t sl = 0; sl < slots && per_slot; ++sl)
+      CUDA_OK(cudaMemcpyAsync(h.sp_act.as<char>() + (size_t)sl * per_slot, h.sp_mand.p, per_slot, cudaMemcpyDeviceToDevice, h.stream));
+  }
   CUDA_OK(cudaMemsetAsync(h.pool.p, 0, h.pool.bytes, h.stream));  // visited tables start empty
   h.d_scalars.ensure(64);
   h.d_counters.ensure(8 * sizeof(unsigned long long));
@@ -526,6 +580,7 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     p.chain = reinterpret_cast<tsr::ChainNode*>(base + (size_t)tier.slots * tier.node_cap * 16);
     p.visited = reinterpret_cast<uint4*>(base + (size_t)tier.slots * tier.node_cap * 32);
     p.vlist = h.vlist.as<uint32_t>();
+    p.sp_act = h.sp_act.as<uint32_t>();
     p.hcache = h.hcache.as<double>();
     p.hc_shared = h.hc_shared ? 1 : 0;
     p.sol_stride = h.sol_stride;
@@ -743,6 +798,20 @@ int tsr_create(const char* dem_text, const tsr_config* cfg, uint32_t flags, tsr_
         h->det_orders.emplace_back(cfg->det_orders + k * D, cfg->det_orders + (k + 1) * D);
     }
     if (cfg->det_beam < 0) throw std::invalid_argument("det_beam must be >= 0");
+    if (cfg->sparsify_errors) {  // tesseract.cc:256-277
+      if (cfg->sparsify_base_degree <= 0)
+        throw std::invalid_argument("sparsify_base_degree must be > 0 when sparsify_errors is enabled.");
+      if (cfg->sparsify_max_degree < -1) throw std::invalid_argument("sparsify_max_degree must be >= -1.");
+      if (cfg->sparsify_reactivate_limit < -1) throw std::invalid_argument("sparsify_reactivate_limit must be >= -1.");
+      if (cfg->sparsify_max_degree >= 0 && cfg->sparsify_max_degree < cfg->sparsify_base_degree)
+        throw std::invalid_argument("sparsify_max_degree must be >= sparsify_base_degree.");
+      h->sparsify_limit = cfg->sparsify_reactivate_limit;
+      if (h->sparsify_limit == -1)
+        h->sparsify_limit = suggest_limit_capped(D, cfg->sparsify_base_degree,
+                                                 (int)std::min<uint64_t>(h->T.num_errors, (uint64_t)std::numeric_limits<int>::max()));
+      if (h->T.num_errors >= (uint64_t{1} << 28))
+        throw std::invalid_argument("tesseract_b200: sparsify_errors supports fewer than 2^28 errors");
+    }
     if (h->T.max_degree > 32)
       throw std::invalid_argument("tesseract_b200: errors touching more than 32 detectors are not supported");
     std::map<std::vector<uint64_t>, uint32_t> perm_ids;
@@ -783,6 +852,12 @@ uint64_t tsr_num_observables(const tsr_decoder* h) { return h->T.num_observables
 uint64_t tsr_num_errors(const tsr_decoder* h) { return h->T.num_errors; }
 uint64_t tsr_num_dem_errors(const tsr_decoder* h) { return h->T.num_dem_errors; }
 uint64_t tsr_num_det_orders(const tsr_decoder* h) { return h->det_orders.size(); }
+int64_t tsr_sparsify_reactivate_limit(const tsr_decoder* h) { return h->sparsify_limit; }
+int64_t tsr_suggest_sparsify_reactivate_limit(uint64_t num_detectors, int32_t sparsify_base_degree) {
+  int64_t out = TSR_E_INVALID_ARGUMENT;
+  guarded([&] { out = suggest_limit_capped(num_detectors, sparsify_base_degree, std::numeric_limits<int>::max()); });
+  return out;
+}
 
 int tsr_error_costs(const tsr_decoder* h, double* out) {
   std::copy(h->T.e_cost.begin(), h->T.e_cost.end(), out);

@@ -41,8 +41,8 @@ struct TesseractConfig {
   double det_penalty = 0;
   bool create_visualization = false;
   bool at_most_two_errors_per_detector = false;  // README.md:59,159 (no code in the reference snapshot)
-  // tesseract.h:52-55.  Accepted and validated like the reference (tesseract.cc:256-270); decoding with
-  // sparsify_errors = true is not implemented on the device yet and fails loudly (never a silent fallback).
+  // tesseract.h:52-55; validated by tsr_create like tesseract.cc:256-277 (same messages).  After construction the
+  // decoder's copy holds the effective sparsify_reactivate_limit, as in the reference.
   bool sparsify_errors = false;
   int sparsify_base_degree = -1;
   int sparsify_max_degree = -1;
@@ -82,17 +82,6 @@ struct TesseractDecoder {
   std::vector<size_t> dem_error_to_error, error_to_dem_error;
 
   explicit TesseractDecoder(TesseractConfig cfg, bool host_only = false) : config(std::move(cfg)) {
-    if (config.sparsify_errors) {  // tesseract.cc:256-270
-      if (config.sparsify_base_degree <= 0)
-        throw std::invalid_argument("sparsify_base_degree must be > 0 when sparsify_errors is enabled.");
-      if (config.sparsify_max_degree < -1) throw std::invalid_argument("sparsify_max_degree must be >= -1.");
-      if (config.sparsify_reactivate_limit < -1) throw std::invalid_argument("sparsify_reactivate_limit must be >= -1.");
-      if (config.sparsify_max_degree >= 0 && config.sparsify_max_degree < config.sparsify_base_degree)
-        throw std::invalid_argument("sparsify_max_degree must be >= sparsify_base_degree.");
-      throw std::runtime_error(
-          "tesseract_b200: sparsify_errors is not implemented on the GPU decode path yet (DESIGN.md, next hot-path row); "
-          "decode with sparsify_errors = false");
-    }
     tsr_config c;
     tsr_config_init(&c);
     c.det_beam = config.det_beam;
@@ -103,6 +92,10 @@ struct TesseractDecoder {
     c.device = config.device;
     c.pqlimit = config.pqlimit;
     c.det_penalty = config.det_penalty;
+    c.sparsify_errors = config.sparsify_errors;
+    c.sparsify_base_degree = config.sparsify_base_degree;
+    c.sparsify_max_degree = config.sparsify_max_degree;
+    c.sparsify_reactivate_limit = config.sparsify_reactivate_limit;
     std::vector<uint64_t> flat;
     for (const auto& o : config.det_orders) {
       if (o.size() != config.det_orders[0].size())
@@ -120,6 +113,7 @@ struct TesseractDecoder {
     num_detectors = tsr_num_detectors(raw);
     num_observables = tsr_num_observables(raw);
     num_errors = tsr_num_errors(raw);
+    if (config.sparsify_errors) config.sparsify_reactivate_limit = (int)tsr_sparsify_reactivate_limit(raw);  // tesseract.cc:272-277
     if (config.det_orders.empty()) {  // tesseract.cc:175-177
       config.det_orders.emplace_back(num_detectors);
       for (size_t i = 0; i < num_detectors; ++i) config.det_orders[0][i] = i;

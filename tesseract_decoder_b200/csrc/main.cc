@@ -205,7 +205,8 @@ int main(int argc, char** argv) {
       {"--verbose", &a.verbose}, {"--print-stats", &a.print_stats}, {"--convert-only", &a.convert_only},
       {"--in-includes-appended-observables", &a.in_includes_appended_observables},
       {"--in_includes_appended_observables", &a.in_includes_appended_observables}};
-  TesseractConfig config_sparsify;  // carries the --sparsify-* flags (validated, then refused: not on the device yet)
+  TesseractConfig config_sparsify;  // carries the --sparsify-* flags
+  bool has_base = false, has_max = false, has_limit = false;
   try {
     for (int i = 1; i < argc; ++i) {
       const std::string k = argv[i];
@@ -232,9 +233,9 @@ int main(int argc, char** argv) {
       else if (k == "--gpus") a.gpus = std::stoi(need());
       else if (k == "--batch") a.batch = std::stoull(need());
       else if (k == "--sparsify-errors") config_sparsify.sparsify_errors = true;
-      else if (k == "--sparsify-base-degree") config_sparsify.sparsify_base_degree = std::stoi(need());
-      else if (k == "--sparsify-max-degree") config_sparsify.sparsify_max_degree = std::stoi(need());
-      else if (k == "--sparsify-reactivate-limit") config_sparsify.sparsify_reactivate_limit = std::stoi(need());
+      else if (k == "--sparsify-base-degree") config_sparsify.sparsify_base_degree = std::stoi(need()), has_base = true;
+      else if (k == "--sparsify-max-degree") config_sparsify.sparsify_max_degree = std::stoi(need()), has_max = true;
+      else if (k == "--sparsify-reactivate-limit") config_sparsify.sparsify_reactivate_limit = std::stoi(need()), has_limit = true;
       else if (k == "-h" || k == "--help") usage("tesseract (B200): A* most-likely-error decoder");
       else usage("unknown argument " + k);
     }
@@ -243,6 +244,18 @@ int main(int argc, char** argv) {
     if ((a.sample_num_shots != 0) == !a.in_fname.empty()) usage("Must provide exactly one of --sample-num-shots or --in");
     if (a.beam_climbing && a.det_beam == INF_DET_BEAM) usage("Beam climbing requires a finite beam");
     if (a.gpus < 1) usage("--gpus must be >= 1");
+    if (!config_sparsify.sparsify_errors) {  // tesseract_main.cc:155-179
+      if (has_base || has_max || has_limit)
+        throw std::invalid_argument(
+            "Cannot use --sparsify-base-degree, --sparsify-max-degree, or --sparsify-reactivate-limit without --sparsify-errors");
+    } else {
+      if (!has_base) throw std::invalid_argument("Must specify --sparsify-base-degree when --sparsify-errors is enabled.");
+      if (config_sparsify.sparsify_base_degree <= 0) throw std::invalid_argument("--sparsify-base-degree must be > 0.");
+      if (has_limit && config_sparsify.sparsify_reactivate_limit < -1)
+        throw std::invalid_argument("--sparsify-reactivate-limit must be >= -1.");
+      if (has_max && config_sparsify.sparsify_max_degree < config_sparsify.sparsify_base_degree)
+        throw std::invalid_argument("--sparsify-max-degree must be >= --sparsify-base-degree.");
+    }
 
     if (a.convert_only) {
       // Host-only helper: re-encode the detection-event file given by --in into --out / --out-format (no decoding).
@@ -421,7 +434,11 @@ int main(int argc, char** argv) {
          << ",\"num_det_orders\":" << a.num_det_orders << ",\"det_order_seed\":" << a.det_order_seed
          << ",\"total_time_seconds\":" << total_time_seconds << ",\"num_errors\":" << (has_obs ? std::to_string(num_errors) : "null")
          << ",\"num_low_confidence\":" << num_low_confidence << ",\"num_shots\":" << done << ",\"num_threads\":" << a.num_threads
-         << ",\"num_gpus\":" << a.gpus << ",\"sample_num_shots\":" << a.sample_num_shots << "}";
+         << ",\"num_gpus\":" << a.gpus << ",\"sample_num_shots\":" << a.sample_num_shots
+         // tesseract_main.cc:676-679; the limit is the decoder's effective value (:641-655)
+         << ",\"sparsify_errors\":" << (config.sparsify_errors ? "true" : "false") << ",\"sparsify_base_degree\":" << config.sparsify_base_degree
+         << ",\"sparsify_max_degree\":" << config.sparsify_max_degree
+         << ",\"sparsify_reactivate_limit\":" << decoders[0]->config.sparsify_reactivate_limit << "}";
       if (a.stats_out_fname == "-") {
         std::cout << js.str() << std::endl;
         print_final_stats = false;

@@ -94,21 +94,29 @@ struct TesseractSinterDecoder {
   size_t num_det_orders = 0;
   DetOrder det_order_method = DetOrder::DetIndex;
   uint64_t seed = 2384753;
-  bool at_most_two_errors_per_detector = false;
+  // tesseract_sinter_compat.pybind.h:114-117
+  bool sparsify_errors = false;
+  int sparsify_base_degree = -1, sparsify_max_degree = -1, sparsify_reactivate_limit = -1;
+  bool at_most_two_errors_per_detector = false;  // extension (README.md:59); last, so the reference's positional order holds
 
   TesseractSinterDecoder() = default;
   TesseractSinterDecoder(int det_beam, bool beam_climbing, bool no_revisit_dets, bool verbose, bool merge_errors, size_t pqlimit,
                          double det_penalty, bool create_visualization, size_t num_det_orders, DetOrder method, uint64_t seed,
-                         bool at_most_two)
+                         bool sparsify_errors = false, int sparsify_base_degree = -1, int sparsify_max_degree = -1,
+                         int sparsify_reactivate_limit = -1, bool at_most_two = false)
       : det_beam(det_beam), beam_climbing(beam_climbing), no_revisit_dets(no_revisit_dets), verbose(verbose),
         merge_errors(merge_errors), pqlimit(pqlimit), det_penalty(det_penalty), create_visualization(create_visualization),
-        num_det_orders(num_det_orders), det_order_method(method), seed(seed), at_most_two_errors_per_detector(at_most_two) {}
+        num_det_orders(num_det_orders), det_order_method(method), seed(seed), sparsify_errors(sparsify_errors),
+        sparsify_base_degree(sparsify_base_degree), sparsify_max_degree(sparsify_max_degree),
+        sparsify_reactivate_limit(sparsify_reactivate_limit), at_most_two_errors_per_detector(at_most_two) {}
 
   bool operator==(const TesseractSinterDecoder& o) const {
     return det_beam == o.det_beam && beam_climbing == o.beam_climbing && no_revisit_dets == o.no_revisit_dets &&
            verbose == o.verbose && merge_errors == o.merge_errors && pqlimit == o.pqlimit && det_penalty == o.det_penalty &&
            create_visualization == o.create_visualization && num_det_orders == o.num_det_orders &&
-           det_order_method == o.det_order_method && seed == o.seed &&
+           det_order_method == o.det_order_method && seed == o.seed && sparsify_errors == o.sparsify_errors &&
+           sparsify_base_degree == o.sparsify_base_degree && sparsify_max_degree == o.sparsify_max_degree &&
+           sparsify_reactivate_limit == o.sparsify_reactivate_limit &&
            at_most_two_errors_per_detector == o.at_most_two_errors_per_detector;
   }
   bool operator!=(const TesseractSinterDecoder& o) const { return !(*this == o); }
@@ -125,6 +133,10 @@ struct TesseractSinterDecoder {
     c.det_penalty = det_penalty;
     c.create_visualization = create_visualization;
     c.at_most_two_errors_per_detector = at_most_two_errors_per_detector;
+    c.sparsify_errors = sparsify_errors;
+    c.sparsify_base_degree = sparsify_base_degree;
+    c.sparsify_max_degree = sparsify_max_degree;
+    c.sparsify_reactivate_limit = sparsify_reactivate_limit;
     c.det_orders = build_det_orders(dem, num_det_orders, det_order_method, seed);  // 0 -> the decoder's iota order
     return std::make_shared<TesseractDecoder>(std::move(c));
   }
@@ -221,6 +233,15 @@ PYBIND11_MODULE(_tesseract_b200, root) {
   // ---- tesseract (tesseract.pybind.h) --------------------------------------------------------------
   auto m = root.def_submodule("tesseract", "Module containing the tesseract algorithm");
   m.attr("INF_DET_BEAM") = INF_DET_BEAM;
+  m.def(
+      "suggest_sparsify_reactivate_limit",  // tesseract.pybind.h:80-82
+      [](size_t num_detectors, int sparsify_base_degree) {
+        const int64_t v = tsr_suggest_sparsify_reactivate_limit(num_detectors, sparsify_base_degree);
+        if (v < 0) throw std::invalid_argument(tsr_last_error());
+        return (int)v;
+      },
+      py::arg("num_detectors"), py::arg("sparsify_base_degree"),
+      "Returns the suggested number of optional high-degree errors to reactivate per shot.");
 
   py::class_<TesseractConfig>(m, "TesseractConfig")
       .def(py::init<>())
@@ -368,11 +389,12 @@ PYBIND11_MODULE(_tesseract_b200, root) {
           py::return_value_policy::reference_internal);
   py::class_<TesseractSinterDecoder>(sc, "TesseractSinterDecoder")
       .def(py::init<>())
-      .def(py::init<int, bool, bool, bool, bool, size_t, double, bool, size_t, DetOrder, uint64_t, bool>(),
+      .def(py::init<int, bool, bool, bool, bool, size_t, double, bool, size_t, DetOrder, uint64_t, bool, int, int, int, bool>(),
            py::arg("det_beam") = DEFAULT_DET_BEAM, py::arg("beam_climbing") = false, py::arg("no_revisit_dets") = true,
            py::arg("verbose") = false, py::arg("merge_errors") = true, py::arg("pqlimit") = DEFAULT_PQLIMIT,
            py::arg("det_penalty") = 0.0, py::arg("create_visualization") = false, py::arg("num_det_orders") = 0,
-           py::arg("det_order_method") = DetOrder::DetIndex, py::arg("seed") = 2384753,
+           py::arg("det_order_method") = DetOrder::DetIndex, py::arg("seed") = 2384753, py::arg("sparsify_errors") = false,
+           py::arg("sparsify_base_degree") = -1, py::arg("sparsify_max_degree") = -1, py::arg("sparsify_reactivate_limit") = -1,
            py::arg("at_most_two_errors_per_detector") = false)
       .def("compile_decoder_for_dem", &TesseractSinterDecoder::compile_decoder_for_dem, py::kw_only(), py::arg("dem"))
       .def("decode_via_files", &TesseractSinterDecoder::decode_via_files, py::kw_only(), py::arg("num_shots"), py::arg("num_dets"),
@@ -389,31 +411,50 @@ PYBIND11_MODULE(_tesseract_b200, root) {
       .def_readwrite("num_det_orders", &TesseractSinterDecoder::num_det_orders)
       .def_readwrite("det_order_method", &TesseractSinterDecoder::det_order_method)
       .def_readwrite("seed", &TesseractSinterDecoder::seed)
+      .def_readwrite("sparsify_errors", &TesseractSinterDecoder::sparsify_errors)
+      .def_readwrite("sparsify_base_degree", &TesseractSinterDecoder::sparsify_base_degree)
+      .def_readwrite("sparsify_max_degree", &TesseractSinterDecoder::sparsify_max_degree)
+      .def_readwrite("sparsify_reactivate_limit", &TesseractSinterDecoder::sparsify_reactivate_limit)
       .def_readwrite("at_most_two_errors_per_detector", &TesseractSinterDecoder::at_most_two_errors_per_detector)
       .def(py::self == py::self)
       .def(py::self != py::self)
       .def(py::pickle(
+          // the reference's 15-tuple (tesseract_sinter_compat.pybind.h:406-439) plus at_most_two_errors_per_detector
           [](const TesseractSinterDecoder& s) {
             return py::make_tuple(s.det_beam, s.beam_climbing, s.no_revisit_dets, s.verbose, s.merge_errors, s.pqlimit,
                                   s.det_penalty, s.create_visualization, s.num_det_orders, s.det_order_method, s.seed,
+                                  s.sparsify_errors, s.sparsify_base_degree, s.sparsify_max_degree, s.sparsify_reactivate_limit,
                                   s.at_most_two_errors_per_detector);
           },
           [](py::tuple t) {
-            if (t.size() != 12 && t.size() != 11) throw std::runtime_error("Invalid state!");
-            return TesseractSinterDecoder(t[0].cast<int>(), t[1].cast<bool>(), t[2].cast<bool>(), t[3].cast<bool>(),
-                                          t[4].cast<bool>(), t[5].cast<size_t>(), t[6].cast<double>(), t[7].cast<bool>(),
-                                          t[8].cast<size_t>(), t[9].cast<DetOrder>(), t[10].cast<uint64_t>(),
-                                          t.size() == 12 ? t[11].cast<bool>() : false);
+            auto head = [&](size_t orders_at, bool sp, int base, int max, int limit, bool amt) {
+              return TesseractSinterDecoder(t[0].cast<int>(), t[1].cast<bool>(), t[2].cast<bool>(), t[3].cast<bool>(),
+                                            t[4].cast<bool>(), t[5].cast<size_t>(), t[6].cast<double>(), t[7].cast<bool>(),
+                                            t[orders_at].cast<size_t>(), t[orders_at + 1].cast<DetOrder>(),
+                                            t[orders_at + 2].cast<uint64_t>(), sp, base, max, limit, amt);
+            };
+            if (t.size() == 11) return head(8, false, -1, -1, -1, false);                 // legacy 11-tuple
+            if (t.size() == 12) return head(8, false, -1, -1, -1, t[11].cast<bool>());    // this module's round-1 state
+            if (t.size() != 15 && t.size() != 16) throw std::runtime_error("Invalid state for TesseractSinterDecoder!");
+            const bool amt = t.size() == 16 ? t[15].cast<bool>() : false;
+            if (py::isinstance<py::bool_>(t[8]))  // legacy order with the sparsify fields at [8..11]
+              return head(12, t[8].cast<bool>(), t[9].cast<int>(), t[10].cast<int>(), t[11].cast<int>(), amt);
+            return head(8, t[11].cast<bool>(), t[12].cast<int>(), t[13].cast<int>(), t[14].cast<int>(), amt);
           }));
-  // Presets of make_tesseract_sinter_decoders_dict (tesseract_sinter_compat.pybind.h:442-490) that do not need
-  // --sparsify-errors.
+  // Presets of make_tesseract_sinter_decoders_dict (tesseract_sinter_compat.pybind.h:442-490).
   sc.def("make_tesseract_sinter_decoders_dict", []() {
     py::dict d;
-    d["tesseract-long-beam"] =
-        TesseractSinterDecoder(20, true, true, false, true, 1000000, 0.0, false, 21, DetOrder::DetIndex, 2384753, false);
+    auto preset = [](int beam, size_t pqlimit, size_t orders, bool sparsify, int base) {
+      return TesseractSinterDecoder(beam, true, true, false, true, pqlimit, 0.0, false, orders, DetOrder::DetIndex, 2384753, sparsify,
+                                    base, -1, -1, false);
+    };
+    d["tesseract-long-beam"] = preset(20, 1000000, 21, false, -1);
     d["tesseract"] = d["tesseract-long-beam"];
-    d["tesseract-short-beam"] =
-        TesseractSinterDecoder(15, true, true, false, true, 200000, 0.0, false, 16, DetOrder::DetIndex, 2384753, false);
+    d["tesseract-long-beam-sparsify-color-code-like"] = preset(20, 1000000, 21, true, 3);
+    d["tesseract-long-beam-sparsify-surface-code-like"] = preset(20, 1000000, 21, true, 2);
+    d["tesseract-short-beam"] = preset(15, 200000, 16, false, -1);
+    d["tesseract-short-beam-sparsify-color-code-like"] = preset(15, 200000, 16, true, 3);
+    d["tesseract-short-beam-sparsify-surface-code-like"] = preset(15, 200000, 16, true, 2);
     return d;
   });
 }

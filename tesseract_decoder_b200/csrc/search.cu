@@ -29,6 +29,7 @@
 #include <cstdint>
 
 #include "search.h"
+#include "sparsify.cuh"
 
 namespace tsr {
 namespace {
@@ -103,8 +104,8 @@ __device__ __forceinline__ Entry decode_entry(const DeviceTables& t, const uint1
 // cost*min_count >= min_cost*size and replaces the minimum at unblocked entries with
 // cost*min_count < min_cost*count.  Each 32-entry chunk is decoded in parallel and then those two
 // event kinds are replayed in row order.
-__device__ __forceinline__ double detcost(const DeviceTables& t, const uint16_t* st, uint32_t d, double det_penalty,
-                                          uint32_t lane, unsigned long long& scanned) {
+__device__ __forceinline__ double detcost(const DeviceTables& t, const uint16_t* st, const uint32_t* act, uint32_t d,
+                                          double det_penalty, uint32_t lane, unsigned long long& scanned) {
   const uint32_t roff = __ldg(t.row_off + d);
   const uint32_t rlen = __ldg(t.row_off + d + 1) - roff;
   const uint32_t Td = st[d] & kThreshMask;
@@ -113,7 +114,8 @@ __device__ __forceinline__ double detcost(const DeviceTables& t, const uint16_t*
   bool done = false;
   for (uint32_t base = 0; base < rlen && !done; base += 32) {
     const uint32_t idx = base + lane;
-    const bool valid = idx < rlen;
+    // sparsify: entries that are not active for this shot are not in the row at all (tesseract.cc:729-736)
+    const bool valid = idx < rlen && (!act || ((__ldcg(act + (size_t)d * t.sp_rw + (base >> 5)) >> lane) & 1u));
     Entry e;
     e.cost = 0;
     e.size = 1;
@@ -250,7 +252,7 @@ struct Counters {
 
 // One search.  Returns the item status; on kItemOk the solution has been written.
 __device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t item, uint32_t lane, uint32_t* fbits,
-                              uint32_t* rbits, uint16_t* st, Counters& ctr, uint64_t& n_visited) {
+                              uint32_t* rbits, uint16_t* st, uint32_t* sp_scratch, Counters& ctr, uint64_t& n_visited) {
   const DeviceTables& t = p.t;
   const uint32_t D = t.D, nwords = t.nwords;
   const uint32_t shot = item / p.n_trials, trial = item - shot * p.n_trials;
@@ -289,6 +291,10 @@ __device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t ite
   }
   const uint32_t root_dets = __reduce_add_sync(kFull, my_fired);
   root_key = warp_xor(root_key);
+  __syncwarp();
+  // sparsify: this shot's active-entry masks (build_sparse_d2e, tesseract.cc:673-737)
+  uint32_t* act = p.t.sp_on ? p.sp_act + (size_t)slot * D * t.sp_rw : nullptr;
+  if (act) sparsify::select(t, rbits, act, sp_scratch, 0, 1, lane, [] { __syncwarp(); });
 
   uint64_t heap_size = 0, chain_size = 0, pushed = 0;
   uint32_t min_dets = root_dets;
@@ -412,7 +418,7 @@ __device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t ite
         while (word) {
           const uint32_t d = (wb + l) * 32 + (uint32_t)__ffs((int)word) - 1;
           word &= word - 1;
-          const double h = detcost(t, st, d, p.det_penalty, lane, ctr.S);
+          const double h = detcost(t, st, act, d, p.det_penalty, lane, ctr.S);
           if (lane == 0) hc[d] = h;
           root_cost = __dadd_rn(root_cost, h);
         }
@@ -450,6 +456,7 @@ __device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t ite
       uint32_t my_err = 0;
       if (idx < m_len) {
         open = !decode_entry(t, st, m_off, idx, m_thr).blocked;
+        if (act) open = open && ((__ldcg(act + (size_t)mind * t.sp_rw + (base >> 5)) >> lane) & 1u);
         my_err = (uint32_t)__ldg(t.row_err + m_off + idx);
       }
       unsigned todo = __ballot_sync(kFull, open);
@@ -502,7 +509,7 @@ __device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t ite
           if ((fired_mask >> j) & 1) {
             cost = __dsub_rn(cost, hc[d]);
           } else {
-            cost = __dadd_rn(cost, detcost(t, st, d, p.det_penalty, lane, ctr.S));
+            cost = __dadd_rn(cost, detcost(t, st, act, d, p.det_penalty, lane, ctr.S));
           }
         }
         // eneighbors[ei] ∩ fired: detectors adjacent to one of the error's detectors, fired in the
@@ -528,7 +535,7 @@ __device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t ite
               const uint32_t od = (wb + l) * 32 + (uint32_t)__ffs((int)word) - 1;
               word &= word - 1;
               cost = __dsub_rn(cost, hc[od]);
-              cost = __dadd_rn(cost, detcost(t, st, od, p.det_penalty, lane, ctr.S));
+              cost = __dadd_rn(cost, detcost(t, st, act, od, p.det_penalty, lane, ctr.S));
             }
           }
         }
@@ -570,10 +577,11 @@ __global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
   const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + warp;
   if (slot >= p.n_slots) return;
   const uint32_t D = p.t.D, nwords = p.t.nwords;
-  const uint32_t per_warp_words = 2 * nwords + (D + 2) / 2;
+  const uint32_t per_warp_words = 2 * nwords + (D + 2) / 2 + (p.t.sp_on ? sparsify::kScratchWords : 0);
   uint32_t* fbits = smem + (size_t)warp * per_warp_words;
   uint32_t* rbits = fbits + nwords;
   uint16_t* st = reinterpret_cast<uint16_t*>(rbits + nwords);
+  uint32_t* sp_scratch = rbits + nwords + (D + 2) / 2;
   Counters ctr;
   unsigned long long searches = 0;
   while (true) {
@@ -584,8 +592,10 @@ __global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
     uint32_t item = p.item_ids ? __ldg(p.item_ids + work) : work;
     if (p.shot_order) item = __ldg(p.shot_order + work / p.n_trials) * p.n_trials + work % p.n_trials;
     uint64_t n_visited = 0;
-    const uint8_t status = run_search(p, slot, item, lane, fbits, rbits, st, ctr, n_visited);
+    const uint8_t status = run_search(p, slot, item, lane, fbits, rbits, st, sp_scratch, ctr, n_visited);
     __syncwarp();
+    if (p.t.sp_on)  // back to the mandatory masks for the slot's next search
+      sparsify::restore(p.t, rbits, p.sp_act + (size_t)slot * D * p.t.sp_rw, 0, 1, lane, [] { __syncwarp(); });
     ++searches;
     if (lane == 0) {
       p.status[item] = status;
@@ -713,14 +723,14 @@ __global__ void resolve_kernel(const ResolveParams p) {
 
 }  // namespace
 
-uint32_t search_smem_bytes_per_warp(uint32_t D) {
+uint32_t search_smem_bytes_per_warp(uint32_t D, bool sparsify) {
   const uint32_t nwords = (D + 31) / 32;
-  return 4 * (2 * nwords + (D + 2) / 2);
+  return 4 * (2 * nwords + (D + 2) / 2 + (sparsify ? sparsify::kScratchWords : 0));
 }
 
-int search_max_blocks_per_sm(uint32_t warps_per_block, uint32_t D) {
+int search_max_blocks_per_sm(uint32_t warps_per_block, uint32_t D, bool sparsify) {
   int n = 0;
-  const size_t smem = (size_t)search_smem_bytes_per_warp(D) * warps_per_block;
+  const size_t smem = (size_t)search_smem_bytes_per_warp(D, sparsify) * warps_per_block;
   if (smem > 48 * 1024)
     if (cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_kernel, (int)(warps_per_block * 32), smem) != cudaSuccess)
@@ -745,7 +755,7 @@ int launch_order(const OrderParams& p, void* stream) {
 
 int launch_search(const SearchParams& p, uint32_t blocks, uint32_t warps_per_block, void* stream) {
   if (p.n_work == 0 || blocks == 0) return 0;
-  const size_t smem = (size_t)search_smem_bytes_per_warp(p.t.D) * warps_per_block;
+  const size_t smem = (size_t)search_smem_bytes_per_warp(p.t.D, p.t.sp_on != 0) * warps_per_block;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -44,6 +44,13 @@ struct DeviceTables {
   const uint32_t* bs_pl_off = nullptr;
   const uint32_t* bs_pl = nullptr;
   uint32_t bs_group = 0, bs_cap = 0;
+  // --sparsify-errors (sparsify.cuh; null / 0 when off): per row word [D][sp_rw], bit i of word w = entry 32 w + i.
+  const uint32_t* sp_mand = nullptr;   // errors of degree <= sparsify_base_degree: always active
+  const uint32_t* sp_opt = nullptr;    // errors of base < degree <= max: reactivated per shot
+  const uint32_t* sp_crank = nullptr;  // [E] dense rank of the error's cost among the distinct costs
+  uint32_t sp_rw = 0;                  // words per row: ceil(max_row_len / 32)
+  uint32_t sp_limit = 0;               // sparsify_reactivate_limit
+  int sp_on = 0;
 };
 
 struct alignas(16) HeapNode {
@@ -96,6 +103,7 @@ struct SearchParams {
   ChainNode* chain = nullptr;
   uint4* visited = nullptr;
   uint32_t* vlist = nullptr;
+  uint32_t* sp_act = nullptr;  // [n_slots][D][sp_rw] active-entry masks (sparsify.cuh), == sp_mand between searches
   double* hcache = nullptr;  // [n_slots][D]
   int hc_shared = 0;         // fast path: the per-detector terms of the expanded node live in shared memory
   // Per-item outputs.
@@ -161,11 +169,11 @@ int launch_resolve(const ResolveParams& p, void* stream);
 // `bits` selects the bit-sliced row scan (needs the bs_* tables); otherwise rows are scanned entry per lane, and
 // `instrumented` additionally counts the reference's visited row entries.
 int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, bool bits, void* stream);
-uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits);
+uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits);  // t.sp_on adds the selection scratch
 int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits);
-// Shared memory bytes one search warp needs for a DEM with D detectors.
-uint32_t search_smem_bytes_per_warp(uint32_t D);
+// Shared memory bytes one search warp needs for a DEM with D detectors (sparsify adds the selection scratch).
+uint32_t search_smem_bytes_per_warp(uint32_t D, bool sparsify);
 // Resident blocks per SM of the search kernel for this block shape (0 on failure).
-int search_max_blocks_per_sm(uint32_t warps_per_block, uint32_t D);
+int search_max_blocks_per_sm(uint32_t warps_per_block, uint32_t D, bool sparsify);
 
 }  // namespace tsr

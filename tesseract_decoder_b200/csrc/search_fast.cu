@@ -34,6 +34,7 @@
 #include <cstdint>
 
 #include "search.h"
+#include "sparsify.cuh"
 
 namespace tsr {
 namespace {
@@ -101,6 +102,10 @@ struct Smem {
   // push staging (phase 7): the other warps' regions, idle while warp 0 pushes
   uint4* stage;
   uint32_t stage_cap;  // in 16-byte nodes
+  // sparsify (sparsify.cuh): this slot's active-entry masks [D][rw] in global memory (null when off), selection scratch
+  const uint32_t* act;
+  uint32_t rw;
+  uint32_t* sp_scratch;
 };
 
 constexpr uint32_t kTL = 64;  // targets evaluated per flush
@@ -115,9 +120,11 @@ __host__ __device__ inline uint32_t dpad_of(uint32_t D) {
 struct Layout {
   uint32_t off_rank, off_rbits, off_fbits, off_pst, off_hc, off_cost, off_meta, off_clist, off_st, total;
   uint32_t off_pbb, off_fz, warp_stride, w_cf, w_tl, w_hv, w_fl, w_bl, w_gc, w_nzw;  // w_*: offsets inside a warp's region
+  uint32_t off_sp;
 };
 __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint32_t rank_entries, uint32_t max_row_len,
-                                               uint32_t warps, bool hc_shared, uint32_t bs_group = 0, uint32_t bs_cap = 0) {
+                                               uint32_t warps, bool hc_shared, uint32_t bs_group = 0, uint32_t bs_cap = 0,
+                                               bool sparsify = false) {
   Layout L;
   uint32_t at = round16(sizeof(Ctl));
   L.off_rank = at;
@@ -140,6 +147,8 @@ __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint3
   if (bs_group) at += round16(nwords * 4);
   L.off_fz = at;
   at += round16(nwords * 2);
+  L.off_sp = at;
+  if (sparsify) at += round16(sparsify::kScratchWords * 4);
   L.off_st = at;
   // this warp's region: the private state copy (entry-per-lane scans) or the bit-sliced scratch
   uint32_t w = bs_group ? 0 : dpad_of(D) * 2;
@@ -220,8 +229,8 @@ __device__ __forceinline__ uint32_t entry_size(const DeviceTables& t, uint32_t r
 // unblocked error touches x.  kInstr additionally counts the row entries the reference loop would have
 // visited before its early exit (counter S of SURVEY.md §8d).
 template <bool kInstr>
-__device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t* st, const uint16_t* rank, uint32_t x,
-                                           uint32_t lane, unsigned long long& scanned) {
+__device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t* st, const uint16_t* rank, const uint32_t* act,
+                                           uint32_t x, uint32_t lane, unsigned long long& scanned) {
   const uint32_t roff = __ldg(t.row_off + x);
   const uint32_t rlen = __ldg(t.row_off + x + 1) - roff;
   const uint32_t Td = st[x] & kThr;
@@ -232,7 +241,9 @@ __device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t
   for (uint32_t base = 0; base < rlen; base += 32) {
     const uint32_t idx = base + lane;
     uint32_t urank = kKeyInf;
-    if (idx < rlen) {
+    // sparsify: entries that are not active for this shot are not in the row at all (tesseract.cc:729-736)
+    const bool present = idx < rlen && (!act || ((__ldcg(act + (size_t)x * t.sp_rw + (base >> 5)) >> lane) & 1u));
+    if (present) {
       const Eval e = eval_entry(t, st, roff, idx, Td);
       const uint32_t cls = e.cost_id * t.fnstride + e.count;
       if (!e.blocked) {
@@ -246,7 +257,7 @@ __device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t
     }
     if (kInstr && counting) {
       uint32_t rs = 0;
-      if (idx < rlen) rs = rank[(ldg16(t.frec_a + roff + idx).x & 0x7F) * t.fnstride + entry_size(t, roff, idx)];
+      if (present) rs = rank[(ldg16(t.frec_a + roff + idx).x & 0x7F) * t.fnstride + entry_size(t, roff, idx)];
       uint32_t incl = urank;
       for (int off = 1; off < 32; off <<= 1) {
         const uint32_t o = __shfl_up_sync(kFull, incl, off);
@@ -255,12 +266,13 @@ __device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t
       uint32_t excl = __shfl_up_sync(kFull, incl, 1);
       if (lane == 0) excl = kKeyInf;
       const uint32_t before = min(carry, excl);
-      const unsigned mb = __ballot_sync(kFull, idx < rlen && before != kKeyInf && rs >= before);
+      const unsigned mp = __ballot_sync(kFull, present);
+      const unsigned mb = __ballot_sync(kFull, present && before != kKeyInf && rs >= before);
       if (mb) {
-        scanned += (unsigned long long)__ffs((int)mb);
+        scanned += (unsigned long long)__popc(mp & ((2u << ((uint32_t)__ffs((int)mb) - 1)) - 1u));  // up to and including the exit
         counting = false;
       } else {
-        scanned += min(32u, rlen - base);
+        scanned += (unsigned long long)__popc(mp);
         carry = min(carry, __shfl_sync(kFull, incl, 31));
       }
     }
@@ -411,7 +423,8 @@ __device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, 
       for (; q < nf; ++q) add(__ldg(mrow + (size_t)fl[q] * nw));
     }
     // C: blocked entries — the row's own prefix, and per blocking neighbour a prefix of the pair list
-    const uint32_t valid = len - lo >= 32 ? 0xFFFFFFFFu : ((1u << (len - lo)) - 1u);
+    uint32_t valid = len - lo >= 32 ? 0xFFFFFFFFu : ((1u << (len - lo)) - 1u);
+    if (sm.act) valid &= __ldcg(sm.act + (size_t)x * sm.rw + wl);  // sparsify: this shot's active entries
     uint32_t B = thr0 <= lo ? 0u : (thr0 - lo >= 32 ? 0xFFFFFFFFu : ((1u << (thr0 - lo)) - 1u));
     for (uint32_t q = 0; q < nb; ++q) {
       const uint32_t jb = sm.bl[g * cap + q];
@@ -713,7 +726,7 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
         if ((fired_mask >> k) & 1) {
           cost = __dsub_rn(cost, sm.hc[d]);
         } else {
-          const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, d, lane, ctr.S), p.det_penalty);
+          const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, sm.act, d, lane, ctr.S), p.det_penalty);
           cost = __dadd_rn(cost, h);
         }
       }
@@ -773,7 +786,7 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
             const uint32_t od = __shfl_sync(kFull, w, (int)l) * 32 + (uint32_t)__ffs((int)word) - 1;
             word &= word - 1;
             cost = __dsub_rn(cost, sm.hc[od]);
-            const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, od, lane, ctr.S), p.det_penalty);
+            const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, sm.act, od, lane, ctr.S), p.det_penalty);
             cost = __dadd_rn(cost, h);
           }
         }
@@ -845,6 +858,8 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
     }
   }
   __syncthreads();
+  // sparsify: this shot's active-entry masks (build_sparse_d2e, tesseract.cc:673-737), by the whole CTA
+  if (sm.act) sparsify::select(t, sm.rbits, const_cast<uint32_t*>(sm.act), sm.sp_scratch, warp, nwarps, lane, [] { __syncthreads(); });
   prof_mark(p, c, 6);
 
   while (true) {
@@ -1088,7 +1103,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           while (word) {
             const uint32_t d = w * 32 + (uint32_t)__ffs((int)word) - 1;
             word &= word - 1;
-            const double h = __dadd_rn(scan_row<kInstr>(t, sm.st, sm.rank, d, lane, ctr.S), p.det_penalty);
+            const double h = __dadd_rn(scan_row<kInstr>(t, sm.st, sm.rank, sm.act, d, lane, ctr.S), p.det_penalty);
             if (lane == 0) sm.hc[d] = h;
           }
         }
@@ -1155,6 +1170,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
             const uint32_t idx = base + lane;
             bool open = false;
             if (idx < m_len) open = !eval_entry(t, sm.st, m_off, idx, m_thr).blocked;
+            if (sm.act) open = open && ((__ldcg(sm.act + (size_t)mind * sm.rw + (base >> 5)) >> lane) & 1u);
             const unsigned mo = __ballot_sync(kFull, open);
             if (open) sm.clist[n + __popc(mo & ((1u << lane) - 1u))] = (uint16_t)idx;
             n += __popc(mo);
@@ -1400,7 +1416,7 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
   const uint32_t D = p.t.D;
   const uint32_t rank_entries = p.t.fn_costs * p.t.fnstride;
   const Layout L = make_layout(D, p.t.nwords, rank_entries, p.t.max_row_len, nwarps, p.hc_shared != 0,
-                               kBits ? p.t.bs_group : 0, kBits ? p.t.bs_cap : 0);
+                               kBits ? p.t.bs_group : 0, kBits ? p.t.bs_cap : 0, p.t.sp_on != 0);
   Smem sm;
   sm.ctl = reinterpret_cast<Ctl*>(base);
   sm.rank = reinterpret_cast<uint16_t*>(base + L.off_rank);
@@ -1422,6 +1438,9 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
   sm.bl = reinterpret_cast<uint32_t*>(wbase + L.w_bl);
   sm.gc = reinterpret_cast<uint32_t*>(wbase + L.w_gc);
   sm.nzw = reinterpret_cast<uint16_t*>(wbase + L.w_nzw);
+  sm.act = p.t.sp_on ? p.sp_act + (size_t)slot * D * p.t.sp_rw : nullptr;
+  sm.rw = p.t.sp_rw;
+  sm.sp_scratch = reinterpret_cast<uint32_t*>(base + L.off_sp);
   sm.stage = reinterpret_cast<uint4*>(base + L.off_st + L.warp_stride);
   sm.stage_cap = (nwarps - 1) * (L.warp_stride / 16);
   for (uint32_t i = tid; i < rank_entries; i += blockDim.x) sm.rank[i] = __ldg(p.t.frank + i);
@@ -1442,6 +1461,8 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
     if (p.shot_order) item = __ldg(p.shot_order + work / p.n_trials) * p.n_trials + work % p.n_trials;
     const uint32_t status = run_search<kInstr, kBits>(p, sm, slot, item, ctr);
     __syncthreads();
+    if (sm.act)  // back to the mandatory masks for the slot's next search
+      sparsify::restore(p.t, sm.rbits, const_cast<uint32_t*>(sm.act), warp, nwarps, lane, [] { __syncthreads(); });
     ++searches;
     if (tid == 0) {
       p.status[item] = (uint8_t)status;
@@ -1490,7 +1511,7 @@ int configure(size_t smem) {
 
 uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits) {
   return make_layout(t.D, t.nwords, t.fn_costs * t.fnstride, t.max_row_len, warps, hc_shared, bits ? t.bs_group : 0,
-                     bits ? t.bs_cap : 0).total;
+                     bits ? t.bs_cap : 0, t.sp_on != 0).total;
 }
 
 int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits) {

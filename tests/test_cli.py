@@ -35,9 +35,14 @@ def test_argument_validation():
     with open(dem, "w") as f:
         f.write("error(0.1) D0 L0\nerror(0.1) D0 D1")
     r = run("--dem", dem, "--sample-num-shots", 5, "--sparsify-errors", "--sparsify-base-degree", 0)
-    assert r.returncode != 0 and "sparsify_base_degree must be > 0" in r.stderr  # tesseract.cc:257-260
-    r = run("--dem", dem, "--sample-num-shots", 5, "--sparsify-errors", "--sparsify-base-degree", 2)
-    assert r.returncode != 0 and "not implemented on the GPU decode path yet" in r.stderr
+    assert r.returncode != 0 and "--sparsify-base-degree must be > 0." in r.stderr  # tesseract_main.cc:170-172
+    # Args::validate of the reference (tesseract_main.cc:155-179)
+    r = run("--dem", dem, "--sample-num-shots", 5, "--sparsify-base-degree", 2)
+    assert r.returncode != 0 and "without --sparsify-errors" in r.stderr
+    r = run("--dem", dem, "--sample-num-shots", 5, "--sparsify-errors")
+    assert r.returncode != 0 and "Must specify --sparsify-base-degree when --sparsify-errors is enabled." in r.stderr
+    r = run("--dem", dem, "--sample-num-shots", 5, "--sparsify-errors", "--sparsify-base-degree", 3, "--sparsify-max-degree", 2)
+    assert r.returncode != 0 and "--sparsify-max-degree must be >= --sparsify-base-degree." in r.stderr
 
 
 @pytest.mark.gpu

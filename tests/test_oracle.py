@@ -305,8 +305,12 @@ def test_sparsify_known_answers(kind):  # tesseract.test.cc:478-540 (HighDegreeE
 def test_golden_vectors(kind, name):
     """Committed outputs of the reference build: the checker in use must reproduce them bit for bit."""
     g = W.load_golden(name)
-    if name in ("g_c3_surface_d11_climb", "g_c4_bb144_p1e-4") and kind == "port":
-        g = {k: (v[:8] if k in ("dets", "obs", "cost", "low_confidence") else v) for k, v in g.items()}
+    # keep the CPU suite to minutes: a prefix of the heavy sets (the literal colour-code set holds a 226-CPU-second shot)
+    cap = {"g_c2_color_d7_literal": 600}.get(name)
+    if name in ("g_c3_surface_d11_climb", "g_c4_bb144_p1e-4"):
+        cap = 8 if kind == "port" else 48
+    if cap:
+        g = {k: (v[:cap] if k in ("dets", "obs", "cost", "low_confidence") else v) for k, v in g.items()}
     from tesseract_decoder_b200 import capi
     dem, kw = W.decoder_kwargs(g["config"], capi.build_det_orders)
     dec = OracleDecoder(dem, kind=kind, num_threads=8, **kw)

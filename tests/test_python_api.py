@@ -65,7 +65,7 @@ def test_invalid_inputs_without_decoding():
         tesseract.TesseractConfig(Dem("error(1.5) D0")).compile_decoder()
 
 
-def test_sparsify_options_are_validated_and_refused_loudly():  # tesseract_test.py:295-465, tesseract.cc:256-270
+def test_sparsify_options_are_validated():  # tesseract_test.py:295-465, tesseract.cc:256-277
     dem = Dem(_DETECTOR_ERROR_MODEL)
     c = tesseract.TesseractConfig(dem, sparsify_errors=True, sparsify_base_degree=2, sparsify_max_degree=4, sparsify_reactivate_limit=3)
     assert (c.sparsify_errors, c.sparsify_base_degree, c.sparsify_max_degree, c.sparsify_reactivate_limit) == (True, 2, 4, 3)
@@ -76,8 +76,10 @@ def test_sparsify_options_are_validated_and_refused_loudly():  # tesseract_test.
                     (dict(sparsify_base_degree=3, sparsify_max_degree=2), "sparsify_max_degree must be >= sparsify_base_degree.")):
         with pytest.raises(ValueError, match=msg.replace(".", r"\.")):
             tesseract.TesseractConfig(dem, sparsify_errors=True, **kw).compile_decoder()
-    with pytest.raises(RuntimeError, match="not implemented on the GPU decode path yet"):  # no silent fallback
-        c.compile_decoder()
+    # tesseract.h:37 / tesseract.cc:45-69, 104-107: round(4.5^(base-2) * D / 3)
+    assert tesseract.suggest_sparsify_reactivate_limit(1728, 3) == 2592
+    assert tesseract.suggest_sparsify_reactivate_limit(120, 2) == 40
+    assert tesseract.suggest_sparsify_reactivate_limit(0, 3) == 0
 
 
 # ---- on the GPU ----------------------------------------------------------------------------------------
