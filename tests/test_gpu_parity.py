@@ -73,11 +73,12 @@ HEAVY_GOLDEN = {"g_c2_color_d7_literal": ("fast", 600)}
 
 
 @pytest.mark.parametrize("path", ["fast-bits", "fast", "generic"])
-@pytest.mark.parametrize("name", W.golden_names())
+@pytest.mark.parametrize("name", W.golden_names() + W.golden_names(sparsify=True))
 def test_golden_vectors(name, path):
     """All three CUDA search variants — the CTA-per-search integer-rank kernel every fixture DEM is certified for
     (csrc/fast.h) with bit-sliced and with entry-per-lane row scans, and the generic event-replay kernel —
-    reproduce the reference build's outputs."""
+    reproduce the reference build's outputs.  The s_* sets decode with --sparsify-errors (tesseract.cc:256-292, 673-737):
+    per-shot active-entry masks built on the device (csrc/sparsify.cuh)."""
     g = W.load_golden(name)
     dem, kw = W.decoder_kwargs(g["config"], capi.build_det_orders)
     dec = capi.Decoder(dem, force_generic_kernel=(path == "generic"), row_scan={"fast": 1, "fast-bits": 2}.get(path, 0), **kw)
@@ -224,6 +225,13 @@ FRESH = [
     (dict(dem="bb144_r12_p0.0001_X", det_beam=W.INF_BEAM, pqlimit=None, no_revisit_dets=True, num_det_orders=24), 40, 28),
     (dict(dem="surface_d11_r11_p0.001_X", det_beam=3, beam_climbing=True, pqlimit=20000, no_revisit_dets=True,
           num_det_orders=0), 60, 29),
+    # --sparsify-errors on fresh shots: the sinter presets' settings (tesseract_sinter_compat.pybind.h:454-488) and a tight limit
+    (dict(dem="transcx_d5_p0.001_X", det_beam=15, beam_climbing=True, pqlimit=200000, no_revisit_dets=True, num_det_orders=16,
+          sparsify_errors=True, sparsify_base_degree=2), 300, 32),
+    (dict(dem="bb144_r12_p0.0001_X", det_beam=W.INF_BEAM, pqlimit=None, no_revisit_dets=True, num_det_orders=24,
+          sparsify_errors=True, sparsify_base_degree=3), 64, 33),
+    (dict(dem="color_superdense_d7_r7_p0.001_X", det_beam=5, pqlimit=200000, no_revisit_dets=True, num_det_orders=2,
+          sparsify_errors=True, sparsify_base_degree=3, sparsify_max_degree=5, sparsify_reactivate_limit=25), 300, 34),
     # real ensembles: BFS and coordinate detector orders (utils.cc:89-171) are distinct permutations
     (dict(dem="transcx_d3_p0.001_X", det_beam=4, pqlimit=50000, no_revisit_dets=True, num_det_orders=6, det_order_method=0), 500, 30),
     (dict(dem="color_superdense_d5_r5_p0.001_Z", det_beam=3, beam_climbing=True, pqlimit=20000, no_revisit_dets=True,

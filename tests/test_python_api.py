@@ -11,7 +11,10 @@ import pytest
 import workloads as W
 import tesseract_decoder_b200 as td
 
+from tesseract_decoder_b200 import capi
+
 tesseract = td.tesseract
+sinter_compat = td.tesseract_sinter_compat
 TesseractSinterDecoder = td.tesseract_sinter_compat.TesseractSinterDecoder
 
 _DETECTOR_ERROR_MODEL = "error(0.125) D0\nerror(0.375) D0 D1\nerror(0.25) D1\ndetector(0, 0, 0) D0\ndetector(1, 0, 0) D1"
@@ -151,3 +154,25 @@ def test_bit_packed_equals_decode_batch_on_color_code_shots():  # tesseract_sint
         cfg = tesseract.TesseractConfig(Dem(dem_text), det_orders=td.utils.build_det_orders(Dem(dem_text), 4, td.utils.DetOrder.DetIndex, 2384753), **kw)
         batch = cfg.compile_decoder().decode_batch(bits)
         assert np.array_equal(np.unpackbits(packed, axis=1, bitorder="little")[:, :1].astype(bool), batch)
+
+
+@pytest.mark.gpu
+def test_sinter_sparsify_presets_decode():  # tesseract_sinter_compat.pybind.h:442-490
+    d = sinter_compat.make_tesseract_sinter_decoders_dict()
+    assert set(d) == {"tesseract", "tesseract-long-beam", "tesseract-short-beam", "tesseract-long-beam-sparsify-color-code-like",
+                      "tesseract-long-beam-sparsify-surface-code-like", "tesseract-short-beam-sparsify-color-code-like",
+                      "tesseract-short-beam-sparsify-surface-code-like"}
+    p = d["tesseract-short-beam-sparsify-surface-code-like"]
+    assert (p.sparsify_errors, p.sparsify_base_degree, p.sparsify_max_degree, p.sparsify_reactivate_limit, p.det_beam) == (True, 2, -1, -1, 15)
+    assert pickle.loads(pickle.dumps(p)) == p
+    dem = W.load_dem("surface_d5_r5_p0.002_X")
+    compiled = p.compile_decoder_for_dem(dem=Dem(dem))
+    assert compiled.decoder.config.sparsify_reactivate_limit == 40  # the suggested limit replaces -1 (tesseract.cc:272-277)
+    dets, obs = capi.sample_dem_b8(dem, 12, 400, 120, 1)
+    got = compiled.decode_shots_bit_packed(bit_packed_detection_event_data=dets)
+    kw = dict(det_beam=15, beam_climbing=True, pqlimit=200000, no_revisit_dets=True, sparsify_errors=True, sparsify_base_degree=2,
+              det_orders=capi.build_det_orders(dem, 16, 1, 2384753))
+    from oracle import oracle
+    kind = "reference" if oracle.available("reference") else "port"
+    ref = oracle.OracleDecoder(dem, kind=kind, num_threads=8, **kw).decode_batch_b8(dets)
+    assert np.array_equal(got, ref["obs"])
