@@ -247,11 +247,21 @@ class Bench:
         self.acc["launches"] += 4 * chunks + 2 * t["search_launches"]  # stage + 3 ordering kernels per chunk, search + resolve per tier
         self.acc["rerun"] += t["rerun_items"]
 
-    def reduce_counts(self, wrong, low):
-        self.tally[0], self.tally[1], self.tally[2] = self.S, wrong, low
+    def init_comm(self):
+        """N > 1: the product's own NCCL communicator (tsr_comm_*, csrc/group.cu).  torch.distributed only ships the
+        128-byte unique id from rank 0 (launcher plumbing) and provides the barrier / max-over-ranks of the timing."""
+        if self.dist is None:
+            return
+        box = [self.capi.comm_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(box, src=0)
+        self.dec.comm_init_rank(box[0], self.rank, self.world)
+
+    def reduce_counts(self, wrong, low, shots=None):
+        counts = [self.S if shots is None else shots, int(wrong), int(low)]
         if self.dist is not None:
-            self.dist.all_reduce(self.tally)  # the path's only collective: {shots, logical errors, low confidence}
-        return self.tally.tolist()
+            # the path's only collective: one ncclAllReduce of {shots, logical errors, low confidence} (tsr_comm_allreduce_sum_u64)
+            counts = self.dec.allreduce_sum(counts).tolist()
+        return counts
 
     def step_device(self):
         self.flush.zero_()  # evict L2 between steps (256 MB > 126 MB)
@@ -364,6 +374,51 @@ def run_side_workload(args, key, rank, world, local):
     return rec
 
 
+def strong_leg(args, b, rank, world):
+    """Strong scaling: a FIXED batch of T shots (the same on every rank: seed 2000) dealt out in interleaved chunks of
+    4096 shots (rank r decodes chunks r, r+N, ...), decoded end to end from host buffers, counters summed
+    by the one all-reduce.  value = T x steps / max-over-ranks time."""
+    from tesseract_decoder_b200 import sharding
+    torch, dist = b.torch, b.dist
+    T, steps, warmup, chunk = args.strong_shots, args.strong_steps, 1, 4096
+    dets, true_obs = b.capi.sample_dem_b8(b.dem, 2000, T, b.D, b.O)
+    mine = np.ascontiguousarray(sharding.shard_rows(dets, rank, world, chunk))
+    truth = np.ascontiguousarray(sharding.shard_rows(true_obs, rank, world, chunk))
+    n = len(mine)
+    h_dets = torch.from_numpy(mine).pin_memory()
+    h_obs = torch.zeros((max(n, 1), b.ostride), dtype=torch.uint8).pin_memory()
+    h_low = torch.zeros(max(n, 1), dtype=torch.uint8).pin_memory()
+
+    def step():
+        b.flush.zero_()
+        torch.cuda.synchronize()
+        if n:
+            b.dec.decode_batch_b8_raw(h_dets.data_ptr(), b.stride, n, h_obs.data_ptr(), 0, h_low.data_ptr())
+        low = h_low.numpy()[:n]
+        bad = int(((h_obs.numpy()[:n] != truth).any(axis=1) & (low == 0)).sum())
+        return b.reduce_counts(bad, int(low.sum()), shots=n)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        counts = step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    return {"value": T * steps / dt, "unit": "shots/s", "total_shots": T, "shots_this_rank": n, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 * dt / steps, "partition": f"interleaved chunks of {chunk} shots over {world} rank(s)",
+            "tally": {"shots": counts[0], "logical_errors": counts[1], "low_confidence": counts[2]},
+            "limiter": "last wave of the search kernel on each rank (per-rank batch shrinks with N); the collective is 24 bytes"}
+
+
 def run_b200(args, wl, rank, world, local):
     import torch
 
@@ -375,6 +430,7 @@ def run_b200(args, wl, rank, world, local):
 
     S = args.shots or wl["shots"]
     b = Bench(args, wl, S, rank, world, local, dist)
+    b.init_comm()
     dec, D, O = b.dec, b.D, b.O
 
     # Algorithmic bytes of one batch, from the search's own operation counters.  Counter S
@@ -426,11 +482,15 @@ def run_b200(args, wl, rank, world, local):
         "e2e": {"value": e2e, "unit": "shots/s", "h2d_bytes_per_step": S * b.stride, "d2h_bytes_per_step": S * (b.ostride + 9),
                 "ms_per_step": 1e3 * dt2 / args.steps},
         "gpu_launches": a["launches"], "rerun_items": a["rerun"],
-        "tally": {"shots": counts[0], "logical_errors": counts[1], "low_confidence": counts[2], "e2e_equal": counts == counts2},
+        "tally": {"shots": counts[0], "logical_errors": counts[1], "low_confidence": counts[2], "e2e_equal": counts == counts2,
+                  "collective": f"ncclAllReduce u64[3] per step via tsr_comm (world {dec.comm_world})" if world > 1 else "none (1 GPU)"},
         "roofline": roofline, "clocks": clocks,
     }
     if issue:
         line["issue"] = issue
+
+    if args.strong_shots and args.workload == "bb144":
+        line["scaling_strong"] = strong_leg(args, b, rank, world)
 
     mismatches = 0
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -472,6 +532,9 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=150.0, help="--impl reference: wall-time budget of the whole run")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-side", action="store_true", help="skip the `workloads` array (the other BASELINE configs)")
+    ap.add_argument("--strong-shots", type=int, default=1 << 20,
+                    help="fixed total batch of the strong-scaling leg (`scaling_strong`), split over the ranks; 0 = skip")
+    ap.add_argument("--strong-steps", type=int, default=2)
     ap.add_argument("--warps", type=int, default=0, help="warps per search CTA (0 = automatic)")
     ap.add_argument("--scan", default="auto", choices=["auto", "bits", "lanes", "generic"],
                     help="search kernel variant (auto = the decoder's choice)")

@@ -170,6 +170,44 @@ int tsr_last_batch_timing(const tsr_decoder* h, double out[4]);
 void* tsr_stream(tsr_decoder* h); /* cudaStream_t the decoder launches on */
 int tsr_device(const tsr_decoder* h);
 
+/* ---- multi-GPU (csrc/group.cu) -------------------------------------------------------------------------
+ * Shots are independent (tesseract.cc:665-671); the reference shards them over host threads with one decoder each
+ * (parallel_for_shots_in_order, utils.h:75-115; tesseract_main.cc:559-616) and sums three counters.  Here every GPU
+ * holds its own copy of the DEM tables and decodes its own shots; the only exchange is ONE ncclAllReduce(sum) of
+ * {shots, logical errors, low confidence} — plus the error-use histogram of --dem-out when asked for
+ * (tesseract_main.cc:618-623) — over NVLink.  NCCL (libnccl.so.2) is loaded on first use.
+ *
+ * One process per GPU: rank 0 calls tsr_comm_unique_id and ships the 128 bytes to the other ranks (launcher's
+ * business); every rank then calls tsr_comm_init_rank on its decoder (collective) and, per batch, sums its counters
+ * with tsr_comm_allreduce_sum_u64 (in place, host values, one collective on tsr_stream(h)). */
+#define TSR_COMM_UNIQUE_ID_BYTES 128
+int tsr_comm_unique_id(uint8_t out[TSR_COMM_UNIQUE_ID_BYTES]);
+int tsr_comm_init_rank(tsr_decoder* h, const uint8_t id[TSR_COMM_UNIQUE_ID_BYTES], int32_t rank, int32_t world);
+int32_t tsr_comm_world(const tsr_decoder* h); /* 0 = no communicator */
+int tsr_comm_allreduce_sum_u64(tsr_decoder* h, uint64_t* values, uint64_t n);
+int tsr_nccl_version(void); /* ncclGetVersion code of the library in use, 0 if NCCL cannot be loaded */
+
+/* One process, several GPUs (the CLI's --gpus N): one decoder, host thread and communicator per listed device
+ * (devices == NULL: 0 .. n_devices-1).  tsr_group_decode_b8 deals the batch out in interleaved chunks of chunk_shots
+ * shots (0 = 16384; chunk k goes to member k mod n — per-shot cost is heavy-tailed, so interleaving balances better
+ * than n contiguous ranges), decodes them concurrently and writes every shot's outputs at its own position in the
+ * caller's host arrays (all nullable).  obs_true (nullable, [shots][ceil(O/8)]) enables the logical-error count:
+ * tally_out = {shots, shots whose prediction differs from obs_true and is not low-confidence, low-confidence shots}
+ * (tesseract_main.cc:580-601), summed over the members by the all-reduce.  error_use_out (nullable,
+ * [num_dem_errors]) receives how often each error was predicted in correctly decoded shots (tesseract_main.cc:586-590). */
+typedef struct tsr_group tsr_group;
+int tsr_group_create(const char* dem_text, const tsr_config* cfg, const int32_t* devices, uint32_t n_devices, tsr_group** out);
+void tsr_group_destroy(tsr_group* g);
+uint32_t tsr_group_size(const tsr_group* g);
+tsr_decoder* tsr_group_member(tsr_group* g, uint32_t i); /* borrowed; for the table getters, counters and timing */
+int tsr_group_decode_b8(tsr_group* g, const uint8_t* dets, uint64_t stride, uint64_t shots, uint64_t chunk_shots,
+                        const uint8_t* obs_true, uint8_t* obs_out, double* cost_out, uint8_t* low_conf_out,
+                        uint64_t tally_out[3], uint64_t* error_use_out);
+/* predicted_errors_buffer of every shot of the last tsr_group_decode_b8 call that asked for error_use_out, in the
+ * caller's shot order (offsets [shots+1], idx [nnz]). */
+uint64_t tsr_group_last_batch_nnz(const tsr_group* g);
+int tsr_group_last_batch_errors(const tsr_group* g, uint64_t* offsets, uint64_t* idx);
+
 /* ---- helpers either side of the path -------------------------------------------------------------*/
 /* build_det_orders (utils.cc:192-205); method 0=DetBFS 1=DetIndex 2=DetCoordinate; out [n][D]. */
 int tsr_build_det_orders(const char* dem_text, uint64_t num_det_orders, int method, uint64_t seed, uint64_t* out);

@@ -103,6 +103,22 @@ def lib() -> C.CDLL:
     L.tsr_sparsify_reactivate_limit.argtypes = [C.c_void_p]
     L.tsr_suggest_sparsify_reactivate_limit.restype = C.c_int64
     L.tsr_suggest_sparsify_reactivate_limit.argtypes = [C.c_uint64, C.c_int32]
+    L.tsr_comm_unique_id.argtypes = [u8p]
+    L.tsr_comm_init_rank.argtypes = [C.c_void_p, u8p, C.c_int32, C.c_int32]
+    L.tsr_comm_world.argtypes = [C.c_void_p]
+    L.tsr_comm_world.restype = C.c_int32
+    L.tsr_comm_allreduce_sum_u64.argtypes = [C.c_void_p, u64p, C.c_uint64]
+    L.tsr_group_create.argtypes = [C.c_char_p, C.POINTER(TsrConfig), i32p, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.tsr_group_destroy.argtypes = [C.c_void_p]
+    L.tsr_group_size.argtypes = [C.c_void_p]
+    L.tsr_group_size.restype = C.c_uint32
+    L.tsr_group_member.argtypes = [C.c_void_p, C.c_uint32]
+    L.tsr_group_member.restype = C.c_void_p
+    L.tsr_group_decode_b8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, u64p, u64p]
+    L.tsr_group_last_batch_nnz.argtypes = [C.c_void_p]
+    L.tsr_group_last_batch_nnz.restype = C.c_uint64
+    L.tsr_group_last_batch_errors.argtypes = [C.c_void_p, u64p, u64p]
     L.tsr_set_profile.argtypes = [C.c_void_p, C.c_int]
     L.tsr_profile.argtypes = [C.c_void_p, u64p, C.c_int]
     L.tsr_stream.restype = C.c_void_p
@@ -131,7 +147,9 @@ EXPORTED_SYMBOLS = [
     "tsr_cost_from_errors", "tsr_flipped_observables", "tsr_counters", "tsr_last_batch_timing", "tsr_stream",
     "tsr_device", "tsr_build_det_orders", "tsr_dem_count_detectors", "tsr_dem_count_observables", "tsr_merge_weights", "tsr_dem_from_counts", "tsr_circuit_to_dem",
     "tsr_sample_dem_b8", "tsr_set_profile", "tsr_profile", "tsr_sparsify_reactivate_limit",
-    "tsr_suggest_sparsify_reactivate_limit",
+    "tsr_suggest_sparsify_reactivate_limit", "tsr_comm_unique_id", "tsr_comm_init_rank", "tsr_comm_world",
+    "tsr_comm_allreduce_sum_u64", "tsr_nccl_version", "tsr_group_create", "tsr_group_destroy", "tsr_group_size",
+    "tsr_group_member", "tsr_group_decode_b8", "tsr_group_last_batch_nnz", "tsr_group_last_batch_errors",
 ]
 
 
@@ -215,48 +233,63 @@ def sample_dem_b8(dem_text: str, seed: int, shots: int, num_detectors: int | Non
     return dets, obs[:, : (num_observables + 7) // 8]
 
 
+def make_config(*, det_beam: int = 5, beam_climbing: bool = False, no_revisit_dets: bool = True, merge_errors: bool = True,
+                pqlimit: int | None = 200000, det_penalty: float = 0.0, det_orders=None,
+                at_most_two_errors_per_detector: bool = False, device: int = -1, search_slots: int = 0, warps_per_block: int = 0,
+                node_pool_bytes: int = 0, max_batch_shots: int = 0, force_generic_kernel: bool = False, row_scan: int = 0,
+                sparsify_errors: bool = False, sparsify_base_degree: int = -1, sparsify_max_degree: int = -1,
+                sparsify_reactivate_limit: int = -1):
+    """(tsr_config, keep-alive object for the det_orders array)."""
+    cfg = TsrConfig()
+    lib().tsr_config_init(C.byref(cfg))
+    cfg.det_beam = det_beam
+    cfg.beam_climbing = int(beam_climbing)
+    cfg.no_revisit_dets = int(no_revisit_dets)
+    cfg.merge_errors = int(merge_errors)
+    cfg.at_most_two_errors_per_detector = int(at_most_two_errors_per_detector)
+    cfg.device = device
+    cfg.pqlimit = PQLIMIT_UNBOUNDED if pqlimit is None or pqlimit >= PQLIMIT_UNBOUNDED else int(pqlimit)
+    cfg.det_penalty = det_penalty
+    orders = None
+    if det_orders is not None and len(det_orders):
+        orders = np.ascontiguousarray(det_orders, dtype=np.uint64)
+        if orders.ndim != 2:
+            raise ValueError("det_orders must be a 2D array [num_det_orders, num_detectors]")
+        cfg.num_det_orders = orders.shape[0]
+        cfg.det_order_len = orders.shape[1]
+        cfg.det_orders = _p(orders, C.c_uint64)
+    cfg.search_slots = search_slots
+    cfg.warps_per_block = warps_per_block
+    cfg.node_pool_bytes = node_pool_bytes
+    cfg.max_batch_shots = max_batch_shots
+    cfg.force_generic_kernel = int(force_generic_kernel)
+    cfg.row_scan = int(row_scan)  # 0 auto, 1 entry per lane, 2 bit-sliced
+    cfg.sparsify_errors = int(sparsify_errors)
+    cfg.sparsify_base_degree = sparsify_base_degree
+    cfg.sparsify_max_degree = sparsify_max_degree
+    cfg.sparsify_reactivate_limit = sparsify_reactivate_limit
+    return cfg, orders
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId (rank 0); ship the bytes to the other ranks, then Decoder.comm_init_rank on every rank."""
+    out = np.zeros(128, dtype=np.uint8)
+    _check(lib().tsr_comm_unique_id(_p(out, C.c_uint8)))
+    return out.tobytes()
+
+
 class Decoder:
     """Owns one tsr_decoder handle."""
 
-    def __init__(self, dem_text: str, *, det_beam: int = 5, beam_climbing: bool = False,
-                 no_revisit_dets: bool = True, merge_errors: bool = True, pqlimit: int | None = 200000,
-                 det_penalty: float = 0.0, det_orders=None, at_most_two_errors_per_detector: bool = False,
-                 device: int = -1, host_only: bool = False, search_slots: int = 0, warps_per_block: int = 0,
-                 node_pool_bytes: int = 0, max_batch_shots: int = 0, force_generic_kernel: bool = False,
-                 row_scan: int = 0, sparsify_errors: bool = False, sparsify_base_degree: int = -1,
-                 sparsify_max_degree: int = -1, sparsify_reactivate_limit: int = -1):
+    def __init__(self, dem_text: str, *, host_only: bool = False, _borrowed=None, **kw):
         L = lib()
-        cfg = TsrConfig()
-        L.tsr_config_init(C.byref(cfg))
-        cfg.det_beam = det_beam
-        cfg.beam_climbing = int(beam_climbing)
-        cfg.no_revisit_dets = int(no_revisit_dets)
-        cfg.merge_errors = int(merge_errors)
-        cfg.at_most_two_errors_per_detector = int(at_most_two_errors_per_detector)
-        cfg.device = device
-        cfg.pqlimit = PQLIMIT_UNBOUNDED if pqlimit is None or pqlimit >= PQLIMIT_UNBOUNDED else int(pqlimit)
-        cfg.det_penalty = det_penalty
-        self._orders = None
-        if det_orders is not None and len(det_orders):
-            self._orders = np.ascontiguousarray(det_orders, dtype=np.uint64)
-            if self._orders.ndim != 2:
-                raise ValueError("det_orders must be a 2D array [num_det_orders, num_detectors]")
-            cfg.num_det_orders = self._orders.shape[0]
-            cfg.det_order_len = self._orders.shape[1]
-            cfg.det_orders = _p(self._orders, C.c_uint64)
-        cfg.search_slots = search_slots
-        cfg.warps_per_block = warps_per_block
-        cfg.node_pool_bytes = node_pool_bytes
-        cfg.max_batch_shots = max_batch_shots
-        cfg.force_generic_kernel = int(force_generic_kernel)
-        cfg.row_scan = int(row_scan)  # 0 auto, 1 entry per lane, 2 bit-sliced
-        cfg.sparsify_errors = int(sparsify_errors)
-        cfg.sparsify_base_degree = sparsify_base_degree
-        cfg.sparsify_max_degree = sparsify_max_degree
-        cfg.sparsify_reactivate_limit = sparsify_reactivate_limit
-        h = C.c_void_p()
-        self.h = None
-        _check(L.tsr_create(dem_text.encode(), C.byref(cfg), CREATE_HOST_ONLY if host_only else 0, C.byref(h)))
+        if _borrowed is not None:  # a member of a Group: the group owns the handle
+            self._owns, h = False, C.c_void_p(_borrowed)
+        else:
+            cfg, self._orders = make_config(**kw)
+            self._owns, h = True, C.c_void_p()
+            self.h = None
+            _check(L.tsr_create(dem_text.encode(), C.byref(cfg), CREATE_HOST_ONLY if host_only else 0, C.byref(h)))
         self.h = h
         self.num_detectors = L.tsr_num_detectors(h)
         self.num_observables = L.tsr_num_observables(h)
@@ -267,8 +300,24 @@ class Decoder:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().tsr_destroy(self.h)
+            if self._owns:
+                lib().tsr_destroy(self.h)
             self.h = None
+
+    # ---- multi-GPU, one process per GPU (csrc/group.cu) ------------------------------------------------
+    def comm_init_rank(self, unique_id: bytes, rank: int, world: int):
+        buf = np.frombuffer(unique_id, dtype=np.uint8).copy()
+        _check(lib().tsr_comm_init_rank(self.h, _p(buf, C.c_uint8), rank, world))
+
+    @property
+    def comm_world(self) -> int:
+        return lib().tsr_comm_world(self.h)
+
+    def allreduce_sum(self, values):
+        """One ncclAllReduce(sum) of u64 counters over the decoder's communicator; returns the sums."""
+        v = np.ascontiguousarray(values, dtype=np.uint64).copy()
+        _check(lib().tsr_comm_allreduce_sum_u64(self.h, _p(v, C.c_uint64), len(v)))
+        return v
 
     def __del__(self):
         try:
@@ -420,3 +469,55 @@ class Decoder:
     @property
     def device(self) -> int:
         return lib().tsr_device(self.h)
+
+
+class Group:
+    """tsr_group: one process driving several GPUs (one decoder, host thread and NCCL communicator per device)."""
+
+    def __init__(self, dem_text: str, devices, **kw):
+        cfg, self._orders = make_config(**kw)
+        devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+        g = C.c_void_p()
+        self.g = None
+        _check(lib().tsr_group_create(dem_text.encode(), C.byref(cfg), _p(devs, C.c_int32), len(devs), C.byref(g)))
+        self.g = g
+        self.size = lib().tsr_group_size(g)
+        self.members = [Decoder("", _borrowed=lib().tsr_group_member(g, i)) for i in range(self.size)]
+        self.num_detectors, self.num_observables = self.members[0].num_detectors, self.members[0].num_observables
+        self.num_dem_errors = self.members[0].num_dem_errors
+
+    def close(self):
+        if getattr(self, "g", None):
+            for m in self.members:
+                m.close()
+            lib().tsr_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def decode_batch_b8(self, dets_b8: np.ndarray, obs_true: np.ndarray | None = None, chunk_shots: int = 0, want_error_use: bool = False):
+        dets_b8 = np.ascontiguousarray(dets_b8, dtype=np.uint8)
+        shots, stride = dets_b8.shape
+        obs = np.zeros((shots, (self.num_observables + 7) // 8), dtype=np.uint8)
+        cost = np.zeros(shots, dtype=np.float64)
+        low = np.zeros(shots, dtype=np.uint8)
+        tally = np.zeros(3, dtype=np.uint64)
+        use = np.zeros(max(self.num_dem_errors, 1), dtype=np.uint64) if want_error_use else None
+        truth = np.ascontiguousarray(obs_true, dtype=np.uint8) if obs_true is not None else None
+        _check(lib().tsr_group_decode_b8(self.g, dets_b8.ctypes.data, stride, shots, chunk_shots,
+                                         truth.ctypes.data if truth is not None else None, obs.ctypes.data, cost.ctypes.data,
+                                         low.ctypes.data, _p(tally, C.c_uint64), _p(use, C.c_uint64) if use is not None else None))
+        out = {"obs": obs, "cost": cost, "low_confidence": low,
+               "tally": {"shots": int(tally[0]), "logical_errors": int(tally[1]), "low_confidence": int(tally[2])}}
+        if use is not None:
+            out["error_use"] = use[: self.num_dem_errors]
+            nnz = lib().tsr_group_last_batch_nnz(self.g)
+            off = np.zeros(shots + 1, dtype=np.uint64)
+            idx = np.zeros(max(nnz, 1), dtype=np.uint64)
+            _check(lib().tsr_group_last_batch_errors(self.g, _p(off, C.c_uint64), _p(idx, C.c_uint64)))
+            out["err_offsets"], out["err_idx"] = off, idx[:nnz]
+        return out

@@ -26,148 +26,23 @@
 #include "ingest.h"
 #include "search.h"
 
-namespace {
+#include "handle.h"
 
-thread_local std::string g_error;
+using namespace tsr_impl;
 
-struct CudaError : std::runtime_error {
-  using std::runtime_error::runtime_error;
-};
-struct DeviceMemoryError : std::runtime_error {
-  using std::runtime_error::runtime_error;
-};
-
-void cuda_check(cudaError_t e, const char* what) {
-  if (e != cudaSuccess) throw CudaError(std::string("CUDA: ") + what + ": " + cudaGetErrorString(e));
+namespace tsr_impl {
+std::string& last_error() {
+  thread_local std::string e;
+  return e;
 }
-#define CUDA_OK(expr) cuda_check((expr), #expr)
+}  // namespace tsr_impl
 
-template <typename F>
-int guarded(F&& f) {
-  try {
-    f();
-    return TSR_OK;
-  } catch (const std::invalid_argument& e) {
-    g_error = e.what();
-    return TSR_E_INVALID_ARGUMENT;
-  } catch (const CudaError& e) {
-    g_error = e.what();
-    return TSR_E_CUDA;
-  } catch (const DeviceMemoryError& e) {
-    g_error = e.what();
-    return TSR_E_DEVICE_MEMORY;
-  } catch (const std::exception& e) {
-    g_error = e.what();
-    return TSR_E_RUNTIME;
-  }
+tsr_decoder::~tsr_decoder() {
+  tsr_impl::comm_release(*this);
+  for (auto& e : ev)
+    if (e) cudaEventDestroy(e);
+  if (stream) cudaStreamDestroy(stream);
 }
-
-// A device allocation that frees itself.
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  DevBuf() = default;
-  DevBuf(const DevBuf&) = delete;
-  DevBuf& operator=(const DevBuf&) = delete;
-  ~DevBuf() { release(); }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-  }
-  void ensure(size_t n) {
-    if (n <= bytes) return;
-    release();
-    CUDA_OK(cudaMalloc(&p, n));
-    bytes = n;
-  }
-  template <typename T>
-  T* as() const {
-    return static_cast<T*>(p);
-  }
-  // Pageable H2D copy on the legacy stream.  The decoder's own stream is non-blocking, so it is NOT ordered after this
-  // copy (and cudaMemcpy may return before the DMA of a small pageable buffer has landed): callers finish a group
-  // of uploads with uploads_done() before anything is launched on another stream.
-  template <typename T>
-  void upload(const std::vector<T>& v) {
-    ensure(std::max<size_t>(v.size() * sizeof(T), 16));
-    if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-  }
-  static void uploads_done() { CUDA_OK(cudaStreamSynchronize(cudaStreamLegacy)); }
-};
-
-struct Tier {
-  uint32_t slots;
-  uint64_t node_cap, visit_cap;
-};
-
-// The (order, beam) trials of one decode call: the reference's literal loop (tesseract.cc:307-344)
-// and the distinct searches behind it (identical detector orders are searched once).
-struct TrialSet {
-  std::vector<uint32_t> perm, beam;        // distinct trials
-  std::vector<uint32_t> literal_to_trial;  // literal trial -> distinct trial
-  DevBuf d_perm, d_beam, d_literal;
-  void upload() {
-    d_perm.upload(perm);
-    d_beam.upload(beam);
-    d_literal.upload(literal_to_trial);
-    DevBuf::uploads_done();
-  }
-};
-
-}  // namespace
-
-struct tsr_decoder {
-  tsr_config cfg{};
-  tsr::DemTables T;
-  tsr::FastTables F;
-  tsr::BitTables B;
-  bool bits = false;          // fast path: bit-sliced row scans (32 row entries per lane)
-  bool fast = false;          // decode with search_fast.cu (CTA per search) instead of search.cu
-  bool instrumented = false;  // fast path: also count the reference's scanned row entries (counter S)
-  bool profile = false;       // fast path: per-phase clock ticks (tsr_profile)
-  bool hc_shared = false;
-  std::vector<std::vector<uint64_t>> det_orders;
-  std::vector<uint32_t> order_to_perm;  // det order index -> distinct permutation id
-  uint32_t n_perms = 0;
-  bool host_only = true;
-  int device = 0;
-  int sm_count = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-
-  // Device tables.
-  DevBuf row_off, row_err, rec_a, rec_b, rec_c, e_off, e_det, e_rank, e_cost, e_nnbr, eo_off, eo_obs, e2dem, adj,
-      zobrist, order_det, order_pos, frec_a, frec_b, frank, fquot, bs_meta, bs_adjpre, bs_masks, bs_cls_cid, bs_pl_off, bs_pl,
-      sp_mand, sp_opt, sp_crank, sp_act;
-  int64_t sparsify_limit = -1;  // effective sparsify_reactivate_limit (tesseract.cc:272-277); -1 = sparsify off
-  tsr::DeviceTables dt;
-  TrialSet ensemble;
-
-  // Node pool and tiers.
-  uint32_t wpb = 4, blocks = 0;
-  std::vector<Tier> tiers;
-  DevBuf pool, hcache, vlist;
-  uint32_t vlist_cap = 256;
-
-  // Per-batch buffers.
-  uint64_t max_batch = 0;
-  DevBuf d_dets, d_status, d_sol_len, d_fcost, d_sol, d_obs, d_cost, d_low, d_err_off, d_err_len, d_err, d_retry,
-      d_items, d_scalars, d_counters, d_prof, d_fired, d_order, d_bins;
-  uint32_t sol_stride = 0;
-  bool collect_errors = true;
-
-  // Results of the last decode call.
-  std::vector<uint64_t> last_off{0};
-  std::vector<uint64_t> last_idx;
-  double timing[4] = {0, 0, 0, 0};
-
-  ~tsr_decoder() {
-    for (auto& e : ev)
-      if (e) cudaEventDestroy(e);
-    if (stream) cudaStreamDestroy(stream);
-  }
-};
 
 namespace {
 
@@ -478,10 +353,12 @@ void init_device(tsr_decoder& h) {
   h.max_batch = h.cfg.max_batch_shots ? h.cfg.max_batch_shots : (uint64_t{1} << 18);
 }
 
-void require_device(const tsr_decoder& h) {
+}  // namespace
+void tsr_impl::require_device(const tsr_decoder& h) {
   if (h.host_only) throw CudaError("CUDA: this decoder was created host-only; decoding needs an sm_100 GPU (no CPU fallback)");
 }
 
+namespace {
 // d_scalars layout (4-byte units): [0] work counter, [1] max fired, [2..3] total fired (u64),
 // [4..5] error cursor (u64), [6] retry count.
 struct Scalars {
@@ -711,8 +588,9 @@ void begin_call(tsr_decoder& h) {
   for (double& v : h.timing) v = 0;
 }
 
-void decode_batch(tsr_decoder& h, const uint8_t* dets, uint64_t stride, uint64_t shots, bool on_device,
-                  const TrialSet& ts, uint8_t* obs, double* cost, uint8_t* low) {
+}  // namespace
+void tsr_impl::decode_batch(tsr_decoder& h, const uint8_t* dets, uint64_t stride, uint64_t shots, bool on_device,
+                            const TrialSet& ts, uint8_t* obs, double* cost, uint8_t* low) {
   require_device(h);
   CUDA_OK(cudaSetDevice(h.device));
   const uint64_t min_stride = (h.T.num_detectors + 7) / 8;
@@ -742,6 +620,7 @@ void decode_batch(tsr_decoder& h, const uint8_t* dets, uint64_t stride, uint64_t
   }
 }
 
+namespace {
 uint64_t mapped_error(const tsr_decoder& h, uint64_t dem_error) {
   // dem_error_to_error.at(i) and the "removed" check (tesseract.cc:620-624).
   if (dem_error >= h.T.dem_error_to_error.size()) throw std::out_of_range("vector::_M_range_check: error index out of range");
@@ -771,7 +650,7 @@ void tsr_config_init(tsr_config* cfg) {
 }
 
 const char* tsr_last_error(void) {
-  return g_error.c_str();
+  return last_error().c_str();
 }
 const char* tsr_version(void) {
   return "tesseract_b200 0.1.0 (sm_100a)";
@@ -898,7 +777,7 @@ int64_t tsr_csr(const tsr_decoder* h, int which, uint64_t* offsets, int32_t* idx
     case 3:
       return emit(T.eo_off, T.eo_obs);
     default:
-      g_error = "unknown table id";
+      last_error() = "unknown table id";
       return TSR_E_INVALID_ARGUMENT;
   }
 }

@@ -68,6 +68,33 @@ struct Error {
   Symptom symptom;
 };
 
+// TesseractConfig -> tsr_config (`flat` keeps the det_orders storage alive for the tsr_create call).
+inline void fill_config(const TesseractConfig& config, tsr_config& c, std::vector<uint64_t>& flat) {
+  tsr_config_init(&c);
+  c.det_beam = config.det_beam;
+  c.beam_climbing = config.beam_climbing;
+  c.no_revisit_dets = config.no_revisit_dets;
+  c.merge_errors = config.merge_errors;
+  c.at_most_two_errors_per_detector = config.at_most_two_errors_per_detector;
+  c.device = config.device;
+  c.pqlimit = config.pqlimit;
+  c.det_penalty = config.det_penalty;
+  c.sparsify_errors = config.sparsify_errors;
+  c.sparsify_base_degree = config.sparsify_base_degree;
+  c.sparsify_max_degree = config.sparsify_max_degree;
+  c.sparsify_reactivate_limit = config.sparsify_reactivate_limit;
+  for (const auto& o : config.det_orders) {
+    if (o.size() != config.det_orders[0].size())
+      throw std::invalid_argument("Each detector order list must have a size equal to the number of detectors.");
+    flat.insert(flat.end(), o.begin(), o.end());
+  }
+  c.num_det_orders = config.det_orders.size();
+  c.det_orders = flat.data();
+  c.det_order_len = config.det_orders.empty() ? 0 : config.det_orders[0].size();
+  if (c.num_det_orders && c.det_order_len == 0 && tsr_dem_count_detectors(config.dem.c_str()) != 0)
+    throw std::invalid_argument("Each detector order list must have a size equal to the number of detectors.");
+}
+
 struct HandleDeleter {
   void operator()(tsr_decoder* h) const { tsr_destroy(h); }
 };
@@ -83,30 +110,8 @@ struct TesseractDecoder {
 
   explicit TesseractDecoder(TesseractConfig cfg, bool host_only = false) : config(std::move(cfg)) {
     tsr_config c;
-    tsr_config_init(&c);
-    c.det_beam = config.det_beam;
-    c.beam_climbing = config.beam_climbing;
-    c.no_revisit_dets = config.no_revisit_dets;
-    c.merge_errors = config.merge_errors;
-    c.at_most_two_errors_per_detector = config.at_most_two_errors_per_detector;
-    c.device = config.device;
-    c.pqlimit = config.pqlimit;
-    c.det_penalty = config.det_penalty;
-    c.sparsify_errors = config.sparsify_errors;
-    c.sparsify_base_degree = config.sparsify_base_degree;
-    c.sparsify_max_degree = config.sparsify_max_degree;
-    c.sparsify_reactivate_limit = config.sparsify_reactivate_limit;
     std::vector<uint64_t> flat;
-    for (const auto& o : config.det_orders) {
-      if (o.size() != config.det_orders[0].size())
-        throw std::invalid_argument("Each detector order list must have a size equal to the number of detectors.");
-      flat.insert(flat.end(), o.begin(), o.end());
-    }
-    c.num_det_orders = config.det_orders.size();
-    c.det_orders = flat.data();
-    c.det_order_len = config.det_orders.empty() ? 0 : config.det_orders[0].size();
-    if (c.num_det_orders && c.det_order_len == 0 && tsr_dem_count_detectors(config.dem.c_str()) != 0)
-      throw std::invalid_argument("Each detector order list must have a size equal to the number of detectors.");
+    fill_config(config, c, flat);
     tsr_decoder* raw = nullptr;
     check(tsr_create(config.dem.c_str(), &c, host_only ? TSR_CREATE_HOST_ONLY : 0, &raw));
     h_.reset(raw);
@@ -214,6 +219,38 @@ struct TesseractDecoder {
     for (size_t r = 0; r < rows; ++r) out[r].assign(idx.begin() + (std::ptrdiff_t)off[r], idx.begin() + (std::ptrdiff_t)off[r + 1]);
     return out;
   }
+};
+
+// Several GPUs driven by one process (tsr_group): what the reference does with one decoder per host thread
+// (tesseract_main.cc:559-616), with the counters summed by one NCCL all-reduce.
+struct DecoderGroup {
+  explicit DecoderGroup(const TesseractConfig& config, int num_gpus) {
+    tsr_config c;
+    std::vector<uint64_t> flat;
+    fill_config(config, c, flat);
+    tsr_group* raw = nullptr;
+    check(tsr_group_create(config.dem.c_str(), &c, nullptr, (uint32_t)num_gpus, &raw));
+    g_.reset(raw);
+  }
+  tsr_decoder* member(uint32_t i) const { return tsr_group_member(g_.get(), i); }
+  // Interleaved chunks over the GPUs; tally = {shots, logical errors, low confidence} after the all-reduce.
+  void decode_batch_b8(const uint8_t* dets, size_t stride, size_t shots, const uint8_t* obs_true, uint8_t* obs_out, double* cost_out,
+                       uint8_t* low_conf_out, uint64_t tally[3], uint64_t* error_use) {
+    check(tsr_group_decode_b8(g_.get(), dets, stride, shots, 0, obs_true, obs_out, cost_out, low_conf_out, tally, error_use));
+  }
+  void last_batch_errors(size_t shots, std::vector<uint64_t>& offsets, std::vector<uint64_t>& idx) const {
+    const uint64_t nnz = tsr_group_last_batch_nnz(g_.get());
+    offsets.assign(shots + 1, 0);
+    idx.assign((size_t)nnz + 1, 0);
+    check(tsr_group_last_batch_errors(g_.get(), offsets.data(), idx.data()));
+    idx.resize((size_t)nnz);
+  }
+
+ private:
+  struct Deleter {
+    void operator()(tsr_group* g) const { tsr_group_destroy(g); }
+  };
+  std::unique_ptr<tsr_group, Deleter> g_;
 };
 
 // utils.cc:192-205

@@ -295,13 +295,15 @@ int main(int argc, char** argv) {
     config.sparsify_max_degree = config_sparsify.sparsify_max_degree;
     config.sparsify_reactivate_limit = config_sparsify.sparsify_reactivate_limit;
 
-    std::vector<std::unique_ptr<TesseractDecoder>> decoders;
-    for (int g = 0; g < a.gpus; ++g) {
-      TesseractConfig c = config;
-      c.device = a.gpus == 1 ? -1 : g;
-      decoders.push_back(std::make_unique<TesseractDecoder>(c));
-    }
-    const uint64_t D = decoders[0]->num_detectors, O = decoders[0]->num_observables;
+    // One GPU: one decoder.  --gpus N: a tsr_group — one decoder, host thread and NCCL communicator per device, batches
+    // dealt out in interleaved chunks, counters summed by one all-reduce (the reference's analogue is one decoder per
+    // host thread, tesseract_main.cc:559-571).
+    std::unique_ptr<TesseractDecoder> single;
+    std::unique_ptr<DecoderGroup> group;
+    if (a.gpus == 1) single = std::make_unique<TesseractDecoder>(config);
+    else group = std::make_unique<DecoderGroup>(config, a.gpus);
+    tsr_decoder* first = single ? single->handle() : group->member(0);
+    const uint64_t D = tsr_num_detectors(first), O = tsr_num_observables(first);
     const uint64_t nb = std::max<uint64_t>((D + 7) / 8, 1), ob = (O + 7) / 8;
 
     // Shots.
@@ -365,30 +367,25 @@ int main(int argc, char** argv) {
     uint64_t num_errors = 0, num_low_confidence = 0, done = 0;
     double total_time_seconds = 0;
     const bool want_use = !a.dem_out_fname.empty();
-    std::vector<uint64_t> error_use(want_use ? (size_t)tsr_num_dem_errors(decoders[0]->handle()) : 0, 0);
-    std::vector<std::vector<uint64_t>> batch_off((size_t)a.gpus), batch_idx((size_t)a.gpus);
-    // Batches in shot order (so --max-errors stops where the reference's in-order consumer would, up to a batch);
-    // each batch is split over the GPUs.
+    std::vector<uint64_t> error_use(want_use ? (size_t)tsr_num_dem_errors(first) : 0, 0), scratch_use(error_use.size(), 0);
+    std::vector<uint64_t> batch_off, batch_idx;
+    uint64_t reduced_shots = 0, reduced_errors = 0, reduced_low = 0;  // the group's all-reduced counters (cross-check)
+    // Batches in shot order (so --max-errors stops where the reference's in-order consumer would, up to a batch).
     for (uint64_t at = 0; at < shots && num_errors < a.max_errors; at += a.batch) {
       const uint64_t n = std::min<uint64_t>(a.batch, shots - at);
       const auto t0 = std::chrono::steady_clock::now();
-      std::vector<std::thread> workers;
-      std::vector<std::string> errors((size_t)a.gpus);
-      for (int g = 0; g < a.gpus; ++g) {
-        const uint64_t b = at + n * (uint64_t)g / (uint64_t)a.gpus, e = at + n * (uint64_t)(g + 1) / (uint64_t)a.gpus;
-        workers.emplace_back([&, g, b, e] {
-          try {
-            decoders[(size_t)g]->decode_batch_b8(dets.data() + b * nb, nb, e - b, obs_pred.data() + b * ob, cost.data() + b,
-                                                 low.data() + b, want_use);
-            if (want_use) decoders[(size_t)g]->last_batch_errors(e - b, batch_off[(size_t)g], batch_idx[(size_t)g]);
-          } catch (const std::exception& ex) {
-            errors[(size_t)g] = ex.what();
-          }
-        });
+      if (single) {
+        single->decode_batch_b8(dets.data() + at * nb, nb, n, obs_pred.data() + at * ob, cost.data() + at, low.data() + at, want_use);
+        if (want_use) single->last_batch_errors(n, batch_off, batch_idx);
+      } else {
+        uint64_t tally[3] = {0, 0, 0};
+        group->decode_batch_b8(dets.data() + at * nb, nb, n, has_obs ? obs_true.data() + at * ob : nullptr, obs_pred.data() + at * ob,
+                               cost.data() + at, low.data() + at, tally, want_use ? scratch_use.data() : nullptr);
+        if (want_use) group->last_batch_errors(n, batch_off, batch_idx);
+        reduced_shots += tally[0];
+        reduced_errors += tally[1];
+        reduced_low += tally[2];
       }
-      for (auto& w : workers) w.join();
-      for (const auto& e : errors)
-        if (!e.empty()) throw std::runtime_error(e);
       total_time_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       for (uint64_t s = at; s < at + n; ++s) {  // consume(shot), tesseract_main.cc:592-616
         if (!a.out_fname.empty()) write_shot(out, a.out_format, obs_pred.data() + s * ob, O, 'L');
@@ -397,10 +394,7 @@ int main(int argc, char** argv) {
         else if (!match) ++num_errors;
         if (want_use && match) {  // error_use: errors of the shots whose prediction matches (tesseract_main.cc:586-590)
           const uint64_t k = s - at;
-          int g = 0;
-          while (g + 1 < a.gpus && k >= n * (uint64_t)(g + 1) / (uint64_t)a.gpus) ++g;
-          const uint64_t local = k - n * (uint64_t)g / (uint64_t)a.gpus;
-          for (uint64_t q = batch_off[(size_t)g][local]; q < batch_off[(size_t)g][local + 1]; ++q) ++error_use[batch_idx[(size_t)g][q]];
+          for (uint64_t q = batch_off[k]; q < batch_off[k + 1]; ++q) ++error_use[batch_idx[q]];
         }
         ++done;
         if (a.print_stats) {
@@ -412,6 +406,11 @@ int main(int argc, char** argv) {
         if (has_obs && num_errors >= a.max_errors) break;
       }
     }
+
+    // With every batch consumed to its end, the in-order host accounting and the all-reduced device-side counters are
+    // the same numbers; a difference means the collective or the scatter lost shots.
+    if (group && done == reduced_shots && (num_low_confidence != reduced_low || (has_obs && num_errors != reduced_errors)))
+      throw std::runtime_error("multi-GPU counters disagree with the per-shot accounting");
 
     if (want_use) {  // tesseract_main.cc:625-639
       const uint64_t usage_shots = has_obs ? done - num_errors : done;
@@ -438,7 +437,7 @@ int main(int argc, char** argv) {
          // tesseract_main.cc:676-679; the limit is the decoder's effective value (:641-655)
          << ",\"sparsify_errors\":" << (config.sparsify_errors ? "true" : "false") << ",\"sparsify_base_degree\":" << config.sparsify_base_degree
          << ",\"sparsify_max_degree\":" << config.sparsify_max_degree
-         << ",\"sparsify_reactivate_limit\":" << decoders[0]->config.sparsify_reactivate_limit << "}";
+         << ",\"sparsify_reactivate_limit\":" << tsr_sparsify_reactivate_limit(first) << "}";
       if (a.stats_out_fname == "-") {
         std::cout << js.str() << std::endl;
         print_final_stats = false;
