@@ -290,6 +290,17 @@ void init_device(tsr_decoder& h) {
       h.blocks = (uint32_t)(h.sm_count * occ);
       slots = h.blocks;
       if (h.cfg.search_slots && h.cfg.search_slots < slots) slots = h.blocks = std::max<uint32_t>(h.cfg.search_slots, 1);
+      // Wide CTAs for the tail: the most warps (<= 32) whose state still fits an SM.
+      uint32_t wide = 32;
+      if (const char* e = std::getenv("TSR_WIDE_WARPS")) wide = (uint32_t)std::max(0, std::atoi(e));
+      int occ_wide = 0;
+      while (wide > w && (occ_wide = tsr::search_fast_max_blocks_per_sm(dt, wide, h.hc_shared, h.bits)) == 0) wide /= 2;
+      if (wide > w && occ_wide > 0) {
+        h.wpb_wide = wide;
+        h.blocks_wide = (uint32_t)(h.sm_count * occ_wide);
+        h.expansion_budget = 256;
+        if (const char* e = std::getenv("TSR_EXPANSION_BUDGET")) h.expansion_budget = (uint32_t)std::max(0, std::atoi(e));
+      }
     }
   }
   if (!h.fast) {
@@ -344,6 +355,7 @@ void init_device(tsr_decoder& h) {
   }
   CUDA_OK(cudaMemsetAsync(h.pool.p, 0, h.pool.bytes, h.stream));  // visited tables start empty
   h.d_scalars.ensure(64);
+  h.d_paused.ensure(std::max<size_t>((size_t)slots * sizeof(tsr::ResumeRec), 64));
   h.d_counters.ensure(8 * sizeof(unsigned long long));
   CUDA_OK(cudaMemsetAsync(h.d_counters.p, 0, 64, h.stream));
   h.d_prof.ensure(8 * sizeof(unsigned long long));
@@ -364,7 +376,7 @@ namespace {
 struct Scalars {
   unsigned int work, max_fired;
   unsigned long long total_fired, err_cursor;
-  unsigned int retry_count, pad;
+  unsigned int retry_count, paused_count;
 };
 
 // Decodes `shots` shots whose bit-packed syndromes are at device pointer d_dets.  Outputs go to the
@@ -498,13 +510,26 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
 
   // Tier 0 over every item.
   const Tier& t0 = h.tiers[0];
-  auto launch = [&](const tsr::SearchParams& sp_, uint32_t tier_slots, uint32_t n_work) {
-    if (h.fast)
-      return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, h.instrumented, h.bits && !h.instrumented, s);
-    return tsr::launch_search(sp_, std::min<uint32_t>((tier_slots + h.wpb - 1) / h.wpb, (n_work + h.wpb - 1) / h.wpb), h.wpb, s);
+  // Fast path: tier 0 runs with an expansion budget and is followed by a launch of wide CTAs that finish whatever was
+  // paused (no host round trip: CTAs beyond the paused count exit at once); the retry tiers run wide from the start.
+  const bool widen = h.fast && h.wpb_wide && h.expansion_budget && !h.instrumented;
+  auto launch = [&](tsr::SearchParams sp_, uint32_t tier_slots, uint32_t n_work, bool tier0) -> int {
+    if (!h.fast)
+      return tsr::launch_search(sp_, std::min<uint32_t>((tier_slots + h.wpb - 1) / h.wpb, (n_work + h.wpb - 1) / h.wpb), h.wpb, s);
+    const bool bits = h.bits && !h.instrumented;
+    if (!widen) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, h.instrumented, bits, s);
+    if (!tier0) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb_wide, false, bits, s);
+    sp_.expansion_budget = h.expansion_budget;
+    sp_.paused = h.d_paused.as<tsr::ResumeRec>();
+    sp_.paused_count = &sc->paused_count;
+    sp_.paused_cap = tier_slots;
+    if (int e = tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, false, bits, s)) return e;
+    sp_.expansion_budget = 0;
+    sp_.resume = 1;
+    return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, h.blocks_wide), h.wpb_wide, false, bits, s);
   };
   CUDA_OK(cudaEventRecord(h.ev[1], s));
-  CUDA_OK((cudaError_t)launch(search_params(t0, nullptr, items), t0.slots, items));
+  CUDA_OK((cudaError_t)launch(search_params(t0, nullptr, items), t0.slots, items, true));
   CUDA_OK(cudaEventRecord(h.ev[2], s));
   uint32_t* retry_a = h.d_retry.as<uint32_t>();
   uint32_t* retry_b = retry_a + shots;
@@ -538,7 +563,7 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     if (tk.visit_cap)
       CUDA_OK(cudaMemsetAsync(h.pool.as<char>() + (size_t)tk.slots * tk.node_cap * 32, 0, (size_t)tk.slots * tk.visit_cap * 16, s));
     CUDA_OK(cudaEventRecord(h.ev[1], s));
-    CUDA_OK((cudaError_t)launch(search_params(tk, d_item_ids, (uint32_t)item_ids.size()), tk.slots, (uint32_t)item_ids.size()));
+    CUDA_OK((cudaError_t)launch(search_params(tk, d_item_ids, (uint32_t)item_ids.size()), tk.slots, (uint32_t)item_ids.size(), false));
     CUDA_OK(cudaEventRecord(h.ev[2], s));
     CUDA_OK((cudaError_t)tsr::launch_resolve(resolve_params(d_shot_ids, n_retry, retry_b), s));
     // Restore the tier-0 invariant (empty visited tables in the tier-0 layout).

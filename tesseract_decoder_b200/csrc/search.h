@@ -71,7 +71,16 @@ enum ItemStatus : uint8_t {
   kItemOk = 0,
   kItemLowConfidence = 1,   // the reference's low_confidence_flag
   kItemNodeOverflow = 2,    // outgrew this tier's per-slot heap / chain / visited capacity
-  kItemSolutionOverflow = 3 // solution longer than sol_stride
+  kItemSolutionOverflow = 3, // solution longer than sol_stride
+  kItemPaused = 4           // fast path: spent its expansion budget; to be resumed by a wider CTA (ResumeRec)
+};
+
+// A paused search (fast path).  Everything else a search owns — heap, chain arena, visited table, sparsify masks — stays
+// in its slot of the node pool; the CTA-local state is rebuilt from the popped node's chain.
+struct alignas(16) ResumeRec {
+  uint32_t item, slot;
+  uint32_t min_dets, max_dets;
+  unsigned long long heap_size, chain_size, pushed, n_visited;
 };
 
 struct SearchParams {
@@ -115,6 +124,15 @@ struct SearchParams {
   unsigned int* work_counter = nullptr;
   unsigned long long* counters = nullptr;  // [8], see tsr_counters
   unsigned long long* prof = nullptr;      // [8] nullable, fast path only: per-phase ticks, see tsr_profile
+  // Tail widening (fast path).  A launch with expansion_budget > 0 pauses every search that expands more nodes than
+  // that: its record goes to paused[atomicAdd(paused_count)] and the CTA retires (its slot stays occupied).  A launch
+  // with resume = 1 runs no new work: CTA b continues paused[b], paused[b + gridDim], ... to the end, typically with
+  // four times the warps.  Heavy-tailed batches then end with a few wide CTAs instead of one narrow one.
+  uint32_t expansion_budget = 0;
+  int resume = 0;
+  ResumeRec* paused = nullptr;
+  unsigned int* paused_count = nullptr;
+  uint32_t paused_cap = 0;
 };
 
 struct ResolveParams {

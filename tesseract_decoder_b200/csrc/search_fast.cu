@@ -73,6 +73,7 @@ struct alignas(16) Ctl {
   uint32_t status;
   uint32_t work;
   uint32_t item;
+  uint32_t n_exp;  // nodes this search has expanded in the current launch (expansion budget)
   // phase profile (SearchParams::prof): clock64 ticks of thread 0 per phase, see tsr_profile
   long long prof_last;
   unsigned long long prof[8];
@@ -120,7 +121,7 @@ __host__ __device__ inline uint32_t dpad_of(uint32_t D) {
 struct Layout {
   uint32_t off_rank, off_rbits, off_fbits, off_pst, off_hc, off_cost, off_meta, off_clist, off_st, total;
   uint32_t off_pbb, off_fz, warp_stride, w_cf, w_tl, w_hv, w_fl, w_bl, w_gc, w_nzw;  // w_*: offsets inside a warp's region
-  uint32_t off_sp;
+  uint32_t off_sp, stage_extra;
 };
 __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint32_t rank_entries, uint32_t max_row_len,
                                                uint32_t warps, bool hc_shared, uint32_t bs_group = 0, uint32_t bs_cap = 0,
@@ -172,6 +173,11 @@ __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint3
   }
   L.warp_stride = w;
   at += warps * w;
+  // Push staging (phase 7) = the regions of warps 1.. plus this tail, contiguous: room for a whole row of children and
+  // their ancestor ranges (about 2 K + depth nodes of 16 bytes), capped so that small DEMs keep their occupancy.
+  const uint32_t want = min(2u * max_row_len + 64u, 768u) * 16u, have = (warps - 1) * w;
+  L.stage_extra = have >= want ? 0u : round16(want - have);
+  at += L.stage_extra;
   L.total = at;
   return L;
 }
@@ -556,38 +562,89 @@ __device__ __forceinline__ void heap_push_warp(HeapNode* heap, unsigned long lon
   __syncwarp();
 }
 
-// top(); pop(): std::pop_heap (bits/stl_heap.h:224-267) then pop_back.  One lane.
-__device__ HeapNode heap_pop(HeapNode* heap, unsigned long long& size) {
-  HeapNode top = heap_ld(heap);
-  if (size > 1) {
-    const long long len = (long long)size - 1;
-    HeapNode value = heap_ld(heap + len);
-    long long hole = 0, child = 0;
-    while (child < (len - 1) / 2) {
-      child = 2 * (child + 1);
-      HeapNode r = heap_ld(heap + child), l = heap_ld(heap + child - 1);
-      if (node_greater(r, l)) {
-        --child;
-        r = l;
-      }
-      heap_st(heap + hole, r);
-      hole = child;
+__device__ __forceinline__ uint4 node_raw(const HeapNode& n) {
+  uint4 v;
+  v.x = (uint32_t)__double2loint(n.cost);
+  v.y = (uint32_t)__double2hiint(n.cost);
+  v.z = n.chain;
+  v.w = (uint32_t)n.num_dets | ((uint32_t)n.depth << 16);
+  return v;
+}
+__device__ __forceinline__ HeapNode node_of(const uint4& v) {
+  HeapNode n;
+  n.cost = __hiloint2double((int)v.y, (int)v.x);
+  n.chain = v.z;
+  n.num_dets = (uint16_t)(v.w & 0xFFFF);
+  n.depth = (uint16_t)(v.w >> 16);
+  return n;
+}
+__device__ __forceinline__ uint4 shfl4(const uint4& v, int src) {
+  return make_uint4(__shfl_sync(kFull, v.x, src), __shfl_sync(kFull, v.y, src), __shfl_sync(kFull, v.z, src),
+                    __shfl_sync(kFull, v.w, src));
+}
+
+// top(); pop(): std::pop_heap (bits/stl_heap.h:224-267) then pop_back, by a whole warp; every lane gets the top.
+// __adjust_heap walks the hole from the root to a leaf, always taking the child that is not greater than its sibling:
+// a chain of dependent loads, one heap level per memory round trip when done by one thread.  Here 30 lanes fetch the
+// whole subtree four levels below the hole in ONE round trip, the same walk is replayed on the fetched nodes with
+// shuffles (every lane computes the same path), and the moves are stored as the walk goes: depth / 4 round trips.
+// The final sift-up of the displaced last element compares it first with the node just moved into the hole's parent,
+// which is still in registers (it almost always stops there).
+__device__ HeapNode heap_pop(HeapNode* heap, unsigned long long& size, uint32_t lane) {
+  uint4 mine = make_uint4(0, 0, 0, 0);
+  const long long len = (long long)size - 1;  // elements that remain
+  if (lane == 0) mine = __ldcg(reinterpret_cast<const uint4*>(heap));
+  if (lane == 1 && len >= 1) mine = __ldcg(reinterpret_cast<const uint4*>(heap + len));      // the displaced last element
+  if (lane == 2 && len >= 2) mine = __ldcg(reinterpret_cast<const uint4*>(heap + len - 1));  // a possible single child
+  const HeapNode top = node_of(shfl4(mine, 0));
+  --size;
+  if (len < 1) return top;
+  const HeapNode value = node_of(shfl4(mine, 1));
+  const uint4 tail_raw = shfl4(mine, 2);
+  long long hole = 0;
+  const long long last_parent = (len - 1) / 2;  // the walk continues while hole < last_parent: both children exist
+  uint4 moved = make_uint4(0, 0, 0, 0);         // the node now stored at the hole's parent
+  bool have_moved = false;
+  // this lane's place in a 4-level fetch: relative level r (1..4), position j within it
+  const uint32_t r = lane < 2 ? 1u : lane < 6 ? 2u : lane < 14 ? 3u : lane < 30 ? 4u : 0u;
+  const uint32_t j = lane - ((1u << r) - 2u);
+  while (hole < last_parent) {
+    uint4 node = make_uint4(0, 0, 0, 0);
+    if (r) {
+      const long long idx = ((hole + 1) << r) - 1 + (long long)j;
+      if (idx < len) node = __ldcg(reinterpret_cast<const uint4*>(heap + idx));
     }
-    if ((len & 1) == 0 && child == (len - 2) / 2) {
-      child = 2 * (child + 1);
-      heap_st(heap + hole, heap_ld(heap + child - 1));
-      hole = child - 1;
+    uint32_t rel = 0;
+    for (uint32_t step = 1; step <= 4 && hole < last_parent; ++step) {
+      const int lbase = (int)((1u << step) - 2u + 2u * rel);
+      const uint4 lraw = shfl4(node, lbase), rraw = shfl4(node, lbase + 1);
+      const bool take_left = node_greater(node_of(rraw), node_of(lraw));
+      moved = take_left ? lraw : rraw;
+      have_moved = true;
+      if (lane == 0) __stcg(reinterpret_cast<uint4*>(heap + hole), moved);
+      hole = 2 * hole + (take_left ? 1 : 2);
+      rel = 2 * rel + (take_left ? 0u : 1u);
     }
+  }
+  if ((len & 1) == 0 && hole == (len - 2) / 2) {  // the hole's only child is the last element
+    moved = tail_raw;
+    have_moved = true;
+    if (lane == 0) __stcg(reinterpret_cast<uint4*>(heap + hole), moved);
+    hole = 2 * hole + 1;
+  }
+  if (lane == 0) {  // __push_heap of the displaced element from the hole (bits/stl_heap.h:135-148)
+    bool first = have_moved;
     while (hole > 0) {
-      long long parent = (hole - 1) / 2;
-      HeapNode pn = heap_ld(heap + parent);
-      if (!node_greater(pn, value)) break;
-      heap_st(heap + hole, pn);
+      const long long parent = (hole - 1) / 2;
+      const uint4 praw = first ? moved : __ldcg(reinterpret_cast<const uint4*>(heap + parent));
+      first = false;
+      if (!node_greater(node_of(praw), value)) break;
+      __stcg(reinterpret_cast<uint4*>(heap + hole), praw);
       hole = parent;
     }
-    heap_st(heap + hole, value);
+    __stcg(reinterpret_cast<uint4*>(heap + hole), node_raw(value));
   }
-  --size;
+  __syncwarp();
   return top;
 }
 
@@ -811,7 +868,8 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
 // ---- one search (whole CTA).  Returns the item status; on kItemOk the solution has been written. ------
 
 template <bool kInstr, bool kBits>
-__device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t slot, uint32_t item, Counters& ctr) {
+__device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t slot, uint32_t item, const ResumeRec* resume,
+                               Counters& ctr) {
   const DeviceTables& t = p.t;
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
   const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
@@ -855,11 +913,21 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       c.root_pending = 1;
       c.state_valid = 0;
       c.heap_size = c.chain_size = c.pushed = c.n_visited = 0;
+      c.n_exp = 0;
+      if (resume) {  // continue a paused search: its queue, arena and visited set are where it left them
+        c.min_dets = resume->min_dets;
+        c.max_dets = resume->max_dets;
+        c.heap_size = resume->heap_size;
+        c.chain_size = resume->chain_size;
+        c.pushed = resume->pushed;
+        c.n_visited = resume->n_visited;
+        c.root_pending = 0;
+      }
     }
   }
   __syncthreads();
   // sparsify: this shot's active-entry masks (build_sparse_d2e, tesseract.cc:673-737), by the whole CTA
-  if (sm.act) sparsify::select(t, sm.rbits, const_cast<uint32_t*>(sm.act), sm.sp_scratch, warp, nwarps, lane, [] { __syncthreads(); });
+  if (sm.act && !resume) sparsify::select(t, sm.rbits, const_cast<uint32_t*>(sm.act), sm.sp_scratch, warp, nwarps, lane, [] { __syncthreads(); });
   prof_mark(p, c, 6);
 
   while (true) {
@@ -883,16 +951,35 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       } else if (heap_size0 == 0) {
         action = kActDone;
         status = kItemLowConfidence;  // tesseract.cc:609-615
-      } else {
-        HeapNode node;
-        node.cost = 0;
-        node.chain = 0;
-        node.num_dets = 0;
-        node.depth = 0;
+      } else if (p.expansion_budget && c.n_exp >= p.expansion_budget) {
+        // Out of budget: park the search for a wider CTA (SearchParams::resume).  If the list is full it simply goes on.
+        unsigned int at = 0;
+        if (lane == 0) at = atomicAdd(p.paused_count, 1u);
+        at = __shfl_sync(kFull, at, 0);
+        if (at < p.paused_cap) {
+          if (lane == 0) {
+            ResumeRec r;
+            r.item = item;
+            r.slot = slot;
+            r.min_dets = c.min_dets;
+            r.max_dets = c.max_dets;
+            r.heap_size = c.heap_size;
+            r.chain_size = c.chain_size;
+            r.pushed = c.pushed;
+            r.n_visited = c.n_visited;
+            p.paused[at] = r;
+          }
+          action = kActDone;
+          status = kItemPaused;
+        } else {
+          if (lane == 0) c.n_exp = 0;
+          __syncwarp();
+        }
+      }
+      if (action == kActExpand && !root_pending && heap_size0 != 0) {
         unsigned long long hs = heap_size0;
-        if (lane == 0) node = heap_pop(heap, hs);
-        __syncwarp();
-        const uint32_t nd = __shfl_sync(kFull, (uint32_t)node.num_dets, 0);
+        const HeapNode node = heap_pop(heap, hs, lane);
+        const uint32_t nd = node.num_dets;
         ++ctr.P;
         if (lane == 0) {
           c.heap_size = hs;
@@ -1144,6 +1231,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
         }
       } else {
         ++ctr.X;
+        if (lane == 0) ++c.n_exp;
         // min_detector: first fired detector in this trial's order (tesseract.cc:522-528)
         uint32_t best_pos = 0xFFFFFFFFu;
         for (uint32_t w = lane; w < nwords; w += 32)
@@ -1216,9 +1304,9 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       const uint32_t n = c.nchild;
       // Staged pushes: the heap nodes K consecutive pushes can touch are the ancestors of leaves [size, size+K),
       // one contiguous index range per level.  They are copied to shared memory (the other warps' scratch, idle
-      // in this phase) in one round trip, the K std::push_heap sifts run there (warp-wide: lane s-1 holds the
-      // ancestor s levels up), and the ranges are written back.  Needs size >= K so that the ranges of
-      // different levels are disjoint; otherwise the windowed path below pushes straight to global memory.
+      // in this phase, plus a dedicated tail) in one round trip, the K std::push_heap sifts run there as a pipeline,
+      // and the ranges are written back.  A sub-batch that does not fit the staging area takes the windowed path
+      // below, which pushes straight to global memory.
       uint32_t K = 0;
       for (uint32_t b0 = 0; b0 < n; b0 += 32) {
         const uint32_t idx = b0 + lane;
@@ -1229,11 +1317,72 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
       __syncwarp();
       uint32_t i0 = 0;  // children (of the compact list) pushed so far
-      if ((K >= 96 || (K >= 8 && heap_size >= 4096)) && c.depth != 0xFFFF && pushed + K <= p.pqlimit && heap_size + K <= p.node_cap && chain_size + K <= p.node_cap &&
+      if (K >= 2 && c.depth != 0xFFFF && pushed + K <= p.pqlimit && heap_size + K <= p.node_cap && chain_size + K <= p.node_cap &&
           chain_size + K < 0xFFFFFFFEull) {
         for (uint32_t i = lane; i < K; i += 32) {  // chain nodes
           const uint4 meta = sm.res_meta[sm.clist[i]];
           __stcg(reinterpret_cast<uint4*>(chain + chain_size + i), make_uint4(meta.x, c.chain, (c.mind << 16) | (meta.z >> 16), meta.y));
+        }
+        if (heap_size + K <= sm.stage_cap) {
+          // Small heap: the WHOLE heap is staged (node n at slot n - 1) and all K pushes run as one pipeline (see below:
+          // push i makes its step s at time 2 i + s; exact for any mix of leaf levels, including leaves whose parent is
+          // an earlier leaf of the same batch).
+          const uint32_t hs = (uint32_t)heap_size;
+          for (uint32_t q = lane; q < hs; q += 32) sm.stage[q] = __ldcg(reinterpret_cast<const uint4*>(heap + q));
+          __syncwarp();
+          uint32_t my = lane, hole1 = 0;
+          bool active = false;
+          uint4 vv = make_uint4(0, 0, 0, 0);
+          HeapNode value;
+          value.cost = 0;
+          value.chain = 0;
+          value.num_dets = 0;
+          value.depth = 0;
+          const uint32_t t_end = 2 * (K - 1) + (32u - (uint32_t)__clz((int)(hs + K))) + 1;
+          for (uint32_t t = 0; t < t_end; ++t) {
+            if (!active && my < K && t == 2 * my) {
+              const uint32_t ci = sm.clist[my];
+              const uint4 meta = sm.res_meta[ci];
+              value.cost = sm.res_cost[ci];
+              value.chain = (uint32_t)(chain_size + my);
+              value.num_dets = (uint16_t)(meta.z & 0xFFFF);
+              value.depth = (uint16_t)(c.depth + 1);
+              vv.x = (uint32_t)__double2loint(value.cost);
+              vv.y = (uint32_t)__double2hiint(value.cost);
+              vv.z = value.chain;
+              vv.w = (uint32_t)value.num_dets | ((uint32_t)value.depth << 16);
+              active = true;
+              hole1 = hs + my + 1;  // 1-based
+            }
+            if (active) {
+              bool up = false;
+              uint4 pv = make_uint4(0, 0, 0, 0);
+              if (hole1 > 1) {
+                pv = sm.stage[(hole1 >> 1) - 1];
+                HeapNode pn;
+                pn.cost = __hiloint2double((int)pv.y, (int)pv.x);
+                pn.chain = pv.z;
+                pn.num_dets = (uint16_t)(pv.w & 0xFFFF);
+                pn.depth = (uint16_t)(pv.w >> 16);
+                up = node_greater(pn, value);
+              }
+              sm.stage[hole1 - 1] = up ? pv : vv;
+              if (up) {
+                hole1 >>= 1;
+              } else {
+                active = false;
+                my += 32;
+              }
+            }
+            __syncwarp();
+          }
+          for (uint32_t q = lane; q < hs + K; q += 32) __stcg(reinterpret_cast<uint4*>(heap + q), sm.stage[q]);
+          __syncwarp();
+          heap_size += K;
+          chain_size += K;
+          pushed += K;
+          ctr.Q += K;
+          i0 = K;
         }
         while (i0 < K) {
           // one sub-batch = new leaves on ONE tree level, so that "s levels up" names a distinct level for every s
@@ -1260,39 +1409,65 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
             for (uint32_t q = lane; q < w_; q += 32) sm.stage[off_ + q] = __ldcg(reinterpret_cast<const uint4*>(heap + (lo_ - 1 + q)));
           }
           __syncwarp();
-          for (uint32_t i = 0; i < Kb; ++i) {
-            const uint32_t ci = sm.clist[i0 + i];
-            const uint4 meta = sm.res_meta[ci];
+          // The Kb sifts, as a systolic pipeline instead of one after the other.  Push i performs its step s (hole at
+          // the s-th ancestor of its leaf: compare with the node one level up, move that node down or settle) at time
+          // 2 i + s.  With a lag of two steps between consecutive pushes every node a push reads or overwrites has
+          // already seen all the steps the earlier pushes make on it, so the heap ends up exactly as after Kb sequential
+          // std::push_heap calls (bits/stl_heap.h:135-148) — in 2 Kb + depth steps instead of Kb x depth.  Lane l runs
+          // pushes l, l + 32, ... (a push lasts at most depth + 1 <= 33 steps, the lane is free again after 64).
+          {
+            uint32_t my = lane, st_lvl = 0;
+            bool active = false;
+            uint4 vv = make_uint4(0, 0, 0, 0);
             HeapNode value;
-            value.cost = sm.res_cost[ci];
-            value.chain = (uint32_t)(chain_size + i);
-            value.num_dets = (uint16_t)(meta.z & 0xFFFF);
-            value.depth = (uint16_t)(c.depth + 1);
-            const bool valid = lane + 1 <= lvl;
-            const uint32_t slot = valid ? off_s + (uint32_t)((lo1 + i) >> (lane + 1)) - lo_s : 0u;
-            uint4 pv = make_uint4(0, 0, 0, 0);
-            if (valid) pv = sm.stage[slot];
-            HeapNode pn;
-            pn.cost = __hiloint2double((int)pv.y, (int)pv.x);
-            pn.chain = pv.z;
-            pn.num_dets = (uint16_t)(pv.w & 0xFFFF);
-            pn.depth = (uint16_t)(pv.w >> 16);
-            const bool up = valid && node_greater(pn, value);
-            const unsigned not_up = ~__ballot_sync(kFull, up);
-            const uint32_t stop = not_up ? (uint32_t)__ffs((int)not_up) - 1 : 32u;
-            uint32_t below = __shfl_up_sync(kFull, slot, 1);  // slot one level closer to the leaf
-            if (lane == 0) below = i;
-            if (lane < stop) sm.stage[below] = pv;
-            const uint32_t vslot = stop == 0 ? i : __shfl_sync(kFull, slot, (int)stop - 1);
-            if (lane == 0) {
-              uint4 vv;
-              vv.x = (uint32_t)__double2loint(value.cost);
-              vv.y = (uint32_t)__double2hiint(value.cost);
-              vv.z = value.chain;
-              vv.w = (uint32_t)value.num_dets | ((uint32_t)value.depth << 16);
-              sm.stage[vslot] = vv;
+            value.cost = 0;
+            value.chain = 0;
+            value.num_dets = 0;
+            value.depth = 0;
+            const uint32_t t_end = 2 * (Kb - 1) + lvl + 1;
+            for (uint32_t t = 0; t < t_end; ++t) {
+              if (!active && my < Kb && t == 2 * my) {
+                const uint32_t ci = sm.clist[i0 + my];
+                const uint4 meta = sm.res_meta[ci];
+                value.cost = sm.res_cost[ci];
+                value.chain = (uint32_t)(chain_size + my);
+                value.num_dets = (uint16_t)(meta.z & 0xFFFF);
+                value.depth = (uint16_t)(c.depth + 1);
+                vv.x = (uint32_t)__double2loint(value.cost);
+                vv.y = (uint32_t)__double2hiint(value.cost);
+                vv.z = value.chain;
+                vv.w = (uint32_t)value.num_dets | ((uint32_t)value.depth << 16);
+                active = true;
+                st_lvl = 0;
+              }
+              // level tables of the hole (st_lvl >= 1: lane st_lvl - 1) and of its parent (lane st_lvl)
+              const int src_h = st_lvl ? (int)st_lvl - 1 : 0, src_p = (int)min(st_lvl, 31u);
+              const uint32_t lo_h = __shfl_sync(kFull, lo_s, src_h), off_h = __shfl_sync(kFull, off_s, src_h);
+              const uint32_t lo_p = __shfl_sync(kFull, lo_s, src_p), off_p = __shfl_sync(kFull, off_s, src_p);
+              if (active) {
+                const unsigned long long leaf1 = lo1 + my;
+                const uint32_t hole = st_lvl ? off_h + (uint32_t)(leaf1 >> st_lvl) - lo_h : my;
+                bool up = false;
+                uint4 pv = make_uint4(0, 0, 0, 0);
+                if (st_lvl < lvl) {
+                  pv = sm.stage[off_p + (uint32_t)(leaf1 >> (st_lvl + 1)) - lo_p];
+                  HeapNode pn;
+                  pn.cost = __hiloint2double((int)pv.y, (int)pv.x);
+                  pn.chain = pv.z;
+                  pn.num_dets = (uint16_t)(pv.w & 0xFFFF);
+                  pn.depth = (uint16_t)(pv.w >> 16);
+                  up = node_greater(pn, value);
+                }
+                sm.stage[hole] = up ? pv : vv;
+                if (up) {
+                  ++st_lvl;
+                } else {
+                  active = false;
+                  my += 32;
+                }
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
           for (uint32_t i = lane; i < Kb; i += 32) __stcg(reinterpret_cast<uint4*>(heap + heap_size + i), sm.stage[i]);
           for (uint32_t sft = 0; sft < lvl && sft < 32; ++sft) {  // write the ancestor ranges back
@@ -1408,7 +1583,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
 }
 
 template <bool kInstr, bool kBits>
-__global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams p) {
   extern __shared__ uint4 smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -1442,7 +1617,7 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
   sm.rw = p.t.sp_rw;
   sm.sp_scratch = reinterpret_cast<uint32_t*>(base + L.off_sp);
   sm.stage = reinterpret_cast<uint4*>(base + L.off_st + L.warp_stride);
-  sm.stage_cap = (nwarps - 1) * (L.warp_stride / 16);
+  sm.stage_cap = ((nwarps - 1) * L.warp_stride + L.stage_extra) / 16;
   for (uint32_t i = tid; i < rank_entries; i += blockDim.x) sm.rank[i] = __ldg(p.t.frank + i);
   if (tid == 0) {
     for (auto& v : sm.ctl->prof) v = 0;
@@ -1452,29 +1627,44 @@ __global__ void __launch_bounds__(512, 2) search_fast_kernel(const SearchParams 
 
   Counters ctr;
   unsigned long long searches = 0;
+  const uint32_t n_paused = p.resume ? min(*p.paused_count, p.paused_cap) : 0u;
+  uint32_t resume_at = blockIdx.x;
   while (true) {
-    if (tid == 0) sm.ctl->work = atomicAdd(p.work_counter, 1u);
+    uint32_t item, cur_slot = slot;
+    const ResumeRec* rec = nullptr;
+    if (p.resume) {  // continue paused searches (one per CTA and round), each in the pool slot it was started in
+      if (resume_at >= n_paused) break;
+      rec = p.paused + resume_at;
+      resume_at += gridDim.x;
+      item = rec->item;
+      cur_slot = rec->slot;
+      sm.hc = p.hc_shared ? sm.hc : p.hcache + (size_t)cur_slot * D;
+      sm.act = p.t.sp_on ? p.sp_act + (size_t)cur_slot * D * p.t.sp_rw : nullptr;
+    } else {
+      if (tid == 0) sm.ctl->work = atomicAdd(p.work_counter, 1u);
+      __syncthreads();
+      const uint32_t work = sm.ctl->work;
+      if (work >= p.n_work) break;
+      item = p.item_ids ? __ldg(p.item_ids + work) : work;
+      if (p.shot_order) item = __ldg(p.shot_order + work / p.n_trials) * p.n_trials + work % p.n_trials;
+    }
+    const uint32_t status = run_search<kInstr, kBits>(p, sm, cur_slot, item, rec, ctr);
     __syncthreads();
-    const uint32_t work = sm.ctl->work;
-    if (work >= p.n_work) break;
-    uint32_t item = p.item_ids ? __ldg(p.item_ids + work) : work;
-    if (p.shot_order) item = __ldg(p.shot_order + work / p.n_trials) * p.n_trials + work % p.n_trials;
-    const uint32_t status = run_search<kInstr, kBits>(p, sm, slot, item, ctr);
-    __syncthreads();
-    if (sm.act)  // back to the mandatory masks for the slot's next search
-      sparsify::restore(p.t, sm.rbits, const_cast<uint32_t*>(sm.act), warp, nwarps, lane, [] { __syncthreads(); });
-    ++searches;
+    if (!rec) ++searches;
     if (tid == 0) {
       p.status[item] = (uint8_t)status;
       if (status != kItemOk) p.sol_len[item] = 0;
     }
+    if (status == kItemPaused) break;  // the slot keeps the search's queue, arena, visited set and masks: this CTA retires
+    if (sm.act)  // back to the mandatory masks for the slot's next search
+      sparsify::restore(p.t, sm.rbits, const_cast<uint32_t*>(sm.act), warp, nwarps, lane, [] { __syncthreads(); });
     // Empty the visited table for the next search of this slot.
     const unsigned long long n_visited = sm.ctl->n_visited;
     if (p.no_revisit && n_visited) {
-      uint4* vtab = p.visited + (size_t)slot * p.visit_cap;
+      uint4* vtab = p.visited + (size_t)cur_slot * p.visit_cap;
       const uint4 zero = make_uint4(0, 0, 0, 0);
       if (n_visited <= p.vlist_cap) {
-        const uint32_t* vlist = p.vlist + (size_t)slot * p.vlist_cap;
+        const uint32_t* vlist = p.vlist + (size_t)cur_slot * p.vlist_cap;
         for (unsigned long long i = tid; i < n_visited; i += blockDim.x) __stcg(vtab + __ldcg(vlist + i), zero);
       } else {
         for (unsigned long long i = tid; i < p.visit_cap; i += blockDim.x) __stcg(vtab + i, zero);
@@ -1529,7 +1719,7 @@ int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc
 }
 
 int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, bool bits, void* stream) {
-  if (p.n_work == 0 || blocks == 0) return 0;
+  if ((p.n_work == 0 && !p.resume) || blocks == 0) return 0;
   const size_t smem = search_fast_smem_bytes(p.t, warps, p.hc_shared != 0, bits);
   if (bits) {
     if (int e = configure<false, true>(smem)) return e;
