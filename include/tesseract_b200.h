@@ -61,6 +61,9 @@ typedef struct tsr_config {
   int32_t sparsify_base_degree;      /* must be > 0 when sparsify_errors */
   int32_t sparsify_max_degree;       /* -1 = no upper bound */
   int32_t sparsify_reactivate_limit; /* -1 = suggest_sparsify_reactivate_limit (tesseract.cc:45-69) capped at num_errors */
+  /* TesseractConfig::create_visualization (tesseract.h:50): tsr_decode calls record the visualization log of
+   * visualization.cc (read it with tsr_visualization_text).  A debugging aid for single shots: batch calls do not log. */
+  int32_t create_visualization;
 } tsr_config;
 
 /* Fills the reference's C++ defaults (tesseract.h:39-58). */
@@ -126,6 +129,13 @@ int tsr_last_batch_errors(const tsr_decoder* h, uint64_t* offsets /* [shots+1] *
  * reference's message (tesseract.cc:400-404). */
 int tsr_decode(tsr_decoder* h, const uint64_t* detections, uint64_t n, int64_t order, uint64_t beam,
                uint64_t* errs_out, uint64_t errs_cap, uint64_t* n_errs, double* cost, int32_t* low_confidence);
+
+/* The Visualizer's lines (visualization.cc; what Visualizer::write puts in the file, '\n'-terminated): "Detector D<d>
+ * coordinate (...)" and "Error{cost=..., symptom=Symptom{...}}" headers written at construction (tesseract.cc:200-204),
+ * then per tsr_decode call and per trial of the reference's loop, for every node the search expanded and for the goal,
+ * "activated_errors = e, e, ..., " (leaf to root) and "activated_detectors = d, d, ..., " (tesseract.cc:442-445, 478-481).
+ * Empty unless the decoder was created with create_visualization.  Caller frees *out with tsr_free. */
+int tsr_visualization_text(const tsr_decoder* h, char** out);
 
 /* cost_from_errors (tesseract.cc:618-628) and get_flipped_observables (tesseract.cc:630-658) over
  * original flattened-DEM error indices; both fail with TSR_E_INVALID_ARGUMENT ("error index does not

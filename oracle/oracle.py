@@ -40,6 +40,7 @@ class OrcConfig(C.Structure):
         ("sparsify_max_degree", C.c_int32),
         ("sparsify_reactivate_limit", C.c_int32),
         ("at_most_two_errors_per_detector", C.c_int32),
+        ("create_visualization", C.c_int32),
     ]
 
 
@@ -84,6 +85,7 @@ def _lib(kind: str) -> C.CDLL:
     lib.orc_merge_weights.restype = C.c_double
     lib.orc_merge_weights.argtypes = [C.c_double, C.c_double]
     lib.orc_counters.argtypes = [C.c_void_p, u64p, C.c_int]
+    lib.orc_visualization_write.argtypes = [C.c_void_p, C.c_char_p]
     lib.orc_sample_dem_b8.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, u8p, u8p]
     _libs[kind] = lib
     return lib
@@ -134,7 +136,8 @@ class OracleDecoder:
                  no_revisit_dets: bool = True, merge_errors: bool = True, pqlimit: int = 200000,
                  det_penalty: float = 0.0, det_orders=None, num_threads: int = 1, kind: str = "reference",
                  sparsify_errors: bool = False, sparsify_base_degree: int = -1, sparsify_max_degree: int = -1,
-                 sparsify_reactivate_limit: int = -1, at_most_two_errors_per_detector: bool = False):
+                 sparsify_reactivate_limit: int = -1, at_most_two_errors_per_detector: bool = False,
+                 create_visualization: bool = False):
         self.lib = _lib(kind)
         self.kind = kind
         cfg = OrcConfig()
@@ -155,6 +158,7 @@ class OracleDecoder:
         cfg.sparsify_max_degree = sparsify_max_degree
         cfg.sparsify_reactivate_limit = sparsify_reactivate_limit
         cfg.at_most_two_errors_per_detector = int(at_most_two_errors_per_detector)
+        cfg.create_visualization = int(create_visualization)
         self.h = self.lib.orc_create(dem_text.encode(), C.byref(cfg))
         if not self.h:
             raise OracleError(self.lib.orc_last_error().decode())
@@ -243,6 +247,13 @@ class OracleDecoder:
         self._check(self.lib.orc_flipped_observables(self.h, _p(errs, C.c_uint64), len(errs), _p(out, C.c_uint8)))
         bits = np.unpackbits(out, bitorder="little")[: self.num_observables]
         return np.nonzero(bits)[0].tolist()
+
+    def visualization_text(self) -> str:
+        """Visualizer::write output (visualization.cc) of the pool's first decoder."""
+        import tempfile
+        with tempfile.NamedTemporaryFile("r", suffix=".log") as f:
+            self._check(self.lib.orc_visualization_write(self.h, f.name.encode()))
+            return open(f.name).read()
 
     def counters(self, reset: bool = False):
         out = np.zeros(8, dtype=np.uint64)

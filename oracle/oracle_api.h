@@ -38,6 +38,7 @@ typedef struct orc_config {
   int32_t sparsify_reactivate_limit;
   int32_t at_most_two_errors_per_detector; /* README.md:59 only — no reference code: the port implements it (port.cc: Config),
                                               the reference build refuses it */
+  int32_t create_visualization; /* tesseract.h:50: record the Visualizer log (visualization.cc) */
 } orc_config;
 
 const char* orc_last_error(void);
@@ -89,6 +90,10 @@ double orc_merge_weights(double a, double b); /* common.cc:118-123 */
  * [4]=S get_detcost loop iterations, [5]=A sum(|edets|+|eneighbors|) over evaluated children,
  * [6]=V visited inserts+probes, [7]=searches.  The reference build reports zeros. */
 int orc_counters(orc_handle* h, uint64_t out[8], int reset);
+
+/* Writes the visualization log of decoder 0 of the pool (Visualizer::write, visualization.cc:53-62): header lines plus
+ * whatever orc_decode calls have logged so far. */
+int orc_visualization_write(orc_handle* h, const char* path);
 
 /* Synthetic i.i.d. shots of a DEM (oracle/sampler.inc): the bench / test workload generator restated on the
  * checker side; bit-identical to the product's tsr_sample_dem_b8.  dets_out [shots][ceil(D/8)],

@@ -16,7 +16,9 @@
 #include <chrono>
 #include <cmath>
 #include <limits>
+#include <iomanip>
 #include <map>
+#include <sstream>
 #include <memory>
 #include <numeric>
 #include <queue>
@@ -81,6 +83,7 @@ struct Config {
   // so the search returns the cheapest explanation among those that use at most two errors per detector
   // (tests/test_oracle.py checks that against brute force on the reference's four literal DEMs).
   bool at_most_two = false;
+  bool create_visualization = false;  // tesseract.h:50
 };
 
 struct Counters {
@@ -161,6 +164,7 @@ struct Decoder {
   std::vector<ChainLink> chain;
   std::vector<uint32_t> blocked, count, child_blocked, child_count;
   std::vector<int> amt_undo;  // at-most-two: errors blocked for the current child only
+  std::vector<std::string> viz;  // visualization.cc: the Visualizer's lines
   // Rows the search walks: the full detector rows, or the shot's sparse rows (tesseract.cc:296-298).
   std::vector<uint32_t> aoff;
   std::vector<int> arow;
@@ -241,6 +245,42 @@ struct Decoder {
           throw std::invalid_argument("Each detector order list must have a size equal to the number of detectors.");
     }
     build_tables();
+    if (cfg.create_visualization) {  // tesseract.cc:200-204, visualization.cc:5-24, common.cc:25-50, 90-94
+      std::vector<std::vector<double>> coords(D);
+      std::vector<double> shift;
+      const stim::DetectorErrorModel flat_cur = cur.flattened();
+      size_t next = 0;  // utils.cc:32-58 pushes one entry per detector INSTRUCTION, in instruction order
+      for (const auto& inst : flat_cur.instructions)
+        if (inst.type == stim::DemInstructionType::DEM_DETECTOR && next < coords.size()) coords[next++] = inst.arg_data;
+      for (uint64_t d = 0; d < D; ++d) {
+        std::stringstream ss;
+        ss << "Detector D" << d << " coordinate (";
+        const size_t e = std::min<size_t>(3, coords[d].size());
+        for (size_t i = 0; i < e; ++i) ss << coords[d][i] << (i + 1 < e ? ", " : "");
+        ss << ")";
+        viz.push_back(ss.str());
+      }
+      auto list = [](const std::vector<int>& v) {
+        std::string t = "[";
+        for (size_t i = 0; i < v.size(); ++i) t += std::to_string(v[i]) + (i + 1 < v.size() ? " " : "");
+        return t + "]";
+      };
+      for (const auto& m : errs) {
+        std::stringstream ss;
+        ss << std::fixed << std::setprecision(6) << m.cost;
+        viz.push_back("Error{cost=" + ss.str() + ", symptom=Symptom{detectors=" + list(m.dets) + ", observables=" + list(m.obs) + "}}");
+      }
+    }
+  }
+
+  void log_node(int64_t chain_idx, const std::vector<bool>& fired) {  // visualization.cc:26-51
+    if (!cfg.create_visualization) return;
+    std::string a = "activated_errors = ", b = "activated_detectors = ";
+    for (int64_t at = chain_idx; at != -1; at = chain[(size_t)at].parent) a += std::to_string(chain[(size_t)at].error) + ", ";
+    for (uint64_t d = 0; d < D; ++d)
+      if (fired[d]) b += std::to_string(d) + ", ";
+    viz.push_back(a);
+    viz.push_back(b);
   }
 
   void build_tables() {  // tesseract.cc:207-254
@@ -362,6 +402,7 @@ struct Decoder {
               for (uint32_t q = aoff[(size_t)edet[k]]; q < aoff[(size_t)edet[k] + 1]; ++q) blocked[(size_t)arow[q]] = 1;
       }
       if (node.num_dets == 0) {  // tesseract.cc:441-473
+        log_node(node.chain, fired);
         predicted.resize(node.depth);
         int64_t at = node.chain;
         for (uint64_t i = 0; i < node.depth; ++i) {
@@ -375,6 +416,7 @@ struct Decoder {
         if (!seen[node.num_dets].insert(fired).second) continue;
       }
       ++ctr.X;
+      log_node(node.chain, fired);
       if (node.num_dets < lo) {  // tesseract.cc:503-511
         lo = node.num_dets;
         if (cfg.no_revisit)
@@ -616,6 +658,7 @@ orc_handle* orc_create(const char* dem_text, const orc_config* cfg) {
     c.sparsify_max_degree = cfg->sparsify_max_degree;
     c.sparsify_reactivate_limit = cfg->sparsify_reactivate_limit;
     c.at_most_two = cfg->at_most_two_errors_per_detector != 0;
+    c.create_visualization = cfg->create_visualization != 0;
     uint64_t D = dem.flattened().count_detectors();
     for (uint64_t k = 0; k < cfg->num_det_orders; ++k)
       c.orders.emplace_back(cfg->det_orders + k * D, cfg->det_orders + (k + 1) * D);
@@ -791,5 +834,14 @@ int orc_counters(orc_handle* h, uint64_t out[8], int reset) {
 }
 
 }  // extern "C"
+
+extern "C" int orc_visualization_write(orc_handle* h, const char* path) {
+  return guarded([&] {
+    FILE* f = fopen(path, "w");
+    if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+    for (const auto& line : h->pool[0]->viz) fprintf(f, "%s\n", line.c_str());
+    fclose(f);
+  });
+}
 
 #include "sampler.inc"

@@ -62,6 +62,7 @@ orc_handle* orc_create(const char* dem_text, const orc_config* cfg) {
     c.sparsify_base_degree = cfg->sparsify_base_degree;
     c.sparsify_max_degree = cfg->sparsify_max_degree;
     c.sparsify_reactivate_limit = cfg->sparsify_reactivate_limit;
+    c.create_visualization = cfg->create_visualization != 0;
     uint64_t D = tesseract_decoder::common::flatten(dem).count_detectors();
     for (uint64_t k = 0; k < cfg->num_det_orders; ++k)
       c.det_orders.emplace_back(cfg->det_orders + k * D, cfg->det_orders + (k + 1) * D);
@@ -264,6 +265,10 @@ int orc_build_det_orders(const char* dem_text, uint64_t num_det_orders, int meth
 
 double orc_merge_weights(double a, double b) {
   return tesseract_decoder::common::merge_weights(a, b);
+}
+
+int orc_visualization_write(orc_handle* h, const char* path) {
+  return guarded([&] { h->pool[0]->visualizer.write(path); });
 }
 
 int orc_counters(orc_handle*, uint64_t out[8], int) {

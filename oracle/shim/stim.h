@@ -34,6 +34,7 @@
 #include <unordered_map>
 #include <unordered_set>
 #include <utility>
+#include <deque>
 #include <vector>
 
 namespace stim {
@@ -144,6 +145,20 @@ struct DetectorErrorModel {
   std::vector<DetectorErrorModel> blocks;
 
   DetectorErrorModel() = default;
+  DetectorErrorModel(const DetectorErrorModel&) = default;
+  DetectorErrorModel(DetectorErrorModel&&) = default;
+  DetectorErrorModel& operator=(const DetectorErrorModel&) = default;
+  DetectorErrorModel& operator=(DetectorErrorModel&&) = default;
+  // The reference iterates `for (... : common::flatten(dem).instructions)` (utils.cc:34, used by get_detector_coords):
+  // the temporary dies before the loop body runs (no lifetime extension through the member access before C++23), so the
+  // loop reads freed storage.  With stim's allocator pattern that happens to work; to keep this checker build
+  // well-defined the shim parks a dying model's instruction storage for a while instead of freeing it at once.
+  ~DetectorErrorModel() {
+    if (instructions.empty()) return;
+    thread_local std::deque<std::vector<DemInstruction>> parked;
+    parked.push_back(std::move(instructions));
+    if (parked.size() > 32) parked.pop_front();
+  }
   explicit DetectorErrorModel(std::string_view text) {
     size_t pos = 0;
     parse_block(text, pos, /*nested=*/false);

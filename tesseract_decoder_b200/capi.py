@@ -53,6 +53,7 @@ class TsrConfig(C.Structure):
         ("sparsify_base_degree", C.c_int32),
         ("sparsify_max_degree", C.c_int32),
         ("sparsify_reactivate_limit", C.c_int32),
+        ("create_visualization", C.c_int32),
     ]
 
 
@@ -119,6 +120,7 @@ def lib() -> C.CDLL:
     L.tsr_group_last_batch_nnz.argtypes = [C.c_void_p]
     L.tsr_group_last_batch_nnz.restype = C.c_uint64
     L.tsr_group_last_batch_errors.argtypes = [C.c_void_p, u64p, u64p]
+    L.tsr_visualization_text.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.tsr_set_profile.argtypes = [C.c_void_p, C.c_int]
     L.tsr_profile.argtypes = [C.c_void_p, u64p, C.c_int]
     L.tsr_stream.restype = C.c_void_p
@@ -150,6 +152,7 @@ EXPORTED_SYMBOLS = [
     "tsr_suggest_sparsify_reactivate_limit", "tsr_comm_unique_id", "tsr_comm_init_rank", "tsr_comm_world",
     "tsr_comm_allreduce_sum_u64", "tsr_nccl_version", "tsr_group_create", "tsr_group_destroy", "tsr_group_size",
     "tsr_group_member", "tsr_group_decode_b8", "tsr_group_last_batch_nnz", "tsr_group_last_batch_errors",
+    "tsr_visualization_text",
 ]
 
 
@@ -238,7 +241,7 @@ def make_config(*, det_beam: int = 5, beam_climbing: bool = False, no_revisit_de
                 at_most_two_errors_per_detector: bool = False, device: int = -1, search_slots: int = 0, warps_per_block: int = 0,
                 node_pool_bytes: int = 0, max_batch_shots: int = 0, force_generic_kernel: bool = False, row_scan: int = 0,
                 sparsify_errors: bool = False, sparsify_base_degree: int = -1, sparsify_max_degree: int = -1,
-                sparsify_reactivate_limit: int = -1):
+                sparsify_reactivate_limit: int = -1, create_visualization: bool = False):
     """(tsr_config, keep-alive object for the det_orders array)."""
     cfg = TsrConfig()
     lib().tsr_config_init(C.byref(cfg))
@@ -268,6 +271,7 @@ def make_config(*, det_beam: int = 5, beam_climbing: bool = False, no_revisit_de
     cfg.sparsify_base_degree = sparsify_base_degree
     cfg.sparsify_max_degree = sparsify_max_degree
     cfg.sparsify_reactivate_limit = sparsify_reactivate_limit
+    cfg.create_visualization = int(create_visualization)
     return cfg, orders
 
 
@@ -350,6 +354,12 @@ class Decoder:
     def rows(self, which: int):
         off, idx = self.csr(which)
         return [idx[int(off[r]):int(off[r + 1])].tolist() for r in range(len(off) - 1)]
+
+    def visualization_text(self) -> str:
+        """The Visualizer's lines (visualization.cc) recorded so far; empty unless create_visualization."""
+        out = C.c_void_p()
+        _check(lib().tsr_visualization_text(self.h, C.byref(out)))
+        return _take_text(out)
 
     def compiled_dem_text(self) -> str:
         out = C.c_void_p()

@@ -12,7 +12,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <iomanip>
 #include <limits>
+#include <sstream>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -480,6 +482,12 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     p.work_counter = &sc->work;
     p.counters = h.d_counters.as<unsigned long long>();
     p.prof = h.profile ? h.d_prof.as<unsigned long long>() : nullptr;
+    if (h.trace_on) {
+      p.trace = h.d_trace.as<uint32_t>();
+      p.trace_cap = h.trace_cap;
+      p.trace_len = h.d_trace_len.as<uint32_t>();
+      p.trace_arena = h.d_trace_arena.as<unsigned long long>();
+    }
     return p;
   };
   auto resolve_params = [&](const uint32_t* shot_ids, uint32_t n, uint32_t* retry_out) {
@@ -528,6 +536,8 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     sp_.resume = 1;
     return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, h.blocks_wide), h.wpb_wide, false, bits, s);
   };
+  // An item no CTA got to must never pass for decoded: every status starts as "overflow" (-> retried in the next tier).
+  CUDA_OK(cudaMemsetAsync(h.d_status.p, tsr::kItemNodeOverflow, items, s));
   CUDA_OK(cudaEventRecord(h.ev[1], s));
   CUDA_OK((cudaError_t)launch(search_params(t0, nullptr, items), t0.slots, items, true));
   CUDA_OK(cudaEventRecord(h.ev[2], s));
@@ -654,6 +664,47 @@ uint64_t mapped_error(const tsr_decoder& h, uint64_t dem_error) {
   return e;
 }
 
+// Turns the device trace of a single-shot decode into Visualizer lines (visualization.cc:26-51), trial by trial in
+// the reference's literal order (identical (order, beam) trials are searched once and logged once per literal trial).
+void append_visualization(tsr_decoder& h, const TrialSet& ts, const std::vector<uint8_t>& packed) {
+  const size_t U = ts.perm.size();
+  std::vector<uint32_t> len(U);
+  std::vector<unsigned long long> arena(U);
+  CUDA_OK(cudaStreamSynchronize(h.stream));
+  CUDA_OK(cudaMemcpy(len.data(), h.d_trace_len.p, U * 4, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(arena.data(), h.d_trace_arena.p, U * 8, cudaMemcpyDeviceToHost));
+  std::vector<std::vector<std::string>> per_trial(U);
+  const uint64_t D = h.T.num_detectors;
+  for (size_t u = 0; u < U; ++u) {
+    if (len[u] > h.trace_cap) throw std::runtime_error("the visualization log of this decode exceeds " + std::to_string(h.trace_cap) + " nodes");
+    std::vector<uint32_t> trace(len[u]);
+    if (len[u]) CUDA_OK(cudaMemcpy(trace.data(), h.d_trace.as<uint32_t>() + u * h.trace_cap, (size_t)len[u] * 4, cudaMemcpyDeviceToHost));
+    uint32_t top = 0;
+    bool any = false;
+    for (uint32_t v : trace)
+      if (v != tsr::kNoChain) {
+        top = std::max(top, v);
+        any = true;
+      }
+    std::vector<tsr::ChainNode> nodes(any ? (size_t)top + 1 : 0);  // a node's ancestors have smaller indices
+    if (any) CUDA_OK(cudaMemcpy(nodes.data(), (const void*)(uintptr_t)arena[u], nodes.size() * sizeof(tsr::ChainNode), cudaMemcpyDeviceToHost));
+    for (uint32_t v : trace) {
+      std::string errs = "activated_errors = ";
+      std::vector<uint8_t> fired(packed);
+      for (uint32_t at = v; at != tsr::kNoChain; at = nodes[at].parent) {
+        errs += std::to_string(nodes[at].error) + ", ";
+        for (int d : h.T.errors[nodes[at].error].detectors) fired[(size_t)d >> 3] ^= (uint8_t)(1u << (d & 7));
+      }
+      std::string dets = "activated_detectors = ";
+      for (uint64_t d = 0; d < D; ++d)
+        if ((fired[d >> 3] >> (d & 7)) & 1) dets += std::to_string(d) + ", ";
+      per_trial[u].push_back(std::move(errs));
+      per_trial[u].push_back(std::move(dets));
+    }
+  }
+  for (uint32_t u : ts.literal_to_trial) h.viz_lines.insert(h.viz_lines.end(), per_trial[u].begin(), per_trial[u].end());
+}
+
 char* dup_text(const std::string& s) {
   char* out = (char*)std::malloc(s.size() + 1);
   if (!out) throw std::bad_alloc();
@@ -739,6 +790,28 @@ int tsr_create(const char* dem_text, const tsr_config* cfg, uint32_t flags, tsr_
       }
     }
     if (h->F.certified && cfg->force_generic_kernel) h->F.why_not = "force_generic_kernel is set";
+    if (cfg->create_visualization) {  // tesseract.cc:200-204, visualization.cc:5-24
+      DemModel compiled = h->T.compiled_dem;
+      for (const auto& coords : tsr::get_detector_coords(compiled)) {
+        std::ostringstream ss;
+        ss << "Detector D" << h->viz_lines.size() << " coordinate (";
+        const size_t e = std::min<size_t>(3, coords.size());
+        for (size_t i = 0; i < e; ++i) ss << coords[i] << (i + 1 < e ? ", " : "");
+        ss << ")";
+        h->viz_lines.push_back(ss.str());
+      }
+      for (const auto& err : h->T.errors) {  // common.cc:25-50, 90-94
+        std::ostringstream ss;
+        ss << std::fixed << std::setprecision(6) << err.cost;
+        auto list = [](const std::vector<int>& v) {
+          std::string t = "[";
+          for (size_t i = 0; i < v.size(); ++i) t += std::to_string(v[i]) + (i + 1 < v.size() ? " " : "");
+          return t + "]";
+        };
+        h->viz_lines.push_back("Error{cost=" + ss.str() + ", symptom=Symptom{detectors=" + list(err.detectors) + ", observables=" +
+                               list(err.observables) + "}}");
+      }
+    }
     h->host_only = (flags & TSR_CREATE_HOST_ONLY) != 0;
     if (!h->host_only) init_device(*h);
     *out = h.release();
@@ -883,19 +956,36 @@ int tsr_decode(tsr_decoder* h, const uint64_t* detections, uint64_t n, int64_t o
     }
     double c = 0;
     uint8_t low = 0;
+    const TrialSet* used = &h->ensemble;
+    TrialSet one;
+    if (h->cfg.create_visualization) {  // per distinct trial: the chain index of every node the reference logs
+      CUDA_OK(cudaSetDevice(h->device));
+      const size_t U = std::max<size_t>(h->ensemble.perm.size(), 1);
+      h->trace_cap = (uint32_t)std::min<uint64_t>(h->cfg.pqlimit == TSR_PQLIMIT_UNBOUNDED ? (1u << 20) : h->cfg.pqlimit + 2, 1u << 20);
+      h->d_trace.ensure(U * h->trace_cap * 4);
+      h->d_trace_len.ensure(U * 4);
+      h->d_trace_arena.ensure(U * 8);
+      CUDA_OK(cudaMemsetAsync(h->d_trace_len.p, 0, U * 4, h->stream));
+      h->trace_on = true;
+    }
+    struct TraceOff {
+      tsr_decoder* h;
+      ~TraceOff() { h->trace_on = false; }
+    } trace_off{h};
     if (order < 0) {
       decode_batch(*h, packed.data(), stride, 1, false, h->ensemble, nullptr, &c, &low);
     } else {
       if ((uint64_t)order >= h->det_orders.size()) throw std::invalid_argument("detector_order is out of range");
       if (beam > TSR_INF_DET_BEAM) beam = TSR_INF_DET_BEAM;
-      TrialSet one;
       one.perm = {h->order_to_perm[(size_t)order]};
       one.beam = {(uint32_t)beam};
       one.literal_to_trial = {0};
       CUDA_OK(cudaSetDevice(h->device));
       one.upload();
       decode_batch(*h, packed.data(), stride, 1, false, one, nullptr, &c, &low);
+      used = &one;
     }
+    if (h->trace_on) append_visualization(*h, *used, packed);
     if (cost) *cost = c;
     if (low_confidence) *low_confidence = low;
     if (n_errs) *n_errs = h->last_idx.size();
@@ -903,6 +993,14 @@ int tsr_decode(tsr_decoder* h, const uint64_t* detections, uint64_t n, int64_t o
       if (h->last_idx.size() > errs_cap) throw std::invalid_argument("errs_out is too small for the predicted errors");
       std::copy(h->last_idx.begin(), h->last_idx.end(), errs_out);
     }
+  });
+}
+
+int tsr_visualization_text(const tsr_decoder* h, char** out) {
+  return guarded([&] {
+    std::string text;
+    for (const std::string& line : h->viz_lines) text += line + "\n";
+    *out = dup_text(text);
   });
 }
 

@@ -3,6 +3,7 @@
 // Header-only C++20; used by the pybind11 module (pybind.cc) and the CLI (main.cc).
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <limits>
 #include <memory>
 #include <sstream>
@@ -83,6 +84,7 @@ inline void fill_config(const TesseractConfig& config, tsr_config& c, std::vecto
   c.sparsify_base_degree = config.sparsify_base_degree;
   c.sparsify_max_degree = config.sparsify_max_degree;
   c.sparsify_reactivate_limit = config.sparsify_reactivate_limit;
+  c.create_visualization = config.create_visualization;
   for (const auto& o : config.det_orders) {
     if (o.size() != config.det_orders[0].size())
       throw std::invalid_argument("Each detector order list must have a size equal to the number of detectors.");
@@ -99,8 +101,29 @@ struct HandleDeleter {
   void operator()(tsr_decoder* h) const { tsr_destroy(h); }
 };
 
+// visualization.h:12-23: the log the decoder fills when config.create_visualization is set.
+struct Visualizer {
+  tsr_decoder* handle = nullptr;  // borrowed from the decoder that owns this object
+  std::string text() const {
+    if (!handle) return "";
+    char* out = nullptr;
+    check(tsr_visualization_text(handle, &out));
+    std::string t(out);
+    tsr_free(out);
+    return t;
+  }
+  void write(const char* fpath) const {
+    FILE* f = std::fopen(fpath, "w");
+    if (!f) throw std::invalid_argument(std::string("Failed to open ") + fpath);
+    const std::string t = text();
+    std::fwrite(t.data(), 1, t.size(), f);
+    std::fclose(f);
+  }
+};
+
 struct TesseractDecoder {
   TesseractConfig config;
+  Visualizer visualizer;  // tesseract.h:84
   // tesseract.h:112-130
   bool low_confidence_flag = false;
   std::vector<size_t> predicted_errors_buffer;
@@ -115,6 +138,7 @@ struct TesseractDecoder {
     tsr_decoder* raw = nullptr;
     check(tsr_create(config.dem.c_str(), &c, host_only ? TSR_CREATE_HOST_ONLY : 0, &raw));
     h_.reset(raw);
+    visualizer.handle = raw;
     num_detectors = tsr_num_detectors(raw);
     num_observables = tsr_num_observables(raw);
     num_errors = tsr_num_errors(raw);

@@ -150,6 +150,12 @@ struct tsr_decoder {
   uint32_t sol_stride = 0;
   bool collect_errors = true;
 
+  // Visualization log (cfg.create_visualization): header + one pair of lines per logged node, like Visualizer::lines.
+  std::vector<std::string> viz_lines;
+  bool trace_on = false;             // set around the single-shot decode of tsr_decode
+  uint32_t trace_cap = 0;
+  tsr_impl::DevBuf d_trace, d_trace_len, d_trace_arena;
+
   // Results of the last decode call.
   std::vector<uint64_t> last_off{0};
   std::vector<uint64_t> last_idx;

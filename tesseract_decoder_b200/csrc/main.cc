@@ -143,8 +143,24 @@ std::vector<uint8_t> read_shots(const std::string& path, const std::string& form
       }
       ++shots_out;
     }
+  } else if (format == "ptb64") {
+    // Partially transposed, bit-packed in groups of 64 shots: per group, for each bit index k, one little-endian
+    // 64-bit word whose bit s is bit k of the group's shot s.  The shot count is a multiple of 64.
+    if (bits == 0 || raw.size() % (bits * 8)) throw std::invalid_argument(path + ": size is not a multiple of the ptb64 group size (64 shots)");
+    const uint64_t groups = raw.size() / (bits * 8);
+    shots_out = groups * 64;
+    out.assign((size_t)(shots_out * nb), 0);
+    for (uint64_t g = 0; g < groups; ++g)
+      for (uint64_t k = 0; k < bits; ++k) {
+        uint64_t word = 0;
+        for (int b = 0; b < 8; ++b) word |= (uint64_t)(uint8_t)raw[(size_t)((g * bits + k) * 8 + b)] << (8 * b);
+        for (; word; word &= word - 1) {
+          const uint64_t sh = g * 64 + (uint64_t)__builtin_ctzll(word);
+          out[(size_t)(sh * nb + k / 8)] |= (uint8_t)(1u << (k % 8));
+        }
+      }
   } else {
-    throw std::invalid_argument("unsupported shot format '" + format + "' (b8, 01, hits, dets and r8 are supported)");
+    throw std::invalid_argument("unsupported shot format '" + format + "' (b8, 01, hits, dets, r8 and ptb64 are supported)");
   }
   return out;
 }
@@ -186,9 +202,37 @@ void write_shot(std::ostream& out, const std::string& format, const uint8_t* row
       }
     }
   } else {
-    throw std::invalid_argument("unsupported --out-format '" + format + "' (b8, 01, hits, dets and r8 are supported)");
+    throw std::invalid_argument("unsupported --out-format '" + format + "' (b8, 01, hits, dets, r8 and ptb64 are supported)");
   }
 }
+
+// Shot-by-shot writer.  ptb64 transposes groups of 64 shots, so its rows are held back until a group is complete;
+// finish() refuses a trailing partial group (the format cannot represent it).
+struct ShotWriter {
+  std::ostream& out;
+  std::string format;
+  uint64_t bits;
+  char letter;
+  std::vector<uint8_t> group;  // ptb64: up to 64 pending rows
+  uint64_t pending = 0;
+  ShotWriter(std::ostream& o, std::string f, uint64_t b, char l) : out(o), format(std::move(f)), bits(b), letter(l) {}
+  void write(const uint8_t* row) {
+    if (format != "ptb64") return write_shot(out, format, row, bits, letter);
+    const uint64_t nb = (bits + 7) / 8;
+    group.insert(group.end(), row, row + nb);
+    if (++pending < 64) return;
+    for (uint64_t k = 0; k < bits; ++k) {
+      uint64_t word = 0;
+      for (uint64_t sh = 0; sh < 64; ++sh) word |= (uint64_t)((group[(size_t)(sh * nb + k / 8)] >> (k % 8)) & 1) << sh;
+      for (int b = 0; b < 8; ++b) out.put((char)((word >> (8 * b)) & 0xFF));
+    }
+    group.clear();
+    pending = 0;
+  }
+  void finish() {
+    if (format == "ptb64" && pending) throw std::invalid_argument("ptb64 output needs a multiple of 64 shots");
+  }
+};
 
 }  // namespace
 
@@ -266,7 +310,9 @@ int main(int argc, char** argv) {
       const std::vector<uint8_t> rows = read_shots(a.in_fname, a.in_format, bits, n);
       std::ofstream f(a.out_fname, std::ios::binary);
       if (!f) throw std::invalid_argument("Failed to open " + a.out_fname);
-      for (uint64_t k = 0; k < n; ++k) write_shot(f, a.out_format, rows.data() + k * ((bits + 7) / 8), bits, 'D');
+      ShotWriter w(f, a.out_format, bits, 'D');
+      for (uint64_t k = 0; k < n; ++k) w.write(rows.data() + k * ((bits + 7) / 8));
+      w.finish();
       return EXIT_SUCCESS;
     }
     std::string dem_text;
@@ -363,6 +409,7 @@ int main(int argc, char** argv) {
       if (!out_file) throw std::invalid_argument("Failed to open " + a.out_fname);
     }
     std::ostream& out = a.out_fname == "-" ? std::cout : static_cast<std::ostream&>(out_file);
+    ShotWriter out_writer(out, a.out_format, O, 'L');
 
     uint64_t num_errors = 0, num_low_confidence = 0, done = 0;
     double total_time_seconds = 0;
@@ -388,7 +435,7 @@ int main(int argc, char** argv) {
       }
       total_time_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       for (uint64_t s = at; s < at + n; ++s) {  // consume(shot), tesseract_main.cc:592-616
-        if (!a.out_fname.empty()) write_shot(out, a.out_format, obs_pred.data() + s * ob, O, 'L');
+        if (!a.out_fname.empty()) out_writer.write(obs_pred.data() + s * ob);
         const bool match = !has_obs || std::memcmp(obs_pred.data() + s * ob, obs_true.data() + s * ob, (size_t)ob) == 0;
         if (low[s]) ++num_low_confidence;
         else if (!match) ++num_errors;
@@ -412,6 +459,7 @@ int main(int argc, char** argv) {
     if (group && done == reduced_shots && (num_low_confidence != reduced_low || (has_obs && num_errors != reduced_errors)))
       throw std::runtime_error("multi-GPU counters disagree with the per-shot accounting");
 
+    if (!a.out_fname.empty()) out_writer.finish();
     if (want_use) {  // tesseract_main.cc:625-639
       const uint64_t usage_shots = has_obs ? done - num_errors : done;
       char* text = nullptr;

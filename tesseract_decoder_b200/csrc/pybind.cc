@@ -243,6 +243,10 @@ PYBIND11_MODULE(_tesseract_b200, root) {
       py::arg("num_detectors"), py::arg("sparsify_base_degree"),
       "Returns the suggested number of optional high-degree errors to reactivate per shot.");
 
+  py::class_<tesseract_b200::Visualizer>(root.def_submodule("viz", "Module containing the visualization tools"), "Visualizer")  // visualization.pybind.h
+      .def("write", &tesseract_b200::Visualizer::write, py::arg("fpath"))
+      .def("text", &tesseract_b200::Visualizer::text);
+
   py::class_<TesseractConfig>(m, "TesseractConfig")
       .def(py::init<>())
       .def(py::init([](int det_beam, bool beam_climbing, bool no_revisit_dets, bool verbose, bool merge_errors, size_t pqlimit,
@@ -349,6 +353,19 @@ PYBIND11_MODULE(_tesseract_b200, root) {
               throw std::invalid_argument("The number of detectors in the input array (" + std::to_string(nd) +
                                           ") does not match the number of detectors in the decoder (" +
                                           std::to_string(self.num_detectors) + ").");
+            if (self.config.create_visualization) {  // the log is written by single-shot decodes: loop like the reference
+              py::array_t<bool> result({shots, self.num_observables});
+              auto r = result.mutable_unchecked<2>();
+              for (size_t i = 0; i < shots; ++i) {
+                std::vector<uint64_t> hits;
+                for (size_t j = 0; j < nd; ++j)
+                  if (s((py::ssize_t)i, (py::ssize_t)j)) hits.push_back(j);
+                std::vector<bool> row(self.num_observables, false);
+                for (int o : self.decode(hits)) row[(size_t)o] = true;
+                for (size_t o = 0; o < self.num_observables; ++o) r((py::ssize_t)i, (py::ssize_t)o) = row[o];
+              }
+              return result;
+            }
             // pack -> one GPU batch -> unpack (the reference loops decode() per row, tesseract.pybind.h:476-490)
             const size_t stride = std::max<size_t>((nd + 7) / 8, 1), ob = (self.num_observables + 7) / 8;
             std::vector<uint8_t> packed(shots * stride, 0), obs(shots * ob + 1, 0);
@@ -374,6 +391,7 @@ PYBIND11_MODULE(_tesseract_b200, root) {
       .def_readwrite("errors", &TesseractDecoder::errors)
       .def_readwrite("num_observables", &TesseractDecoder::num_observables)
       .def_readwrite("num_detectors", &TesseractDecoder::num_detectors)
+      .def_readonly("visualizer", &TesseractDecoder::visualizer)  // tesseract.pybind.h:525-527
       .def_readonly("dem_error_to_error", &TesseractDecoder::dem_error_to_error)
       .def_readonly("error_to_dem_error", &TesseractDecoder::error_to_dem_error);
 

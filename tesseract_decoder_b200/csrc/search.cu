@@ -296,6 +296,16 @@ __device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t ite
   uint32_t* act = p.t.sp_on ? p.sp_act + (size_t)slot * D * t.sp_rw : nullptr;
   if (act) sparsify::select(t, rbits, act, sp_scratch, 0, 1, lane, [] { __syncwarp(); });
 
+  if (p.trace && lane == 0) {
+    p.trace_len[item] = 0;
+    p.trace_arena[item] = (unsigned long long)(uintptr_t)chain;
+  }
+  auto log_node = [&](uint32_t chain_idx) {  // visualization log (tesseract.cc:442-445, 478-481)
+    if (p.trace && lane == 0) {
+      const uint32_t n = p.trace_len[item]++;
+      if (n < p.trace_cap) p.trace[(size_t)item * p.trace_cap + n] = chain_idx;
+    }
+  };
   uint64_t heap_size = 0, chain_size = 0, pushed = 0;
   uint32_t min_dets = root_dets;
   uint32_t max_dets = root_dets + beam;
@@ -364,6 +374,7 @@ __device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t ite
     if (!root_pending) {
       if (node.num_dets == 0) {
         // Goal (tesseract.cc:441-473): chain errors in root -> leaf order.
+        log_node(node.chain);
         if (node.depth > p.sol_stride) return kItemSolutionOverflow;
         if (lane == 0) {
           uint32_t* out = p.sol + (size_t)item * p.sol_stride;
@@ -395,6 +406,7 @@ __device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t ite
         if (inserted == 0) continue;
         ++n_visited;
       }
+      log_node(node.chain);
       if (node.num_dets < min_dets) {  // tesseract.cc:503-511
         min_dets = node.num_dets;
         max_dets = min(max_dets, min_dets + beam);

@@ -124,8 +124,15 @@ struct SearchParams {
   unsigned int* work_counter = nullptr;
   unsigned long long* counters = nullptr;  // [8], see tsr_counters
   unsigned long long* prof = nullptr;      // [8] nullable, fast path only: per-phase ticks, see tsr_profile
-  // Tail widening (fast path).  A launch with expansion_budget > 0 pauses every search that expands more nodes than
-  // that: its record goes to paused[atomicAdd(paused_count)] and the CTA retires (its slot stays occupied).  A launch
+  // Visualization log (debug decodes of one shot; visualization.cc, tesseract.cc:442-445, 478-481): per item, the chain
+  // index of every node the reference would log — each expanded node and the goal — in pop order, and the address of
+  // the item's chain arena.  Null = off.
+  uint32_t* trace = nullptr;          // [items][trace_cap]
+  uint32_t trace_cap = 0;
+  uint32_t* trace_len = nullptr;      // [items] entries the search wanted to log (may exceed trace_cap)
+  unsigned long long* trace_arena = nullptr;  // [items]
+  // Tail widening (fast path).  A launch with expansion_budget > 0 pauses every search that has expanded more nodes
+  // than that once the work queue is empty: its record goes to paused[atomicAdd(paused_count)] and the CTA retires (its slot stays occupied).  A launch
   // with resume = 1 runs no new work: CTA b continues paused[b], paused[b + gridDim], ... to the end, typically with
   // four times the warps.  Heavy-tailed batches then end with a few wide CTAs instead of one narrow one.
   uint32_t expansion_budget = 0;

@@ -914,6 +914,10 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       c.state_valid = 0;
       c.heap_size = c.chain_size = c.pushed = c.n_visited = 0;
       c.n_exp = 0;
+      if (p.trace && !resume) {
+        p.trace_len[item] = 0;
+        p.trace_arena[item] = (unsigned long long)(uintptr_t)chain;
+      }
       if (resume) {  // continue a paused search: its queue, arena and visited set are where it left them
         c.min_dets = resume->min_dets;
         c.max_dets = resume->max_dets;
@@ -951,8 +955,11 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       } else if (heap_size0 == 0) {
         action = kActDone;
         status = kItemLowConfidence;  // tesseract.cc:609-615
-      } else if (p.expansion_budget && c.n_exp >= p.expansion_budget) {
-        // Out of budget: park the search for a wider CTA (SearchParams::resume).  If the list is full it simply goes on.
+      } else if (p.expansion_budget && c.n_exp >= p.expansion_budget &&
+                 __shfl_sync(kFull, lane == 0 ? __ldcg(p.work_counter) : 0u, 0) >= p.n_work) {
+        // Over budget AND no work left to claim: this search is part of the batch's tail.  Park it for a wider CTA
+        // (SearchParams::resume); while the queue still holds work a long search simply runs on — a CTA that retired
+        // then would take its slot out of service.  (If the list is full the search also runs on.)
         unsigned int at = 0;
         if (lane == 0) at = atomicAdd(p.paused_count, 1u);
         at = __shfl_sync(kFull, at, 0);
@@ -971,9 +978,6 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           }
           action = kActDone;
           status = kItemPaused;
-        } else {
-          if (lane == 0) c.n_exp = 0;
-          __syncwarp();
         }
       }
       if (action == kActExpand && !root_pending && heap_size0 != 0) {
@@ -1082,6 +1086,10 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
         if (c.num_dets == 0) {
           // Goal (tesseract.cc:441-473): chain errors in root -> leaf order.
           action = kActDone;
+          if (p.trace && lane == 0) {
+            const uint32_t n = p.trace_len[item]++;
+            if (n < p.trace_cap) p.trace[(size_t)item * p.trace_cap + n] = c.chain;
+          }
           if (c.depth > p.sol_stride) {
             status = kItemSolutionOverflow;
           } else if (lane == 0) {
@@ -1117,6 +1125,10 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
             } else if (lane == 0) {
               ++c.n_visited;
             }
+          }
+          if (action == kActExpand && p.trace && lane == 0) {  // tesseract.cc:478-481
+            const uint32_t n = p.trace_len[item]++;
+            if (n < p.trace_cap) p.trace[(size_t)item * p.trace_cap + n] = c.chain;
           }
           if (action == kActExpand && lane == 0 && c.num_dets < c.min_dets) {  // tesseract.cc:503-511
             c.min_dets = c.num_dets;
@@ -1317,72 +1329,11 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
       __syncwarp();
       uint32_t i0 = 0;  // children (of the compact list) pushed so far
-      if (K >= 2 && c.depth != 0xFFFF && pushed + K <= p.pqlimit && heap_size + K <= p.node_cap && chain_size + K <= p.node_cap &&
+      if (K >= 4 && c.depth != 0xFFFF && pushed + K <= p.pqlimit && heap_size + K <= p.node_cap && chain_size + K <= p.node_cap &&
           chain_size + K < 0xFFFFFFFEull) {
         for (uint32_t i = lane; i < K; i += 32) {  // chain nodes
           const uint4 meta = sm.res_meta[sm.clist[i]];
           __stcg(reinterpret_cast<uint4*>(chain + chain_size + i), make_uint4(meta.x, c.chain, (c.mind << 16) | (meta.z >> 16), meta.y));
-        }
-        if (heap_size + K <= sm.stage_cap) {
-          // Small heap: the WHOLE heap is staged (node n at slot n - 1) and all K pushes run as one pipeline (see below:
-          // push i makes its step s at time 2 i + s; exact for any mix of leaf levels, including leaves whose parent is
-          // an earlier leaf of the same batch).
-          const uint32_t hs = (uint32_t)heap_size;
-          for (uint32_t q = lane; q < hs; q += 32) sm.stage[q] = __ldcg(reinterpret_cast<const uint4*>(heap + q));
-          __syncwarp();
-          uint32_t my = lane, hole1 = 0;
-          bool active = false;
-          uint4 vv = make_uint4(0, 0, 0, 0);
-          HeapNode value;
-          value.cost = 0;
-          value.chain = 0;
-          value.num_dets = 0;
-          value.depth = 0;
-          const uint32_t t_end = 2 * (K - 1) + (32u - (uint32_t)__clz((int)(hs + K))) + 1;
-          for (uint32_t t = 0; t < t_end; ++t) {
-            if (!active && my < K && t == 2 * my) {
-              const uint32_t ci = sm.clist[my];
-              const uint4 meta = sm.res_meta[ci];
-              value.cost = sm.res_cost[ci];
-              value.chain = (uint32_t)(chain_size + my);
-              value.num_dets = (uint16_t)(meta.z & 0xFFFF);
-              value.depth = (uint16_t)(c.depth + 1);
-              vv.x = (uint32_t)__double2loint(value.cost);
-              vv.y = (uint32_t)__double2hiint(value.cost);
-              vv.z = value.chain;
-              vv.w = (uint32_t)value.num_dets | ((uint32_t)value.depth << 16);
-              active = true;
-              hole1 = hs + my + 1;  // 1-based
-            }
-            if (active) {
-              bool up = false;
-              uint4 pv = make_uint4(0, 0, 0, 0);
-              if (hole1 > 1) {
-                pv = sm.stage[(hole1 >> 1) - 1];
-                HeapNode pn;
-                pn.cost = __hiloint2double((int)pv.y, (int)pv.x);
-                pn.chain = pv.z;
-                pn.num_dets = (uint16_t)(pv.w & 0xFFFF);
-                pn.depth = (uint16_t)(pv.w >> 16);
-                up = node_greater(pn, value);
-              }
-              sm.stage[hole1 - 1] = up ? pv : vv;
-              if (up) {
-                hole1 >>= 1;
-              } else {
-                active = false;
-                my += 32;
-              }
-            }
-            __syncwarp();
-          }
-          for (uint32_t q = lane; q < hs + K; q += 32) __stcg(reinterpret_cast<uint4*>(heap + q), sm.stage[q]);
-          __syncwarp();
-          heap_size += K;
-          chain_size += K;
-          pushed += K;
-          ctr.Q += K;
-          i0 = K;
         }
         while (i0 < K) {
           // one sub-batch = new leaves on ONE tree level, so that "s levels up" names a distinct level for every s
@@ -1409,64 +1360,60 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
             for (uint32_t q = lane; q < w_; q += 32) sm.stage[off_ + q] = __ldcg(reinterpret_cast<const uint4*>(heap + (lo_ - 1 + q)));
           }
           __syncwarp();
-          // The Kb sifts, as a systolic pipeline instead of one after the other.  Push i performs its step s (hole at
-          // the s-th ancestor of its leaf: compare with the node one level up, move that node down or settle) at time
-          // 2 i + s.  With a lag of two steps between consecutive pushes every node a push reads or overwrites has
-          // already seen all the steps the earlier pushes make on it, so the heap ends up exactly as after Kb sequential
-          // std::push_heap calls (bits/stl_heap.h:135-148) — in 2 Kb + depth steps instead of Kb x depth.  Lane l runs
-          // pushes l, l + 32, ... (a push lasts at most depth + 1 <= 33 steps, the lane is free again after 64).
+          // The Kb pushes, 32 at a time.  A push whose value is not smaller than its parent leaves the rest of the heap
+          // alone, so every lane checks its own push against its (staged) parent and the leading run of non-sifting
+          // pushes commits at once; the first push that does sift is replayed warp-wide (lane s-1 holds the ancestor s
+          // levels up, the ballot of `ancestor > value` gives the stop level, the ancestors below it move down one
+          // level: the moves of std::push_heap, bits/stl_heap.h:135-148) and the lanes behind it check again.
           {
-            uint32_t my = lane, st_lvl = 0;
-            bool active = false;
-            uint4 vv = make_uint4(0, 0, 0, 0);
-            HeapNode value;
-            value.cost = 0;
-            value.chain = 0;
-            value.num_dets = 0;
-            value.depth = 0;
-            const uint32_t t_end = 2 * (Kb - 1) + lvl + 1;
-            for (uint32_t t = 0; t < t_end; ++t) {
-              if (!active && my < Kb && t == 2 * my) {
-                const uint32_t ci = sm.clist[i0 + my];
+            const uint32_t lo_1 = __shfl_sync(kFull, lo_s, 0), off_1 = __shfl_sync(kFull, off_s, 0);
+            for (uint32_t w0 = 0; w0 < Kb; w0 += 32) {
+              const uint32_t j = w0 + lane;
+              const bool have = j < Kb;
+              HeapNode value;
+              value.cost = 0;
+              value.chain = 0;
+              value.num_dets = 0;
+              value.depth = 0;
+              if (have) {
+                const uint32_t ci = sm.clist[i0 + j];
                 const uint4 meta = sm.res_meta[ci];
                 value.cost = sm.res_cost[ci];
-                value.chain = (uint32_t)(chain_size + my);
+                value.chain = (uint32_t)(chain_size + j);
                 value.num_dets = (uint16_t)(meta.z & 0xFFFF);
                 value.depth = (uint16_t)(c.depth + 1);
-                vv.x = (uint32_t)__double2loint(value.cost);
-                vv.y = (uint32_t)__double2hiint(value.cost);
-                vv.z = value.chain;
-                vv.w = (uint32_t)value.num_dets | ((uint32_t)value.depth << 16);
-                active = true;
-                st_lvl = 0;
               }
-              // level tables of the hole (st_lvl >= 1: lane st_lvl - 1) and of its parent (lane st_lvl)
-              const int src_h = st_lvl ? (int)st_lvl - 1 : 0, src_p = (int)min(st_lvl, 31u);
-              const uint32_t lo_h = __shfl_sync(kFull, lo_s, src_h), off_h = __shfl_sync(kFull, off_s, src_h);
-              const uint32_t lo_p = __shfl_sync(kFull, lo_s, src_p), off_p = __shfl_sync(kFull, off_s, src_p);
-              if (active) {
-                const unsigned long long leaf1 = lo1 + my;
-                const uint32_t hole = st_lvl ? off_h + (uint32_t)(leaf1 >> st_lvl) - lo_h : my;
-                bool up = false;
-                uint4 pv = make_uint4(0, 0, 0, 0);
-                if (st_lvl < lvl) {
-                  pv = sm.stage[off_p + (uint32_t)(leaf1 >> (st_lvl + 1)) - lo_p];
-                  HeapNode pn;
-                  pn.cost = __hiloint2double((int)pv.y, (int)pv.x);
-                  pn.chain = pv.z;
-                  pn.num_dets = (uint16_t)(pv.w & 0xFFFF);
-                  pn.depth = (uint16_t)(pv.w >> 16);
-                  up = node_greater(pn, value);
+              const uint4 vv = node_raw(value);
+              unsigned remaining = __ballot_sync(kFull, have);
+              while (remaining) {
+                bool sift = false;
+                if (((remaining >> lane) & 1) && lvl >= 1)
+                  sift = node_greater(node_of(sm.stage[off_1 + (uint32_t)((lo1 + j) >> 1) - lo_1]), value);
+                const unsigned sifting = __ballot_sync(kFull, sift);
+                const uint32_t first = sifting ? (uint32_t)__ffs((int)sifting) - 1 : 32u;
+                const unsigned run = remaining & (first >= 32 ? kFull : ((1u << first) - 1u));
+                if ((run >> lane) & 1) sm.stage[j] = vv;
+                remaining &= ~run;
+                if (first < 32) {
+                  const uint32_t jf = w0 + first;
+                  const uint4 braw = shfl4(vv, (int)first);
+                  const HeapNode bvalue = node_of(braw);
+                  const bool valid = lane + 1 <= lvl;
+                  const uint32_t slot = valid ? off_s + (uint32_t)((lo1 + jf) >> (lane + 1)) - lo_s : 0u;
+                  uint4 pv = make_uint4(0, 0, 0, 0);
+                  if (valid) pv = sm.stage[slot];
+                  const bool up = valid && node_greater(node_of(pv), bvalue);
+                  const unsigned not_up = ~__ballot_sync(kFull, up);
+                  const uint32_t stop = not_up ? (uint32_t)__ffs((int)not_up) - 1 : 32u;  // ancestors 0..stop-1 move down
+                  uint32_t below = __shfl_up_sync(kFull, slot, 1);  // slot one level closer to the leaf
+                  if (lane == 0) below = jf;
+                  if (lane < stop) sm.stage[below] = pv;
+                  const uint32_t vslot = stop == 0 ? jf : __shfl_sync(kFull, slot, (int)stop - 1);
+                  if (lane == 0) sm.stage[vslot] = braw;
+                  remaining &= ~(1u << first);
                 }
-                sm.stage[hole] = up ? pv : vv;
-                if (up) {
-                  ++st_lvl;
-                } else {
-                  active = false;
-                  my += 32;
-                }
+                __syncwarp();
               }
-              __syncwarp();
             }
           }
           for (uint32_t i = lane; i < Kb; i += 32) __stcg(reinterpret_cast<uint4*>(heap + heap_size + i), sm.stage[i]);

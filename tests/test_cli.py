@@ -91,7 +91,7 @@ def test_cli_matches_the_library(tmp_path):
 
 
 def test_shot_file_formats_round_trip(tmp_path):
-    """stim result formats the CLI reads and writes (--in-format / --out-format): b8, 01, hits, dets, r8.
+    """stim result formats the CLI reads and writes (--in-format / --out-format): b8, 01, hits, dets, r8, ptb64.
     Host-only (--convert-only): every format re-encodes to the same b8 bytes."""
     dem = W.load_dem("surface_d5_r5_p0.002_X")
     (tmp_path / "m.dem").write_text(dem)
@@ -112,5 +112,19 @@ def test_shot_file_formats_round_trip(tmp_path):
     assert (tmp_path / "a.dets").read_text().splitlines()[0] == "shot" + "".join(f" D{i}" for i in first)
     raw = (tmp_path / "a.r8").read_bytes()
     assert raw[0] == first[0]  # run of zeros before the first one
+    # ptb64 (tesseract_main.cc:259-330 accepts every stim format name): groups of 64 shots, transposed — for each bit k
+    # one little-endian u64 whose bit s is bit k of the group's shot s.  Checked against numpy, and round-tripped.
     r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / "a.b8", "--out", tmp_path / "x", "--out-format", "ptb64")
+    assert r.returncode != 0 and "multiple of 64" in r.stderr  # 200 shots
+    dets[:192].tofile(tmp_path / "b.b8")
+    r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / "b.b8", "--out", tmp_path / "b.ptb64", "--out-format", "ptb64")
+    assert r.returncode == 0, r.stderr
+    bits = np.unpackbits(dets[:192], axis=1, bitorder="little")[:, :120]          # [shot, bit]
+    expect = np.packbits(bits.reshape(3, 64, 120).transpose(0, 2, 1), axis=2, bitorder="little")  # [group, bit, 8 bytes]
+    assert (tmp_path / "b.ptb64").read_bytes() == expect.tobytes()
+    r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / "b.ptb64", "--in-format", "ptb64", "--out",
+            tmp_path / "back_ptb64.b8", "--out-format", "b8")
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.fromfile(tmp_path / "back_ptb64.b8", dtype=np.uint8).reshape(192, 15), dets[:192])
+    r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / "a.b8", "--out", tmp_path / "x", "--out-format", "nope")
     assert r.returncode != 0 and "unsupported" in r.stderr

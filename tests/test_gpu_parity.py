@@ -396,3 +396,31 @@ def test_at_most_two_exhaustive_small_dems(which):
             assert mask not in best
         else:
             assert abs(out["cost"][mask] - best[mask]) <= 1e-7
+
+
+def test_visualization_log_equals_the_reference():
+    """The visualization log (visualization.cc; tesseract.cc:442-445, 478-481): for every node a search expands, and for
+    the goal, the chosen errors (leaf to root) and the fired detectors — per trial of the reference's loop, in pop order.
+    The GPU records chain indices on the device and rebuilds the lines on the host; the text must equal the CPU decoder's
+    after the same sequence of single-shot decodes."""
+    cases = [
+        ("surface_d5_r5_p0.002_X", dict(det_beam=5, pqlimit=200000, no_revisit_dets=True, num_det_orders=3)),
+        ("color_superdense_d5_r5_p0.001_Z", dict(det_beam=2, beam_climbing=True, pqlimit=10000, no_revisit_dets=True, num_det_orders=2)),
+        ("transcx_d3_p0.001_X", dict(det_beam=W.INF_BEAM, pqlimit=None, no_revisit_dets=False, num_det_orders=0, det_penalty=0.5)),
+    ]
+    for name, cfg in cases:
+        dem, kw = W.decoder_kwargs(dict(cfg, dem=name), capi.build_det_orders)
+        for variant in (dict(), dict(force_generic_kernel=True), dict(row_scan=2)):
+            dec = capi.Decoder(dem, create_visualization=True, **variant, **kw)
+            ref = OracleDecoder(dem, kind=KIND, create_visualization=True, **kw)
+            dets, _ = capi.sample_dem_b8(dem, 17, 12, dec.num_detectors, dec.num_observables)
+            bits = np.unpackbits(dets, axis=1, bitorder="little")[:, :dec.num_detectors]
+            for s in range(len(bits)):
+                hits = np.nonzero(bits[s])[0]
+                assert dec.decode_to_errors(hits) == ref.decode_to_errors(hits)
+            if kw["det_orders"] is not None:  # the (detections, order, beam) overload logs one search (tesseract.cc:371-378)
+                hits = np.nonzero(bits[0])[0]
+                assert dec.decode_to_errors(hits, order=1, beam=1) == ref.decode_to_errors(hits, order=1, beam=1)
+            a, b = dec.visualization_text(), ref.visualization_text()
+            assert a == b, (name, variant, len(a), len(b))
+            assert a.count("activated_errors") > 12

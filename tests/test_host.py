@@ -220,3 +220,17 @@ def test_the_checker_side_sampler_draws_the_same_shots():
             if oracle.available(kind):
                 b = oracle.sample_dem_b8(dem, seed, shots, kind=kind)
                 assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (name, kind)
+
+
+def test_visualization_header_equals_the_reference():
+    """create_visualization (tesseract.h:50): at construction the Visualizer holds one line per detector coordinate and one
+    per compiled error (tesseract.cc:200-204, visualization.cc:5-24, common.cc:25-50, 90-94).  No GPU needed."""
+    from oracle import oracle
+    for name in ("surface_d5_r5_p0.002_X", "transcx_d3_p0.001_X"):
+        dem = W.load_dem(name)
+        mine = capi.Decoder(dem, host_only=True, create_visualization=True).visualization_text()
+        assert mine.count("\n") == mine.count("Detector D") + mine.count("Error{cost=")
+        for kind in ("reference", "port"):
+            if oracle.available(kind):
+                assert OracleDecoder(dem, kind=kind, create_visualization=True).visualization_text() == mine, (name, kind)
+    assert capi.Decoder(W.load_dem("surface_d5_r5_p0.002_X"), host_only=True).visualization_text() == ""
