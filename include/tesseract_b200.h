@@ -166,6 +166,14 @@ int64_t tsr_cross_check_detcost(const tsr_decoder* h, uint64_t trials, uint64_t 
  * [5]=A sum(|edets|+|fired neighbours|) over evaluated children [6]=V visited inserts+probes
  * [7]=searches run (distinct (order, beam) trials only). */
 int tsr_counters(tsr_decoder* h, uint64_t out[8], int reset);
+/* Visited-set audit (certified DEMs, no_revisit_dets).  The device's visited set holds 128-bit Zobrist fingerprints of
+ * the fired-detector sets; the reference holds the sets themselves (tesseract.cc:394, 475-476, 563-565).  With the audit
+ * on, every fingerprint hit — at a pop and at every child probe — is checked against the truth: the fired set of the node
+ * that made the entry is rebuilt from its error chain and compared bit for bit with the candidate's.  out[0] = hits
+ * checked, out[1] = hits whose sets differ (a fingerprint collision; two distinct sets collide with probability 2^-128
+ * per pair).  Slower; results are unchanged. */
+int tsr_set_visited_audit(tsr_decoder* h, int on);
+int tsr_visited_audit(tsr_decoder* h, uint64_t out[2], int reset);
 /* Phase profile of the CTA-per-search kernel (diagnostic; off by default, a few clock reads per expansion when on).
  * Ticks of the SM clock summed over every search CTA since the last reset, by phase of an expansion
  * (csrc/search_fast.cu): [0]=pop [1]=state rebuild + goal / visited test [2]=detector terms of the node

@@ -121,6 +121,8 @@ def lib() -> C.CDLL:
     L.tsr_group_last_batch_nnz.restype = C.c_uint64
     L.tsr_group_last_batch_errors.argtypes = [C.c_void_p, u64p, u64p]
     L.tsr_visualization_text.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.tsr_set_visited_audit.argtypes = [C.c_void_p, C.c_int]
+    L.tsr_visited_audit.argtypes = [C.c_void_p, u64p, C.c_int]
     L.tsr_set_profile.argtypes = [C.c_void_p, C.c_int]
     L.tsr_profile.argtypes = [C.c_void_p, u64p, C.c_int]
     L.tsr_stream.restype = C.c_void_p
@@ -152,7 +154,7 @@ EXPORTED_SYMBOLS = [
     "tsr_suggest_sparsify_reactivate_limit", "tsr_comm_unique_id", "tsr_comm_init_rank", "tsr_comm_world",
     "tsr_comm_allreduce_sum_u64", "tsr_nccl_version", "tsr_group_create", "tsr_group_destroy", "tsr_group_size",
     "tsr_group_member", "tsr_group_decode_b8", "tsr_group_last_batch_nnz", "tsr_group_last_batch_errors",
-    "tsr_visualization_text",
+    "tsr_visualization_text", "tsr_set_visited_audit", "tsr_visited_audit",
 ]
 
 
@@ -453,6 +455,15 @@ class Decoder:
         out = np.zeros(8, dtype=np.uint64)
         _check(lib().tsr_counters(self.h, _p(out, C.c_uint64), int(reset)))
         return dict(zip(["Q", "P", "X", "L", "S", "A", "V", "searches"], out.tolist()))
+
+    def set_visited_audit(self, on: bool):
+        _check(lib().tsr_set_visited_audit(self.h, int(on)))
+
+    def visited_audit(self, reset: bool = False):
+        """(fingerprint hits checked against the real fired sets, hits whose sets differ)."""
+        out = np.zeros(2, dtype=np.uint64)
+        _check(lib().tsr_visited_audit(self.h, _p(out, C.c_uint64), int(reset)))
+        return int(out[0]), int(out[1])
 
     def set_profile(self, on: bool):
         _check(lib().tsr_set_profile(self.h, int(on)))

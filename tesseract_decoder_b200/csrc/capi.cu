@@ -482,6 +482,11 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     p.work_counter = &sc->work;
     p.counters = h.d_counters.as<unsigned long long>();
     p.prof = h.profile ? h.d_prof.as<unsigned long long>() : nullptr;
+    if (h.visited_audit && h.fast && tier.visit_cap) {
+      p.vchain = h.d_vchain.as<uint32_t>();
+      p.audit = h.d_audit.as<unsigned long long>();
+      p.audit_scratch = h.d_audit_scratch.as<uint32_t>();
+    }
     if (h.trace_on) {
       p.trace = h.d_trace.as<uint32_t>();
       p.trace_cap = h.trace_cap;
@@ -1029,6 +1034,34 @@ int tsr_counters(tsr_decoder* h, uint64_t out[8], int reset) {
     CUDA_OK(cudaStreamSynchronize(h->stream));
     CUDA_OK(cudaMemcpyAsync(out, h->d_counters.p, 64, cudaMemcpyDeviceToHost, h->stream));
     if (reset) CUDA_OK(cudaMemsetAsync(h->d_counters.p, 0, 64, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int tsr_set_visited_audit(tsr_decoder* h, int on) {
+  return guarded([&] {
+    require_device(*h);
+    CUDA_OK(cudaSetDevice(h->device));
+    h->visited_audit = on != 0;
+    if (!on) return;
+    size_t entries = 0;  // the largest slots x visit_cap of any tier
+    for (const Tier& t : h->tiers) entries = std::max<size_t>(entries, (size_t)t.slots * t.visit_cap);
+    h->d_vchain.ensure(std::max<size_t>(entries * 4, 16));
+    h->d_audit.ensure(16);
+    h->d_audit_scratch.ensure(std::max<size_t>((size_t)h->tiers[0].slots * 32 * h->dt.nwords * 4, 16));
+    CUDA_OK(cudaMemsetAsync(h->d_audit.p, 0, 16, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int tsr_visited_audit(tsr_decoder* h, uint64_t out[2], int reset) {
+  return guarded([&] {
+    require_device(*h);
+    out[0] = out[1] = 0;
+    if (!h->d_audit.p) return;
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaMemcpyAsync(out, h->d_audit.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    if (reset) CUDA_OK(cudaMemsetAsync(h->d_audit.p, 0, 16, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
   });
 }

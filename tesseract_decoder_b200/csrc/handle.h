@@ -116,6 +116,7 @@ struct tsr_decoder {
   bool fast = false;          // decode with search_fast.cu (CTA per search) instead of search.cu
   bool instrumented = false;  // fast path: also count the reference's scanned row entries (counter S)
   bool profile = false;       // fast path: per-phase clock ticks (tsr_profile)
+  bool visited_audit = false; // fast path: check every visited-set fingerprint hit against the real fired sets
   bool hc_shared = false;
   std::vector<std::vector<uint64_t>> det_orders;
   std::vector<uint32_t> order_to_perm;  // det order index -> distinct permutation id
@@ -146,7 +147,7 @@ struct tsr_decoder {
   // Per-batch buffers.
   uint64_t max_batch = 0;
   tsr_impl::DevBuf d_dets, d_status, d_sol_len, d_fcost, d_sol, d_obs, d_cost, d_low, d_err_off, d_err_len, d_err, d_retry,
-      d_items, d_scalars, d_counters, d_prof, d_fired, d_order, d_bins, d_paused;
+      d_items, d_scalars, d_counters, d_prof, d_fired, d_order, d_bins, d_paused, d_vchain, d_audit, d_audit_scratch;
   uint32_t sol_stride = 0;
   bool collect_errors = true;
 

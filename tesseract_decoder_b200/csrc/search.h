@@ -124,6 +124,14 @@ struct SearchParams {
   unsigned int* work_counter = nullptr;
   unsigned long long* counters = nullptr;  // [8], see tsr_counters
   unsigned long long* prof = nullptr;      // [8] nullable, fast path only: per-phase ticks, see tsr_profile
+  // Visited-set audit (tsr_set_visited_audit; fast path).  The visited set stores 128-bit Zobrist fingerprints of fired
+  // sets, not the sets themselves (the reference keeps the bitsets: tesseract.cc:394, 475-476, 563-565).  With the audit
+  // on, every table entry also remembers the chain index of the node that inserted it, and every fingerprint HIT is
+  // checked against the truth: the hit node's fired set is rebuilt from its chain and compared bit for bit with the
+  // candidate's.  audit[0] counts the hits checked, audit[1] the hits whose sets differ (a collision; never observed).
+  uint32_t* vchain = nullptr;            // [n_slots][visit_cap] chain index per table entry
+  unsigned long long* audit = nullptr;   // [2]
+  uint32_t* audit_scratch = nullptr;     // [n_slots][32 warps][nwords]
   // Visualization log (debug decodes of one shot; visualization.cc, tesseract.cc:442-445, 478-481): per item, the chain
   // index of every node the reference would log — each expanded node and the goal — in pop order, and the address of
   // the item's chain arena.  Null = off.

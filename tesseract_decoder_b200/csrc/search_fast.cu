@@ -103,6 +103,9 @@ struct Smem {
   // push staging (phase 7): the other warps' regions, idle while warp 0 pushes
   uint4* stage;
   uint32_t stage_cap;  // in 16-byte nodes
+  // this search's pool slot and chain arena (visited-set audit)
+  uint32_t slot;
+  const ChainNode* chain;
   // sparsify (sparsify.cuh): this slot's active-entry masks [D][rw] in global memory (null when off), selection scratch
   const uint32_t* act;
   uint32_t rw;
@@ -657,13 +660,16 @@ __device__ __forceinline__ uint4 key_fix(uint4 k) {
   if ((k.x | k.y | k.z | k.w) == 0) k.w = 1;  // all-zero marks an empty slot
   return k;
 }
-__device__ bool visited_contains(const uint4* tab, uint64_t cap, uint4 key) {
+__device__ bool visited_contains(const uint4* tab, uint64_t cap, uint4 key, uint64_t& where) {
   key = key_fix(key);
   uint64_t i = ((uint64_t)key.x * cap) >> 32;
   while (true) {
     const uint4 v = __ldcg(tab + i);
     if ((v.x | v.y | v.z | v.w) == 0) return false;
-    if (key_eq(v, key)) return true;
+    if (key_eq(v, key)) {
+      where = i;
+      return true;
+    }
     if (++i == cap) i = 0;
   }
 }
@@ -677,8 +683,41 @@ __device__ int visited_insert(uint4* tab, uint64_t cap, uint4 key, uint64_t& whe
       where = i;
       return 1;
     }
-    if (key_eq(v, key)) return 0;
+    if (key_eq(v, key)) {
+      where = i;
+      return 0;
+    }
     if (++i == cap) i = 0;
+  }
+}
+
+// Visited-set audit: a fingerprint hit on table entry `where` claims that the candidate state — the node's fired set
+// `fbits`, with the `deg` detectors `dj` (one per lane) toggled for a child — equals the state of the node that inserted
+// the entry.  Rebuild that node's fired set from its chain and compare: scratch = candidate ^ root ^ toggles(chain) must
+// be all zero.
+__device__ void audit_hit(const SearchParams& p, const DeviceTables& t, const uint32_t* fbits, const uint32_t* rbits,
+                          const ChainNode* chain, uint32_t slot, uint64_t where, uint32_t deg, uint32_t dj, uint32_t lane) {
+  uint32_t* scratch = p.audit_scratch + ((size_t)slot * 32 + (threadIdx.x >> 5)) * t.nwords;
+  for (uint32_t w = lane; w < t.nwords; w += 32) scratch[w] = fbits[w] ^ rbits[w];
+  __syncwarp();
+  if (lane < deg) atomicXor(&scratch[dj >> 5], 1u << (dj & 31));
+  __syncwarp();
+  for (uint32_t at = __ldcg(p.vchain + (size_t)slot * p.visit_cap + where); at != kNoChain;) {
+    const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(chain + at));
+    const uint32_t eb = __ldg(t.e_off + raw.x), n = __ldg(t.e_off + raw.x + 1) - eb;
+    if (lane < n) {
+      const uint32_t d = (uint32_t)__ldg(t.e_det + eb + lane);
+      atomicXor(&scratch[d >> 5], 1u << (d & 31));
+    }
+    __syncwarp();
+    at = raw.y;
+  }
+  uint32_t diff = 0;
+  for (uint32_t w = lane; w < t.nwords; w += 32) diff |= scratch[w];
+  const bool differs = __any_sync(kFull, diff != 0);
+  if (lane == 0) {
+    atomicAdd(p.audit, 1ull);
+    if (differs) atomicAdd(p.audit + 1, 1ull);
   }
 }
 __device__ __forceinline__ uint4 warp_xor(uint4 k) {
@@ -739,10 +778,13 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
     z = warp_xor(z);
     key_xor(z, c.key);
     int seen = 0;
-    if (lane == 0) seen = visited_contains(vtab, p.visit_cap, z) ? 1 : 0;
+    uint64_t where = 0;
+    if (lane == 0) seen = visited_contains(vtab, p.visit_cap, z, where) ? 1 : 0;
     seen = __shfl_sync(kFull, seen, 0);
     ++ctr.V;
     if (seen) status = kChildDropped;
+    if (seen && p.audit)
+      audit_hit(p, t, sm.fbits, sm.rbits, sm.chain, sm.slot, __shfl_sync(kFull, where, 0), deg, dj, lane);
   }
   if (status == kChildOk) {
     // The child's state: toggle the error's detectors, block the min-detector row up to this entry.
@@ -1106,17 +1148,19 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
         } else {
           if (p.no_revisit) {  // tesseract.cc:475-476
             int inserted = 0;
+            uint64_t where = 0;
             if (lane == 0) {
               if ((c.n_visited + 1) * 2 > p.visit_cap) {
                 inserted = -1;
               } else {
-                uint64_t where = 0;
                 inserted = visited_insert(vtab, p.visit_cap, key, where);
                 if (inserted == 1 && c.n_visited < p.vlist_cap) vlist[c.n_visited] = (uint32_t)where;
+                if (inserted == 1 && p.vchain) p.vchain[(size_t)slot * p.visit_cap + where] = c.chain;
               }
             }
             inserted = __shfl_sync(kFull, inserted, 0);
             ++ctr.V;
+            if (inserted == 0 && p.audit) audit_hit(p, t, sm.fbits, sm.rbits, chain, slot, __shfl_sync(kFull, where, 0), 0, 0, lane);
             if (inserted < 0) {
               action = kActDone;
               status = kItemNodeOverflow;
@@ -1595,6 +1639,8 @@ __global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams
       item = p.item_ids ? __ldg(p.item_ids + work) : work;
       if (p.shot_order) item = __ldg(p.shot_order + work / p.n_trials) * p.n_trials + work % p.n_trials;
     }
+    sm.slot = cur_slot;
+    sm.chain = p.chain + (size_t)cur_slot * p.node_cap;
     const uint32_t status = run_search<kInstr, kBits>(p, sm, cur_slot, item, rec, ctr);
     __syncthreads();
     if (!rec) ++searches;

@@ -424,3 +424,33 @@ def test_visualization_log_equals_the_reference():
             a, b = dec.visualization_text(), ref.visualization_text()
             assert a == b, (name, variant, len(a), len(b))
             assert a.count("activated_errors") > 12
+
+
+def test_visited_set_fingerprints_never_stand_in_for_a_different_set():
+    """The reference's visited set holds the fired-detector bitsets themselves (tesseract.cc:394, 475-476, 563-565); the
+    device holds 128-bit Zobrist fingerprints of them.  The audit mode checks every fingerprint hit — pops and child probes
+    — against the real sets (rebuilt from the error chains): over more than 10^8 probes on the no-revisit workloads there
+    is not a single hit whose sets differ, and the answers are those of the unaudited run."""
+    total_probes = total_hits = 0
+    for cfg, shots in ((W.CONFIGS["C4"], 81920),
+                       (dict(dem="surface_d5_r5_p0.002_X", det_beam=5, pqlimit=200000, no_revisit_dets=True, num_det_orders=20,
+                             det_order_seed=2384753), 40000),
+                       (dict(dem="bb72_r6_p0.001_X", det_beam=W.INF_BEAM, pqlimit=20000, no_revisit_dets=True, num_det_orders=2), 400),
+                       (dict(dem="surface_d11_r11_p0.001_X", det_beam=3, beam_climbing=True, pqlimit=20000, no_revisit_dets=True,
+                             num_det_orders=0), 300)):
+        dem, kw = W.decoder_kwargs(cfg, capi.build_det_orders)
+        dec = capi.Decoder(dem, **kw)
+        dets, _ = capi.sample_dem_b8(dem, 606, shots, dec.num_detectors, dec.num_observables)
+        plain = dec.decode_batch_b8(dets, want_errors=False)
+        dec.set_visited_audit(True)
+        dec.counters(reset=True)
+        audited = dec.decode_batch_b8(dets, want_errors=False)
+        for k in ("obs", "cost", "low_confidence"):
+            assert np.array_equal(plain[k], audited[k]), k
+        hits, differing = dec.visited_audit(reset=True)
+        assert differing == 0, (cfg["dem"], hits, differing)
+        assert hits > 0
+        total_probes += dec.counters()["V"]
+        total_hits += hits
+    assert total_probes >= 10 ** 8, total_probes
+    assert total_hits >= 10 ** 6, total_hits

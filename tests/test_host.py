@@ -126,6 +126,23 @@ def test_det_orders_equal_the_reference(method):
             assert np.array_equal(capi.build_det_orders(dem, 7, method, seed), oracle.build_det_orders(dem, 7, method, seed, kind=KIND))
 
 
+def test_det_coordinate_orders_with_near_tied_projections():
+    """DetCoordinate (utils.cc:135-171) sorts detectors by their projection on a Gaussian direction.  4000 detectors whose
+    coordinates pair up to within a few ulps: the order of a near-tied pair depends on the last bit of  proj += c * dir
+    (fused or not) and of libstdc++'s normal_distribution.  csrc/detorder.cc is compiled with the reference build's
+    floating-point flavour, so the orders agree here too (a -ffp-contract=off build differs in 14 of these 48 orders)."""
+    if not oracle.available("reference"):
+        pytest.skip("coordinate orders are only restated in the reference build")
+    rng = np.random.default_rng(3)
+    D = 4000
+    base = rng.uniform(-50, 50, size=(D // 2, 3))
+    coords = np.concatenate([base, base * (1 + rng.integers(-2, 3, size=(D // 2, 3)) * 2.0 ** -52)])
+    dem = "\n".join([f"error(0.01) D{i} D{(i + 1) % D}" for i in range(D)] +
+                    [f"detector({float(c[0])!r}, {float(c[1])!r}, {float(c[2])!r}) D{i}" for i, c in enumerate(coords)])
+    for seed in range(6):
+        assert np.array_equal(capi.build_det_orders(dem, 8, 2, seed), oracle.build_det_orders(dem, 8, 2, seed, kind="reference"))
+
+
 def test_det_order_size_is_validated():  # tesseract.cc:178-184
     with pytest.raises(ValueError):
         capi.Decoder("error(0.1) D0 D1", det_orders=np.zeros((1, 5), dtype=np.uint64), host_only=True)
