@@ -556,9 +556,14 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
   CUDA_OK(cudaEventElapsedTime(&ms_search, h.ev[1], h.ev[2]));
 
   // Retry tiers for searches that outgrew their slot.
+  // Retried shots write their solutions to a separate buffer with longer rows (a search can also be sent here because
+  // its solution did not fit the tier-0 row, which is sized from the batch's largest syndrome).
+  const uint32_t retry_stride = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(std::max<uint64_t>(T.num_errors, 1), 65535),
+                                                              std::max<uint64_t>(8ull * h.sol_stride, 2048));
   for (size_t tier = 1; hs.retry_count > 0; ++tier) {
     if (tier >= h.tiers.size())
-      throw DeviceMemoryError("a search outgrew the device node pool (" + std::to_string(hs.retry_count) +
+      throw DeviceMemoryError("a search outgrew the device node pool, or its solution the " + std::to_string(retry_stride) +
+                              "-error solution buffer (" + std::to_string(hs.retry_count) +
                               " shot(s)); raise node_pool_bytes, lower pqlimit or set a finite beam");
     const uint32_t n_retry = hs.retry_count;
     std::vector<uint32_t> shot_ids(n_retry), item_ids((size_t)n_retry * U);
@@ -578,9 +583,18 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     if (tk.visit_cap)
       CUDA_OK(cudaMemsetAsync(h.pool.as<char>() + (size_t)tk.slots * tk.node_cap * 32, 0, (size_t)tk.slots * tk.visit_cap * 16, s));
     CUDA_OK(cudaEventRecord(h.ev[1], s));
-    CUDA_OK((cudaError_t)launch(search_params(tk, d_item_ids, (uint32_t)item_ids.size()), tk.slots, (uint32_t)item_ids.size(), false));
+    h.d_sol_retry.ensure(item_ids.size() * (size_t)retry_stride * 4);
+    tsr::SearchParams rp = search_params(tk, d_item_ids, (uint32_t)item_ids.size());
+    rp.sol = h.d_sol_retry.as<uint32_t>();
+    rp.sol_stride = retry_stride;
+    rp.sol_by_work = 1;
+    CUDA_OK((cudaError_t)launch(rp, tk.slots, (uint32_t)item_ids.size(), false));
     CUDA_OK(cudaEventRecord(h.ev[2], s));
-    CUDA_OK((cudaError_t)tsr::launch_resolve(resolve_params(d_shot_ids, n_retry, retry_b), s));
+    tsr::ResolveParams rr = resolve_params(d_shot_ids, n_retry, retry_b);
+    rr.sol = h.d_sol_retry.as<uint32_t>();
+    rr.sol_stride = retry_stride;
+    rr.sol_by_rank = 1;
+    CUDA_OK((cudaError_t)tsr::launch_resolve(rr, s));
     // Restore the tier-0 invariant (empty visited tables in the tier-0 layout).
     if (t0.visit_cap)
       CUDA_OK(cudaMemsetAsync(h.pool.as<char>() + (size_t)t0.slots * t0.node_cap * 32, 0, (size_t)t0.slots * t0.visit_cap * 16, s));

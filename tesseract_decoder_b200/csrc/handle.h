@@ -147,7 +147,7 @@ struct tsr_decoder {
   // Per-batch buffers.
   uint64_t max_batch = 0;
   tsr_impl::DevBuf d_dets, d_status, d_sol_len, d_fcost, d_sol, d_obs, d_cost, d_low, d_err_off, d_err_len, d_err, d_retry,
-      d_items, d_scalars, d_counters, d_prof, d_fired, d_order, d_bins, d_paused, d_vchain, d_audit, d_audit_scratch;
+      d_items, d_scalars, d_counters, d_prof, d_fired, d_order, d_bins, d_paused, d_vchain, d_audit, d_audit_scratch, d_sol_retry;
   uint32_t sol_stride = 0;
   bool collect_errors = true;
 

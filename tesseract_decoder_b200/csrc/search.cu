@@ -251,7 +251,7 @@ struct Counters {
 };
 
 // One search.  Returns the item status; on kItemOk the solution has been written.
-__device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t item, uint32_t lane, uint32_t* fbits,
+__device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t item, uint32_t sol_row, uint32_t lane, uint32_t* fbits,
                               uint32_t* rbits, uint16_t* st, uint32_t* sp_scratch, Counters& ctr, uint64_t& n_visited) {
   const DeviceTables& t = p.t;
   const uint32_t D = t.D, nwords = t.nwords;
@@ -377,7 +377,7 @@ __device__ uint8_t run_search(const SearchParams& p, uint32_t slot, uint32_t ite
         log_node(node.chain);
         if (node.depth > p.sol_stride) return kItemSolutionOverflow;
         if (lane == 0) {
-          uint32_t* out = p.sol + (size_t)item * p.sol_stride;
+          uint32_t* out = p.sol + (size_t)sol_row * p.sol_stride;
           uint32_t at = node.chain;
           for (uint32_t i = 0; i < node.depth; ++i) {
             const ChainNode cn = chain[at];
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(256) search_kernel(const SearchParams p) {
     uint32_t item = p.item_ids ? __ldg(p.item_ids + work) : work;
     if (p.shot_order) item = __ldg(p.shot_order + work / p.n_trials) * p.n_trials + work % p.n_trials;
     uint64_t n_visited = 0;
-    const uint8_t status = run_search(p, slot, item, lane, fbits, rbits, st, sp_scratch, ctr, n_visited);
+    const uint8_t status = run_search(p, slot, item, p.sol_by_work ? work : item, lane, fbits, rbits, st, sp_scratch, ctr, n_visited);
     __syncwarp();
     if (p.t.sp_on)  // back to the mandatory masks for the slot's next search
       sparsify::restore(p.t, rbits, p.sp_act + (size_t)slot * D * p.t.sp_rw, 0, 1, lane, [] { __syncwarp(); });
@@ -688,31 +688,33 @@ __global__ void resolve_kernel(const ResolveParams p) {
   const uint32_t shot = p.shot_ids ? p.shot_ids[k] : k;
   const DeviceTables& t = p.t;
   double best = 1.7976931348623157e308;  // std::numeric_limits<double>::max()
-  int64_t best_item = -1;
+  int64_t best_item = -1, best_row = -1;
   bool overflow = false;
   for (uint32_t u = 0; u < p.n_trials; ++u) overflow |= p.status[(size_t)shot * p.n_trials + u] >= kItemNodeOverflow;
   if (overflow) {
     if (p.retry_shots) p.retry_shots[atomicAdd(p.retry_count, 1u)] = shot;
     return;
   }
+  const size_t row0 = p.sol_by_rank ? (size_t)k * p.n_trials : (size_t)shot * p.n_trials;
   for (uint32_t lt = 0; lt < p.n_literal; ++lt) {
     const size_t item = (size_t)shot * p.n_trials + p.literal_to_trial[lt];
     if (p.status[item] != kItemOk) continue;
     // cost_from_errors: sum in buffer order from 0.0 (tesseract.cc:618-628).
-    const uint32_t* s = p.sol + item * p.sol_stride;
+    const uint32_t* s = p.sol + (row0 + p.literal_to_trial[lt]) * p.sol_stride;
     const uint32_t n = p.sol_len[item];
     double c = 0;
     for (uint32_t i = 0; i < n; ++i) c = __dadd_rn(c, t.e_cost[s[i]]);
     if (c < best) {  // strict: the earliest trial wins ties (tesseract.cc:314-317)
       best = c;
       best_item = (int64_t)item;
+      best_row = (int64_t)(row0 + p.literal_to_trial[lt]);
     }
   }
   const bool low = best_item < 0;
   if (p.low_conf_out) p.low_conf_out[shot] = low ? 1 : 0;
   if (p.cost_out) p.cost_out[shot] = low ? 0.0 : best;
   const uint32_t n = low ? 0 : p.sol_len[best_item];
-  const uint32_t* s = low ? nullptr : p.sol + (size_t)best_item * p.sol_stride;
+  const uint32_t* s = low ? nullptr : p.sol + (size_t)best_row * p.sol_stride;
   if (p.obs_out) {
     uint8_t* o = p.obs_out + (size_t)shot * p.obs_stride;
     for (uint32_t b = 0; b < p.obs_stride; ++b) o[b] = 0;

@@ -117,6 +117,7 @@ struct SearchParams {
   int hc_shared = 0;         // fast path: the per-detector terms of the expanded node live in shared memory
   // Per-item outputs.
   uint32_t sol_stride = 0;
+  int sol_by_work = 0;          // retry tiers: the solution row is the work index (position in item_ids), not the item id
   uint32_t* sol = nullptr;      // [items][sol_stride] compiled error ids, root -> leaf
   uint32_t* sol_len = nullptr;  // [items]
   uint8_t* status = nullptr;    // [items] ItemStatus
@@ -158,6 +159,7 @@ struct ResolveParams {
   uint32_t n_literal = 1;        // literal trials of the reference loop
   const uint32_t* literal_to_trial = nullptr;  // [n_literal]
   uint32_t sol_stride = 0;
+  int sol_by_rank = 0;           // retry tiers: the row of (k-th listed shot, trial u) is k * n_trials + u
   const uint32_t* sol = nullptr;
   const uint32_t* sol_len = nullptr;
   const uint8_t* status = nullptr;

@@ -910,8 +910,8 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
 // ---- one search (whole CTA).  Returns the item status; on kItemOk the solution has been written. ------
 
 template <bool kInstr, bool kBits>
-__device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t slot, uint32_t item, const ResumeRec* resume,
-                               Counters& ctr) {
+__device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t slot, uint32_t item, uint32_t sol_row,
+                               const ResumeRec* resume, Counters& ctr) {
   const DeviceTables& t = p.t;
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
   const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
@@ -1135,7 +1135,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           if (c.depth > p.sol_stride) {
             status = kItemSolutionOverflow;
           } else if (lane == 0) {
-            uint32_t* out = p.sol + (size_t)item * p.sol_stride;
+            uint32_t* out = p.sol + (size_t)sol_row * p.sol_stride;
             uint32_t at = c.chain;
             for (uint32_t i = 0; i < c.depth; ++i) {
               const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(chain + at));
@@ -1621,13 +1621,14 @@ __global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams
   const uint32_t n_paused = p.resume ? min(*p.paused_count, p.paused_cap) : 0u;
   uint32_t resume_at = blockIdx.x;
   while (true) {
-    uint32_t item, cur_slot = slot;
+    uint32_t item, cur_slot = slot, sol_row = 0;
     const ResumeRec* rec = nullptr;
     if (p.resume) {  // continue paused searches (one per CTA and round), each in the pool slot it was started in
       if (resume_at >= n_paused) break;
       rec = p.paused + resume_at;
       resume_at += gridDim.x;
       item = rec->item;
+      sol_row = item;
       cur_slot = rec->slot;
       sm.hc = p.hc_shared ? sm.hc : p.hcache + (size_t)cur_slot * D;
       sm.act = p.t.sp_on ? p.sp_act + (size_t)cur_slot * D * p.t.sp_rw : nullptr;
@@ -1638,10 +1639,11 @@ __global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams
       if (work >= p.n_work) break;
       item = p.item_ids ? __ldg(p.item_ids + work) : work;
       if (p.shot_order) item = __ldg(p.shot_order + work / p.n_trials) * p.n_trials + work % p.n_trials;
+      sol_row = p.sol_by_work ? work : item;
     }
     sm.slot = cur_slot;
     sm.chain = p.chain + (size_t)cur_slot * p.node_cap;
-    const uint32_t status = run_search<kInstr, kBits>(p, sm, cur_slot, item, rec, ctr);
+    const uint32_t status = run_search<kInstr, kBits>(p, sm, cur_slot, item, sol_row, rec, ctr);
     __syncthreads();
     if (!rec) ++searches;
     if (tid == 0) {
