@@ -374,6 +374,41 @@ def run_side_workload(args, key, rank, world, local):
     return rec
 
 
+def api_legs(args, local):
+    """The entry points a reference user actually calls, on BASELINE configs[0] (surface code d=5): the pybind11
+    sinter decoder's decode_shots_bit_packed with a pageable numpy array (tesseract_sinter_compat.pybind.h:45-97) and the
+    latency of a single-shot decode_to_errors (tesseract.cc:295-347; the reference CLI and Python decode call it per shot)."""
+    import tesseract_decoder_b200 as td
+    from tesseract_decoder_b200 import capi
+    cfg = W.CONFIGS["C1"]
+    dem, kw = W.decoder_kwargs(cfg, capi.build_det_orders)
+    S = 1 << 18
+    dets, _ = capi.sample_dem_b8(dem, 1000, S)
+
+    class Dem:
+        def __str__(self):
+            return dem
+    sinter = td.tesseract_sinter_compat.TesseractSinterDecoder(det_beam=kw["det_beam"], beam_climbing=False, no_revisit_dets=kw["no_revisit_dets"],
+                                                                 pqlimit=kw["pqlimit"], num_det_orders=0)
+    compiled = sinter.compile_decoder_for_dem(dem=Dem())
+    compiled.decode_shots_bit_packed(bit_packed_detection_event_data=dets[:4096])
+    t0 = time.perf_counter()
+    for _ in range(3):
+        compiled.decode_shots_bit_packed(bit_packed_detection_event_data=dets)
+    pybind_rate = 3 * S / (time.perf_counter() - t0)
+    dec = capi.Decoder(dem, device=local, **kw)
+    bits = np.unpackbits(dets[:256], axis=1, bitorder="little")[:, :dec.num_detectors]
+    hits = [np.nonzero(r)[0] for r in bits]
+    for h in hits[:16]:
+        dec.decode_to_errors(h)
+    t0 = time.perf_counter()
+    for h in hits:
+        dec.decode_to_errors(h)
+    single_ms = 1e3 * (time.perf_counter() - t0) / len(hits)
+    return {"workload": "surface code d=5 (configs[0])", "pybind_decode_shots_bit_packed_shots_per_s": round(pybind_rate, 1),
+            "pybind_input": f"pageable numpy uint8[{S}, {dets.shape[1]}]", "single_shot_decode_to_errors_ms": round(single_ms, 4)}
+
+
 def strong_leg(args, b, rank, world):
     """Strong scaling: a FIXED batch of T shots (the same on every rank: seed 2000) dealt out in interleaved chunks of
     4096 shots (rank r decodes chunks r, r+N, ...), decoded end to end from host buffers, counters summed
@@ -501,6 +536,10 @@ def run_b200(args, wl, rank, world, local):
         line["tally"]["mismatches"] = cpu["mismatches"]
     if rank == 0 and world == 1 and not args.no_side and args.workload == "bb144" and not args.shots:
         del b
+        try:
+            line["api"] = api_legs(args, local)
+        except Exception as e:
+            line["api"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         side = []
         for key in SIDE_ORDER:
             try:

@@ -82,6 +82,7 @@ struct alignas(16) Ctl {
 struct Smem {
   Ctl* ctl;
   uint16_t* rank;   // [n_costs * nstride]
+  double* fq;       // [n_costs * nstride] fl(cost / count) per class (copy of DeviceTables::fquot)
   uint32_t* rbits;  // [nwords]
   uint32_t* fbits;  // [nwords]
   uint16_t* pst;    // [dpad]
@@ -122,7 +123,7 @@ __host__ __device__ inline uint32_t dpad_of(uint32_t D) {
 }
 
 struct Layout {
-  uint32_t off_rank, off_rbits, off_fbits, off_pst, off_hc, off_cost, off_meta, off_clist, off_st, total;
+  uint32_t off_fq, off_rank, off_rbits, off_fbits, off_pst, off_hc, off_cost, off_meta, off_clist, off_st, total;
   uint32_t off_pbb, off_fz, warp_stride, w_cf, w_tl, w_hv, w_fl, w_bl, w_gc, w_nzw;  // w_*: offsets inside a warp's region
   uint32_t off_sp, stage_extra;
 };
@@ -131,6 +132,8 @@ __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint3
                                                bool sparsify = false) {
   Layout L;
   uint32_t at = round16(sizeof(Ctl));
+  L.off_fq = at;
+  at += round16(rank_entries * 8);
   L.off_rank = at;
   at += round16(rank_entries * 2);
   L.off_rbits = at;
@@ -238,10 +241,9 @@ __device__ __forceinline__ uint32_t entry_size(const DeviceTables& t, uint32_t r
 // unblocked error touches x.  kInstr additionally counts the row entries the reference loop would have
 // visited before its early exit (counter S of SURVEY.md §8d).
 template <bool kInstr>
-__device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t* st, const uint16_t* rank, const uint32_t* act,
-                                           uint32_t x, uint32_t lane, unsigned long long& scanned) {
-  const uint32_t roff = __ldg(t.row_off + x);
-  const uint32_t rlen = __ldg(t.row_off + x + 1) - roff;
+__device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t* st, const uint16_t* rank, const double* fq,
+                                           const uint32_t* act, uint32_t x, uint32_t roff, uint32_t rlen, uint32_t lane,
+                                           unsigned long long& scanned) {
   const uint32_t Td = st[x] & kThr;
   uint32_t best = kKeyInf, best_cls = 0;
   uint32_t carry = kKeyInf;  // kInstr: best rank before this chunk
@@ -290,7 +292,24 @@ __device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t
   if (m == kKeyInf) return __longlong_as_double(0x7FF0000000000000LL);
   const int winner = __ffs((int)__ballot_sync(kFull, best == m)) - 1;
   const uint32_t cls = __shfl_sync(kFull, best_cls, winner);
-  return __ldg(t.fquot + cls);
+  return fq[cls];
+}
+
+// Row extents of up to 32 detectors at once (lane i asks for detector x; one memory round trip for all of them), and
+// with `prefetch` the row's records on their way into L1: the scans that follow walk the rows one after the other, each
+// a chain of dependent loads, and would otherwise pay an L2 round trip per 64 entries.
+__device__ __forceinline__ void row_extent(const DeviceTables& t, uint32_t x, bool valid, bool prefetch, uint32_t& roff,
+                                           uint32_t& rlen) {
+  roff = rlen = 0;
+  if (valid) {
+    roff = __ldg(t.row_off + x);
+    rlen = __ldg(t.row_off + x + 1) - roff;
+    if (prefetch) {
+      const char* p = reinterpret_cast<const char*>(t.frec_a + roff);
+      const char* end = reinterpret_cast<const char*>(t.frec_a + roff + rlen);
+      for (const char* q = (const char*)((uintptr_t)p & ~(uintptr_t)127); q < end; q += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+    }
+  }
 }
 
 
@@ -506,7 +525,7 @@ __device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm
         bcls = oc;
       }
     }
-    if (active && wl == 0) sm.hv[k] = best == kKeyInf ? __longlong_as_double(0x7FF0000000000000LL) : __ldg(t.fquot + bcls);
+    if (active && wl == 0) sm.hv[k] = best == kKeyInf ? __longlong_as_double(0x7FF0000000000000LL) : sm.fq[bcls];
   }
   __syncwarp();
 }
@@ -820,12 +839,15 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
       if (lane < deg && !((fired_mask >> lane) & 1)) sm.tl[__popc(newly & ((1u << lane) - 1u))] = (uint16_t)dj;
       nt = (uint32_t)__popc(newly);
     } else {
+      uint32_t my_off, my_len;  // row extents of the error's detectors, fetched together
+      row_extent(t, dj, lane < deg, lane < deg && !((fired_mask >> lane) & 1), my_off, my_len);
       for (uint32_t k = 0; k < deg; ++k) {
         const uint32_t d = __shfl_sync(kFull, dj, (int)k);
+        const uint32_t roff = __shfl_sync(kFull, my_off, (int)k), rlen = __shfl_sync(kFull, my_len, (int)k);
         if ((fired_mask >> k) & 1) {
           cost = __dsub_rn(cost, sm.hc[d]);
         } else {
-          const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, sm.act, d, lane, ctr.S), p.det_penalty);
+          const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, sm.fq, sm.act, d, roff, rlen, lane, ctr.S), p.det_penalty);
           cost = __dadd_rn(cost, h);
         }
       }
@@ -880,12 +902,22 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
         while (nz) {
           const uint32_t l = (uint32_t)__ffs((int)nz) - 1;
           nz &= nz - 1;
-          uint32_t word = __shfl_sync(kFull, mine, (int)l);
-          while (word) {
-            const uint32_t od = __shfl_sync(kFull, w, (int)l) * 32 + (uint32_t)__ffs((int)word) - 1;
-            word &= word - 1;
+          const uint32_t word = __shfl_sync(kFull, mine, (int)l), wbase = __shfl_sync(kFull, w, (int)l) * 32;
+          // lane i takes the i-th set bit: the extents of all the word's rows arrive in one round trip
+          const uint32_t cnt = (uint32_t)__popc(word);
+          uint32_t my_od = 0;
+          if (lane < cnt) {
+            uint32_t rest = word;
+            for (uint32_t i = 0; i < lane; ++i) rest &= rest - 1;
+            my_od = wbase + (uint32_t)__ffs((int)rest) - 1;
+          }
+          uint32_t my_off, my_len;
+          row_extent(t, my_od, lane < cnt, lane < cnt, my_off, my_len);
+          for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t od = __shfl_sync(kFull, my_od, (int)i);
+            const uint32_t roff = __shfl_sync(kFull, my_off, (int)i), rlen = __shfl_sync(kFull, my_len, (int)i);
             cost = __dsub_rn(cost, sm.hc[od]);
-            const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, sm.act, od, lane, ctr.S), p.det_penalty);
+            const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, sm.fq, sm.act, od, roff, rlen, lane, ctr.S), p.det_penalty);
             cost = __dadd_rn(cost, h);
           }
         }
@@ -1242,11 +1274,19 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
         }
       } else {
         for (uint32_t w = warp; w < nwords; w += nwarps) {
-          uint32_t word = sm.fbits[w];
-          while (word) {
-            const uint32_t d = w * 32 + (uint32_t)__ffs((int)word) - 1;
-            word &= word - 1;
-            const double h = __dadd_rn(scan_row<kInstr>(t, sm.st, sm.rank, sm.act, d, lane, ctr.S), p.det_penalty);
+          const uint32_t word = sm.fbits[w], cnt = (uint32_t)__popc(word);
+          uint32_t my_d = 0;
+          if (lane < cnt) {
+            uint32_t rest = word;
+            for (uint32_t i = 0; i < lane; ++i) rest &= rest - 1;
+            my_d = w * 32 + (uint32_t)__ffs((int)rest) - 1;
+          }
+          uint32_t my_off, my_len;
+          row_extent(t, my_d, lane < cnt, lane < cnt, my_off, my_len);
+          for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t d = __shfl_sync(kFull, my_d, (int)i);
+            const uint32_t roff = __shfl_sync(kFull, my_off, (int)i), rlen = __shfl_sync(kFull, my_len, (int)i);
+            const double h = __dadd_rn(scan_row<kInstr>(t, sm.st, sm.rank, sm.fq, sm.act, d, roff, rlen, lane, ctr.S), p.det_penalty);
             if (lane == 0) sm.hc[d] = h;
           }
         }
@@ -1586,6 +1626,7 @@ __global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams
   Smem sm;
   sm.ctl = reinterpret_cast<Ctl*>(base);
   sm.rank = reinterpret_cast<uint16_t*>(base + L.off_rank);
+  sm.fq = reinterpret_cast<double*>(base + L.off_fq);
   sm.rbits = reinterpret_cast<uint32_t*>(base + L.off_rbits);
   sm.fbits = reinterpret_cast<uint32_t*>(base + L.off_fbits);
   sm.pst = reinterpret_cast<uint16_t*>(base + L.off_pst);
@@ -1609,7 +1650,10 @@ __global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams
   sm.sp_scratch = reinterpret_cast<uint32_t*>(base + L.off_sp);
   sm.stage = reinterpret_cast<uint4*>(base + L.off_st + L.warp_stride);
   sm.stage_cap = ((nwarps - 1) * L.warp_stride + L.stage_extra) / 16;
-  for (uint32_t i = tid; i < rank_entries; i += blockDim.x) sm.rank[i] = __ldg(p.t.frank + i);
+  for (uint32_t i = tid; i < rank_entries; i += blockDim.x) {
+    sm.rank[i] = __ldg(p.t.frank + i);
+    sm.fq[i] = __ldg(p.t.fquot + i);
+  }
   if (tid == 0) {
     for (auto& v : sm.ctl->prof) v = 0;
     sm.ctl->prof_last = clock64();
