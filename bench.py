@@ -71,7 +71,7 @@ WORKLOADS = {
     # 4.105 CPU-seconds per shot on their hardware
     "bb144_p1e-3_longbeam": dict(cfg=dict(dem="bb144_r12_p0.001_X", det_beam=20, beam_climbing=True, pqlimit=1000000,
                                           no_revisit_dets=True, num_det_orders=21), shots=1024, tag="bb144 p=1e-3 long-beam",
-                                 side=(256, 1, 1, 4.0), counters_from="port",
+                                 side=(256, 1, 1, 4.0), counters_from="port", cpu_first=16, counter_shots=8,
                                  name="bivariate-bicycle [[144,12,12]] r=12 si1000 p=1e-3 X, --beam 20 --beam-climbing --num-det-orders 21 "
                                       "--pqlimit 1000000 --no-revisit-dets (the reference's long-beam sweep point)"),
     "bb144_p5e-4": dict(cfg=dict(W.CONFIGS["C4"], dem="bb144_r12_p0.0005_X"), shots=4096, tag="C4 bb144 p=5e-4",
@@ -161,9 +161,9 @@ def cpu_decoder(dem, kw, threads, kind=None):
     return oracle.OracleDecoder(dem, kind=kind, num_threads=threads, **kw), kind
 
 
-def cpu_sample(dec, dets, target_seconds, threads):
+def cpu_sample(dec, dets, target_seconds, threads, n_first=None):
     """Decode a prefix of `dets` sized for about target_seconds of wall time; returns (n, wall, result)."""
-    n0 = min(len(dets), max(2 * threads, 16))
+    n0 = min(len(dets), n_first or max(2 * threads, 16))
     r0 = dec.decode_batch_b8(dets[:n0])
     if r0["wall_seconds"] >= target_seconds or n0 == len(dets):
         return n0, r0["wall_seconds"], r0
@@ -320,7 +320,7 @@ class Bench:
         (observables, cost, low-confidence flag and the error lists)."""
         threads = os.cpu_count() or 1
         cpu, kind = cpu_decoder(self.dem, self.kw, threads, kind)
-        n, wall, ref = cpu_sample(cpu, self.dets, seconds, threads)
+        n, wall, ref = cpu_sample(cpu, self.dets, seconds, threads, self.wl.get("cpu_first"))
         self.dec.set_collect_errors(True)
         out = self.dec.decode_batch_b8(self.dets[:n])
         self.dec.set_collect_errors(False)
@@ -341,8 +341,9 @@ class Bench:
             from oracle import oracle
             port = oracle.OracleDecoder(self.dem, kind="port", num_threads=threads,
                                         **{k: v for k, v in self.kw.items() if not (k == "at_most_two_errors_per_detector" and not v)})
-            port.decode_batch_b8(self.dets[:n])
-            ctr = port.counters()
+            n_ctr = min(n, self.wl.get("counter_shots", n))
+            port.decode_batch_b8(self.dets[:n_ctr])
+            ctr = dict(port.counters(), shots=n_ctr)
         return rec, n, ctr
 
 
@@ -357,8 +358,8 @@ def run_side_workload(args, key, rank, world, local):
     (dt2, _, _), counts2, _, _, _ = b.timed(b.step_e2e, steps, warmup)
     cpu, n_cpu, port_ctr = b.compare_with_cpu(cpu_s, wl.get("cpu_kind"), want_counters=wl.get("counters_from") == "port")
     if port_ctr is not None:  # counters of the CPU port on its prefix, scaled to the batch (distinct trials == literal trials here)
-        b_shot = algorithmic_bytes(port_ctr, n_cpu, b.D, b.O) / n_cpu
-        src = f"CPU port on {n_cpu} shots"
+        b_shot = algorithmic_bytes(port_ctr, port_ctr["shots"], b.D, b.O) / port_ctr["shots"]
+        src = f"CPU port on {port_ctr['shots']} shots"
     else:
         c1 = b.instrumented_counters()
         assert all(ctr[k] == c1[k] * steps for k in ("Q", "P", "X", "L", "V")), (ctr, c1)

@@ -296,7 +296,7 @@ void init_device(tsr_decoder& h) {
       uint32_t wide = 32;
       if (const char* e = std::getenv("TSR_WIDE_WARPS")) wide = (uint32_t)std::max(0, std::atoi(e));
       int occ_wide = 0;
-      while (wide > w && (occ_wide = tsr::search_fast_max_blocks_per_sm(dt, wide, h.hc_shared, h.bits)) == 0) wide /= 2;
+      while (wide > w && (occ_wide = tsr::search_fast_max_blocks_per_sm(dt, wide, h.hc_shared, h.bits, true)) == 0) wide /= 2;
       if (wide > w && occ_wide > 0) {
         h.wpb_wide = wide;
         h.blocks_wide = (uint32_t)(h.sm_count * occ_wide);
@@ -530,16 +530,16 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     if (!h.fast)
       return tsr::launch_search(sp_, std::min<uint32_t>((tier_slots + h.wpb - 1) / h.wpb, (n_work + h.wpb - 1) / h.wpb), h.wpb, s);
     const bool bits = h.bits && !h.instrumented;
-    if (!widen) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, h.instrumented, bits, s);
-    if (!tier0) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb_wide, false, bits, s);
+    if (!widen) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, h.instrumented, bits, false, s);
+    if (!tier0) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb_wide, false, bits, true, s);
     sp_.expansion_budget = h.expansion_budget;
     sp_.paused = h.d_paused.as<tsr::ResumeRec>();
     sp_.paused_count = &sc->paused_count;
     sp_.paused_cap = tier_slots;
-    if (int e = tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, false, bits, s)) return e;
+    if (int e = tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, false, bits, false, s)) return e;
     sp_.expansion_budget = 0;
     sp_.resume = 1;
-    return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, h.blocks_wide), h.wpb_wide, false, bits, s);
+    return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, h.blocks_wide), h.wpb_wide, false, bits, true, s);
   };
   // An item no CTA got to must never pass for decoded: every status starts as "overflow" (-> retried in the next tier).
   CUDA_OK(cudaMemsetAsync(h.d_status.p, tsr::kItemNodeOverflow, items, s));

@@ -203,9 +203,10 @@ int launch_resolve(const ResolveParams& p, void* stream);
 // Fast path (search_fast.cu): one CTA of `warps` warps per search.
 // `bits` selects the bit-sliced row scan (needs the bs_* tables); otherwise rows are scanned entry per lane, and
 // `instrumented` additionally counts the reference's visited row entries.
-int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, bool bits, void* stream);
-uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits);  // t.sp_on adds the selection scratch
-int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits);
+// `latency` selects the variant tuned for a lone search per SM (wide CTAs: tail and retry tiers; entry-per-lane scan only).
+int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, bool bits, bool latency, void* stream);
+uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits, bool latency = false);  // t.sp_on adds the selection scratch
+int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits, bool latency = false);
 // Shared memory bytes one search warp needs for a DEM with D detectors (sparsify adds the selection scratch).
 uint32_t search_smem_bytes_per_warp(uint32_t D, bool sparsify);
 // Resident blocks per SM of the search kernel for this block shape (0 on failure).

@@ -82,7 +82,7 @@ struct alignas(16) Ctl {
 struct Smem {
   Ctl* ctl;
   uint16_t* rank;   // [n_costs * nstride]
-  double* fq;       // [n_costs * nstride] fl(cost / count) per class (copy of DeviceTables::fquot)
+  double* fq;       // latency variant: [n_costs * nstride] copy of DeviceTables::fquot (else null)
   uint32_t* rbits;  // [nwords]
   uint32_t* fbits;  // [nwords]
   uint16_t* pst;    // [dpad]
@@ -123,17 +123,15 @@ __host__ __device__ inline uint32_t dpad_of(uint32_t D) {
 }
 
 struct Layout {
-  uint32_t off_fq, off_rank, off_rbits, off_fbits, off_pst, off_hc, off_cost, off_meta, off_clist, off_st, total;
+  uint32_t off_rank, off_rbits, off_fbits, off_pst, off_hc, off_cost, off_meta, off_clist, off_st, total;
   uint32_t off_pbb, off_fz, warp_stride, w_cf, w_tl, w_hv, w_fl, w_bl, w_gc, w_nzw;  // w_*: offsets inside a warp's region
-  uint32_t off_sp, stage_extra;
+  uint32_t off_sp, off_fq, stage_extra;
 };
 __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint32_t rank_entries, uint32_t max_row_len,
                                                uint32_t warps, bool hc_shared, uint32_t bs_group = 0, uint32_t bs_cap = 0,
-                                               bool sparsify = false) {
+                                               bool sparsify = false, bool latency = false) {
   Layout L;
   uint32_t at = round16(sizeof(Ctl));
-  L.off_fq = at;
-  at += round16(rank_entries * 8);
   L.off_rank = at;
   at += round16(rank_entries * 2);
   L.off_rbits = at;
@@ -156,6 +154,8 @@ __host__ __device__ inline Layout make_layout(uint32_t D, uint32_t nwords, uint3
   at += round16(nwords * 2);
   L.off_sp = at;
   if (sparsify) at += round16(sparsify::kScratchWords * 4);
+  L.off_fq = at;
+  if (latency) at += round16(rank_entries * 8);
   L.off_st = at;
   // this warp's region: the private state copy (entry-per-lane scans) or the bit-sliced scratch
   uint32_t w = bs_group ? 0 : dpad_of(D) * 2;
@@ -240,10 +240,30 @@ __device__ __forceinline__ uint32_t entry_size(const DeviceTables& t, uint32_t r
 // get_detcost (tesseract.cc:128-154) without det_penalty for fired detector x in state st; +inf when no
 // unblocked error touches x.  kInstr additionally counts the row entries the reference loop would have
 // visited before its early exit (counter S of SURVEY.md §8d).
-template <bool kInstr>
-__device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t* st, const uint16_t* rank, const double* fq,
-                                           const uint32_t* act, uint32_t x, uint32_t roff, uint32_t rlen, uint32_t lane,
-                                           unsigned long long& scanned) {
+// Row extents of up to 32 detectors at once (lane i asks for detector x: one memory round trip for all of them), with the
+// rows' records on their way into L1.  Latency variant of the kernel only (a lone search per SM): there the scans
+// that follow are one chain of dependent loads after the other; with many searches per SM the extra instructions
+// cost more than the latency they hide (measured: surface d=5 1.41 M -> 1.17 M shots/s).
+__device__ __forceinline__ void row_extent(const DeviceTables& t, uint32_t x, bool valid, bool prefetch, uint32_t& roff,
+                                           uint32_t& rlen) {
+  roff = rlen = 0;
+  if (valid) {
+    roff = __ldg(t.row_off + x);
+    rlen = __ldg(t.row_off + x + 1) - roff;
+    if (prefetch) {
+      const char* q = reinterpret_cast<const char*>((uintptr_t)(t.frec_a + roff) & ~(uintptr_t)127);
+      const char* end = reinterpret_cast<const char*>(t.frec_a + roff + rlen);
+      for (; q < end; q += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+    }
+  }
+}
+
+template <bool kInstr, bool kLat = false>
+__device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t* st, const uint16_t* rank, const uint32_t* act,
+                                           uint32_t x, uint32_t lane, unsigned long long& scanned, uint32_t roff_in = 0,
+                                           uint32_t rlen_in = 0, const double* fq = nullptr) {
+  const uint32_t roff = kLat ? roff_in : __ldg(t.row_off + x);
+  const uint32_t rlen = kLat ? rlen_in : __ldg(t.row_off + x + 1) - roff;
   const uint32_t Td = st[x] & kThr;
   uint32_t best = kKeyInf, best_cls = 0;
   uint32_t carry = kKeyInf;  // kInstr: best rank before this chunk
@@ -292,24 +312,7 @@ __device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t
   if (m == kKeyInf) return __longlong_as_double(0x7FF0000000000000LL);
   const int winner = __ffs((int)__ballot_sync(kFull, best == m)) - 1;
   const uint32_t cls = __shfl_sync(kFull, best_cls, winner);
-  return fq[cls];
-}
-
-// Row extents of up to 32 detectors at once (lane i asks for detector x; one memory round trip for all of them), and
-// with `prefetch` the row's records on their way into L1: the scans that follow walk the rows one after the other, each
-// a chain of dependent loads, and would otherwise pay an L2 round trip per 64 entries.
-__device__ __forceinline__ void row_extent(const DeviceTables& t, uint32_t x, bool valid, bool prefetch, uint32_t& roff,
-                                           uint32_t& rlen) {
-  roff = rlen = 0;
-  if (valid) {
-    roff = __ldg(t.row_off + x);
-    rlen = __ldg(t.row_off + x + 1) - roff;
-    if (prefetch) {
-      const char* p = reinterpret_cast<const char*>(t.frec_a + roff);
-      const char* end = reinterpret_cast<const char*>(t.frec_a + roff + rlen);
-      for (const char* q = (const char*)((uintptr_t)p & ~(uintptr_t)127); q < end; q += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
-    }
-  }
+  return kLat ? fq[cls] : __ldg(t.fquot + cls);
 }
 
 
@@ -525,7 +528,7 @@ __device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm
         bcls = oc;
       }
     }
-    if (active && wl == 0) sm.hv[k] = best == kKeyInf ? __longlong_as_double(0x7FF0000000000000LL) : sm.fq[bcls];
+    if (active && wl == 0) sm.hv[k] = best == kKeyInf ? __longlong_as_double(0x7FF0000000000000LL) : __ldg(t.fquot + bcls);
   }
   __syncwarp();
 }
@@ -769,7 +772,7 @@ __device__ __forceinline__ void prof_mark(const SearchParams& p, Ctl& c, uint32_
 
 // ---- one child (one warp): tesseract.cc:533-606 up to, not including, the push ----------------------
 
-template <bool kInstr, bool kBits>
+template <bool kInstr, bool kBits, bool kLat>
 __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm, uint32_t j, uint32_t lane,
                                            const uint4* vtab, Counters& ctr) {
   const DeviceTables& t = p.t;
@@ -839,15 +842,15 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
       if (lane < deg && !((fired_mask >> lane) & 1)) sm.tl[__popc(newly & ((1u << lane) - 1u))] = (uint16_t)dj;
       nt = (uint32_t)__popc(newly);
     } else {
-      uint32_t my_off, my_len;  // row extents of the error's detectors, fetched together
-      row_extent(t, dj, lane < deg, lane < deg && !((fired_mask >> lane) & 1), my_off, my_len);
+      uint32_t my_off = 0, my_len = 0;  // latency variant: row extents of the error's detectors, fetched together
+      if (kLat) row_extent(t, dj, lane < deg, lane < deg && !((fired_mask >> lane) & 1), my_off, my_len);
       for (uint32_t k = 0; k < deg; ++k) {
         const uint32_t d = __shfl_sync(kFull, dj, (int)k);
-        const uint32_t roff = __shfl_sync(kFull, my_off, (int)k), rlen = __shfl_sync(kFull, my_len, (int)k);
+        const uint32_t roff = kLat ? __shfl_sync(kFull, my_off, (int)k) : 0u, rlen = kLat ? __shfl_sync(kFull, my_len, (int)k) : 0u;
         if ((fired_mask >> k) & 1) {
           cost = __dsub_rn(cost, sm.hc[d]);
         } else {
-          const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, sm.fq, sm.act, d, roff, rlen, lane, ctr.S), p.det_penalty);
+          const double h = __dadd_rn(scan_row<kInstr, kLat>(t, st, sm.rank, sm.act, d, lane, ctr.S, roff, rlen, sm.fq), p.det_penalty);
           cost = __dadd_rn(cost, h);
         }
       }
@@ -902,22 +905,32 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
         while (nz) {
           const uint32_t l = (uint32_t)__ffs((int)nz) - 1;
           nz &= nz - 1;
-          const uint32_t word = __shfl_sync(kFull, mine, (int)l), wbase = __shfl_sync(kFull, w, (int)l) * 32;
-          // lane i takes the i-th set bit: the extents of all the word's rows arrive in one round trip
-          const uint32_t cnt = (uint32_t)__popc(word);
-          uint32_t my_od = 0;
-          if (lane < cnt) {
-            uint32_t rest = word;
-            for (uint32_t i = 0; i < lane; ++i) rest &= rest - 1;
-            my_od = wbase + (uint32_t)__ffs((int)rest) - 1;
+          uint32_t word = __shfl_sync(kFull, mine, (int)l);
+          if (kLat) {
+            // lane i takes the word's i-th set bit: extents of all its rows in one round trip, records prefetched
+            const uint32_t wbase = __shfl_sync(kFull, w, (int)l) * 32, cnt = (uint32_t)__popc(word);
+            uint32_t my_od = 0;
+            if (lane < cnt) {
+              uint32_t rest = word;
+              for (uint32_t i = 0; i < lane; ++i) rest &= rest - 1;
+              my_od = wbase + (uint32_t)__ffs((int)rest) - 1;
+            }
+            uint32_t my_off, my_len;
+            row_extent(t, my_od, lane < cnt, lane < cnt, my_off, my_len);
+            for (uint32_t i = 0; i < cnt; ++i) {
+              const uint32_t od = __shfl_sync(kFull, my_od, (int)i);
+              cost = __dsub_rn(cost, sm.hc[od]);
+              const double h = __dadd_rn(scan_row<kInstr, true>(t, st, sm.rank, sm.act, od, lane, ctr.S, __shfl_sync(kFull, my_off, (int)i),
+                                                                __shfl_sync(kFull, my_len, (int)i), sm.fq), p.det_penalty);
+              cost = __dadd_rn(cost, h);
+            }
+            word = 0;
           }
-          uint32_t my_off, my_len;
-          row_extent(t, my_od, lane < cnt, lane < cnt, my_off, my_len);
-          for (uint32_t i = 0; i < cnt; ++i) {
-            const uint32_t od = __shfl_sync(kFull, my_od, (int)i);
-            const uint32_t roff = __shfl_sync(kFull, my_off, (int)i), rlen = __shfl_sync(kFull, my_len, (int)i);
+          while (word) {
+            const uint32_t od = __shfl_sync(kFull, w, (int)l) * 32 + (uint32_t)__ffs((int)word) - 1;
+            word &= word - 1;
             cost = __dsub_rn(cost, sm.hc[od]);
-            const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, sm.fq, sm.act, od, roff, rlen, lane, ctr.S), p.det_penalty);
+            const double h = __dadd_rn(scan_row<kInstr>(t, st, sm.rank, sm.act, od, lane, ctr.S), p.det_penalty);
             cost = __dadd_rn(cost, h);
           }
         }
@@ -941,7 +954,7 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
 
 // ---- one search (whole CTA).  Returns the item status; on kItemOk the solution has been written. ------
 
-template <bool kInstr, bool kBits>
+template <bool kInstr, bool kBits, bool kLat>
 __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t slot, uint32_t item, uint32_t sol_row,
                                const ResumeRec* resume, Counters& ctr) {
   const DeviceTables& t = p.t;
@@ -1274,19 +1287,11 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
         }
       } else {
         for (uint32_t w = warp; w < nwords; w += nwarps) {
-          const uint32_t word = sm.fbits[w], cnt = (uint32_t)__popc(word);
-          uint32_t my_d = 0;
-          if (lane < cnt) {
-            uint32_t rest = word;
-            for (uint32_t i = 0; i < lane; ++i) rest &= rest - 1;
-            my_d = w * 32 + (uint32_t)__ffs((int)rest) - 1;
-          }
-          uint32_t my_off, my_len;
-          row_extent(t, my_d, lane < cnt, lane < cnt, my_off, my_len);
-          for (uint32_t i = 0; i < cnt; ++i) {
-            const uint32_t d = __shfl_sync(kFull, my_d, (int)i);
-            const uint32_t roff = __shfl_sync(kFull, my_off, (int)i), rlen = __shfl_sync(kFull, my_len, (int)i);
-            const double h = __dadd_rn(scan_row<kInstr>(t, sm.st, sm.rank, sm.fq, sm.act, d, roff, rlen, lane, ctr.S), p.det_penalty);
+          uint32_t word = sm.fbits[w];
+          while (word) {
+            const uint32_t d = w * 32 + (uint32_t)__ffs((int)word) - 1;
+            word &= word - 1;
+            const double h = __dadd_rn(scan_row<kInstr>(t, sm.st, sm.rank, sm.act, d, lane, ctr.S), p.det_penalty);
             if (lane == 0) sm.hc[d] = h;
           }
         }
@@ -1387,7 +1392,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       if (lane == 0) j = atomicAdd(&c.next_child, 1u);
       j = __shfl_sync(kFull, j, 0);
       if (j >= c.nchild) break;
-      eval_child<kInstr, kBits>(p, sm, j, lane, vtab, ctr);
+      eval_child<kInstr, kBits, kLat>(p, sm, j, lane, vtab, ctr);
     }
     __syncthreads();
     prof_mark(p, c, 4);
@@ -1413,7 +1418,9 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
       __syncwarp();
       uint32_t i0 = 0;  // children (of the compact list) pushed so far
-      if (K >= 4 && c.depth != 0xFFFF && pushed + K <= p.pqlimit && heap_size + K <= p.node_cap && chain_size + K <= p.node_cap &&
+      // (staging costs a few memory round trips of its own: it pays for a long row of children, or a deep heap; measured:
+      // staging every expansion slows surface d=5 from 1.8 M to 1.4 M shots/s)
+      if ((K >= 96 || (K >= 8 && heap_size >= 4096)) && c.depth != 0xFFFF && pushed + K <= p.pqlimit && heap_size + K <= p.node_cap && chain_size + K <= p.node_cap &&
           chain_size + K < 0xFFFFFFFEull) {
         for (uint32_t i = lane; i < K; i += 32) {  // chain nodes
           const uint4 meta = sm.res_meta[sm.clist[i]];
@@ -1438,10 +1445,20 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           }
           const uint32_t off_s = Kb + incl - width_s;
           if (Kb + __shfl_sync(kFull, incl, 31) > sm.stage_cap) break;  // does not fit: windowed path for the rest
-          for (uint32_t sft = 0; sft < lvl && sft < 32; ++sft) {  // load the ancestor ranges
-            const uint32_t w_ = __shfl_sync(kFull, width_s, (int)sft);
-            const uint32_t lo_ = __shfl_sync(kFull, lo_s, (int)sft), off_ = __shfl_sync(kFull, off_s, (int)sft);
-            for (uint32_t q = lane; q < w_; q += 32) sm.stage[off_ + q] = __ldcg(reinterpret_cast<const uint4*>(heap + (lo_ - 1 + q)));
+          // Load the ancestor ranges, two levels per memory round trip (both loads are issued before either is stored to
+          // shared memory; one level after the other costs a round trip per level).
+          for (uint32_t s0 = 0; s0 < lvl && s0 < 32; s0 += 2) {
+            const int sa = (int)s0, sb = (int)min(s0 + 1, 31u);
+            const uint32_t wa = __shfl_sync(kFull, width_s, sa), la = __shfl_sync(kFull, lo_s, sa), oa = __shfl_sync(kFull, off_s, sa);
+            const uint32_t wb = s0 + 1 < lvl ? __shfl_sync(kFull, width_s, sb) : 0u;
+            const uint32_t lb = __shfl_sync(kFull, lo_s, sb), ob = __shfl_sync(kFull, off_s, sb);
+            uint4 ga = make_uint4(0, 0, 0, 0), gb = make_uint4(0, 0, 0, 0);
+            if (lane < wa) ga = __ldcg(reinterpret_cast<const uint4*>(heap + (la - 1 + lane)));
+            if (lane < wb) gb = __ldcg(reinterpret_cast<const uint4*>(heap + (lb - 1 + lane)));
+            if (lane < wa) sm.stage[oa + lane] = ga;
+            if (lane < wb) sm.stage[ob + lane] = gb;
+            for (uint32_t q = lane + 32; q < wa; q += 32) sm.stage[oa + q] = __ldcg(reinterpret_cast<const uint4*>(heap + (la - 1 + q)));
+            for (uint32_t q = lane + 32; q < wb; q += 32) sm.stage[ob + q] = __ldcg(reinterpret_cast<const uint4*>(heap + (lb - 1 + q)));
           }
           __syncwarp();
           // The Kb pushes, 32 at a time.  A push whose value is not smaller than its parent leaves the rest of the heap
@@ -1613,7 +1630,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
   }
 }
 
-template <bool kInstr, bool kBits>
+template <bool kInstr, bool kBits, bool kLat>
 __global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams p) {
   extern __shared__ uint4 smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
@@ -1622,11 +1639,10 @@ __global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams
   const uint32_t D = p.t.D;
   const uint32_t rank_entries = p.t.fn_costs * p.t.fnstride;
   const Layout L = make_layout(D, p.t.nwords, rank_entries, p.t.max_row_len, nwarps, p.hc_shared != 0,
-                               kBits ? p.t.bs_group : 0, kBits ? p.t.bs_cap : 0, p.t.sp_on != 0);
+                               kBits ? p.t.bs_group : 0, kBits ? p.t.bs_cap : 0, p.t.sp_on != 0, kLat);
   Smem sm;
   sm.ctl = reinterpret_cast<Ctl*>(base);
   sm.rank = reinterpret_cast<uint16_t*>(base + L.off_rank);
-  sm.fq = reinterpret_cast<double*>(base + L.off_fq);
   sm.rbits = reinterpret_cast<uint32_t*>(base + L.off_rbits);
   sm.fbits = reinterpret_cast<uint32_t*>(base + L.off_fbits);
   sm.pst = reinterpret_cast<uint16_t*>(base + L.off_pst);
@@ -1650,9 +1666,10 @@ __global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams
   sm.sp_scratch = reinterpret_cast<uint32_t*>(base + L.off_sp);
   sm.stage = reinterpret_cast<uint4*>(base + L.off_st + L.warp_stride);
   sm.stage_cap = ((nwarps - 1) * L.warp_stride + L.stage_extra) / 16;
+  sm.fq = kLat ? reinterpret_cast<double*>(base + L.off_fq) : nullptr;
   for (uint32_t i = tid; i < rank_entries; i += blockDim.x) {
     sm.rank[i] = __ldg(p.t.frank + i);
-    sm.fq[i] = __ldg(p.t.fquot + i);
+    if (kLat) sm.fq[i] = __ldg(p.t.fquot + i);
   }
   if (tid == 0) {
     for (auto& v : sm.ctl->prof) v = 0;
@@ -1687,7 +1704,7 @@ __global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams
     }
     sm.slot = cur_slot;
     sm.chain = p.chain + (size_t)cur_slot * p.node_cap;
-    const uint32_t status = run_search<kInstr, kBits>(p, sm, cur_slot, item, sol_row, rec, ctr);
+    const uint32_t status = run_search<kInstr, kBits, kLat>(p, sm, cur_slot, item, sol_row, rec, ctr);
     __syncthreads();
     if (!rec) ++searches;
     if (tid == 0) {
@@ -1729,46 +1746,57 @@ __global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams
   }
 }
 
-template <bool kInstr, bool kBits>
+template <bool kInstr, bool kBits, bool kLat>
 int configure(size_t smem) {
   if (smem > 48 * 1024)
-    return (int)cudaFuncSetAttribute(search_fast_kernel<kInstr, kBits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return (int)cudaFuncSetAttribute(search_fast_kernel<kInstr, kBits, kLat>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   return 0;
 }
 
 }  // namespace
 
-uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits) {
+// `latency`: the variant for a lone search per SM (wide CTAs of the tail and of the retry tiers): entry-per-lane scans
+// with batched row extents, L1 prefetch and the quotient table in shared memory.  The bit-sliced scan has no such variant.
+uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits, bool latency) {
   return make_layout(t.D, t.nwords, t.fn_costs * t.fnstride, t.max_row_len, warps, hc_shared, bits ? t.bs_group : 0,
-                     bits ? t.bs_cap : 0, t.sp_on != 0).total;
+                     bits ? t.bs_cap : 0, t.sp_on != 0, latency && !bits).total;
 }
 
-int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits) {
+int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits, bool latency) {
   int n = 0;
-  const size_t smem = search_fast_smem_bytes(t, warps, hc_shared, bits);
+  const size_t smem = search_fast_smem_bytes(t, warps, hc_shared, bits, latency);
   if (smem > 227 * 1024) return 0;
+  cudaError_t e;
   if (bits) {
-    if (configure<false, true>(smem) != 0) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, true>, (int)(warps * 32), smem) != cudaSuccess) return 0;
+    if (configure<false, true, false>(smem) != 0) return 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, true, false>, (int)(warps * 32), smem);
+  } else if (latency) {
+    if (configure<false, false, true>(smem) != 0) return 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, false, true>, (int)(warps * 32), smem);
   } else {
-    if (configure<false, false>(smem) != 0 || configure<true, false>(smem) != 0) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, false>, (int)(warps * 32), smem) != cudaSuccess) return 0;
+    if (configure<false, false, false>(smem) != 0 || configure<true, false, false>(smem) != 0) return 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, false, false>, (int)(warps * 32), smem);
   }
-  return n;
+  return e == cudaSuccess ? n : 0;
 }
 
-int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, bool bits, void* stream) {
+int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, bool bits, bool latency,
+                       void* stream) {
   if ((p.n_work == 0 && !p.resume) || blocks == 0) return 0;
-  const size_t smem = search_fast_smem_bytes(p.t, warps, p.hc_shared != 0, bits);
+  const size_t smem = search_fast_smem_bytes(p.t, warps, p.hc_shared != 0, bits, latency);
+  cudaStream_t st = (cudaStream_t)stream;
   if (bits) {
-    if (int e = configure<false, true>(smem)) return e;
-    search_fast_kernel<false, true><<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+    if (int e = configure<false, true, false>(smem)) return e;
+    search_fast_kernel<false, true, false><<<blocks, warps * 32, smem, st>>>(p);
   } else if (instrumented) {
-    if (int e = configure<true, false>(smem)) return e;
-    search_fast_kernel<true, false><<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+    if (int e = configure<true, false, false>(smem)) return e;
+    search_fast_kernel<true, false, false><<<blocks, warps * 32, smem, st>>>(p);
+  } else if (latency) {
+    if (int e = configure<false, false, true>(smem)) return e;
+    search_fast_kernel<false, false, true><<<blocks, warps * 32, smem, st>>>(p);
   } else {
-    if (int e = configure<false, false>(smem)) return e;
-    search_fast_kernel<false, false><<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(p);
+    if (int e = configure<false, false, false>(smem)) return e;
+    search_fast_kernel<false, false, false><<<blocks, warps * 32, smem, st>>>(p);
   }
   return (int)cudaGetLastError();
 }
