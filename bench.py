@@ -74,10 +74,20 @@ WORKLOADS = {
                                  side=(256, 1, 1, 4.0), counters_from="port", cpu_first=16, counter_shots=8,
                                  name="bivariate-bicycle [[144,12,12]] r=12 si1000 p=1e-3 X, --beam 20 --beam-climbing --num-det-orders 21 "
                                       "--pqlimit 1000000 --no-revisit-dets (the reference's long-beam sweep point)"),
+    # ... and the same point with --sparsify-errors at the reference's own best setting for it (base degree 3, reactivate limit
+    # 128: 0.116 CPU-seconds per shot, aggregated_results.jsonl; tesseract.cc:256-292, 673-737)
+    "bb144_p1e-3_longbeam_sparsify": dict(cfg=dict(dem="bb144_r12_p0.001_X", det_beam=20, beam_climbing=True, pqlimit=1000000,
+                                                   no_revisit_dets=True, num_det_orders=21, sparsify_errors=True, sparsify_base_degree=3,
+                                                   sparsify_reactivate_limit=128),
+                                          shots=4096, tag="bb144 p=1e-3 long-beam --sparsify-errors (base 3, limit 128)",
+                                          side=(2048, 2, 1, 4.0), counters_from="port", counter_shots=64,
+                                          name="bivariate-bicycle [[144,12,12]] r=12 si1000 p=1e-3 X, long-beam flags + --sparsify-errors "
+                                               "--sparsify-base-degree 3 --sparsify-reactivate-limit 128"),
     "bb144_p5e-4": dict(cfg=dict(W.CONFIGS["C4"], dem="bb144_r12_p0.0005_X"), shots=4096, tag="C4 bb144 p=5e-4",
                         name="bivariate-bicycle [[144,12,12]] r=12 si1000 p=5e-4 X, --num-det-orders 24 --no-revisit-dets"),
 }
-SIDE_ORDER = ["surface_d5", "color_d7", "surface_d11", "transcx_d5", "transcx_d5_amt", "bb144_p1e-3_longbeam"]
+SIDE_ORDER = ["surface_d5", "color_d7", "surface_d11", "transcx_d5", "transcx_d5_amt", "bb144_p1e-3_longbeam",
+              "bb144_p1e-3_longbeam_sparsify"]
 L2_FLUSH_BYTES = 256 << 20
 MAX_CHUNK = 1 << 18  # tsr_config.max_batch_shots default: shots per search launch
 # Issue-slot peak of one B200: 148 SMs x 4 schedulers x 1 warp instruction per cycle at the measured max SM clock.

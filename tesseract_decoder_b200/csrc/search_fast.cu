@@ -1631,7 +1631,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
 }
 
 template <bool kInstr, bool kBits, bool kLat>
-__global__ void __launch_bounds__(1024, 1) search_fast_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_kernel(const SearchParams p) {
   extern __shared__ uint4 smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -1755,11 +1755,11 @@ int configure(size_t smem) {
 
 }  // namespace
 
-// `latency`: the variant for a lone search per SM (wide CTAs of the tail and of the retry tiers): entry-per-lane scans
-// with batched row extents, L1 prefetch and the quotient table in shared memory.  The bit-sliced scan has no such variant.
+// `latency`: the variant for a lone search per SM (wide CTAs of up to 1024 threads: the tail and the retry tiers).
+// Entry-per-lane scans then use batched row extents, L1 prefetch and the quotient table in shared memory.
 uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits, bool latency) {
   return make_layout(t.D, t.nwords, t.fn_costs * t.fnstride, t.max_row_len, warps, hc_shared, bits ? t.bs_group : 0,
-                     bits ? t.bs_cap : 0, t.sp_on != 0, latency && !bits).total;
+                     bits ? t.bs_cap : 0, t.sp_on != 0, latency).total;
 }
 
 int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits, bool latency) {
@@ -1767,7 +1767,10 @@ int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc
   const size_t smem = search_fast_smem_bytes(t, warps, hc_shared, bits, latency);
   if (smem > 227 * 1024) return 0;
   cudaError_t e;
-  if (bits) {
+  if (bits && latency) {
+    if (configure<false, true, true>(smem) != 0) return 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, true, true>, (int)(warps * 32), smem);
+  } else if (bits) {
     if (configure<false, true, false>(smem) != 0) return 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, true, false>, (int)(warps * 32), smem);
   } else if (latency) {
@@ -1785,7 +1788,10 @@ int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, b
   if ((p.n_work == 0 && !p.resume) || blocks == 0) return 0;
   const size_t smem = search_fast_smem_bytes(p.t, warps, p.hc_shared != 0, bits, latency);
   cudaStream_t st = (cudaStream_t)stream;
-  if (bits) {
+  if (bits && latency) {
+    if (int e = configure<false, true, true>(smem)) return e;
+    search_fast_kernel<false, true, true><<<blocks, warps * 32, smem, st>>>(p);
+  } else if (bits) {
     if (int e = configure<false, true, false>(smem)) return e;
     search_fast_kernel<false, true, false><<<blocks, warps * 32, smem, st>>>(p);
   } else if (instrumented) {
