@@ -302,6 +302,8 @@ void init_device(tsr_decoder& h) {
         h.blocks_wide = (uint32_t)(h.sm_count * occ_wide);
         h.expansion_budget = 256;
         if (const char* e = std::getenv("TSR_EXPANSION_BUDGET")) h.expansion_budget = (uint32_t)std::max(0, std::atoi(e));
+        h.cluster_max = 8;  // the portable maximum
+        if (const char* e = std::getenv("TSR_CLUSTER")) h.cluster_max = (uint32_t)std::min(std::max(1, std::atoi(e)), 8);
       }
     }
   }
@@ -531,15 +533,31 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
       return tsr::launch_search(sp_, std::min<uint32_t>((tier_slots + h.wpb - 1) / h.wpb, (n_work + h.wpb - 1) / h.wpb), h.wpb, s);
     const bool bits = h.bits && !h.instrumented;
     if (!widen) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, h.instrumented, bits, false, s);
-    if (!tier0) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb_wide, false, bits, true, s);
+    // Few long searches left: give each a thread-block cluster (up to 8 SMs share the children of one search).
+    auto cluster_for = [&](uint32_t searches) {
+      uint32_t c = h.cluster_max;
+      while (c > 1 && (uint64_t)searches * c > h.blocks_wide) c /= 2;
+      return std::max<uint32_t>(c, 1);
+    };
+    if (!tier0) {
+      const uint32_t units = std::min<uint32_t>(tier_slots, n_work);
+      sp_.cluster = cluster_for(units);
+      return tsr::launch_search_fast(sp_, units * sp_.cluster, h.wpb_wide, false, bits, true, s);
+    }
     sp_.expansion_budget = h.expansion_budget;
     sp_.paused = h.d_paused.as<tsr::ResumeRec>();
     sp_.paused_count = &sc->paused_count;
     sp_.paused_cap = tier_slots;
     if (int e = tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, false, bits, false, s)) return e;
+    unsigned int n_paused = 0;  // (a host round trip, but only at the very end of the chunk's search work)
+    if (cudaError_t e = cudaMemcpyAsync(&n_paused, &sc->paused_count, 4, cudaMemcpyDeviceToHost, s)) return (int)e;
+    if (cudaError_t e = cudaStreamSynchronize(s)) return (int)e;
+    if (n_paused == 0) return 0;
+    const uint32_t units = std::min<uint32_t>(std::min<uint32_t>(n_paused, tier_slots), h.blocks_wide);
     sp_.expansion_budget = 0;
     sp_.resume = 1;
-    return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, h.blocks_wide), h.wpb_wide, false, bits, true, s);
+    sp_.cluster = cluster_for(units);
+    return tsr::launch_search_fast(sp_, units * sp_.cluster, h.wpb_wide, false, bits, true, s);
   };
   // An item no CTA got to must never pass for decoded: every status starts as "overflow" (-> retried in the next tier).
   CUDA_OK(cudaMemsetAsync(h.d_status.p, tsr::kItemNodeOverflow, items, s));

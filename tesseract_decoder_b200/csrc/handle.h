@@ -139,7 +139,7 @@ struct tsr_decoder {
   uint32_t wpb = 4, blocks = 0;
   // Tail widening (fast path; SearchParams::expansion_budget): searches that outlive the budget are resumed by CTAs of
   // wpb_wide warps, and the retry tiers (few, long searches) run wide from the start.  0 = off.
-  uint32_t wpb_wide = 0, blocks_wide = 0, expansion_budget = 0;
+  uint32_t wpb_wide = 0, blocks_wide = 0, expansion_budget = 0, cluster_max = 1;
   std::vector<tsr_impl::Tier> tiers;
   tsr_impl::DevBuf pool, hcache, vlist;
   uint32_t vlist_cap = 256;

@@ -145,6 +145,12 @@ struct SearchParams {
   // with resume = 1 runs no new work: CTA b continues paused[b], paused[b + gridDim], ... to the end, typically with
   // four times the warps.  Heavy-tailed batches then end with a few wide CTAs instead of one narrow one.
   uint32_t expansion_budget = 0;
+  // Wide launches only: thread-block clusters of this many CTAs (1 = off).  CTA 0 of a cluster owns the search; during
+  // the children phase of an expansion the other CTAs claim children from its counter, read the node's state from its
+  // shared memory (distributed shared memory) and write their results there.  A lone search is bound by the
+  // instruction issue rate of ONE SM (profiles/r02_f_*: 2.2 M warp instructions per expansion on the colour code);
+  // a cluster spreads the children over up to 8 SMs.
+  uint32_t cluster = 1;
   int resume = 0;
   ResumeRec* paused = nullptr;
   unsigned int* paused_count = nullptr;

@@ -29,6 +29,7 @@
 //
 // Exactness: the child cost is still node.cost + cost(e) then -= / += detector terms in the reference's
 // order with round-to-nearest adds; pushes happen in row order; the heap performs the same moves.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -45,6 +46,7 @@ constexpr uint32_t kThr = 0x7FFu;
 constexpr uint32_t kKeyInf = 0xFFFFFFFFu;
 
 enum Action : int { kActExpand = 0, kActSkip = 1, kActDone = 2 };
+enum ClusterState : uint32_t { kClGo = 1, kClExit = 2 };
 enum ChildStatus : uint32_t { kChildOk = 0, kChildDropped = 1 };
 
 struct alignas(16) Ctl {
@@ -74,6 +76,9 @@ struct alignas(16) Ctl {
   uint32_t work;
   uint32_t item;
   uint32_t n_exp;  // nodes this search has expanded in the current launch (expansion budget)
+  // cluster mode: what the helper CTAs read after the "children are ready" barrier
+  uint32_t cl_state;  // kClGo / kClExit
+  uint32_t cl_slot;   // pool slot of the running search
   // phase profile (SearchParams::prof): clock64 ticks of thread 0 per phase, see tsr_profile
   long long prof_last;
   unsigned long long prof[8];
@@ -107,6 +112,7 @@ struct Smem {
   // this search's pool slot and chain arena (visited-set audit)
   uint32_t slot;
   const ChainNode* chain;
+  uint32_t cluster;  // CTAs cooperating on this search (1 = this CTA alone)
   // sparsify (sparsify.cuh): this slot's active-entry masks [D][rw] in global memory (null when off), selection scratch
   const uint32_t* act;
   uint32_t rw;
@@ -1387,6 +1393,16 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
     }
 
     // ---- phase 6 (all warps): the children, round-robin ----------------------------------------------------
+    // Cluster mode: the helper CTAs wait at the first barrier, then claim children from the same counter (they read this
+    // CTA's state and write res_cost / res_meta through distributed shared memory); the second barrier ends the phase.
+    const bool clustered = kLat && sm.cluster > 1;
+    if (clustered) {
+      if (tid == 0) {
+        c.cl_state = kClGo;
+        c.cl_slot = slot;
+      }
+      cooperative_groups::this_cluster().sync();
+    }
     while (true) {
       uint32_t j = 0;
       if (lane == 0) j = atomicAdd(&c.next_child, 1u);
@@ -1394,7 +1410,8 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       if (j >= c.nchild) break;
       eval_child<kInstr, kBits, kLat>(p, sm, j, lane, vtab, ctr);
     }
-    __syncthreads();
+    if (clustered) cooperative_groups::this_cluster().sync();
+    else __syncthreads();
     prof_mark(p, c, 4);
 
     // ---- phase 7 (warp 0): pushes, in row order (tesseract.cc:590-605) ----------------------------------------
@@ -1635,7 +1652,12 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
   extern __shared__ uint4 smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const uint32_t slot = blockIdx.x;
+  // Cluster mode (wide launches): `C` CTAs per search; CTA 0 of the cluster is the search's owner, the others help with
+  // the children.  A "unit" is what owns a pool slot and claims work: a CTA, or a cluster.
+  const uint32_t C = kLat ? max(p.cluster, 1u) : 1u;
+  const uint32_t crank = C > 1 ? cooperative_groups::this_cluster().block_rank() : 0u;
+  const uint32_t unit = blockIdx.x / C, n_units = gridDim.x / C;
+  const uint32_t slot = unit;
   const uint32_t D = p.t.D;
   const uint32_t rank_entries = p.t.fn_costs * p.t.fnstride;
   const Layout L = make_layout(D, p.t.nwords, rank_entries, p.t.max_row_len, nwarps, p.hc_shared != 0,
@@ -1667,6 +1689,7 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
   sm.stage = reinterpret_cast<uint4*>(base + L.off_st + L.warp_stride);
   sm.stage_cap = ((nwarps - 1) * L.warp_stride + L.stage_extra) / 16;
   sm.fq = kLat ? reinterpret_cast<double*>(base + L.off_fq) : nullptr;
+  sm.cluster = C;
   for (uint32_t i = tid; i < rank_entries; i += blockDim.x) {
     sm.rank[i] = __ldg(p.t.frank + i);
     if (kLat) sm.fq[i] = __ldg(p.t.fquot + i);
@@ -1679,15 +1702,61 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
 
   Counters ctr;
   unsigned long long searches = 0;
+  if (kLat && crank != 0) {
+    // Helper CTA of a cluster: per expansion of the owner's search, evaluate children.  The node's state, the child list
+    // and the result arrays are the OWNER's shared memory, reached through distributed shared memory; only the per-warp
+    // scratch (state copy / bit-sliced lists) and the rank and quotient tables are local.
+    auto cluster = cooperative_groups::this_cluster();
+    Smem hs = sm;
+    hs.ctl = cluster.map_shared_rank(sm.ctl, 0);
+    hs.rbits = cluster.map_shared_rank(sm.rbits, 0);
+    hs.fbits = cluster.map_shared_rank(sm.fbits, 0);
+    hs.pst = cluster.map_shared_rank(sm.pst, 0);
+    hs.pbb = cluster.map_shared_rank(sm.pbb, 0);
+    hs.fz = cluster.map_shared_rank(sm.fz, 0);
+    hs.clist = cluster.map_shared_rank(sm.clist, 0);
+    hs.res_cost = cluster.map_shared_rank(sm.res_cost, 0);
+    hs.res_meta = cluster.map_shared_rank(sm.res_meta, 0);
+    if (p.hc_shared) hs.hc = cluster.map_shared_rank(sm.hc, 0);
+    Ctl* owner = hs.ctl;
+    const uint32_t dpad = dpad_of(D);
+    while (true) {
+      cluster.sync();  // the owner has a list of children ready, or is done
+      if (owner->cl_state == kClExit) break;
+      const uint32_t cs = owner->cl_slot;
+      hs.slot = cs;
+      hs.chain = p.chain + (size_t)cs * p.node_cap;
+      if (!p.hc_shared) hs.hc = p.hcache + (size_t)cs * D;
+      hs.act = p.t.sp_on ? p.sp_act + (size_t)cs * D * p.t.sp_rw : nullptr;
+      const uint4* vtab = p.no_revisit ? p.visited + (size_t)cs * p.visit_cap : nullptr;
+      if (kBits) {  // this warp's copy of the node's state (phase 4 of the owner's loop)
+        for (uint32_t w = lane; w < p.t.nwords; w += 32) hs.cf[w] = hs.fbits[w];
+      } else {
+        const uint4* src = reinterpret_cast<const uint4*>(hs.pst);
+        uint4* dst = reinterpret_cast<uint4*>(hs.st);
+        for (uint32_t i = lane; i < dpad / 8; i += 32) dst[i] = src[i];
+      }
+      __syncwarp();
+      const uint32_t nchild = owner->nchild;
+      while (true) {
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(&owner->next_child, 1u);
+        j = __shfl_sync(kFull, j, 0);
+        if (j >= nchild) break;
+        eval_child<kInstr, kBits, kLat>(p, hs, j, lane, vtab, ctr);
+      }
+      cluster.sync();  // all children of this expansion are evaluated
+    }
+  } else {
   const uint32_t n_paused = p.resume ? min(*p.paused_count, p.paused_cap) : 0u;
-  uint32_t resume_at = blockIdx.x;
+  uint32_t resume_at = unit;
   while (true) {
     uint32_t item, cur_slot = slot, sol_row = 0;
     const ResumeRec* rec = nullptr;
     if (p.resume) {  // continue paused searches (one per CTA and round), each in the pool slot it was started in
       if (resume_at >= n_paused) break;
       rec = p.paused + resume_at;
-      resume_at += gridDim.x;
+      resume_at += n_units;
       item = rec->item;
       sol_row = item;
       cur_slot = rec->slot;
@@ -1727,6 +1796,11 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
       }
     }
     __syncthreads();
+  }
+  if (kLat && C > 1) {  // release the helpers
+    if (tid == 0) sm.ctl->cl_state = kClExit;
+    cooperative_groups::this_cluster().sync();
+  }
   }
   if (tid == 0 && p.prof) {
     sm.ctl->prof[7] = ctr.X;
@@ -1788,6 +1862,26 @@ int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, b
   if ((p.n_work == 0 && !p.resume) || blocks == 0) return 0;
   const size_t smem = search_fast_smem_bytes(p.t, warps, p.hc_shared != 0, bits, latency);
   cudaStream_t st = (cudaStream_t)stream;
+  if (latency && p.cluster > 1) {  // thread-block clusters: blocks = units x cluster size
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks, 1, 1);
+    cfg.blockDim = dim3(warps * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (bits) {
+      if (int e = configure<false, true, true>(smem)) return e;
+      return (int)cudaLaunchKernelEx(&cfg, search_fast_kernel<false, true, true>, p);
+    }
+    if (int e = configure<false, false, true>(smem)) return e;
+    return (int)cudaLaunchKernelEx(&cfg, search_fast_kernel<false, false, true>, p);
+  }
   if (bits && latency) {
     if (int e = configure<false, true, true>(smem)) return e;
     search_fast_kernel<false, true, true><<<blocks, warps * 32, smem, st>>>(p);
