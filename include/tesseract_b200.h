@@ -185,6 +185,10 @@ int tsr_profile(tsr_decoder* h, uint64_t out[8], int reset);
  * [1]=whole device pipeline ms (stage + search + resolve), [2]=search kernel launches,
  * [3]=items rerun in a larger node-pool tier. */
 int tsr_last_batch_timing(const tsr_decoder* h, double out[4]);
+/* The tail of the last batch (certified DEMs): [0]=searches that were still running when the work queue emptied and were
+ * handed to wide CTAs, [1]=ms of that second launch (part of the search ms above), [2]=CTAs per search in it (thread-block
+ * cluster size; 1 = no clusters). */
+int tsr_last_batch_tail(const tsr_decoder* h, double out[3]);
 void* tsr_stream(tsr_decoder* h); /* cudaStream_t the decoder launches on */
 int tsr_device(const tsr_decoder* h);
 

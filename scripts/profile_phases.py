@@ -49,7 +49,8 @@ def run(name, extra=None):
         t = dec.last_batch_timing()
         if not prof:
             rec.update(wall_s=round(wall, 4), search_ms=round(t["search_ms"], 3), shots_per_s=round(len(dets) / wall, 1),
-                       launches=t["search_launches"], rerun=t["rerun_items"], counters=dec.counters())
+                       launches=t["search_launches"], rerun=t["rerun_items"], counters=dec.counters(),
+                       tail=dict(searches=t["tail_searches"], ms=round(t["tail_ms"], 2), cluster=t["tail_cluster"]))
         else:
             p = dec.profile()
             ticks = sum(v for k, v in p.items() if k != "expansions")

@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
     L.tsr_flipped_observables.argtypes = [C.c_void_p, u64p, C.c_uint64, u8p]
     L.tsr_counters.argtypes = [C.c_void_p, u64p, C.c_int]
     L.tsr_last_batch_timing.argtypes = [C.c_void_p, f64p]
+    L.tsr_last_batch_tail.argtypes = [C.c_void_p, f64p]
     L.tsr_sparsify_reactivate_limit.restype = C.c_int64
     L.tsr_sparsify_reactivate_limit.argtypes = [C.c_void_p]
     L.tsr_suggest_sparsify_reactivate_limit.restype = C.c_int64
@@ -154,7 +155,7 @@ EXPORTED_SYMBOLS = [
     "tsr_suggest_sparsify_reactivate_limit", "tsr_comm_unique_id", "tsr_comm_init_rank", "tsr_comm_world",
     "tsr_comm_allreduce_sum_u64", "tsr_nccl_version", "tsr_group_create", "tsr_group_destroy", "tsr_group_size",
     "tsr_group_member", "tsr_group_decode_b8", "tsr_group_last_batch_nnz", "tsr_group_last_batch_errors",
-    "tsr_visualization_text", "tsr_set_visited_audit", "tsr_visited_audit",
+    "tsr_visualization_text", "tsr_set_visited_audit", "tsr_visited_audit", "tsr_last_batch_tail",
 ]
 
 
@@ -481,7 +482,10 @@ class Decoder:
     def last_batch_timing(self):
         out = np.zeros(4, dtype=np.float64)
         _check(lib().tsr_last_batch_timing(self.h, _p(out, C.c_double)))
-        return {"search_ms": out[0], "pipeline_ms": out[1], "search_launches": int(out[2]), "rerun_items": int(out[3])}
+        tail = np.zeros(3, dtype=np.float64)
+        _check(lib().tsr_last_batch_tail(self.h, _p(tail, C.c_double)))
+        return {"search_ms": out[0], "pipeline_ms": out[1], "search_launches": int(out[2]), "rerun_items": int(out[3]),
+                "tail_searches": int(tail[0]), "tail_ms": float(tail[1]), "tail_cluster": int(tail[2])}
 
     @property
     def stream(self) -> int:

@@ -528,6 +528,7 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
   // Fast path: tier 0 runs with an expansion budget and is followed by a launch of wide CTAs that finish whatever was
   // paused (no host round trip: CTAs beyond the paused count exit at once); the retry tiers run wide from the start.
   const bool widen = h.fast && h.wpb_wide && h.expansion_budget && !h.instrumented;
+  bool resumed = false;
   auto launch = [&](tsr::SearchParams sp_, uint32_t tier_slots, uint32_t n_work, bool tier0) -> int {
     if (!h.fast)
       return tsr::launch_search(sp_, std::min<uint32_t>((tier_slots + h.wpb - 1) / h.wpb, (n_work + h.wpb - 1) / h.wpb), h.wpb, s);
@@ -557,7 +558,13 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     sp_.expansion_budget = 0;
     sp_.resume = 1;
     sp_.cluster = cluster_for(units);
-    return tsr::launch_search_fast(sp_, units * sp_.cluster, h.wpb_wide, false, bits, true, s);
+    h.tail[0] += n_paused;
+    h.tail[2] = std::max<double>(h.tail[2], sp_.cluster);
+    resumed = true;
+    if (cudaError_t e = cudaEventRecord(h.ev[4], s)) return (int)e;
+    const int rc = tsr::launch_search_fast(sp_, units * sp_.cluster, h.wpb_wide, false, bits, true, s);
+    if (cudaError_t e = cudaEventRecord(h.ev[5], s)) return (int)e;
+    return rc;
   };
   // An item no CTA got to must never pass for decoded: every status starts as "overflow" (-> retried in the next tier).
   CUDA_OK(cudaMemsetAsync(h.d_status.p, tsr::kItemNodeOverflow, items, s));
@@ -572,6 +579,12 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
   double launches = 1, rerun = 0;
   float ms_search = 0;
   CUDA_OK(cudaEventElapsedTime(&ms_search, h.ev[1], h.ev[2]));
+  if (resumed) {
+    float ms_tail = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms_tail, h.ev[4], h.ev[5]));
+    h.tail[1] += ms_tail;
+    launches += 1;
+  }
 
   // Retry tiers for searches that outgrew their slot.
   // Retried shots write their solutions to a separate buffer with longer rows (a search can also be sent here because
@@ -658,6 +671,7 @@ void begin_call(tsr_decoder& h) {
   h.last_off.assign(1, 0);
   h.last_idx.clear();
   for (double& v : h.timing) v = 0;
+  for (double& v : h.tail) v = 0;
 }
 
 }  // namespace
@@ -1080,7 +1094,7 @@ int tsr_set_visited_audit(tsr_decoder* h, int on) {
     for (const Tier& t : h->tiers) entries = std::max<size_t>(entries, (size_t)t.slots * t.visit_cap);
     h->d_vchain.ensure(std::max<size_t>(entries * 4, 16));
     h->d_audit.ensure(16);
-    h->d_audit_scratch.ensure(std::max<size_t>((size_t)h->tiers[0].slots * 32 * h->dt.nwords * 4, 16));
+    h->d_audit_scratch.ensure(std::max<size_t>((size_t)h->tiers[0].slots * 8 * 32 * h->dt.nwords * 4, 16));
     CUDA_OK(cudaMemsetAsync(h->d_audit.p, 0, 16, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
   });
@@ -1111,6 +1125,11 @@ int tsr_profile(tsr_decoder* h, uint64_t out[8], int reset) {
     if (reset) CUDA_OK(cudaMemsetAsync(h->d_prof.p, 0, 64, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));
   });
+}
+
+int tsr_last_batch_tail(const tsr_decoder* h, double out[3]) {
+  for (int i = 0; i < 3; ++i) out[i] = h->tail[i];
+  return TSR_OK;
 }
 
 int tsr_last_batch_timing(const tsr_decoder* h, double out[4]) {

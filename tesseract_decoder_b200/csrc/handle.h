@@ -125,7 +125,7 @@ struct tsr_decoder {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   // Device tables.
   tsr_impl::DevBuf row_off, row_err, rec_a, rec_b, rec_c, e_off, e_det, e_rank, e_cost, e_nnbr, eo_off, eo_obs, e2dem, adj,
@@ -161,6 +161,7 @@ struct tsr_decoder {
   std::vector<uint64_t> last_off{0};
   std::vector<uint64_t> last_idx;
   double timing[4] = {0, 0, 0, 0};
+  double tail[3] = {0, 0, 0};  // tsr_last_batch_tail: paused searches, ms of the resume launch, largest cluster size used
 
   tsr_comm* comm = nullptr;  // set by tsr_comm_init_rank / tsr_group_create (group.cu)
 

@@ -113,6 +113,7 @@ struct Smem {
   uint32_t slot;
   const ChainNode* chain;
   uint32_t cluster;  // CTAs cooperating on this search (1 = this CTA alone)
+  uint32_t crank;    // this CTA's rank among them
   // sparsify (sparsify.cuh): this slot's active-entry masks [D][rw] in global memory (null when off), selection scratch
   const uint32_t* act;
   uint32_t rw;
@@ -724,8 +725,10 @@ __device__ int visited_insert(uint4* tab, uint64_t cap, uint4 key, uint64_t& whe
 // the entry.  Rebuild that node's fired set from its chain and compare: scratch = candidate ^ root ^ toggles(chain) must
 // be all zero.
 __device__ void audit_hit(const SearchParams& p, const DeviceTables& t, const uint32_t* fbits, const uint32_t* rbits,
-                          const ChainNode* chain, uint32_t slot, uint64_t where, uint32_t deg, uint32_t dj, uint32_t lane) {
-  uint32_t* scratch = p.audit_scratch + ((size_t)slot * 32 + (threadIdx.x >> 5)) * t.nwords;
+                          const ChainNode* chain, uint32_t slot, uint32_t crank, uint64_t where, uint32_t deg, uint32_t dj,
+                          uint32_t lane) {
+  // one scratch bitset per warp of every CTA that can work on the slot's search (up to 8 CTAs of 32 warps in cluster mode)
+  uint32_t* scratch = p.audit_scratch + (((size_t)slot * 8 + crank) * 32 + (threadIdx.x >> 5)) * t.nwords;
   for (uint32_t w = lane; w < t.nwords; w += 32) scratch[w] = fbits[w] ^ rbits[w];
   __syncwarp();
   if (lane < deg) atomicXor(&scratch[dj >> 5], 1u << (dj & 31));
@@ -812,7 +815,7 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
     ++ctr.V;
     if (seen) status = kChildDropped;
     if (seen && p.audit)
-      audit_hit(p, t, sm.fbits, sm.rbits, sm.chain, sm.slot, __shfl_sync(kFull, where, 0), deg, dj, lane);
+      audit_hit(p, t, sm.fbits, sm.rbits, sm.chain, sm.slot, sm.crank, __shfl_sync(kFull, where, 0), deg, dj, lane);
   }
   if (status == kChildOk) {
     // The child's state: toggle the error's detectors, block the min-detector row up to this entry.
@@ -1211,7 +1214,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
             }
             inserted = __shfl_sync(kFull, inserted, 0);
             ++ctr.V;
-            if (inserted == 0 && p.audit) audit_hit(p, t, sm.fbits, sm.rbits, chain, slot, __shfl_sync(kFull, where, 0), 0, 0, lane);
+            if (inserted == 0 && p.audit) audit_hit(p, t, sm.fbits, sm.rbits, chain, slot, 0, __shfl_sync(kFull, where, 0), 0, 0, lane);
             if (inserted < 0) {
               action = kActDone;
               status = kItemNodeOverflow;
@@ -1690,6 +1693,7 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
   sm.stage_cap = ((nwarps - 1) * L.warp_stride + L.stage_extra) / 16;
   sm.fq = kLat ? reinterpret_cast<double*>(base + L.off_fq) : nullptr;
   sm.cluster = C;
+  sm.crank = crank;
   for (uint32_t i = tid; i < rank_entries; i += blockDim.x) {
     sm.rank[i] = __ldg(p.t.frank + i);
     if (kLat) sm.fq[i] = __ldg(p.t.fquot + i);
