@@ -512,7 +512,7 @@ def run_b200(args, wl, rank, world, local):
                 pk = ISSUE_PEAK_PER_CLOCK * sm_max_mhz * 1e6
                 issue = {"bound": "issue", "achieved": wi / 1e9, "peak": pk / 1e9, "unit": "G warp-instr/s", "frac": wi / pk,
                          "warp_instructions_per_shot": rec["warp_instructions_per_shot"], "source": rec.get("source", "profiles/")}
-                for k in ("l2_hit_pct", "l2_throughput_pct", "achieved_occupancy_pct", "dram_pct_of_peak"):
+                for k in ("l2_hit_pct", "l2_throughput_pct", "achieved_occupancy_pct", "dram_pct_of_peak", "issue_active_pct"):
                     if k in rec:
                         issue[k] = rec[k]
         except Exception:

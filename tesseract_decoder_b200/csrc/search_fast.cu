@@ -1465,12 +1465,27 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           }
           const uint32_t off_s = Kb + incl - width_s;
           if (Kb + __shfl_sync(kFull, incl, 31) > sm.stage_cap) break;  // does not fit: windowed path for the rest
-          // Load the ancestor ranges, two levels per memory round trip (both loads are issued before either is stored to
-          // shared memory; one level after the other costs a round trip per level).
-          for (uint32_t s0 = 0; s0 < lvl && s0 < 32; s0 += 2) {
+          // Load the ancestor ranges.  Far above the leaves a range is one or two nodes: every lane fetches its own
+          // level's (lane s-1 owns level s), all of them in one memory round trip.  The wide ranges near the leaves go
+          // two levels per round trip (both loads are issued before either is stored to shared memory).
+          uint32_t n_wide = 0;  // levels 1..n_wide have more than two nodes (widths shrink towards the root)
+          {
+            const bool narrow = lane + 1 <= lvl && width_s <= 2;
+            uint4 g0 = make_uint4(0, 0, 0, 0), g1 = make_uint4(0, 0, 0, 0);
+            if (narrow) {
+              g0 = __ldcg(reinterpret_cast<const uint4*>(heap + (lo_s - 1)));
+              if (width_s == 2) g1 = __ldcg(reinterpret_cast<const uint4*>(heap + lo_s));
+            }
+            n_wide = (uint32_t)__popc(__ballot_sync(kFull, lane + 1 <= lvl && width_s > 2));
+            if (narrow) {
+              sm.stage[off_s] = g0;
+              if (width_s == 2) sm.stage[off_s + 1] = g1;
+            }
+          }
+          for (uint32_t s0 = 0; s0 < n_wide; s0 += 2) {
             const int sa = (int)s0, sb = (int)min(s0 + 1, 31u);
             const uint32_t wa = __shfl_sync(kFull, width_s, sa), la = __shfl_sync(kFull, lo_s, sa), oa = __shfl_sync(kFull, off_s, sa);
-            const uint32_t wb = s0 + 1 < lvl ? __shfl_sync(kFull, width_s, sb) : 0u;
+            const uint32_t wb = s0 + 1 < n_wide ? __shfl_sync(kFull, width_s, sb) : 0u;
             const uint32_t lb = __shfl_sync(kFull, lo_s, sb), ob = __shfl_sync(kFull, off_s, sb);
             uint4 ga = make_uint4(0, 0, 0, 0), gb = make_uint4(0, 0, 0, 0);
             if (lane < wa) ga = __ldcg(reinterpret_cast<const uint4*>(heap + (la - 1 + lane)));
