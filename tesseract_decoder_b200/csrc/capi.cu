@@ -302,6 +302,8 @@ void init_device(tsr_decoder& h) {
         h.blocks_wide = (uint32_t)(h.sm_count * occ_wide);
         h.expansion_budget = 256;
         if (const char* e = std::getenv("TSR_EXPANSION_BUDGET")) h.expansion_budget = (uint32_t)std::max(0, std::atoi(e));
+        h.stage_budget = 1024;
+        if (const char* e = std::getenv("TSR_STAGE_BUDGET")) h.stage_budget = (uint32_t)std::max(0, std::atoi(e));
         h.cluster_max = 8;  // the portable maximum
         if (const char* e = std::getenv("TSR_CLUSTER")) h.cluster_max = (uint32_t)std::min(std::max(1, std::atoi(e)), 8);
       }
@@ -360,6 +362,8 @@ void init_device(tsr_decoder& h) {
   CUDA_OK(cudaMemsetAsync(h.pool.p, 0, h.pool.bytes, h.stream));  // visited tables start empty
   h.d_scalars.ensure(64);
   h.d_paused.ensure(std::max<size_t>((size_t)slots * sizeof(tsr::ResumeRec), 64));
+  h.d_paused2.ensure(std::max<size_t>((size_t)slots * sizeof(tsr::ResumeRec), 64));
+  h.d_stage_counts.ensure(64);
   h.d_counters.ensure(8 * sizeof(unsigned long long));
   CUDA_OK(cudaMemsetAsync(h.d_counters.p, 0, 64, h.stream));
   h.d_prof.ensure(8 * sizeof(unsigned long long));
@@ -550,21 +554,43 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     sp_.paused_count = &sc->paused_count;
     sp_.paused_cap = tier_slots;
     if (int e = tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, false, bits, false, s)) return e;
-    unsigned int n_paused = 0;  // (a host round trip, but only at the very end of the chunk's search work)
+    // The tail, in stages (a host round trip each, but only at the very end of the chunk's search work): wide CTAs
+    // continue the paused searches for another slice of expansions and park the survivors again; once few enough are
+    // left for a full-size cluster each, the last stage runs them to the end.
+    unsigned int n_paused = 0;
     if (cudaError_t e = cudaMemcpyAsync(&n_paused, &sc->paused_count, 4, cudaMemcpyDeviceToHost, s)) return (int)e;
     if (cudaError_t e = cudaStreamSynchronize(s)) return (int)e;
     if (n_paused == 0) return 0;
-    const uint32_t units = std::min<uint32_t>(std::min<uint32_t>(n_paused, tier_slots), h.blocks_wide);
-    sp_.expansion_budget = 0;
-    sp_.resume = 1;
-    sp_.cluster = cluster_for(units);
+    n_paused = std::min<uint32_t>(n_paused, tier_slots);
     h.tail[0] += n_paused;
-    h.tail[2] = std::max<double>(h.tail[2], sp_.cluster);
     resumed = true;
     if (cudaError_t e = cudaEventRecord(h.ev[4], s)) return (int)e;
-    const int rc = tsr::launch_search_fast(sp_, units * sp_.cluster, h.wpb_wide, false, bits, true, s);
-    if (cudaError_t e = cudaEventRecord(h.ev[5], s)) return (int)e;
-    return rc;
+    const tsr::ResumeRec* in = h.d_paused.as<tsr::ResumeRec>();
+    unsigned int* counts = h.d_stage_counts.as<unsigned int>();
+    for (int stage = 0; n_paused > 0; ++stage) {
+      const uint32_t units = std::min<uint32_t>(n_paused, h.blocks_wide);
+      tsr::SearchParams rp = sp_;
+      rp.resume = 1;
+      rp.resume_list = in;
+      rp.resume_n = n_paused;
+      rp.cluster = cluster_for(units);
+      const bool last = rp.cluster >= h.cluster_max || stage >= 8 || h.stage_budget == 0;
+      tsr::ResumeRec* out = in == h.d_paused.as<tsr::ResumeRec>() ? h.d_paused2.as<tsr::ResumeRec>() : h.d_paused.as<tsr::ResumeRec>();
+      rp.expansion_budget = last ? 0 : h.stage_budget;
+      rp.paused = out;
+      rp.paused_count = counts + (stage & 1);
+      rp.paused_cap = tier_slots;
+      if (cudaError_t e = cudaMemsetAsync(rp.paused_count, 0, 4, s)) return (int)e;
+      h.tail[2] = std::max<double>(h.tail[2], rp.cluster);
+      if (int e = tsr::launch_search_fast(rp, units * rp.cluster, h.wpb_wide, false, bits, true, s)) return e;
+      if (cudaError_t e = cudaEventRecord(h.ev[5], s)) return (int)e;
+      if (last) break;
+      if (cudaError_t e = cudaMemcpyAsync(&n_paused, rp.paused_count, 4, cudaMemcpyDeviceToHost, s)) return (int)e;
+      if (cudaError_t e = cudaStreamSynchronize(s)) return (int)e;
+      n_paused = std::min<uint32_t>(n_paused, tier_slots);
+      in = out;
+    }
+    return 0;
   };
   // An item no CTA got to must never pass for decoded: every status starts as "overflow" (-> retried in the next tier).
   CUDA_OK(cudaMemsetAsync(h.d_status.p, tsr::kItemNodeOverflow, items, s));

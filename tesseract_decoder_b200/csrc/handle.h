@@ -139,7 +139,7 @@ struct tsr_decoder {
   uint32_t wpb = 4, blocks = 0;
   // Tail widening (fast path; SearchParams::expansion_budget): searches that outlive the budget are resumed by CTAs of
   // wpb_wide warps, and the retry tiers (few, long searches) run wide from the start.  0 = off.
-  uint32_t wpb_wide = 0, blocks_wide = 0, expansion_budget = 0, cluster_max = 1;
+  uint32_t wpb_wide = 0, blocks_wide = 0, expansion_budget = 0, stage_budget = 0, cluster_max = 1;
   std::vector<tsr_impl::Tier> tiers;
   tsr_impl::DevBuf pool, hcache, vlist;
   uint32_t vlist_cap = 256;
@@ -147,7 +147,7 @@ struct tsr_decoder {
   // Per-batch buffers.
   uint64_t max_batch = 0;
   tsr_impl::DevBuf d_dets, d_status, d_sol_len, d_fcost, d_sol, d_obs, d_cost, d_low, d_err_off, d_err_len, d_err, d_retry,
-      d_items, d_scalars, d_counters, d_prof, d_fired, d_order, d_bins, d_paused, d_vchain, d_audit, d_audit_scratch, d_sol_retry;
+      d_items, d_scalars, d_counters, d_prof, d_fired, d_order, d_bins, d_paused, d_paused2, d_stage_counts, d_vchain, d_audit, d_audit_scratch, d_sol_retry;
   uint32_t sol_stride = 0;
   bool collect_errors = true;
 

@@ -141,9 +141,11 @@ struct SearchParams {
   uint32_t* trace_len = nullptr;      // [items] entries the search wanted to log (may exceed trace_cap)
   unsigned long long* trace_arena = nullptr;  // [items]
   // Tail widening (fast path).  A launch with expansion_budget > 0 pauses every search that has expanded more nodes
-  // than that once the work queue is empty: its record goes to paused[atomicAdd(paused_count)] and the CTA retires (its slot stays occupied).  A launch
-  // with resume = 1 runs no new work: CTA b continues paused[b], paused[b + gridDim], ... to the end, typically with
-  // four times the warps.  Heavy-tailed batches then end with a few wide CTAs instead of one narrow one.
+  // than that once the work queue is empty: its record goes to paused[atomicAdd(paused_count)] and the CTA retires (its
+  // slot stays occupied).  A launch with resume = 1 runs no new work: unit b continues resume_list[b], [b + units], ...
+  // with four times the warps — to the end, or (budget > 0) for another `expansion_budget` expansions each, parking the
+  // survivors in its own `paused` list for the next, wider stage.  Heavy-tailed batches then end with a few clusters
+  // instead of one narrow CTA.
   uint32_t expansion_budget = 0;
   // Wide launches only: thread-block clusters of this many CTAs (1 = off).  CTA 0 of a cluster owns the search; during
   // the children phase of an expansion the other CTAs claim children from its counter, read the node's state from its
@@ -151,8 +153,10 @@ struct SearchParams {
   // instruction issue rate of ONE SM (profiles/r02_f_*: 2.2 M warp instructions per expansion on the colour code);
   // a cluster spreads the children over up to 8 SMs.
   uint32_t cluster = 1;
-  int resume = 0;
-  ResumeRec* paused = nullptr;
+  int resume = 0;                           // this launch continues resume_list[0 .. resume_n) instead of claiming work
+  const ResumeRec* resume_list = nullptr;
+  uint32_t resume_n = 0;
+  ResumeRec* paused = nullptr;              // where this launch parks the searches it pauses (may be null when budget == 0)
   unsigned int* paused_count = nullptr;
   uint32_t paused_cap = 0;
 };

@@ -1052,7 +1052,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
         action = kActDone;
         status = kItemLowConfidence;  // tesseract.cc:609-615
       } else if (p.expansion_budget && c.n_exp >= p.expansion_budget &&
-                 __shfl_sync(kFull, lane == 0 ? __ldcg(p.work_counter) : 0u, 0) >= p.n_work) {
+                 (p.resume || __shfl_sync(kFull, lane == 0 ? __ldcg(p.work_counter) : 0u, 0) >= p.n_work)) {
         // Over budget AND no work left to claim: this search is part of the batch's tail.  Park it for a wider CTA
         // (SearchParams::resume); while the queue still holds work a long search simply runs on — a CTA that retired
         // then would take its slot out of service.  (If the list is full the search also runs on.)
@@ -1741,7 +1741,10 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
     const uint32_t dpad = dpad_of(D);
     while (true) {
       cluster.sync();  // the owner has a list of children ready, or is done
-      if (owner->cl_state == kClExit) break;
+      if (owner->cl_state == kClExit) {
+        cluster.sync();  // the owner's shared memory must outlive this read: nobody leaves before everybody has looked
+        break;
+      }
       const uint32_t cs = owner->cl_slot;
       hs.slot = cs;
       hs.chain = p.chain + (size_t)cs * p.node_cap;
@@ -1767,14 +1770,14 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
       cluster.sync();  // all children of this expansion are evaluated
     }
   } else {
-  const uint32_t n_paused = p.resume ? min(*p.paused_count, p.paused_cap) : 0u;
+  const uint32_t n_paused = p.resume ? p.resume_n : 0u;
   uint32_t resume_at = unit;
   while (true) {
     uint32_t item, cur_slot = slot, sol_row = 0;
     const ResumeRec* rec = nullptr;
     if (p.resume) {  // continue paused searches (one per CTA and round), each in the pool slot it was started in
       if (resume_at >= n_paused) break;
-      rec = p.paused + resume_at;
+      rec = p.resume_list + resume_at;
       resume_at += n_units;
       item = rec->item;
       sol_row = item;
@@ -1799,7 +1802,12 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
       p.status[item] = (uint8_t)status;
       if (status != kItemOk) p.sol_len[item] = 0;
     }
-    if (status == kItemPaused) break;  // the slot keeps the search's queue, arena, visited set and masks: this CTA retires
+    // A paused search keeps its queue, arena, visited set and masks in its slot.  In the narrow launch that is this
+    // CTA's own slot: the CTA retires.  A resume launch works on the searches' slots and simply takes its next one.
+    if (status == kItemPaused) {
+      if (p.resume) continue;
+      break;
+    }
     if (sm.act)  // back to the mandatory masks for the slot's next search
       sparsify::restore(p.t, sm.rbits, const_cast<uint32_t*>(sm.act), warp, nwarps, lane, [] { __syncthreads(); });
     // Empty the visited table for the next search of this slot.
@@ -1816,8 +1824,9 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
     }
     __syncthreads();
   }
-  if (kLat && C > 1) {  // release the helpers
+  if (kLat && C > 1) {  // release the helpers; the second barrier keeps this CTA's shared memory alive while they read the flag
     if (tid == 0) sm.ctl->cl_state = kClExit;
+    cooperative_groups::this_cluster().sync();
     cooperative_groups::this_cluster().sync();
   }
   }
