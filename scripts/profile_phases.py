@@ -17,6 +17,8 @@ LONGBEAM = dict(dem="bb144_r12_p0.001_X", det_beam=20, beam_climbing=True, pqlim
 CASES = {
     # name: (config, sampler seed, shots sampled, slice)
     "c3_surface_d11_2048": (W.CONFIGS["C3"], 1000, 2048, slice(None)),
+    "c3_shot1532_41755_expansions": (W.CONFIGS["C3"], 1000, 2048, slice(1532, 1533)),
+    "c3_shot1007_2.5M_pushes": (W.CONFIGS["C3"], 1000, 2048, slice(1007, 1008)),
     "c2_color_d7_first600": (W.CONFIGS["C2"], 1002, 2000, slice(0, 600)),
     "c2_color_d7_shot6_305k_pushes": (W.CONFIGS["C2"], 1002, 2000, slice(6, 7)),
     "c2_color_d7_shot877_1.2M_pushes": (W.CONFIGS["C2"], 1002, 2000, slice(877, 878)),

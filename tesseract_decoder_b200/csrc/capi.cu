@@ -304,7 +304,11 @@ void init_device(tsr_decoder& h) {
         if (const char* e = std::getenv("TSR_EXPANSION_BUDGET")) h.expansion_budget = (uint32_t)std::max(0, std::atoi(e));
         h.stage_budget = 1024;
         if (const char* e = std::getenv("TSR_STAGE_BUDGET")) h.stage_budget = (uint32_t)std::max(0, std::atoi(e));
-        h.cluster_max = 8;  // the portable maximum
+        // Cluster size: as many CTAs of `wide` warps as one expansion has children for (a row of the min detector), up
+        // to the portable maximum of 8 — surface d=11 (rows of ~60) gets pairs, the colour and BB codes (177 / 226) eight.
+        const double mean_row = (double)T.row_err.size() / std::max<uint32_t>(D, 1);
+        h.cluster_max = 1;
+        while (h.cluster_max < 8 && (double)h.cluster_max * wide < mean_row) h.cluster_max *= 2;
         if (const char* e = std::getenv("TSR_CLUSTER")) h.cluster_max = (uint32_t)std::min(std::max(1, std::atoi(e)), 8);
       }
     }

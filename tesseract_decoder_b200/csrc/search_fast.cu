@@ -1722,49 +1722,56 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
   Counters ctr;
   unsigned long long searches = 0;
   if (kLat && crank != 0) {
-    // Helper CTA of a cluster: per expansion of the owner's search, evaluate children.  The node's state, the child list
-    // and the result arrays are the OWNER's shared memory, reached through distributed shared memory; only the per-warp
-    // scratch (state copy / bit-sliced lists) and the rank and quotient tables are local.
+    // Helper CTA of a cluster: per expansion of the owner's search, evaluate children.  After the "children are ready"
+    // barrier the helper copies the node's state — thresholds, fired / blocking bitsets, detector terms, child list, the
+    // control block — from the OWNER's shared memory into its own (distributed shared memory, one 16-byte load per
+    // thread), so that the scans run on local memory exactly as in the owner; only the claims (an atomicAdd on the
+    // owner's counter) and the results (res_cost / res_meta) cross SMs.
     auto cluster = cooperative_groups::this_cluster();
     Smem hs = sm;
-    hs.ctl = cluster.map_shared_rank(sm.ctl, 0);
-    hs.rbits = cluster.map_shared_rank(sm.rbits, 0);
-    hs.fbits = cluster.map_shared_rank(sm.fbits, 0);
-    hs.pst = cluster.map_shared_rank(sm.pst, 0);
-    hs.pbb = cluster.map_shared_rank(sm.pbb, 0);
-    hs.fz = cluster.map_shared_rank(sm.fz, 0);
-    hs.clist = cluster.map_shared_rank(sm.clist, 0);
     hs.res_cost = cluster.map_shared_rank(sm.res_cost, 0);
     hs.res_meta = cluster.map_shared_rank(sm.res_meta, 0);
-    if (p.hc_shared) hs.hc = cluster.map_shared_rank(sm.hc, 0);
-    Ctl* owner = hs.ctl;
+    Ctl* owner = cluster.map_shared_rank(sm.ctl, 0);
+    const uint4* o_base = reinterpret_cast<const uint4*>(cluster.map_shared_rank(base, 0));
+    uint4* l_base = reinterpret_cast<uint4*>(base);
     const uint32_t dpad = dpad_of(D);
+    // [off_rbits, off_st): rbits, fbits, pst, hc (when shared), res arrays (skipped below), clist, pbb, fz, ... — contiguous
+    const uint32_t copy_lo = L.off_rbits / 16, copy_hi = L.off_st / 16;
+    const uint32_t skip_lo = L.off_cost / 16, skip_hi = L.off_clist / 16;  // res_cost / res_meta stay the owner's
     while (true) {
       cluster.sync();  // the owner has a list of children ready, or is done
       if (owner->cl_state == kClExit) {
         cluster.sync();  // the owner's shared memory must outlive this read: nobody leaves before everybody has looked
         break;
       }
-      const uint32_t cs = owner->cl_slot;
+      for (uint32_t i = tid; i < round16(sizeof(Ctl)) / 16; i += blockDim.x) l_base[i] = reinterpret_cast<const uint4*>(owner)[i];
+      for (uint32_t i = copy_lo + tid; i < copy_hi; i += blockDim.x)
+        if (i < skip_lo || i >= skip_hi) l_base[i] = o_base[i];
+      __syncthreads();
+      const uint32_t cs = hs.ctl->cl_slot;
       hs.slot = cs;
       hs.chain = p.chain + (size_t)cs * p.node_cap;
       if (!p.hc_shared) hs.hc = p.hcache + (size_t)cs * D;
       hs.act = p.t.sp_on ? p.sp_act + (size_t)cs * D * p.t.sp_rw : nullptr;
       const uint4* vtab = p.no_revisit ? p.visited + (size_t)cs * p.visit_cap : nullptr;
-      if (kBits) {  // this warp's copy of the node's state (phase 4 of the owner's loop)
-        for (uint32_t w = lane; w < p.t.nwords; w += 32) hs.cf[w] = hs.fbits[w];
-      } else {
-        const uint4* src = reinterpret_cast<const uint4*>(hs.pst);
-        uint4* dst = reinterpret_cast<uint4*>(hs.st);
-        for (uint32_t i = lane; i < dpad / 8; i += 32) dst[i] = src[i];
-      }
-      __syncwarp();
-      const uint32_t nchild = owner->nchild;
+      const uint32_t nchild = hs.ctl->nchild;
+      bool have_state = false;  // this warp's private copy of the node's state, made when it gets its first child
       while (true) {
         uint32_t j = 0;
         if (lane == 0) j = atomicAdd(&owner->next_child, 1u);
         j = __shfl_sync(kFull, j, 0);
         if (j >= nchild) break;
+        if (!have_state) {
+          if (kBits) {
+            for (uint32_t w = lane; w < p.t.nwords; w += 32) hs.cf[w] = hs.fbits[w];
+          } else {
+            const uint4* src = reinterpret_cast<const uint4*>(hs.pst);
+            uint4* dst = reinterpret_cast<uint4*>(hs.st);
+            for (uint32_t i = lane; i < dpad / 8; i += 32) dst[i] = src[i];
+          }
+          __syncwarp();
+          have_state = true;
+        }
         eval_child<kInstr, kBits, kLat>(p, hs, j, lane, vtab, ctr);
       }
       cluster.sync();  // all children of this expansion are evaluated
@@ -1830,7 +1837,7 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
     cooperative_groups::this_cluster().sync();
   }
   }
-  if (tid == 0 && p.prof) {
+  if (tid == 0 && p.prof && crank == 0) {  // (a helper's control block is a copy of its owner's)
     sm.ctl->prof[7] = ctr.X;
     for (int i = 0; i < 8; ++i) atomicAdd(p.prof + i, sm.ctl->prof[i]);
   }
