@@ -302,14 +302,16 @@ void init_device(tsr_decoder& h) {
         h.blocks_wide = (uint32_t)(h.sm_count * occ_wide);
         h.expansion_budget = 256;
         if (const char* e = std::getenv("TSR_EXPANSION_BUDGET")) h.expansion_budget = (uint32_t)std::max(0, std::atoi(e));
-        h.stage_budget = 1024;
-        if (const char* e = std::getenv("TSR_STAGE_BUDGET")) h.stage_budget = (uint32_t)std::max(0, std::atoi(e));
-        // Cluster size: as many CTAs of `wide` warps as one expansion has children for (a row of the min detector), up
-        // to the portable maximum of 8 — surface d=11 (rows of ~60) gets pairs, the colour and BB codes (177 / 226) eight.
+        // Clusters pay where an expansion has several CTAs' worth of children AND the children dominate it: the
+        // entry-per-lane path on long rows (colour codes: rows of ~177, lone 1.2 M-push search 3.05 s -> 1.50 s with 8
+        // CTAs).  Measured slower with them (profiles/r02_l_cluster_stage_sweep.txt): surface d=11 (rows of ~60; its long
+        // searches are bound by pops and chain rebuilds, 1.74 s -> 2.11 s) and the bit-sliced path (BB144 long-beam
+        // 2.93 s -> 3.56 s) — those keep single wide CTAs.  With clusters the tail runs in stages of 1024 expansions.
         const double mean_row = (double)T.row_err.size() / std::max<uint32_t>(D, 1);
-        h.cluster_max = 1;
-        while (h.cluster_max < 8 && (double)h.cluster_max * wide < mean_row) h.cluster_max *= 2;
+        h.cluster_max = (!h.bits && mean_row >= 128.0) ? 8 : 1;
         if (const char* e = std::getenv("TSR_CLUSTER")) h.cluster_max = (uint32_t)std::min(std::max(1, std::atoi(e)), 8);
+        h.stage_budget = h.cluster_max > 1 ? 1024 : 0;
+        if (const char* e = std::getenv("TSR_STAGE_BUDGET")) h.stage_budget = (uint32_t)std::max(0, std::atoi(e));
       }
     }
   }
