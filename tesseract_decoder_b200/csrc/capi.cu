@@ -538,12 +538,14 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
   // Fast path: tier 0 runs with an expansion budget and is followed by a launch of wide CTAs that finish whatever was
   // paused (no host round trip: CTAs beyond the paused count exit at once); the retry tiers run wide from the start.
   const bool widen = h.fast && h.wpb_wide && h.expansion_budget && !h.instrumented;
+  // counter S, the phase profile, the visited audit and the visualization trace exist only in the diagnostics variants
+  const bool diag = h.instrumented || h.profile || h.visited_audit || h.trace_on;
   bool resumed = false;
   auto launch = [&](tsr::SearchParams sp_, uint32_t tier_slots, uint32_t n_work, bool tier0) -> int {
     if (!h.fast)
       return tsr::launch_search(sp_, std::min<uint32_t>((tier_slots + h.wpb - 1) / h.wpb, (n_work + h.wpb - 1) / h.wpb), h.wpb, s);
     const bool bits = h.bits && !h.instrumented;
-    if (!widen) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, h.instrumented, bits, false, s);
+    if (!widen) return tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, diag, bits, false, s);
     // Few long searches left: give each a thread-block cluster (up to 8 SMs share the children of one search).
     auto cluster_for = [&](uint32_t searches) {
       uint32_t c = h.cluster_max;
@@ -553,13 +555,13 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
     if (!tier0) {
       const uint32_t units = std::min<uint32_t>(tier_slots, n_work);
       sp_.cluster = cluster_for(units);
-      return tsr::launch_search_fast(sp_, units * sp_.cluster, h.wpb_wide, false, bits, true, s);
+      return tsr::launch_search_fast(sp_, units * sp_.cluster, h.wpb_wide, diag, bits, true, s);
     }
     sp_.expansion_budget = h.expansion_budget;
     sp_.paused = h.d_paused.as<tsr::ResumeRec>();
     sp_.paused_count = &sc->paused_count;
     sp_.paused_cap = tier_slots;
-    if (int e = tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, false, bits, false, s)) return e;
+    if (int e = tsr::launch_search_fast(sp_, std::min<uint32_t>(tier_slots, n_work), h.wpb, diag, bits, false, s)) return e;
     // The tail, in stages (a host round trip each, but only at the very end of the chunk's search work): wide CTAs
     // continue the paused searches for another slice of expansions and park the survivors again; once few enough are
     // left for a full-size cluster each, the last stage runs them to the end.
@@ -588,7 +590,7 @@ void run_chunk(tsr_decoder& h, const uint8_t* d_dets, uint64_t stride, uint32_t 
       rp.paused_cap = tier_slots;
       if (cudaError_t e = cudaMemsetAsync(rp.paused_count, 0, 4, s)) return (int)e;
       h.tail[2] = std::max<double>(h.tail[2], rp.cluster);
-      if (int e = tsr::launch_search_fast(rp, units * rp.cluster, h.wpb_wide, false, bits, true, s)) return e;
+      if (int e = tsr::launch_search_fast(rp, units * rp.cluster, h.wpb_wide, diag, bits, true, s)) return e;
       if (cudaError_t e = cudaEventRecord(h.ev[5], s)) return (int)e;
       if (last) break;
       if (cudaError_t e = cudaMemcpyAsync(&n_paused, rp.paused_count, 4, cudaMemcpyDeviceToHost, s)) return (int)e;

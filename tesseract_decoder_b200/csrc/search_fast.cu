@@ -622,7 +622,7 @@ __device__ __forceinline__ uint4 shfl4(const uint4& v, int src) {
 // shuffles (every lane computes the same path), and the moves are stored as the walk goes: depth / 4 round trips.
 // The final sift-up of the displaced last element compares it first with the node just moved into the hole's parent,
 // which is still in registers (it almost always stops there).
-__device__ HeapNode heap_pop(HeapNode* heap, unsigned long long& size, uint32_t lane) {
+__device__ __noinline__ HeapNode heap_pop(HeapNode* heap, unsigned long long& size, uint32_t lane) {
   uint4 mine = make_uint4(0, 0, 0, 0);
   const long long len = (long long)size - 1;  // elements that remain
   if (lane == 0) mine = __ldcg(reinterpret_cast<const uint4*>(heap));
@@ -724,32 +724,51 @@ __device__ int visited_insert(uint4* tab, uint64_t cap, uint4 key, uint64_t& whe
 // `fbits`, with the `deg` detectors `dj` (one per lane) toggled for a child — equals the state of the node that inserted
 // the entry.  Rebuild that node's fired set from its chain and compare: scratch = candidate ^ root ^ toggles(chain) must
 // be all zero.
-__device__ void audit_hit(const SearchParams& p, const DeviceTables& t, const uint32_t* fbits, const uint32_t* rbits,
-                          const ChainNode* chain, uint32_t slot, uint32_t crank, uint64_t where, uint32_t deg, uint32_t dj,
-                          uint32_t lane) {
-  // one scratch bitset per warp of every CTA that can work on the slot's search (up to 8 CTAs of 32 warps in cluster mode)
-  uint32_t* scratch = p.audit_scratch + (((size_t)slot * 8 + crank) * 32 + (threadIdx.x >> 5)) * t.nwords;
-  for (uint32_t w = lane; w < t.nwords; w += 32) scratch[w] = fbits[w] ^ rbits[w];
+struct AuditArgs {  // passed by value: the cold audit code must not pin the kernel's parameter block in local memory
+  const uint32_t* vchain;
+  unsigned long long* audit;
+  uint32_t* scratch;  // this warp's scratch bitset
+  const uint32_t* e_off;
+  const int32_t* e_det;
+  uint64_t visit_cap;
+  uint32_t nwords;
+};
+__device__ __noinline__ void audit_hit(AuditArgs a, const uint32_t* fbits, const uint32_t* rbits, const ChainNode* chain, uint32_t slot,
+                                       uint64_t where, uint32_t deg, uint32_t dj, uint32_t lane) {
+  uint32_t* scratch = a.scratch;
+  for (uint32_t w = lane; w < a.nwords; w += 32) scratch[w] = fbits[w] ^ rbits[w];
   __syncwarp();
   if (lane < deg) atomicXor(&scratch[dj >> 5], 1u << (dj & 31));
   __syncwarp();
-  for (uint32_t at = __ldcg(p.vchain + (size_t)slot * p.visit_cap + where); at != kNoChain;) {
+  for (uint32_t at = __ldcg(a.vchain + (size_t)slot * a.visit_cap + where); at != kNoChain;) {
     const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(chain + at));
-    const uint32_t eb = __ldg(t.e_off + raw.x), n = __ldg(t.e_off + raw.x + 1) - eb;
+    const uint32_t eb = __ldg(a.e_off + raw.x), n = __ldg(a.e_off + raw.x + 1) - eb;
     if (lane < n) {
-      const uint32_t d = (uint32_t)__ldg(t.e_det + eb + lane);
+      const uint32_t d = (uint32_t)__ldg(a.e_det + eb + lane);
       atomicXor(&scratch[d >> 5], 1u << (d & 31));
     }
     __syncwarp();
     at = raw.y;
   }
   uint32_t diff = 0;
-  for (uint32_t w = lane; w < t.nwords; w += 32) diff |= scratch[w];
+  for (uint32_t w = lane; w < a.nwords; w += 32) diff |= scratch[w];
   const bool differs = __any_sync(kFull, diff != 0);
   if (lane == 0) {
-    atomicAdd(p.audit, 1ull);
-    if (differs) atomicAdd(p.audit + 1, 1ull);
+    atomicAdd(a.audit, 1ull);
+    if (differs) atomicAdd(a.audit + 1, 1ull);
   }
+}
+__device__ __forceinline__ AuditArgs audit_args(const SearchParams& p, uint32_t slot, uint32_t crank) {
+  AuditArgs a;
+  a.vchain = p.vchain;
+  a.audit = p.audit;
+  // one scratch bitset per warp of every CTA that can work on the slot's search (up to 8 CTAs of 32 warps in cluster mode)
+  a.scratch = p.audit_scratch + (((size_t)slot * 8 + crank) * 32 + (threadIdx.x >> 5)) * p.t.nwords;
+  a.e_off = p.t.e_off;
+  a.e_det = p.t.e_det;
+  a.visit_cap = p.visit_cap;
+  a.nwords = p.t.nwords;
+  return a;
 }
 __device__ __forceinline__ uint4 warp_xor(uint4 k) {
   k.x = __reduce_xor_sync(kFull, k.x);
@@ -771,8 +790,9 @@ struct Counters {
 
 // Phase profile: thread 0 charges the ticks since the previous mark to `phase`.  Called right after a CTA barrier, so a
 // phase's ticks are its critical path including the wait for the slowest warp.
+template <bool kDiag>
 __device__ __forceinline__ void prof_mark(const SearchParams& p, Ctl& c, uint32_t phase) {
-  if (p.prof && threadIdx.x == 0) {
+  if (kDiag && p.prof && threadIdx.x == 0) {
     const long long now = clock64();
     c.prof[phase] += (unsigned long long)(now - c.prof_last);
     c.prof_last = now;
@@ -814,8 +834,8 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
     seen = __shfl_sync(kFull, seen, 0);
     ++ctr.V;
     if (seen) status = kChildDropped;
-    if (seen && p.audit)
-      audit_hit(p, t, sm.fbits, sm.rbits, sm.chain, sm.slot, sm.crank, __shfl_sync(kFull, where, 0), deg, dj, lane);
+    if (kInstr && seen && p.audit)
+      audit_hit(audit_args(p, sm.slot, sm.crank), sm.fbits, sm.rbits, sm.chain, sm.slot, __shfl_sync(kFull, where, 0), deg, dj, lane);
   }
   if (status == kChildOk) {
     // The child's state: toggle the error's detectors, block the min-detector row up to this entry.
@@ -1010,7 +1030,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       c.state_valid = 0;
       c.heap_size = c.chain_size = c.pushed = c.n_visited = 0;
       c.n_exp = 0;
-      if (p.trace && !resume) {
+      if (kInstr && p.trace && !resume) {
         p.trace_len[item] = 0;
         p.trace_arena[item] = (unsigned long long)(uintptr_t)chain;
       }
@@ -1028,7 +1048,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
   __syncthreads();
   // sparsify: this shot's active-entry masks (build_sparse_d2e, tesseract.cc:673-737), by the whole CTA
   if (sm.act && !resume) sparsify::select(t, sm.rbits, const_cast<uint32_t*>(sm.act), sm.sp_scratch, warp, nwarps, lane, [] { __syncthreads(); });
-  prof_mark(p, c, 6);
+  prof_mark<kInstr>(p, c, 6);
 
   while (true) {
     // ---- phase 1 (warp 0): next node ----------------------------------------------------------------
@@ -1052,7 +1072,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
         action = kActDone;
         status = kItemLowConfidence;  // tesseract.cc:609-615
       } else if (p.expansion_budget && c.n_exp >= p.expansion_budget &&
-                 (p.resume || __shfl_sync(kFull, lane == 0 ? __ldcg(p.work_counter) : 0u, 0) >= p.n_work)) {
+                 ((kLat && p.resume) || __shfl_sync(kFull, lane == 0 ? __ldcg(p.work_counter) : 0u, 0) >= p.n_work)) {
         // Over budget AND no work left to claim: this search is part of the batch's tail.  Park it for a wider CTA
         // (SearchParams::resume); while the queue still holds work a long search simply runs on — a CTA that retired
         // then would take its slot out of service.  (If the list is full the search also runs on.)
@@ -1109,7 +1129,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
     }
     __syncthreads();
-    prof_mark(p, c, 0);
+    prof_mark<kInstr>(p, c, 0);
     if (c.action == kActDone) return c.status;
     if (c.action == kActSkip) {
       __syncthreads();
@@ -1182,7 +1202,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
         if (c.num_dets == 0) {
           // Goal (tesseract.cc:441-473): chain errors in root -> leaf order.
           action = kActDone;
-          if (p.trace && lane == 0) {
+          if (kInstr && p.trace && lane == 0) {
             const uint32_t n = p.trace_len[item]++;
             if (n < p.trace_cap) p.trace[(size_t)item * p.trace_cap + n] = c.chain;
           }
@@ -1209,12 +1229,13 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
               } else {
                 inserted = visited_insert(vtab, p.visit_cap, key, where);
                 if (inserted == 1 && c.n_visited < p.vlist_cap) vlist[c.n_visited] = (uint32_t)where;
-                if (inserted == 1 && p.vchain) p.vchain[(size_t)slot * p.visit_cap + where] = c.chain;
+                if (kInstr && inserted == 1 && p.vchain) p.vchain[(size_t)slot * p.visit_cap + where] = c.chain;
               }
             }
             inserted = __shfl_sync(kFull, inserted, 0);
             ++ctr.V;
-            if (inserted == 0 && p.audit) audit_hit(p, t, sm.fbits, sm.rbits, chain, slot, 0, __shfl_sync(kFull, where, 0), 0, 0, lane);
+            if (kInstr && inserted == 0 && p.audit)
+              audit_hit(audit_args(p, slot, 0), sm.fbits, sm.rbits, chain, slot, __shfl_sync(kFull, where, 0), 0, 0, lane);
             if (inserted < 0) {
               action = kActDone;
               status = kItemNodeOverflow;
@@ -1224,7 +1245,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
               ++c.n_visited;
             }
           }
-          if (action == kActExpand && p.trace && lane == 0) {  // tesseract.cc:478-481
+          if (kInstr && action == kActExpand && p.trace && lane == 0) {  // tesseract.cc:478-481
             const uint32_t n = p.trace_len[item]++;
             if (n < p.trace_cap) p.trace[(size_t)item * p.trace_cap + n] = c.chain;
           }
@@ -1241,7 +1262,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
     }
     __syncthreads();
-    prof_mark(p, c, 1);
+    prof_mark<kInstr>(p, c, 1);
     if (c.action == kActDone) return c.status;
     if (c.action == kActSkip) {
       __syncthreads();
@@ -1307,7 +1328,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
     }
     __syncthreads();
-    prof_mark(p, c, 2);
+    prof_mark<kInstr>(p, c, 2);
 
     // ---- phase 5 (warp 0): root push, or min detector and the list of children --------------------------
     if (warp == 0) {
@@ -1388,7 +1409,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
     }
     __syncthreads();
-    prof_mark(p, c, 3);
+    prof_mark<kInstr>(p, c, 3);
     if (c.action == kActDone) return c.status;
     if (c.action == kActSkip) {
       __syncthreads();
@@ -1415,7 +1436,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
     }
     if (clustered) cooperative_groups::this_cluster().sync();
     else __syncthreads();
-    prof_mark(p, c, 4);
+    prof_mark<kInstr>(p, c, 4);
 
     // ---- phase 7 (warp 0): pushes, in row order (tesseract.cc:590-605) ----------------------------------------
     if (warp == 0) {
@@ -1445,6 +1466,67 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
         for (uint32_t i = lane; i < K; i += 32) {  // chain nodes
           const uint4 meta = sm.res_meta[sm.clist[i]];
           __stcg(reinterpret_cast<uint4*>(chain + chain_size + i), make_uint4(meta.x, c.chain, (c.mind << 16) | (meta.z >> 16), meta.y));
+        }
+#ifndef TSR_WHOLE_HEAP_MIN_K
+#define TSR_WHOLE_HEAP_MIN_K 96
+#endif
+        if (K >= TSR_WHOLE_HEAP_MIN_K && heap_size + K <= sm.stage_cap) {
+          // A long row of children onto a small heap (the BB-code regime): the WHOLE heap is staged (node n at slot
+          // n - 1) and the K sifts run as a systolic pipeline instead of one after the other.  Push i performs its step s
+          // (hole at the s-th ancestor of its leaf: compare with the node one level up, move that node down or settle) at
+          // time 2 i + s.  With a lag of two steps between consecutive pushes every node a push reads or overwrites has
+          // already seen all the steps the earlier pushes make on it, so the heap ends up exactly as after K sequential
+          // std::push_heap calls (bits/stl_heap.h:135-148) - for any mix of leaf levels, including leaves whose parent is
+          // an earlier leaf of the same batch - in 2 K + depth steps instead of K x depth.  Lane l runs pushes l, l + 32,
+          // ... (a push lasts at most depth + 1 <= 33 steps, the lane is free again after 64).
+          const uint32_t hs = (uint32_t)heap_size;
+          for (uint32_t q = lane; q < hs; q += 32) sm.stage[q] = __ldcg(reinterpret_cast<const uint4*>(heap + q));
+          __syncwarp();
+          uint32_t my = lane, hole1 = 0;
+          bool active = false;
+          uint4 vv = make_uint4(0, 0, 0, 0);
+          HeapNode value;
+          value.cost = 0;
+          value.chain = 0;
+          value.num_dets = 0;
+          value.depth = 0;
+          const uint32_t t_end = 2 * (K - 1) + (32u - (uint32_t)__clz((int)(hs + K))) + 1;
+          for (uint32_t t = 0; t < t_end; ++t) {
+            if (!active && my < K && t == 2 * my) {
+              const uint32_t ci = sm.clist[my];
+              const uint4 meta = sm.res_meta[ci];
+              value.cost = sm.res_cost[ci];
+              value.chain = (uint32_t)(chain_size + my);
+              value.num_dets = (uint16_t)(meta.z & 0xFFFF);
+              value.depth = (uint16_t)(c.depth + 1);
+              vv = node_raw(value);
+              active = true;
+              hole1 = hs + my + 1;  // 1-based
+            }
+            if (active) {
+              bool up = false;
+              uint4 pv = make_uint4(0, 0, 0, 0);
+              if (hole1 > 1) {
+                pv = sm.stage[(hole1 >> 1) - 1];
+                up = node_greater(node_of(pv), value);
+              }
+              sm.stage[hole1 - 1] = up ? pv : vv;
+              if (up) {
+                hole1 >>= 1;
+              } else {
+                active = false;
+                my += 32;
+              }
+            }
+            __syncwarp();
+          }
+          for (uint32_t q = lane; q < hs + K; q += 32) __stcg(reinterpret_cast<uint4*>(heap + q), sm.stage[q]);
+          __syncwarp();
+          heap_size += K;
+          chain_size += K;
+          pushed += K;
+          ctr.Q += K;
+          i0 = K;
         }
         while (i0 < K) {
           // one sub-batch = new leaves on ONE tree level, so that "s levels up" names a distinct level for every s
@@ -1659,7 +1741,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
       }
     }
     __syncthreads();
-    prof_mark(p, c, 5);
+    prof_mark<kInstr>(p, c, 5);
     if (c.action == kActDone) return c.status;
     __syncthreads();
   }
@@ -1777,12 +1859,13 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
       cluster.sync();  // all children of this expansion are evaluated
     }
   } else {
-  const uint32_t n_paused = p.resume ? p.resume_n : 0u;
+  const bool resuming = kLat && p.resume;  // paused searches are continued by the wide variants only
+  const uint32_t n_paused = p.resume_n;
   uint32_t resume_at = unit;
   while (true) {
     uint32_t item, cur_slot = slot, sol_row = 0;
     const ResumeRec* rec = nullptr;
-    if (p.resume) {  // continue paused searches (one per CTA and round), each in the pool slot it was started in
+    if (resuming) {  // continue paused searches (one per CTA and round), each in the pool slot it was started in
       if (resume_at >= n_paused) break;
       rec = p.resume_list + resume_at;
       resume_at += n_units;
@@ -1812,7 +1895,7 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
     // A paused search keeps its queue, arena, visited set and masks in its slot.  In the narrow launch that is this
     // CTA's own slot: the CTA retires.  A resume launch works on the searches' slots and simply takes its next one.
     if (status == kItemPaused) {
-      if (p.resume) continue;
+      if (resuming) continue;
       break;
     }
     if (sm.act)  // back to the mandatory masks for the slot's next search
@@ -1837,7 +1920,7 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
     cooperative_groups::this_cluster().sync();
   }
   }
-  if (tid == 0 && p.prof && crank == 0) {  // (a helper's control block is a copy of its owner's)
+  if (kInstr && tid == 0 && p.prof && crank == 0) {  // (a helper's control block is a copy of its owner's)
     sm.ctl->prof[7] = ctr.X;
     for (int i = 0; i < 8; ++i) atomicAdd(p.prof + i, sm.ctl->prof[i]);
   }
@@ -1864,40 +1947,28 @@ int configure(size_t smem) {
 
 }  // namespace
 
-// `latency`: the variant for a lone search per SM (wide CTAs of up to 1024 threads: the tail and the retry tiers).
-// Entry-per-lane scans then use batched row extents, L1 prefetch and the quotient table in shared memory.
+// Variants.  `diag` (template kInstr): the diagnostics build — counter S of the entry-per-lane scan, the visited-set audit,
+// the visualization trace and the phase profile are compiled in only there, so that production launches carry none of
+// that code (measured: the audit's hit index alone cost the headline 3.6 %).  `latency`: the variant for a lone search
+// per SM (wide CTAs of up to 1024 threads: the tail and the retry tiers); entry-per-lane scans then use batched row
+// extents, L1 prefetch and the quotient table in shared memory.
 uint32_t search_fast_smem_bytes(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits, bool latency) {
   return make_layout(t.D, t.nwords, t.fn_costs * t.fnstride, t.max_row_len, warps, hc_shared, bits ? t.bs_group : 0,
                      bits ? t.bs_cap : 0, t.sp_on != 0, latency).total;
 }
 
-int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits, bool latency) {
+namespace {
+template <bool kInstr, bool kBits, bool kLat>
+int occupancy_of(uint32_t warps, size_t smem) {
   int n = 0;
-  const size_t smem = search_fast_smem_bytes(t, warps, hc_shared, bits, latency);
-  if (smem > 227 * 1024) return 0;
-  cudaError_t e;
-  if (bits && latency) {
-    if (configure<false, true, true>(smem) != 0) return 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, true, true>, (int)(warps * 32), smem);
-  } else if (bits) {
-    if (configure<false, true, false>(smem) != 0) return 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, true, false>, (int)(warps * 32), smem);
-  } else if (latency) {
-    if (configure<false, false, true>(smem) != 0) return 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, false, true>, (int)(warps * 32), smem);
-  } else {
-    if (configure<false, false, false>(smem) != 0 || configure<true, false, false>(smem) != 0) return 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<false, false, false>, (int)(warps * 32), smem);
-  }
-  return e == cudaSuccess ? n : 0;
+  if (configure<kInstr, kBits, kLat>(smem) != 0) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_fast_kernel<kInstr, kBits, kLat>, (int)(warps * 32), smem) != cudaSuccess) return 0;
+  return n;
 }
-
-int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool instrumented, bool bits, bool latency,
-                       void* stream) {
-  if ((p.n_work == 0 && !p.resume) || blocks == 0) return 0;
-  const size_t smem = search_fast_smem_bytes(p.t, warps, p.hc_shared != 0, bits, latency);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (latency && p.cluster > 1) {  // thread-block clusters: blocks = units x cluster size
+template <bool kInstr, bool kBits, bool kLat>
+int launch_variant(const SearchParams& p, uint32_t blocks, uint32_t warps, size_t smem, cudaStream_t st) {
+  if (int e = configure<kInstr, kBits, kLat>(smem)) return e;
+  if (kLat && p.cluster > 1) {  // thread-block clusters: blocks = units x cluster size
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(blocks, 1, 1);
     cfg.blockDim = dim3(warps * 32, 1, 1);
@@ -1910,30 +1981,39 @@ int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, b
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (bits) {
-      if (int e = configure<false, true, true>(smem)) return e;
-      return (int)cudaLaunchKernelEx(&cfg, search_fast_kernel<false, true, true>, p);
-    }
-    if (int e = configure<false, false, true>(smem)) return e;
-    return (int)cudaLaunchKernelEx(&cfg, search_fast_kernel<false, false, true>, p);
+    return (int)cudaLaunchKernelEx(&cfg, search_fast_kernel<kInstr, kBits, kLat>, p);
   }
-  if (bits && latency) {
-    if (int e = configure<false, true, true>(smem)) return e;
-    search_fast_kernel<false, true, true><<<blocks, warps * 32, smem, st>>>(p);
-  } else if (bits) {
-    if (int e = configure<false, true, false>(smem)) return e;
-    search_fast_kernel<false, true, false><<<blocks, warps * 32, smem, st>>>(p);
-  } else if (instrumented) {
-    if (int e = configure<true, false, false>(smem)) return e;
-    search_fast_kernel<true, false, false><<<blocks, warps * 32, smem, st>>>(p);
-  } else if (latency) {
-    if (int e = configure<false, false, true>(smem)) return e;
-    search_fast_kernel<false, false, true><<<blocks, warps * 32, smem, st>>>(p);
-  } else {
-    if (int e = configure<false, false, false>(smem)) return e;
-    search_fast_kernel<false, false, false><<<blocks, warps * 32, smem, st>>>(p);
-  }
+  search_fast_kernel<kInstr, kBits, kLat><<<blocks, warps * 32, smem, st>>>(p);
   return (int)cudaGetLastError();
+}
+}  // namespace
+
+int search_fast_max_blocks_per_sm(const DeviceTables& t, uint32_t warps, bool hc_shared, bool bits, bool latency) {
+  const size_t smem = search_fast_smem_bytes(t, warps, hc_shared, bits, latency);
+  if (smem > 227 * 1024) return 0;
+  // a production variant and its diagnostics twin share the block shape
+  if (latency) {
+    if (bits) return std::min(occupancy_of<false, true, true>(warps, smem), occupancy_of<true, true, true>(warps, smem));
+    return std::min(occupancy_of<false, false, true>(warps, smem), occupancy_of<true, false, true>(warps, smem));
+  }
+  if (bits) return std::min(occupancy_of<false, true, false>(warps, smem), occupancy_of<true, true, false>(warps, smem));
+  return std::min(occupancy_of<false, false, false>(warps, smem), occupancy_of<true, false, false>(warps, smem));
+}
+
+int launch_search_fast(const SearchParams& p, uint32_t blocks, uint32_t warps, bool diag, bool bits, bool latency, void* stream) {
+  if ((p.n_work == 0 && !p.resume) || blocks == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = search_fast_smem_bytes(p.t, warps, p.hc_shared != 0, bits, latency);
+  switch ((diag ? 4 : 0) | (bits ? 2 : 0) | (latency ? 1 : 0)) {
+    case 0: return launch_variant<false, false, false>(p, blocks, warps, smem, st);
+    case 1: return launch_variant<false, false, true>(p, blocks, warps, smem, st);
+    case 2: return launch_variant<false, true, false>(p, blocks, warps, smem, st);
+    case 3: return launch_variant<false, true, true>(p, blocks, warps, smem, st);
+    case 4: return launch_variant<true, false, false>(p, blocks, warps, smem, st);
+    case 5: return launch_variant<true, false, true>(p, blocks, warps, smem, st);
+    case 6: return launch_variant<true, true, false>(p, blocks, warps, smem, st);
+    default: return launch_variant<true, true, true>(p, blocks, warps, smem, st);
+  }
 }
 
 }  // namespace tsr
