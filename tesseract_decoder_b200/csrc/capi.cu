@@ -289,6 +289,7 @@ void init_device(tsr_decoder& h) {
       h.F.why_not = "the per-search state does not fit in shared memory";
     } else {
       h.wpb = w;
+      if (const char* e = std::getenv("TSR_CTAS_PER_SM")) occ = std::max(1, std::min(occ, std::atoi(e)));  // experiments
       h.blocks = (uint32_t)(h.sm_count * occ);
       slots = h.blocks;
       if (h.cfg.search_slots && h.cfg.search_slots < slots) slots = h.blocks = std::max<uint32_t>(h.cfg.search_slots, 1);

@@ -33,6 +33,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "search.h"
 #include "sparsify.cuh"
@@ -1940,6 +1941,9 @@ __global__ void __launch_bounds__(kLat ? 1024 : 512, kLat ? 1 : 2) search_fast_k
 
 template <bool kInstr, bool kBits, bool kLat>
 int configure(size_t smem) {
+  if (const char* e = std::getenv("TSR_CARVEOUT"))  // experiments: shared-memory carveout in percent (the rest is L1)
+    if (cudaError_t err = cudaFuncSetAttribute(search_fast_kernel<kInstr, kBits, kLat>, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e)))
+      return (int)err;
   if (smem > 48 * 1024)
     return (int)cudaFuncSetAttribute(search_fast_kernel<kInstr, kBits, kLat>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   return 0;
