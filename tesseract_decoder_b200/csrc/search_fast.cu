@@ -450,16 +450,17 @@ __device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, 
         r.c3 ^= t2;
       };
       const uint16_t* fl = sm.fl + g * cap;
-      uint32_t q = 0;
-      for (; q + 4 <= nf; q += 4) {
-        const uint32_t m0 = __ldg(mrow + (size_t)fl[q] * nw), m1 = __ldg(mrow + (size_t)fl[q + 1] * nw);
-        const uint32_t m2 = __ldg(mrow + (size_t)fl[q + 2] * nw), m3 = __ldg(mrow + (size_t)fl[q + 3] * nw);
+      // four loads in flight also for the last (usually the only) group: adding an empty mask changes nothing
+      for (uint32_t q = 0; q < nf; q += 4) {
+        const uint32_t m0 = __ldg(mrow + (size_t)fl[q] * nw);
+        const uint32_t m1 = q + 1 < nf ? __ldg(mrow + (size_t)fl[q + 1] * nw) : 0u;
+        const uint32_t m2 = q + 2 < nf ? __ldg(mrow + (size_t)fl[q + 2] * nw) : 0u;
+        const uint32_t m3 = q + 3 < nf ? __ldg(mrow + (size_t)fl[q + 3] * nw) : 0u;
         add(m0);
         add(m1);
         add(m2);
         add(m3);
       }
-      for (; q < nf; ++q) add(__ldg(mrow + (size_t)fl[q] * nw));
     }
     // C: blocked entries — the row's own prefix, and per blocking neighbour a prefix of the pair list
     uint32_t valid = len - lo >= 32 ? 0xFFFFFFFFu : ((1u << (len - lo)) - 1u);
@@ -500,16 +501,21 @@ __device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm
       const uint32_t* cid4 = reinterpret_cast<const uint32_t*>(t.bs_cls_cid + r.cls_off);  // 4 class ids per word
       auto consider = [&](uint32_t cm, uint32_t cid) {
         if (cm) {
-          uint32_t m = cm, q;
+          // keep, plane by plane from the top, the entries whose count has that bit set whenever one does: what is left
+          // shares the largest count, whose bits are the outcomes of those tests
+          uint32_t m = cm, q, v;
           q = m & r.c3;
+          v = q ? 8u : 0u;
           m = q ? q : m;
           q = m & r.c2;
+          v |= q ? 4u : 0u;
           m = q ? q : m;
           q = m & r.c1;
+          v |= q ? 2u : 0u;
           m = q ? q : m;
           q = m & r.c0;
+          v |= q ? 1u : 0u;
           m = q ? q : m;
-          const uint32_t v = ((m & r.c3) ? 8u : 0u) | ((m & r.c2) ? 4u : 0u) | ((m & r.c1) ? 2u : 0u) | ((m & r.c0) ? 1u : 0u);
           const uint32_t cls = cid * t.fnstride + v + 1;
           const uint32_t key = ((uint32_t)sm.rank[cls] << 12) | (wl * 32 + (uint32_t)__ffs((int)m) - 1);
           if (key < best) {
@@ -545,7 +551,8 @@ __device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm
 // the list when fewer than 32 free slots remain.
 __device__ __forceinline__ void tl_append(const Smem& sm, uint32_t& nt, uint32_t word, uint32_t base_det, uint32_t lane) {
   const uint32_t cnt = (uint32_t)__popc(word);
-  if (lane < cnt) sm.tl[nt + lane] = (uint16_t)(base_det + __fns(word, 0, (int)lane + 1));
+  // lane b owns bit b: its place in the list is the number of set bits below it
+  if ((word >> lane) & 1u) sm.tl[nt + (uint32_t)__popc(word & ((1u << lane) - 1u))] = (uint16_t)(base_det + lane);
   nt += cnt;
 }
 
@@ -914,9 +921,16 @@ __device__ __forceinline__ void eval_child(const SearchParams& p, const Smem& sm
       const uint32_t wi = wb + lane;
       const uint32_t w = wi < n_fz ? sm.fz[wi] : 0xFFFFFFFFu;
       uint32_t mine = 0;
-      for (uint32_t k = 0; k < deg; ++k) {
-        const uint32_t d = __shfl_sync(kFull, dj, (int)k);
-        if (wi < n_fz) mine |= __ldg(t.adj + (size_t)d * nwords + w);
+      for (uint32_t k = 0; k < deg; k += 4) {  // four adjacency words in flight
+        const uint32_t d0 = __shfl_sync(kFull, dj, (int)k), d1 = __shfl_sync(kFull, dj, (int)((k + 1) & 31));
+        const uint32_t d2 = __shfl_sync(kFull, dj, (int)((k + 2) & 31)), d3 = __shfl_sync(kFull, dj, (int)((k + 3) & 31));
+        if (wi < n_fz) {
+          const uint32_t a0 = __ldg(t.adj + (size_t)d0 * nwords + w);
+          const uint32_t a1 = k + 1 < deg ? __ldg(t.adj + (size_t)d1 * nwords + w) : 0u;
+          const uint32_t a2 = k + 2 < deg ? __ldg(t.adj + (size_t)d2 * nwords + w) : 0u;
+          const uint32_t a3 = k + 3 < deg ? __ldg(t.adj + (size_t)d3 * nwords + w) : 0u;
+          mine |= a0 | a1 | a2 | a3;
+        }
       }
       for (uint32_t k = 0; k < deg; ++k) {
         const uint32_t d = __shfl_sync(kFull, dj, (int)k);
@@ -1468,10 +1482,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           const uint4 meta = sm.res_meta[sm.clist[i]];
           __stcg(reinterpret_cast<uint4*>(chain + chain_size + i), make_uint4(meta.x, c.chain, (c.mind << 16) | (meta.z >> 16), meta.y));
         }
-#ifndef TSR_WHOLE_HEAP_MIN_K
-#define TSR_WHOLE_HEAP_MIN_K 96
-#endif
-        if (K >= TSR_WHOLE_HEAP_MIN_K && heap_size + K <= sm.stage_cap) {
+        if (K >= 96 && heap_size + K <= sm.stage_cap) {
           // A long row of children onto a small heap (the BB-code regime): the WHOLE heap is staged (node n at slot
           // n - 1) and the K sifts run as a systolic pipeline instead of one after the other.  Push i performs its step s
           // (hole at the s-th ancestor of its leaf: compare with the node one level up, move that node down or settle) at
@@ -1492,15 +1503,25 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
           value.num_dets = 0;
           value.depth = 0;
           const uint32_t t_end = 2 * (K - 1) + (32u - (uint32_t)__clz((int)(hs + K))) + 1;
+          // Every new node starts at its leaf (push_back, bits/stl_heap.h:135): placed there up front by all lanes, a
+          // push then begins with one load of its own slot (nobody else touches that slot before: only later pushes
+          // have it on their paths), fetched as soon as the lane's previous push has settled.
+          for (uint32_t i = lane; i < K; i += 32) {
+            const uint32_t ci = sm.clist[i];
+            const uint4 meta = sm.res_meta[ci];
+            HeapNode nv;
+            nv.cost = sm.res_cost[ci];
+            nv.chain = (uint32_t)(chain_size + i);
+            nv.num_dets = (uint16_t)(meta.z & 0xFFFF);
+            nv.depth = (uint16_t)(c.depth + 1);
+            sm.stage[hs + i] = node_raw(nv);
+          }
+          __syncwarp();
+          uint4 nextv = my < K ? sm.stage[hs + my] : make_uint4(0, 0, 0, 0);
           for (uint32_t t = 0; t < t_end; ++t) {
-            if (!active && my < K && t == 2 * my) {
-              const uint32_t ci = sm.clist[my];
-              const uint4 meta = sm.res_meta[ci];
-              value.cost = sm.res_cost[ci];
-              value.chain = (uint32_t)(chain_size + my);
-              value.num_dets = (uint16_t)(meta.z & 0xFFFF);
-              value.depth = (uint16_t)(c.depth + 1);
-              vv = node_raw(value);
+            if (!active && t == 2 * my && my < K) {
+              vv = nextv;
+              value = node_of(vv);
               active = true;
               hole1 = hs + my + 1;  // 1-based
             }
@@ -1517,6 +1538,7 @@ __device__ uint32_t run_search(const SearchParams& p, const Smem& sm, uint32_t s
               } else {
                 active = false;
                 my += 32;
+                if (my < K) nextv = sm.stage[hs + my];
               }
             }
             __syncwarp();
