@@ -1,6 +1,11 @@
 #!/bin/bash
 # Final session of a round: GPU tests, the default bench (as the driver runs it), launch list, one full ncu capture.
 tag=$1
+# 0. one full ncu capture of the headline kernel (16384 shots, after its plain run exits 0), then profiles/traffic.json from it
+SKIP=1 bash scripts/gpu_ncu.sh ${tag} c4_bb144_p1e-4_65536:16384 > gpurun_out/${tag}_ncu_capture.log 2>&1
+if [ -s gpurun_out/${tag}_c4_bb144_p1e-4_65536.txt ]; then
+  python scripts/update_traffic.py gpurun_out/${tag}_c4_bb144_p1e-4_65536.txt gpurun_out/${tag}_c4_bb144_p1e-4_65536.lines.txt 16384 profiles/${FINAL_NAME:-r02_z}_bb144_search_fast_bits && cp profiles/traffic.json gpurun_out/${tag}_traffic.json
+fi
 timeout 600 python -m pytest tests -m gpu -q --durations=8 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log; tail -3 gpurun_out/${tag}_pytest.log
 timeout 900 python bench.py --steps ${STEPS:-5} --warmup ${WARMUP:-3} > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
 tail -c 2500 gpurun_out/${tag}_bench.json; tail -12 gpurun_out/${tag}_bench.err | cut -c1-400
