@@ -208,13 +208,11 @@ void init_device(tsr_decoder& h) {
       h.bs_meta.upload(h.B.rowmeta);
       h.bs_adjpre.upload(h.B.adjpre);
       h.bs_masks.upload(h.B.masks);
-      h.bs_cls_cid.upload(h.B.cls_cid);
       h.bs_pl_off.upload(h.B.pl_off);
       h.bs_pl.upload(h.B.pl);
       dt.bs_meta = h.bs_meta.as<uint4>();
       dt.bs_adjpre = h.bs_adjpre.as<uint16_t>();
       dt.bs_masks = h.bs_masks.as<uint32_t>();
-      dt.bs_cls_cid = h.bs_cls_cid.as<uint8_t>();
       dt.bs_pl_off = h.bs_pl_off.as<uint32_t>();
       dt.bs_pl = h.bs_pl.as<uint32_t>();
       dt.bs_group = h.B.group;

@@ -147,9 +147,8 @@ BitTables build_bit_tables(const DemTables& T, const FastTables& F) {
   B.rowmeta.resize(D);
   B.adjpre.assign((size_t)D * aw + 1, 0);
   uint32_t max_nw = 1;
-  uint64_t mask_words = 0, pairs = 0, classes = 0;
+  uint64_t mask_words = 0, pairs = 0;
   std::vector<std::vector<uint32_t>> nbrs(D);
-  std::vector<std::vector<uint8_t>> row_cls(D);
   for (uint64_t x = 0; x < D; ++x) {
     uint32_t run = 0;
     for (uint32_t w = 0; w < aw; ++w) {
@@ -165,24 +164,26 @@ BitTables build_bit_tables(const DemTables& T, const FastTables& F) {
     const uint32_t len = T.row_off[x + 1] - T.row_off[x];
     const uint32_t nw = std::max<uint32_t>((len + 31) / 32, 1);
     max_nw = std::max(max_nw, nw);
-    std::vector<uint8_t> cls;
-    for (uint32_t k = T.row_off[x]; k < T.row_off[x + 1]; ++k) cls.push_back(F.cost_id[(size_t)T.row_err[k]]);
-    std::sort(cls.begin(), cls.end());
-    cls.erase(std::unique(cls.begin(), cls.end()), cls.end());  // ascending cost id == ascending cost
-    row_cls[x] = cls;
+    uint32_t slots = 0;  // most distinct costs in one 32-entry word of the row
+    for (uint32_t w0 = 0; w0 < len; w0 += 32) {
+      std::vector<uint8_t> cls;
+      for (uint32_t i = w0; i < std::min(len, w0 + 32); ++i) cls.push_back(F.cost_id[(size_t)T.row_err[T.row_off[x] + i]]);
+      std::sort(cls.begin(), cls.end());
+      slots = std::max<uint32_t>(slots, (uint32_t)(std::unique(cls.begin(), cls.end()) - cls.begin()));
+    }
     BitRowMeta& m = B.rowmeta[x];
     m.len = len;
     m.nw = nw;
-    m.ncls = ((uint32_t)cls.size() + 3) & ~3u;  // padded to 4 with empty classes (the kernel reads 4 at a time)
+    m.ncls = std::max<uint32_t>((slots + 1) & ~1u, 2);  // even: the kernel reads two slots per 16-byte load
     m.pad = 0;
+    m.reserved = 0;
     m.mask_off = (uint32_t)mask_words;
     mask_words += (uint64_t)nbrs[x].size() * nw;
+    mask_words = (mask_words + 3) & ~uint64_t{3};
     m.cmask_off = (uint32_t)mask_words;
-    mask_words += (uint64_t)m.ncls * nw;
+    mask_words += (uint64_t)2 * m.ncls * nw;
     m.pair_base = (uint32_t)pairs;
     pairs += nbrs[x].size();
-    m.cls_off = (uint32_t)classes;
-    classes += m.ncls;
     if (mask_words > 0x7FFFFFFFull) {
       B.why_not = "the bit-sliced row masks exceed 8 GB";
       return B;
@@ -195,15 +196,24 @@ BitTables build_bit_tables(const DemTables& T, const FastTables& F) {
     return B;
   }
   B.masks.assign((size_t)mask_words + 4, 0);
-  B.cls_cid.assign((size_t)classes + 4, 0);
   std::vector<std::vector<uint32_t>> lists((size_t)pairs);
   for (uint64_t x = 0; x < D; ++x) {
     const BitRowMeta& m = B.rowmeta[x];
-    for (uint32_t k = 0; k < row_cls[x].size(); ++k) B.cls_cid[m.cls_off + k] = row_cls[x][k];
+    for (uint32_t w0 = 0; w0 < m.len; w0 += 32) {  // this word's classes, ascending cost id == ascending cost
+      std::vector<uint8_t> cls;
+      for (uint32_t i = w0; i < std::min(m.len, w0 + 32); ++i) cls.push_back(F.cost_id[(size_t)T.row_err[T.row_off[x] + i]]);
+      std::sort(cls.begin(), cls.end());
+      cls.erase(std::unique(cls.begin(), cls.end()), cls.end());
+      uint32_t* slot = B.masks.data() + m.cmask_off + (size_t)2 * m.ncls * (w0 >> 5);
+      for (size_t k = 0; k < cls.size(); ++k) slot[2 * k + 1] = cls[k];
+      for (uint32_t i = w0; i < std::min(m.len, w0 + 32); ++i) {
+        const uint8_t cid = F.cost_id[(size_t)T.row_err[T.row_off[x] + i]];
+        const size_t k = (size_t)(std::lower_bound(cls.begin(), cls.end(), cid) - cls.begin());
+        slot[2 * k] |= 1u << (i & 31);
+      }
+    }
     for (uint32_t i = 0; i < m.len; ++i) {
       const uint64_t e = (uint64_t)T.row_err[T.row_off[x] + i];
-      const uint32_t kc = (uint32_t)(std::lower_bound(row_cls[x].begin(), row_cls[x].end(), F.cost_id[e]) - row_cls[x].begin());
-      B.masks[m.cmask_off + (size_t)kc * m.nw + (i >> 5)] |= 1u << (i & 31);
       const auto& dets = T.errors[e].detectors;
       for (size_t q = 0; q < dets.size(); ++q) {
         const uint32_t y = (uint32_t)dets[q];
@@ -380,7 +390,8 @@ uint64_t cross_check_detcost(const DemTables& T, const FastTables& F, const BitT
           const uint32_t U = valid & ~Bm;
           if (!U) continue;
           for (uint32_t kc = 0; kc < m.ncls; ++kc) {
-            uint32_t cm = B.masks[m.cmask_off + (size_t)kc * m.nw + wl] & U;
+            const uint32_t* slot = B.masks.data() + m.cmask_off + ((size_t)wl * m.ncls + kc) * 2;
+            uint32_t cm = slot[0] & U;
             if (!cm) continue;
             uint32_t q;
             q = cm & c3;
@@ -392,7 +403,7 @@ uint64_t cross_check_detcost(const DemTables& T, const FastTables& F, const BitT
             q = cm & c0;
             cm = q ? q : cm;
             const uint32_t v = ((cm & c3) ? 8u : 0u) | ((cm & c2) ? 4u : 0u) | ((cm & c1) ? 2u : 0u) | ((cm & c0) ? 1u : 0u);
-            const uint32_t cls = (uint32_t)B.cls_cid[m.cls_off + kc] * F.nstride + v + 1;
+            const uint32_t cls = slot[1] * F.nstride + v + 1;
             const uint32_t key = ((uint32_t)F.rank[cls] << 12) | (lo + (uint32_t)__builtin_ctz(cm));
             if (key < bbest) {
               bbest = key;

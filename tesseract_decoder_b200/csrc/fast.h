@@ -60,13 +60,15 @@ FastTables build_fast_tables(const DemTables& T);
 //     of every row entry is 1 + the bit-sliced sum of the masks of the FIRED neighbours;
 //   * for each pair (x, y) and each 32-entry word of row[x]: the entries of that word containing y as
 //     (rank in row[y], bit) sorted by rank — the entries a block threshold on y removes are a prefix of that list;
-//   * for each distinct cost in row[x] (ascending): the L-bit mask of entries with that cost.
+//   * for each 32-entry word of row[x]: the distinct costs among its entries (ascending) as `ncls` slots of
+//     (mask of the word's entries with that cost, cost id); unused slots are (0, 0).  A word of a BB [[144,12,12]]
+//     row holds 3.4 cost classes on average (at most 9) while the row has 9-12: a lane scans its own word's classes.
 struct BitRowMeta {   // 32 bytes, one per detector
   uint32_t mask_off;  // word offset of the neighbour masks [j][word] in `masks`
-  uint32_t cmask_off; // word offset of the cost-class masks [k][word] in `masks`
+  uint32_t cmask_off; // word offset (a multiple of 4) of the class slots [word][ncls] x {mask, cost id} in `masks`
   uint32_t pair_base; // pair index of (x, first neighbour); pair lists are pl[pl_off[p] .. pl_off[p+1])
-  uint32_t cls_off;   // index of the first cost class of the row in cls_cid
-  uint32_t len, nw, ncls, pad;
+  uint32_t reserved;
+  uint32_t len, nw, ncls, pad;  // ncls: class slots per word (even)
 };
 struct BitTables {
   bool ok = false;
@@ -76,7 +78,6 @@ struct BitTables {
   std::vector<BitRowMeta> rowmeta;  // [D]
   std::vector<uint16_t> adjpre;     // [D * adj_words] set bits of adj[x] before word w
   std::vector<uint32_t> masks;
-  std::vector<uint8_t> cls_cid;
   std::vector<uint32_t> pl_off;     // [masks.size() + 1], indexed like the neighbour masks: per (pair, row word)
   std::vector<uint32_t> pl;         // rank in the neighbour's row << 16 | bit within the row word
 };

@@ -129,7 +129,7 @@ struct tsr_decoder {
 
   // Device tables.
   tsr_impl::DevBuf row_off, row_err, rec_a, rec_b, rec_c, e_off, e_det, e_rank, e_cost, e_nnbr, eo_off, eo_obs, e2dem, adj,
-      zobrist, order_det, order_pos, frec_a, frec_b, frank, fquot, bs_meta, bs_adjpre, bs_masks, bs_cls_cid, bs_pl_off, bs_pl,
+      zobrist, order_det, order_pos, frec_a, frec_b, frank, fquot, bs_meta, bs_adjpre, bs_masks, bs_pl_off, bs_pl,
       sp_mand, sp_opt, sp_crank, sp_act;
   int64_t sparsify_limit = -1;  // effective sparsify_reactivate_limit (tesseract.cc:272-277); -1 = sparsify off
   tsr::DeviceTables dt;

@@ -40,7 +40,6 @@ struct DeviceTables {
   const uint4* bs_meta = nullptr;       // [D][2] BitRowMeta
   const uint16_t* bs_adjpre = nullptr;  // [D][nwords]
   const uint32_t* bs_masks = nullptr;
-  const uint8_t* bs_cls_cid = nullptr;
   const uint32_t* bs_pl_off = nullptr;
   const uint32_t* bs_pl = nullptr;
   uint32_t bs_group = 0, bs_cap = 0;

@@ -332,7 +332,7 @@ __device__ __forceinline__ double scan_row(const DeviceTables& t, const uint16_t
 struct BsRow {
   uint32_t U;               // unblocked entries of this lane's word
   uint32_t c0, c1, c2, c3;  // bit planes of (fired-detector count - 1) per entry
-  uint32_t nw, cmask_off, cls_off, ncls;
+  uint32_t nw, cmask_off, ncls;
 };
 
 // The warp's current state is the node's (sm.pst thresholds, sm.fbits fired, sm.pbb detectors with a threshold)
@@ -432,7 +432,6 @@ __device__ __forceinline__ BsRow bs_core(const DeviceTables& t, const Smem& sm, 
   r.U = r.c0 = r.c1 = r.c2 = r.c3 = 0;
   r.nw = mb.y;
   r.cmask_off = ma.y;
-  r.cls_off = ma.w;
   r.ncls = mb.z;
   if (active && wl < mb.y) {
     const uint32_t nw = mb.y, len = mb.x, lo = wl * 32;
@@ -497,8 +496,8 @@ __device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm
     // strictly with n), ties going to the lowest position; the classes then compete on (rank, position).
     // Straight-line per class, so the lanes of a warp stay converged.
     if (r.U) {
-      const uint32_t* crow = t.bs_masks + r.cmask_off + wl;
-      const uint32_t* cid4 = reinterpret_cast<const uint32_t*>(t.bs_cls_cid + r.cls_off);  // 4 class ids per word
+      // this lane's word: r.ncls slots of {mask of the word's entries with one cost, cost id}, two slots per 16-byte load
+      const uint4* cslots = reinterpret_cast<const uint4*>(t.bs_masks + r.cmask_off) + (size_t)wl * (r.ncls >> 1);
       auto consider = [&](uint32_t cm, uint32_t cid) {
         if (cm) {
           // keep, plane by plane from the top, the entries whose count has that bit set whenever one does: what is left
@@ -524,14 +523,14 @@ __device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm
           }
         }
       };
-      for (uint32_t kc = 0; kc < r.ncls; kc += 4) {  // ncls is padded to a multiple of 4 with empty classes
-        const uint32_t ids = __ldg(cid4 + (kc >> 2));
-        const uint32_t m0 = __ldg(crow + (size_t)(kc + 0) * r.nw), m1 = __ldg(crow + (size_t)(kc + 1) * r.nw);
-        const uint32_t m2 = __ldg(crow + (size_t)(kc + 2) * r.nw), m3 = __ldg(crow + (size_t)(kc + 3) * r.nw);
-        consider(m0 & r.U, ids & 0xFF);
-        consider(m1 & r.U, (ids >> 8) & 0xFF);
-        consider(m2 & r.U, (ids >> 16) & 0xFF);
-        consider(m3 & r.U, ids >> 24);
+      const uint32_t nload = r.ncls >> 1;
+      for (uint32_t k = 0; k < nload; k += 2) {  // two loads (four slots) in flight
+        const uint4 sa = ldg16(cslots + k);
+        const uint4 sb = k + 1 < nload ? ldg16(cslots + k + 1) : make_uint4(0, 0, 0, 0);
+        consider(sa.x & r.U, sa.y);
+        consider(sa.z & r.U, sa.w);
+        consider(sb.x & r.U, sb.y);
+        consider(sb.z & r.U, sb.w);
       }
     }
     for (uint32_t off = G >> 1; off >= 1; off >>= 1) {
