@@ -516,7 +516,7 @@ __device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm
           v |= q ? 1u : 0u;
           m = q ? q : m;
           const uint32_t cls = cid * t.fnstride + v + 1;
-          const uint32_t key = ((uint32_t)sm.rank[cls] << 12) | (wl * 32 + (uint32_t)__ffs((int)m) - 1);
+          const uint32_t key = ((uint32_t)sm.rank[cls] << 12) | ((uint32_t)__ffs((int)m) - 1);  // the word's offset is added below
           if (key < best) {
             best = key;
             bcls = cls;
@@ -533,6 +533,7 @@ __device__ __forceinline__ void bs_targets(const DeviceTables& t, const Smem& sm
         consider(sb.z & r.U, sb.w);
       }
     }
+    if (best != kKeyInf) best += wl * 32;
     for (uint32_t off = G >> 1; off >= 1; off >>= 1) {
       const uint32_t ob = __shfl_xor_sync(kFull, best, (int)off);
       const uint32_t oc = __shfl_xor_sync(kFull, bcls, (int)off);
