@@ -241,6 +241,29 @@ double tsr_merge_weights(double a, double b);           /* common.cc:118-123 */
  * Used by the CLI's --dem-out (tesseract_main.cc:625-639).  Caller frees *dem_text_out with tsr_free. */
 int tsr_dem_from_counts(const char* dem_text, const uint64_t* counts, uint64_t n_counts, uint64_t num_shots,
                         char** dem_text_out);
+/* The ingestion stages on their own — what tesseract_decoder.common / .utils export next to the decoder
+ * (common.pybind.h:143-213, utils.pybind.h:43-135); DEM text in, flattened DEM text out (caller frees with tsr_free;
+ * dem_text_out may be NULL).  Host only, no device needed.
+ *   tsr_merge_indistinguishable_errors  common::merge_indistinguishable_errors (common.cc:139-190): errors with the same
+ *       symptom merged with merge_weights, first-seen order, DETECTOR / LOGICAL_OBSERVABLE instructions first;
+ *       error_index_map [tsr_dem_count_errors(dem_text)] (may be NULL) = merged index of every input error.
+ *   tsr_remove_zero_probability_errors  common::remove_zero_probability_errors (common.cc:192-218);
+ *       error_index_map[i] = output index, or UINT64_MAX for a dropped error. */
+int tsr_merge_indistinguishable_errors(const char* dem_text, char** dem_text_out, uint64_t* error_index_map);
+int tsr_remove_zero_probability_errors(const char* dem_text, char** dem_text_out, uint64_t* error_index_map);
+int64_t tsr_dem_count_errors(const char* dem_text); /* error instructions of the flattened DEM; < 0 = status */
+/* get_errors_from_dem (utils.cc:253-261): the errors with probability > 0 as common::Error values (common.cc:52-88:
+ * likelihood_cost = -log(p/(1-p)); detectors and observables XOR-reduced, ascending).  Returns their number (< 0 =
+ * status).  Call once with NULL arrays for the sizes (*n_dets, *n_obs), then with cost [n], det_offsets [n+1],
+ * dets [*n_dets], obs_offsets [n+1], obs [*n_obs].  Every pointer may be NULL. */
+int64_t tsr_get_errors_from_dem(const char* dem_text, double* cost, uint64_t* det_offsets, int32_t* dets,
+                                uint64_t* obs_offsets, int32_t* obs, uint64_t* n_dets, uint64_t* n_obs);
+/* build_detector_graph (utils.cc:60-87): detectors are neighbours when one error flips both; sorted, unique.
+ * offsets [D+1], neighbors [returned count]; either may be NULL (sizing call).  Returns the count, < 0 = status. */
+int64_t tsr_build_detector_graph(const char* dem_text, uint64_t* offsets, uint64_t* neighbors);
+/* get_detector_coords (utils.cc:32-58): the coordinate list of every DETECTOR instruction, in DEM order.
+ * *n_rows = number of DETECTOR instructions; offsets [*n_rows+1], coords [returned count]; pointers may be NULL. */
+int64_t tsr_get_detector_coords(const char* dem_text, uint64_t* n_rows, uint64_t* offsets, double* coords);
 /* Stand-ins for the stim services the reference CLI uses (tesseract_main.cc:191-211, utils.cc:207-251):
  * circuit text -> DEM text (caller frees with tsr_free) and an i.i.d. DEM shot sampler into bit-packed
  * rows ([shots][ceil(D/8)], [shots][ceil(O/8)]; obs_out may be NULL). */

@@ -87,6 +87,17 @@ def _lib(kind: str) -> C.CDLL:
     lib.orc_counters.argtypes = [C.c_void_p, u64p, C.c_int]
     lib.orc_visualization_write.argtypes = [C.c_void_p, C.c_char_p]
     lib.orc_sample_dem_b8.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, u8p, u8p]
+    if kind == "reference":  # the reference's standalone ingestion functions (oracle_api.h: REFERENCE BUILD ONLY)
+        lib.orc_dem_dump.restype = C.c_int64
+        lib.orc_dem_dump.argtypes = [C.c_char_p, C.c_int, u64p, u8p, u64p, f64p, u64p, u64p, u64p]
+        lib.orc_get_errors_from_dem.restype = C.c_int64
+        lib.orc_get_errors_from_dem.argtypes = [C.c_char_p, f64p, u64p, i32p, u64p, i32p, u64p, u64p]
+        lib.orc_build_detector_graph.restype = C.c_int64
+        lib.orc_build_detector_graph.argtypes = [C.c_char_p, u64p, u64p]
+        lib.orc_get_detector_coords.restype = C.c_int64
+        lib.orc_get_detector_coords.argtypes = [C.c_char_p, u64p, u64p, f64p]
+        lib.orc_error_text.argtypes = [C.c_double, i32p, C.c_uint64, i32p, C.c_uint64, C.c_char_p, C.c_uint64, f64p]
+        lib.orc_cost_of_probability.argtypes = [C.c_double, f64p]
     _libs[kind] = lib
     return lib
 
@@ -110,6 +121,91 @@ def build_det_orders(dem_text: str, num_det_orders: int, method: int = 1, seed: 
     if lib.orc_build_det_orders(dem_text.encode(), num_det_orders, method, seed, _p(out, C.c_uint64)) != 0:
         raise OracleError(lib.orc_last_error().decode())
     return out
+
+
+def dem_dump(dem_text: str, which: int = 0):
+    """Reference build only.  The DEM's instructions after which = 0 flatten / 1 merge_indistinguishable_errors /
+    2 remove_zero_probability_errors (common.cc:135-218) as (instructions, error_index_map): each instruction is
+    (kind, args tuple, targets tuple) with kind 0 error / 1 detector / 2 logical_observable, targets as detector id,
+    observable id | 1<<63, or U64_MAX for the separator.  Doubles are compared as the bits they are."""
+    lib = _lib("reference")
+    b = dem_text.encode()
+    sizes = np.zeros(4, dtype=np.uint64)
+    if lib.orc_dem_dump(b, which, None, None, None, None, None, None, _p(sizes, C.c_uint64)) < 0:
+        raise OracleError(lib.orc_last_error().decode())
+    n, na, nt, nm = (int(v) for v in sizes)
+    kind = np.zeros(max(n, 1), dtype=np.uint8)
+    aoff, toff = np.zeros(n + 1, dtype=np.uint64), np.zeros(n + 1, dtype=np.uint64)
+    args, tgt = np.zeros(max(na, 1), dtype=np.float64), np.zeros(max(nt, 1), dtype=np.uint64)
+    imap = np.zeros(max(nm, 1), dtype=np.uint64)
+    lib.orc_dem_dump(b, which, _p(imap, C.c_uint64), _p(kind, C.c_uint8), _p(aoff, C.c_uint64), _p(args, C.c_double),
+                     _p(toff, C.c_uint64), _p(tgt, C.c_uint64), _p(sizes, C.c_uint64))
+    inst = [(int(kind[i]), tuple(args[int(aoff[i]):int(aoff[i + 1])].tolist()), tuple(tgt[int(toff[i]):int(toff[i + 1])].tolist()))
+            for i in range(n)]
+    return inst, imap[:nm]
+
+
+def get_errors_from_dem(dem_text: str):
+    """Reference build only.  get_errors_from_dem (utils.cc:253-261) -> (cost [n], detector lists, observable lists)."""
+    lib = _lib("reference")
+    b = dem_text.encode()
+    nd, no = C.c_uint64(), C.c_uint64()
+    n = lib.orc_get_errors_from_dem(b, None, None, None, None, None, C.byref(nd), C.byref(no))
+    if n < 0:
+        raise OracleError(lib.orc_last_error().decode())
+    cost = np.zeros(n, dtype=np.float64)
+    doff, ooff = np.zeros(n + 1, dtype=np.uint64), np.zeros(n + 1, dtype=np.uint64)
+    dets, obs = np.zeros(max(nd.value, 1), dtype=np.int32), np.zeros(max(no.value, 1), dtype=np.int32)
+    lib.orc_get_errors_from_dem(b, _p(cost, C.c_double), _p(doff, C.c_uint64), _p(dets, C.c_int32), _p(ooff, C.c_uint64),
+                                _p(obs, C.c_int32), None, None)
+    return (cost, [dets[int(doff[i]):int(doff[i + 1])].tolist() for i in range(n)],
+            [obs[int(ooff[i]):int(ooff[i + 1])].tolist() for i in range(n)])
+
+
+def build_detector_graph(dem_text: str, num_detectors: int):
+    """Reference build only.  build_detector_graph (utils.cc:60-87)."""
+    lib = _lib("reference")
+    b = dem_text.encode()
+    n = lib.orc_build_detector_graph(b, None, None)
+    if n < 0:
+        raise OracleError(lib.orc_last_error().decode())
+    off, idx = np.zeros(num_detectors + 1, dtype=np.uint64), np.zeros(max(n, 1), dtype=np.uint64)
+    lib.orc_build_detector_graph(b, _p(off, C.c_uint64), _p(idx, C.c_uint64))
+    return [idx[int(off[d]):int(off[d + 1])].tolist() for d in range(num_detectors)]
+
+
+def get_detector_coords(dem_text: str):
+    """Reference build only.  get_detector_coords (utils.cc:32-58)."""
+    lib = _lib("reference")
+    b = dem_text.encode()
+    rows = C.c_uint64()
+    n = lib.orc_get_detector_coords(b, C.byref(rows), None, None)
+    if n < 0:
+        raise OracleError(lib.orc_last_error().decode())
+    off, xs = np.zeros(rows.value + 1, dtype=np.uint64), np.zeros(max(n, 1), dtype=np.float64)
+    lib.orc_get_detector_coords(b, None, _p(off, C.c_uint64), _p(xs, C.c_double))
+    return [xs[int(off[r]):int(off[r + 1])].tolist() for r in range(rows.value)]
+
+
+def error_text(likelihood_cost: float, detectors, observables):
+    """Reference build only.  (common::Error(...).str(), .get_probability()) — common.cc:88-98."""
+    lib = _lib("reference")
+    d, o = np.asarray(list(detectors) + [0], dtype=np.int32), np.asarray(list(observables) + [0], dtype=np.int32)
+    buf = C.create_string_buffer(4096)
+    p = C.c_double()
+    if lib.orc_error_text(likelihood_cost, _p(d, C.c_int32), len(detectors), _p(o, C.c_int32), len(observables), buf, 4096,
+                          C.byref(p)) != 0:
+        raise OracleError(lib.orc_last_error().decode())
+    return buf.value.decode(), p.value
+
+
+def cost_of_probability(p: float) -> float:
+    """Reference build only.  Error::set_with_probability (common.cc:100-105); raises OracleError outside (0, 1)."""
+    lib = _lib("reference")
+    c = C.c_double()
+    if lib.orc_cost_of_probability(p, C.byref(c)) != 0:
+        raise OracleError(lib.orc_last_error().decode())
+    return c.value
 
 
 def sample_dem_b8(dem_text: str, seed: int, shots: int, kind: str = "reference"):

@@ -8,7 +8,7 @@
  *   oracle/_build/libtesseract_port.so an independent CPU restatement of the same algorithm with
  *                                     search counters (port.cc)
  *
- * Both export exactly these symbols.  All functions returning int return 0 on success and -1 on
+ * Both export these symbols (the block marked REFERENCE BUILD ONLY excepted).  All functions returning int return 0 on success and -1 on
  * failure, in which case orc_last_error() gives the exception text (thread-local).
  */
 #ifndef ORACLE_API_H
@@ -84,6 +84,27 @@ int orc_flipped_observables(const orc_handle* h, const uint64_t* errs, uint64_t 
 int orc_build_det_orders(const char* dem_text, uint64_t num_det_orders, int method, uint64_t seed,
                          uint64_t* out);
 double orc_merge_weights(double a, double b); /* common.cc:118-123 */
+
+/* ---- REFERENCE BUILD ONLY (libtesseract_ref.so): the reference's standalone ingestion functions, for the parity tests of
+ * the product's tsr_merge_indistinguishable_errors / tsr_remove_zero_probability_errors / tsr_get_errors_from_dem /
+ * tsr_build_detector_graph / tsr_get_detector_coords.  The port restates these inside its own constructor only. ---- */
+/* The instructions of a DEM after `which`: 0 = common::flatten, 1 = common::merge_indistinguishable_errors
+ * (common.cc:139-190), 2 = common::remove_zero_probability_errors (common.cc:192-218).  kind [n]: 0 error 1 detector
+ * 2 logical_observable; args / targets as CSR (target = detector id, observable id | 1<<63, UINT64_MAX for '^');
+ * index_map = the function's error_index_map (UINT64_MAX = dropped); sizes = {n, n_args, n_targets, map length}.
+ * Every pointer may be NULL (sizing call).  Returns n or -1. */
+int64_t orc_dem_dump(const char* dem_text, int which, uint64_t* index_map, uint8_t* kind, uint64_t* arg_off, double* args,
+                     uint64_t* tgt_off, uint64_t* tgt, uint64_t sizes[4]);
+/* get_errors_from_dem (utils.cc:253-261) of the flattened DEM; same array convention as tsr_get_errors_from_dem. */
+int64_t orc_get_errors_from_dem(const char* dem_text, double* cost, uint64_t* det_offsets, int32_t* dets,
+                                uint64_t* obs_offsets, int32_t* obs, uint64_t* n_dets, uint64_t* n_obs);
+int64_t orc_build_detector_graph(const char* dem_text, uint64_t* offsets, uint64_t* neighbors); /* utils.cc:60-87 */
+int64_t orc_get_detector_coords(const char* dem_text, uint64_t* n_rows, uint64_t* offsets, double* coords); /* utils.cc:32-58 */
+/* common::Error(cost, detectors, observables).str() and .get_probability() (common.cc:88-98); set_with_probability
+ * (common.cc:100-105). */
+int orc_error_text(double likelihood_cost, const int32_t* dets, uint64_t n_dets, const int32_t* obs, uint64_t n_obs, char* out,
+                   uint64_t cap, double* probability);
+int orc_cost_of_probability(double p, double* cost);
 
 /* Search counters summed over every search run through this handle since the last reset
  * (SURVEY.md §8d): out[0]=Q pushes, [1]=P pops, [2]=X expanded, [3]=L chain-walk steps,

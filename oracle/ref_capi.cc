@@ -263,6 +263,141 @@ int orc_build_det_orders(const char* dem_text, uint64_t num_det_orders, int meth
   });
 }
 
+// ---- the ingestion stages on their own (reference build only; oracle_api.h) ------------------------------
+
+int64_t orc_dem_dump(const char* dem_text, int which, uint64_t* index_map, uint8_t* kind, uint64_t* arg_off, double* args,
+                     uint64_t* tgt_off, uint64_t* tgt, uint64_t sizes[4]) {
+  int64_t n = 0;
+  int rc = guarded([&] {
+    namespace cm = tesseract_decoder::common;
+    stim::DetectorErrorModel dem(dem_text);
+    std::vector<size_t> map;
+    stim::DetectorErrorModel out = which == 1   ? cm::merge_indistinguishable_errors(dem, map)
+                                   : which == 2 ? cm::remove_zero_probability_errors(dem, map)
+                                                : cm::flatten(dem);
+    uint64_t na = 0, nt = 0, i = 0;
+    for (const stim::DemInstruction& inst : out.instructions) {
+      if (kind)
+        kind[i] = inst.type == stim::DemInstructionType::DEM_ERROR      ? 0
+                  : inst.type == stim::DemInstructionType::DEM_DETECTOR ? 1
+                  : inst.type == stim::DemInstructionType::DEM_LOGICAL_OBSERVABLE ? 2 : 255;
+      if (arg_off) arg_off[i] = na;
+      if (tgt_off) tgt_off[i] = nt;
+      for (double a : inst.arg_data) {
+        if (args) args[na] = a;
+        ++na;
+      }
+      for (const stim::DemTarget& t : inst.target_data) {
+        if (tgt) tgt[nt] = t.is_separator() ? UINT64_MAX : (t.is_observable_id() ? (t.raw_id() | (uint64_t{1} << 63)) : t.raw_id());
+        ++nt;
+      }
+      ++i;
+    }
+    if (arg_off) arg_off[i] = na;
+    if (tgt_off) tgt_off[i] = nt;
+    if (index_map)
+      for (size_t k = 0; k < map.size(); ++k) index_map[k] = map[k] == std::numeric_limits<size_t>::max() ? UINT64_MAX : map[k];
+    if (sizes) {
+      sizes[0] = i;
+      sizes[1] = na;
+      sizes[2] = nt;
+      sizes[3] = map.size();
+    }
+    n = (int64_t)i;
+  });
+  return rc == 0 ? n : -1;
+}
+
+int64_t orc_get_errors_from_dem(const char* dem_text, double* cost, uint64_t* det_offsets, int32_t* dets,
+                                uint64_t* obs_offsets, int32_t* obs, uint64_t* n_dets, uint64_t* n_obs) {
+  int64_t n = 0;
+  int rc = guarded([&] {
+    stim::DetectorErrorModel dem(dem_text);
+    // the function reads dem.instructions as they are (utils.cc:255); every caller hands it a flattened DEM
+    auto errors = tesseract_decoder::get_errors_from_dem(tesseract_decoder::common::flatten(dem));
+    uint64_t nd = 0, no = 0;
+    for (size_t e = 0; e < errors.size(); ++e) {
+      if (cost) cost[e] = errors[e].likelihood_cost;
+      if (det_offsets) det_offsets[e] = nd;
+      if (obs_offsets) obs_offsets[e] = no;
+      for (int d : errors[e].symptom.detectors) {
+        if (dets) dets[nd] = d;
+        ++nd;
+      }
+      for (int o : errors[e].symptom.observables) {
+        if (obs) obs[no] = o;
+        ++no;
+      }
+    }
+    if (det_offsets) det_offsets[errors.size()] = nd;
+    if (obs_offsets) obs_offsets[errors.size()] = no;
+    if (n_dets) *n_dets = nd;
+    if (n_obs) *n_obs = no;
+    n = (int64_t)errors.size();
+  });
+  return rc == 0 ? n : -1;
+}
+
+int64_t orc_build_detector_graph(const char* dem_text, uint64_t* offsets, uint64_t* neighbors) {
+  int64_t n = 0;
+  int rc = guarded([&] {
+    stim::DetectorErrorModel dem(dem_text);
+    auto graph = tesseract_decoder::build_detector_graph(dem);
+    uint64_t at = 0;
+    for (size_t d = 0; d < graph.size(); ++d) {
+      if (offsets) offsets[d] = at;
+      for (size_t v : graph[d]) {
+        if (neighbors) neighbors[at] = v;
+        ++at;
+      }
+    }
+    if (offsets) offsets[graph.size()] = at;
+    n = (int64_t)at;
+  });
+  return rc == 0 ? n : -1;
+}
+
+int64_t orc_get_detector_coords(const char* dem_text, uint64_t* n_rows, uint64_t* offsets, double* coords) {
+  int64_t n = 0;
+  int rc = guarded([&] {
+    stim::DetectorErrorModel dem(dem_text);
+    auto rows = tesseract_decoder::get_detector_coords(dem);
+    uint64_t at = 0;
+    for (size_t r = 0; r < rows.size(); ++r) {
+      if (offsets) offsets[r] = at;
+      for (double v : rows[r]) {
+        if (coords) coords[at] = v;
+        ++at;
+      }
+    }
+    if (offsets) offsets[rows.size()] = at;
+    if (n_rows) *n_rows = rows.size();
+    n = (int64_t)at;
+  });
+  return rc == 0 ? n : -1;
+}
+
+int orc_error_text(double likelihood_cost, const int32_t* dets, uint64_t n_dets, const int32_t* obs, uint64_t n_obs, char* out,
+                   uint64_t cap, double* probability) {
+  return guarded([&] {
+    std::vector<int> d(dets, dets + n_dets), o(obs, obs + n_obs);
+    tesseract_decoder::common::Error e(likelihood_cost, d, o);
+    const std::string s = e.str();
+    if (s.size() + 1 > cap) throw std::invalid_argument("buffer too small");
+    std::copy(s.begin(), s.end(), out);
+    out[s.size()] = 0;
+    if (probability) *probability = e.get_probability();
+  });
+}
+
+int orc_cost_of_probability(double p, double* cost) {
+  return guarded([&] {
+    tesseract_decoder::common::Error e;
+    e.set_with_probability(p);
+    *cost = e.likelihood_cost;
+  });
+}
+
 double orc_merge_weights(double a, double b) {
   return tesseract_decoder::common::merge_weights(a, b);
 }

@@ -139,6 +139,16 @@ def lib() -> C.CDLL:
     L.tsr_circuit_to_dem.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.tsr_dem_from_counts.argtypes = [C.c_char_p, u64p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
     L.tsr_sample_dem_b8.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, u8p, u8p]
+    L.tsr_merge_indistinguishable_errors.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), u64p]
+    L.tsr_remove_zero_probability_errors.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), u64p]
+    L.tsr_dem_count_errors.restype = C.c_int64
+    L.tsr_dem_count_errors.argtypes = [C.c_char_p]
+    L.tsr_get_errors_from_dem.restype = C.c_int64
+    L.tsr_get_errors_from_dem.argtypes = [C.c_char_p, f64p, u64p, i32p, u64p, i32p, u64p, u64p]
+    L.tsr_build_detector_graph.restype = C.c_int64
+    L.tsr_build_detector_graph.argtypes = [C.c_char_p, u64p, u64p]
+    L.tsr_get_detector_coords.restype = C.c_int64
+    L.tsr_get_detector_coords.argtypes = [C.c_char_p, u64p, u64p, f64p]
     _lib = L
     return L
 
@@ -156,6 +166,8 @@ EXPORTED_SYMBOLS = [
     "tsr_comm_allreduce_sum_u64", "tsr_nccl_version", "tsr_group_create", "tsr_group_destroy", "tsr_group_size",
     "tsr_group_member", "tsr_group_decode_b8", "tsr_group_last_batch_nnz", "tsr_group_last_batch_errors",
     "tsr_visualization_text", "tsr_set_visited_audit", "tsr_visited_audit", "tsr_last_batch_tail",
+    "tsr_merge_indistinguishable_errors", "tsr_remove_zero_probability_errors", "tsr_dem_count_errors",
+    "tsr_get_errors_from_dem", "tsr_build_detector_graph", "tsr_get_detector_coords",
 ]
 
 
@@ -198,6 +210,72 @@ def dem_from_counts(dem_text: str, counts, num_shots: int) -> str:
     out = C.c_void_p()
     _check(lib().tsr_dem_from_counts(dem_text.encode(), _p(counts, C.c_uint64), len(counts), num_shots, C.byref(out)))
     return _take_text(out)
+
+
+def dem_count_errors(dem_text: str) -> int:
+    n = lib().tsr_dem_count_errors(dem_text.encode())
+    if n < 0:
+        _raise(n)
+    return n
+
+
+def _dem_stage(fn, dem_text: str):
+    index_map = np.zeros(dem_count_errors(dem_text), dtype=np.uint64)
+    out = C.c_void_p()
+    _check(fn(dem_text.encode(), C.byref(out), _p(index_map, C.c_uint64)))
+    return _take_text(out), index_map
+
+
+def merge_indistinguishable_errors(dem_text: str):
+    """common::merge_indistinguishable_errors (common.cc:139-190) -> (DEM text, error_index_map)."""
+    return _dem_stage(lib().tsr_merge_indistinguishable_errors, dem_text)
+
+
+def remove_zero_probability_errors(dem_text: str):
+    """common::remove_zero_probability_errors (common.cc:192-218) -> (DEM text, error_index_map); dropped errors map to
+    NO_ERROR_INDEX."""
+    return _dem_stage(lib().tsr_remove_zero_probability_errors, dem_text)
+
+
+def get_errors_from_dem(dem_text: str):
+    """get_errors_from_dem (utils.cc:253-261) -> (cost [n], list of detector lists, list of observable lists)."""
+    b = dem_text.encode()
+    nd, no = C.c_uint64(), C.c_uint64()
+    n = lib().tsr_get_errors_from_dem(b, None, None, None, None, None, C.byref(nd), C.byref(no))
+    if n < 0:
+        _raise(n)
+    cost = np.zeros(n, dtype=np.float64)
+    doff, ooff = np.zeros(n + 1, dtype=np.uint64), np.zeros(n + 1, dtype=np.uint64)
+    dets, obs = np.zeros(max(nd.value, 1), dtype=np.int32), np.zeros(max(no.value, 1), dtype=np.int32)
+    n2 = lib().tsr_get_errors_from_dem(b, _p(cost, C.c_double), _p(doff, C.c_uint64), _p(dets, C.c_int32), _p(ooff, C.c_uint64),
+                                       _p(obs, C.c_int32), None, None)
+    assert n2 == n
+    return (cost, [dets[int(doff[i]):int(doff[i + 1])].tolist() for i in range(n)],
+            [obs[int(ooff[i]):int(ooff[i + 1])].tolist() for i in range(n)])
+
+
+def build_detector_graph(dem_text: str):
+    """build_detector_graph (utils.cc:60-87) -> one sorted neighbour list per detector."""
+    b = dem_text.encode()
+    D = dem_count_detectors(dem_text)
+    n = lib().tsr_build_detector_graph(b, None, None)
+    if n < 0:
+        _raise(n)
+    off, idx = np.zeros(D + 1, dtype=np.uint64), np.zeros(max(n, 1), dtype=np.uint64)
+    lib().tsr_build_detector_graph(b, _p(off, C.c_uint64), _p(idx, C.c_uint64))
+    return [idx[int(off[d]):int(off[d + 1])].tolist() for d in range(D)]
+
+
+def get_detector_coords(dem_text: str):
+    """get_detector_coords (utils.cc:32-58) -> the coordinates of every DETECTOR instruction, in DEM order."""
+    b = dem_text.encode()
+    rows = C.c_uint64()
+    n = lib().tsr_get_detector_coords(b, C.byref(rows), None, None)
+    if n < 0:
+        _raise(n)
+    off, xs = np.zeros(rows.value + 1, dtype=np.uint64), np.zeros(max(n, 1), dtype=np.float64)
+    lib().tsr_get_detector_coords(b, None, _p(off, C.c_uint64), _p(xs, C.c_double))
+    return [xs[int(off[r]):int(off[r + 1])].tolist() for r in range(rows.value)]
 
 
 def dem_count_detectors(dem_text: str) -> int:

@@ -1223,6 +1223,95 @@ int tsr_dem_from_counts(const char* dem_text, const uint64_t* counts, uint64_t n
   });
 }
 
+int tsr_merge_indistinguishable_errors(const char* dem_text, char** dem_text_out, uint64_t* error_index_map) {
+  return guarded([&] {
+    std::vector<uint64_t> map;
+    DemModel out = tsr::merge_indistinguishable_errors(DemModel::parse(dem_text), map);
+    if (error_index_map) std::copy(map.begin(), map.end(), error_index_map);
+    if (dem_text_out) *dem_text_out = dup_text(out.str());
+  });
+}
+
+int tsr_remove_zero_probability_errors(const char* dem_text, char** dem_text_out, uint64_t* error_index_map) {
+  return guarded([&] {
+    std::vector<uint64_t> map;
+    DemModel out = tsr::remove_zero_probability_errors(DemModel::parse(dem_text), map);
+    if (error_index_map) std::copy(map.begin(), map.end(), error_index_map);
+    if (dem_text_out) *dem_text_out = dup_text(out.str());
+  });
+}
+
+int64_t tsr_dem_count_errors(const char* dem_text) {
+  int64_t n = 0;
+  const int rc = guarded([&] { n = (int64_t)DemModel::parse(dem_text).count_errors(); });
+  return rc == TSR_OK ? n : rc;
+}
+
+int64_t tsr_get_errors_from_dem(const char* dem_text, double* cost, uint64_t* det_offsets, int32_t* dets, uint64_t* obs_offsets,
+                                int32_t* obs, uint64_t* n_dets, uint64_t* n_obs) {
+  int64_t n = 0;
+  const int rc = guarded([&] {
+    const std::vector<tsr::CompiledError> errors = tsr::get_errors_from_dem(DemModel::parse(dem_text));
+    uint64_t nd = 0, no = 0;
+    for (size_t e = 0; e < errors.size(); ++e) {
+      if (cost) cost[e] = errors[e].cost;
+      if (det_offsets) det_offsets[e] = nd;
+      if (obs_offsets) obs_offsets[e] = no;
+      for (int d : errors[e].detectors) {
+        if (dets) dets[nd] = d;
+        ++nd;
+      }
+      for (int o : errors[e].observables) {
+        if (obs) obs[no] = o;
+        ++no;
+      }
+    }
+    if (det_offsets) det_offsets[errors.size()] = nd;
+    if (obs_offsets) obs_offsets[errors.size()] = no;
+    if (n_dets) *n_dets = nd;
+    if (n_obs) *n_obs = no;
+    n = (int64_t)errors.size();
+  });
+  return rc == TSR_OK ? n : rc;
+}
+
+int64_t tsr_build_detector_graph(const char* dem_text, uint64_t* offsets, uint64_t* neighbors) {
+  int64_t n = 0;
+  const int rc = guarded([&] {
+    const auto graph = tsr::build_detector_graph(DemModel::parse(dem_text));
+    uint64_t at = 0;
+    for (size_t d = 0; d < graph.size(); ++d) {
+      if (offsets) offsets[d] = at;
+      for (uint64_t v : graph[d]) {
+        if (neighbors) neighbors[at] = v;
+        ++at;
+      }
+    }
+    if (offsets) offsets[graph.size()] = at;
+    n = (int64_t)at;
+  });
+  return rc == TSR_OK ? n : rc;
+}
+
+int64_t tsr_get_detector_coords(const char* dem_text, uint64_t* n_rows, uint64_t* offsets, double* coords) {
+  int64_t n = 0;
+  const int rc = guarded([&] {
+    const auto rows = tsr::get_detector_coords(DemModel::parse(dem_text));
+    uint64_t at = 0;
+    for (size_t r = 0; r < rows.size(); ++r) {
+      if (offsets) offsets[r] = at;
+      for (double v : rows[r]) {
+        if (coords) coords[at] = v;
+        ++at;
+      }
+    }
+    if (offsets) offsets[rows.size()] = at;
+    if (n_rows) *n_rows = rows.size();
+    n = (int64_t)at;
+  });
+  return rc == TSR_OK ? n : rc;
+}
+
 int tsr_circuit_to_dem(const char* circuit_text, char** dem_text_out) {
   return guarded([&] { *dem_text_out = dup_text(tsr::circuit_to_dem_text(circuit_text)); });
 }

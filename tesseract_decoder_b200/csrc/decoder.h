@@ -2,13 +2,16 @@
 // (include/tesseract_b200.h).  Same names, argument meaning and error behaviour; the search runs on the GPU.
 // Header-only C++20; used by the pybind11 module (pybind.cc) and the CLI (main.cc).
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <iomanip>
 #include <limits>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "tesseract_b200.h"
@@ -59,14 +62,40 @@ struct TesseractConfig {
   }
 };
 
-// common::Symptom / common::Error (common.h:29-50), as far as the decoder exposes them.
+// common::Symptom / common::Error (common.h:25-75, common.cc:22-105).
 struct Symptom {
   std::vector<int> detectors;
   std::vector<int> observables;
+  Symptom() = default;
+  Symptom(std::vector<int> detectors_, std::vector<int> observables_)
+      : detectors(std::move(detectors_)), observables(std::move(observables_)) {}
+  bool operator==(const Symptom& other) const { return detectors == other.detectors && observables == other.observables; }
+  bool operator!=(const Symptom& other) const { return !(*this == other); }
+  std::string str() const {  // common.cc:22-50
+    auto list = [](const std::vector<int>& v) {
+      std::string s = "[";
+      for (size_t i = 0; i < v.size(); ++i) s += (i ? " " : "") + std::to_string(v[i]);
+      return s + "]";
+    };
+    return "Symptom{detectors=" + list(detectors) + ", observables=" + list(observables) + "}";
+  }
 };
 struct Error {
   double likelihood_cost = 0;
   Symptom symptom;
+  Error() = default;
+  Error(double likelihood_cost_, std::vector<int> detectors, std::vector<int> observables)
+      : likelihood_cost(likelihood_cost_), symptom(std::move(detectors), std::move(observables)) {}
+  std::string str() const {  // common.cc:88-94
+    std::stringstream ss;
+    ss << std::fixed << std::setprecision(6) << likelihood_cost;
+    return "Error{cost=" + ss.str() + ", symptom=" + symptom.str() + "}";
+  }
+  double get_probability() const { return 1.0 / (1.0 + std::exp(likelihood_cost)); }  // common.cc:96-98
+  void set_with_probability(double p) {                                               // common.cc:100-105
+    if (p <= 0 || p >= 1) throw std::invalid_argument("Probability must be between 0 and 1.");
+    likelihood_cost = -std::log(p / (1.0 - p));
+  }
 };
 
 // TesseractConfig -> tsr_config (`flat` keeps the det_orders storage alive for the tsr_create call).
@@ -288,6 +317,63 @@ inline std::vector<std::vector<size_t>> build_det_orders(const std::string& dem,
   std::vector<std::vector<size_t>> out(num_det_orders);
   for (size_t k = 0; k < num_det_orders; ++k) out[k].assign(flat.begin() + (std::ptrdiff_t)(k * D), flat.begin() + (std::ptrdiff_t)((k + 1) * D));
   return out;
+}
+
+// The ingestion stages on their own (common.cc:139-218, utils.cc:32-87, 253-261); DEMs as text, like everywhere at this boundary.
+inline std::string dem_stage(int (*fn)(const char*, char**, uint64_t*), const std::string& dem, std::vector<size_t>& error_index_map) {
+  const int64_t n = tsr_dem_count_errors(dem.c_str());
+  if (n < 0) throw_last((int)n);
+  std::vector<uint64_t> map((size_t)n + 1);
+  char* out = nullptr;
+  check(fn(dem.c_str(), &out, map.data()));
+  std::string text(out);
+  tsr_free(out);
+  error_index_map.assign(map.begin(), map.begin() + (std::ptrdiff_t)n);  // UINT64_MAX == std::numeric_limits<size_t>::max()
+  return text;
+}
+inline std::string merge_indistinguishable_errors(const std::string& dem, std::vector<size_t>& error_index_map) {
+  return dem_stage(tsr_merge_indistinguishable_errors, dem, error_index_map);
+}
+inline std::string remove_zero_probability_errors(const std::string& dem, std::vector<size_t>& error_index_map) {
+  return dem_stage(tsr_remove_zero_probability_errors, dem, error_index_map);
+}
+inline std::vector<Error> get_errors_from_dem(const std::string& dem) {
+  uint64_t nd = 0, no = 0;
+  const int64_t n = tsr_get_errors_from_dem(dem.c_str(), nullptr, nullptr, nullptr, nullptr, nullptr, &nd, &no);
+  if (n < 0) throw_last((int)n);
+  std::vector<double> cost((size_t)n + 1);
+  std::vector<uint64_t> doff((size_t)n + 1), ooff((size_t)n + 1);
+  std::vector<int32_t> dets(nd + 1), obs(no + 1);
+  tsr_get_errors_from_dem(dem.c_str(), cost.data(), doff.data(), dets.data(), ooff.data(), obs.data(), nullptr, nullptr);
+  std::vector<Error> errors((size_t)n);
+  for (size_t e = 0; e < (size_t)n; ++e) {
+    errors[e].likelihood_cost = cost[e];
+    errors[e].symptom.detectors.assign(dets.begin() + (std::ptrdiff_t)doff[e], dets.begin() + (std::ptrdiff_t)doff[e + 1]);
+    errors[e].symptom.observables.assign(obs.begin() + (std::ptrdiff_t)ooff[e], obs.begin() + (std::ptrdiff_t)ooff[e + 1]);
+  }
+  return errors;
+}
+inline std::vector<std::vector<size_t>> build_detector_graph(const std::string& dem) {
+  const uint64_t D = tsr_dem_count_detectors(dem.c_str());
+  if (D == UINT64_MAX) throw std::invalid_argument(tsr_last_error());
+  const int64_t n = tsr_build_detector_graph(dem.c_str(), nullptr, nullptr);
+  if (n < 0) throw_last((int)n);
+  std::vector<uint64_t> off(D + 1), idx((size_t)n + 1);
+  tsr_build_detector_graph(dem.c_str(), off.data(), idx.data());
+  std::vector<std::vector<size_t>> graph(D);
+  for (uint64_t d = 0; d < D; ++d) graph[d].assign(idx.begin() + (std::ptrdiff_t)off[d], idx.begin() + (std::ptrdiff_t)off[d + 1]);
+  return graph;
+}
+inline std::vector<std::vector<double>> get_detector_coords(const std::string& dem) {
+  uint64_t rows = 0;
+  const int64_t n = tsr_get_detector_coords(dem.c_str(), &rows, nullptr, nullptr);
+  if (n < 0) throw_last((int)n);
+  std::vector<uint64_t> off(rows + 1);
+  std::vector<double> xs((size_t)n + 1);
+  tsr_get_detector_coords(dem.c_str(), nullptr, off.data(), xs.data());
+  std::vector<std::vector<double>> coords(rows);
+  for (uint64_t r = 0; r < rows; ++r) coords[r].assign(xs.begin() + (std::ptrdiff_t)off[r], xs.begin() + (std::ptrdiff_t)off[r + 1]);
+  return coords;
 }
 
 }  // namespace tesseract_b200

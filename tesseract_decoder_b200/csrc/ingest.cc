@@ -56,65 +56,86 @@ std::vector<DemTarget> symptom_targets(const CompiledError& e) {
 
 }  // namespace
 
+DemModel merge_indistinguishable_errors(const DemModel& flat, std::vector<uint64_t>& error_index_map) {
+  // First-seen order defines the merged index.  The reference keys an unordered_map by symptom (common.cc:146); only
+  // find / insert are used, so any exact map gives the same indices.
+  DemModel out;
+  error_index_map.clear();
+  std::map<std::pair<std::vector<int>, std::vector<int>>, uint64_t> index_of;
+  std::vector<CompiledError> merged;
+  for (const DemInstruction& inst : flat.instructions) {
+    if (inst.kind != DemKind::Error) {
+      out.instructions.push_back(inst);
+      continue;
+    }
+    CompiledError e = compile_error(inst);
+    if (e.detectors.empty()) std::cout << "Warning: the circuit has errors that do not flip any detectors \n";
+    auto key = std::make_pair(e.detectors, e.observables);
+    auto it = index_of.find(key);
+    if (it == index_of.end()) {
+      index_of.emplace(std::move(key), merged.size());
+      error_index_map.push_back(merged.size());
+      merged.push_back(std::move(e));
+    } else {
+      merged[it->second].cost = merge_weights(e.cost, merged[it->second].cost);
+      error_index_map.push_back(it->second);
+    }
+  }
+  for (const CompiledError& e : merged) out.append_error(e.probability(), symptom_targets(e));
+  return out;
+}
+
+DemModel remove_zero_probability_errors(const DemModel& flat, std::vector<uint64_t>& error_index_map) {
+  DemModel out;
+  error_index_map.clear();
+  uint64_t kept = 0;
+  for (const DemInstruction& inst : flat.instructions) {
+    if (inst.kind == DemKind::Error) {
+      if (inst.args[0] > 0) {
+        error_index_map.push_back(kept++);
+        out.instructions.push_back(inst);
+      } else {
+        error_index_map.push_back(kNoError);
+      }
+    } else {
+      out.instructions.push_back(inst);
+    }
+  }
+  return out;
+}
+
+std::vector<CompiledError> get_errors_from_dem(const DemModel& flat) {
+  std::vector<CompiledError> errors;
+  for (const DemInstruction& inst : flat.instructions)
+    if (inst.kind == DemKind::Error && inst.args[0] > 0) errors.push_back(compile_error(inst));
+  return errors;
+}
+
 DemTables ingest(const DemModel& flat, bool merge_errors) {
   DemTables T;
   T.num_dem_errors = flat.count_errors();
   std::vector<uint64_t> to_compiled(T.num_dem_errors);
   std::iota(to_compiled.begin(), to_compiled.end(), uint64_t{0});
 
-  // Stage 1 (common.cc:139-190): merge errors with identical symptoms; first-seen order defines the
-  // merged index; DETECTOR / LOGICAL_OBSERVABLE instructions keep their order and move to the front.
+  // Stage 1 (common.cc:139-190, tesseract.cc:159-164): merge errors with identical symptoms.
   DemModel stage1;
   if (merge_errors) {
-    std::map<std::pair<std::vector<int>, std::vector<int>>, uint64_t> index_of;
-    std::vector<CompiledError> merged;
     std::vector<uint64_t> merge_map;
-    for (const DemInstruction& inst : flat.instructions) {
-      if (inst.kind != DemKind::Error) {
-        stage1.instructions.push_back(inst);
-        continue;
-      }
-      CompiledError e = compile_error(inst);
-      if (e.detectors.empty()) std::cout << "Warning: the circuit has errors that do not flip any detectors \n";
-      auto key = std::make_pair(e.detectors, e.observables);
-      auto it = index_of.find(key);
-      if (it == index_of.end()) {
-        index_of.emplace(std::move(key), merged.size());
-        merge_map.push_back(merged.size());
-        merged.push_back(std::move(e));
-      } else {
-        merged[it->second].cost = merge_weights(e.cost, merged[it->second].cost);
-        merge_map.push_back(it->second);
-      }
-    }
-    for (const CompiledError& e : merged) stage1.append_error(e.probability(), symptom_targets(e));
+    stage1 = merge_indistinguishable_errors(flat, merge_map);
     for (uint64_t& v : to_compiled) v = merge_map[v];
   } else {
     stage1 = flat;
   }
 
-  // Stage 2 (common.cc:192-218): drop errors whose probability is not > 0.
+  // Stage 2 (common.cc:192-218, tesseract.cc:165-168): drop errors whose probability is not > 0.
   std::vector<uint64_t> keep_map;
-  uint64_t kept = 0;
-  for (const DemInstruction& inst : stage1.instructions) {
-    if (inst.kind == DemKind::Error) {
-      if (inst.args[0] > 0) {
-        keep_map.push_back(kept++);
-        T.compiled_dem.instructions.push_back(inst);
-      } else {
-        keep_map.push_back(kNoError);
-      }
-    } else {
-      T.compiled_dem.instructions.push_back(inst);
-    }
-  }
-  for (uint64_t& v : to_compiled) v = keep_map[v];
+  T.compiled_dem = remove_zero_probability_errors(stage1, keep_map);
+  for (uint64_t& v : to_compiled) v = keep_map[v];  // common::chain_error_maps; nothing is kNoError before this stage
   T.dem_error_to_error = to_compiled;
 
   // Stage 3 (utils.cc:253-261): the compiled error list; costs are recomputed from the printed
   // probabilities, i.e. after the cost -> p -> cost round trip.
-  for (const DemInstruction& inst : T.compiled_dem.instructions)
-    if (inst.kind == DemKind::Error && inst.args[0] > 0) T.errors.push_back(compile_error(inst));
+  T.errors = get_errors_from_dem(T.compiled_dem);
   T.num_errors = T.errors.size();
   T.num_detectors = T.compiled_dem.count_detectors();
   T.num_observables = T.compiled_dem.count_observables();

@@ -80,6 +80,15 @@ struct DemTables {
 // Throws std::invalid_argument for the same inputs the reference rejects.
 DemTables ingest(const DemModel& flat_dem, bool merge_errors);
 
+// The ingestion stages on their own (the reference exposes them as tesseract_decoder.common / .utils functions).
+// common.cc:139-190: errors with identical symptoms merged (merge_weights), first-seen order; DETECTOR and
+// LOGICAL_OBSERVABLE instructions keep their order and come first.  error_index_map[i] = merged index of input error i.
+DemModel merge_indistinguishable_errors(const DemModel& flat_dem, std::vector<uint64_t>& error_index_map);
+// common.cc:192-218: errors whose probability is not > 0 dropped; error_index_map[i] = output index or kNoError.
+DemModel remove_zero_probability_errors(const DemModel& flat_dem, std::vector<uint64_t>& error_index_map);
+// utils.cc:253-261: the error instructions with probability > 0, canonicalised (common.cc:52-88).
+std::vector<CompiledError> get_errors_from_dem(const DemModel& flat_dem);
+
 enum class DetOrder { DetBFS = 0, DetIndex = 1, DetCoordinate = 2 };
 // utils.cc:192-205 (std::mt19937_64 + libstdc++ distributions, same draws as the reference).
 std::vector<std::vector<uint64_t>> build_det_orders(const DemModel& dem, uint64_t num_det_orders, DetOrder method,

@@ -199,7 +199,10 @@ PYBIND11_MODULE(_tesseract_b200, root) {
       [](const py::object& dem, size_t num_det_orders, DetOrder method, uint64_t seed) {
         return build_det_orders(dem_text(dem), num_det_orders, method, seed);
       },
-      py::arg("dem"), py::arg("num_det_orders"), py::arg("method") = DetOrder::DetBFS, py::arg("seed") = 0);
+      py::arg("dem"), py::arg("num_det_orders"), py::arg("method") = DetOrder::DetIndex, py::arg("seed") = 0);  // utils.pybind.h:95-96
+  u.def("get_detector_coords", [](const py::object& dem) { return get_detector_coords(dem_text(dem)); }, py::arg("dem"));    // utils.pybind.h:43-61
+  u.def("build_detector_graph", [](const py::object& dem) { return build_detector_graph(dem_text(dem)); }, py::arg("dem"));  // utils.pybind.h:63-86
+  u.def("get_errors_from_dem", [](const py::object& dem) { return get_errors_from_dem(dem_text(dem)); }, py::arg("dem"));    // utils.pybind.h:118-135
   u.def("circuit_to_dem", [](const std::string& circuit) {
     char* out = nullptr;
     check(tsr_circuit_to_dem(circuit.c_str(), &out));
@@ -212,12 +215,65 @@ PYBIND11_MODULE(_tesseract_b200, root) {
 
   // ---- common (common.pybind.h, the parts the decoder exposes) --------------------------------------
   auto cm = root.def_submodule("common", "classes commonly used by the decoder");
-  py::class_<Symptom>(cm, "Symptom")
+  py::class_<Symptom>(cm, "Symptom")  // common.pybind.h:33-75
+      .def(py::init<std::vector<int>, std::vector<int>>(), py::arg("detectors") = std::vector<int>(),
+           py::arg("observables") = std::vector<int>())
       .def_readwrite("detectors", &Symptom::detectors)
-      .def_readwrite("observables", &Symptom::observables);
-  py::class_<Error>(cm, "Error")
+      .def_readwrite("observables", &Symptom::observables)
+      .def("__str__", &Symptom::str)
+      .def(py::self == py::self)
+      .def(py::self != py::self)
+      .def(
+          "as_dem_instruction_targets",
+          [](const Symptom& s) {  // stim.DemTarget objects where python-stim is importable, their text ("D1", "L2") otherwise
+            py::list out;
+            py::object make = py::none();
+            try {
+              make = py::module_::import("stim").attr("DemTarget");
+            } catch (py::error_already_set&) {
+            }
+            auto add = [&](const std::string& t) {
+              if (make.is_none())
+                out.append(py::str(t));
+              else
+                out.append(make(t));
+            };
+            for (int d : s.detectors) add("D" + std::to_string(d));
+            for (int o : s.observables) add("L" + std::to_string(o));
+            return out;
+          });
+  py::class_<Error>(cm, "Error")  // common.pybind.h:77-135
+      .def(py::init<>())
+      .def(py::init<double, std::vector<int>, std::vector<int>>(), py::arg("likelihood_cost"), py::arg("detectors"),
+           py::arg("observables"))
+      .def(py::init([](const py::object& error) {  // a stim.DemInstruction, or its text: "error(0.125) D0 D1 L0"
+             const std::vector<Error> parsed = get_errors_from_dem(py::cast<std::string>(py::str(error)));
+             if (parsed.size() != 1)
+               throw std::invalid_argument("Error must be loaded from an error dem instruction, but received: " +
+                                           py::cast<std::string>(py::str(error)));
+             return parsed[0];
+           }),
+           py::arg("error"))
       .def_readwrite("likelihood_cost", &Error::likelihood_cost)
-      .def_readwrite("symptom", &Error::symptom);
+      .def_readwrite("symptom", &Error::symptom)
+      .def("__str__", &Error::str)
+      .def("get_probability", &Error::get_probability)
+      .def("set_with_probability", &Error::set_with_probability, py::arg("probability"));
+  // common.pybind.h:143-191: DEM in (anything whose str() is DEM text), DEM text out
+  cm.def(
+      "merge_indistinguishable_errors",
+      [](const py::object& dem) {
+        std::vector<size_t> map;
+        return merge_indistinguishable_errors(dem_text(dem), map);
+      },
+      py::arg("dem"));
+  cm.def(
+      "remove_zero_probability_errors",
+      [](const py::object& dem) {
+        std::vector<size_t> map;
+        return remove_zero_probability_errors(dem_text(dem), map);
+      },
+      py::arg("dem"));
   cm.def("merge_weights", &tsr_merge_weights, py::arg("a"), py::arg("b"));
   cm.def(
       "dem_from_counts",

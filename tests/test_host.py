@@ -251,3 +251,106 @@ def test_visualization_header_equals_the_reference():
             if oracle.available(kind):
                 assert OracleDecoder(dem, kind=kind, create_visualization=True).visualization_text() == mine, (name, kind)
     assert capi.Decoder(W.load_dem("surface_d5_r5_p0.002_X"), host_only=True).visualization_text() == ""
+
+
+# ---- the ingestion stages on their own (common.cc:139-218, utils.cc:32-87, 253-261) ----------------------------------
+# What tesseract_decoder.common / .utils export next to the decoder.  Checked against the reference's own functions
+# (oracle/_ref) instruction by instruction: kinds, targets, index maps, and the doubles as the bits they are.
+
+needs_reference = pytest.mark.skipif(not oracle.available("reference"), reason="needs oracle/_ref (the compiled reference)")
+
+# duplicates in both target orders, a zero-probability error, targets that cancel (D0 ^ D0), a repeated observable,
+# an error without detectors, probabilities above 1/2, a repeat block with shift_detectors, tags' absence, and
+# detector / logical_observable instructions between the errors
+_MESSY_DEM = """
+error(0.1) D0 D1
+error(0.2) D1 D0
+error(0) D2
+detector(1, 2, 3) D0
+error(0.3) D2 L0
+error(0.1) D0 ^ D0 D1 L0 L1 L1
+error(0.05) D1 L0
+logical_observable L1
+error(0.8) D3
+error(0.9) D3
+error(0.01) L1
+detector(4.5, -1) D3
+repeat 3 {
+    error(0.125) D0 D4
+    error(0.25) D4 D0 L0
+    detector(0, 0, 1) D4
+    shift_detectors(0, 0, 1) 2
+}
+error(0.02) D2 L0
+error(0) D9 D10
+"""
+
+
+def _all_dems():
+    return sorted(f[:-7] for f in os.listdir(os.path.join(W.GOLDEN, "dems")) if f.endswith(".dem.gz"))
+
+
+@needs_reference
+@pytest.mark.parametrize("name", ["messy"] + _all_dems())
+def test_ingestion_stages_equal_the_reference(name):
+    dem = _MESSY_DEM if name == "messy" else W.load_dem(name)
+    for which, fn in ((1, capi.merge_indistinguishable_errors), (2, capi.remove_zero_probability_errors)):
+        ref_inst, ref_map = oracle.dem_dump(dem, which)
+        text, index_map = fn(dem)
+        mine_inst, _ = oracle.dem_dump(text, 0)  # our text, read back by the reference's DEM parser
+        assert mine_inst == ref_inst, (name, which)
+        assert np.array_equal(index_map, ref_map), (name, which)
+    cost, dets, obs = capi.get_errors_from_dem(dem)
+    rcost, rdets, robs = oracle.get_errors_from_dem(dem)
+    assert np.array_equal(cost, rcost) and dets == rdets and obs == robs
+    assert capi.build_detector_graph(dem) == oracle.build_detector_graph(dem, capi.dem_count_detectors(dem))
+    assert capi.get_detector_coords(dem) == oracle.get_detector_coords(dem)
+
+
+@needs_reference
+def test_ingestion_stages_chain_like_the_constructor():
+    """tesseract.cc:156-173: flatten -> merge -> strip zeros -> get_errors_from_dem is what the decoder holds."""
+    dem = _MESSY_DEM
+    merged, m1 = capi.merge_indistinguishable_errors(dem)
+    stripped, m2 = capi.remove_zero_probability_errors(merged)
+    cost, dets, obs = capi.get_errors_from_dem(stripped)
+    dec = capi.Decoder(dem, host_only=True)
+    ref = OracleDecoder(dem, kind="reference")
+    assert np.array_equal(cost, dec.error_costs()) and np.array_equal(cost, ref.error_costs())
+    chained = np.array([m2[int(i)] for i in m1], dtype=np.uint64)  # common::chain_error_maps
+    assert np.array_equal(chained, dec.maps()[0]) and np.array_equal(chained, ref.maps()[0])
+    assert capi.NO_ERROR_INDEX in chained.tolist()  # the zero-probability errors are gone
+    edets = dec.csr(1)
+    assert [edets[1][int(edets[0][e]):int(edets[0][e + 1])].tolist() for e in range(dec.num_errors)] == dets
+
+
+def test_ingestion_stage_known_answers():
+    # common.test.cc:22-29: a pathological error instruction
+    cost, dets, obs = capi.get_errors_from_dem("error(0.1) D0 ^  D0 D1  L0 L1 L1")
+    assert dets == [[1]] and obs == [[0]] and cost[0] == -math.log(0.1 / (1 - 0.1))
+    # common.test.cc:94-113
+    dem = "error(0.1) D0\nerror(0) D1\nerror(0.2) D2\ndetector(0, 0, 0) D0\ndetector(0, 0, 0) D1\ndetector(0, 0, 0) D2"
+    text, index_map = capi.remove_zero_probability_errors(dem)
+    assert capi.dem_count_errors(text) == 2 and index_map.tolist() == [0, capi.NO_ERROR_INDEX, 1]
+    assert text.splitlines()[:2] == ["error(0.1) D0", "error(0.2) D2"]
+    # common.test.cc:31-68: ... and dem_from_counts of the cleaned DEM
+    out = capi.dem_from_counts(text, [1, 4], 10)
+    assert out.splitlines()[:2] == ["error(0.1) D0", "error(0.4) D2"]
+    # common.test.cc:166-199: two errors on the same detector merge to p1 (1 - p2) + p2 (1 - p1)
+    for p1, p2 in ((0.1, 0.2), (0.1, 0.8), (0.8, 0.1), (0.8, 0.9)):
+        text, index_map = capi.merge_indistinguishable_errors(f"error({p1}) D0\nerror({p2}) D0")
+        assert index_map.tolist() == [0, 0] and capi.dem_count_errors(text) == 1
+        p = float(re.match(r"error\((.*)\) D0$", text.strip()).group(1))
+        assert abs(p - (p1 * (1 - p2) + p2 * (1 - p1))) < 1e-9
+    # utils_test.py:78-93 (get_errors_from_dem), and the graph / coordinates of the same model
+    dem = "error(0.125) D0\nerror(0.375) D0 D1\nerror(0.25) D1\ndetector(0, 0, 0) D0\ndetector(1, 0, 0) D1"
+    cost, dets, obs = capi.get_errors_from_dem(dem)
+    assert [f"{c:.6f}" for c in cost] == ["1.945910", "0.510826", "1.098612"] and dets == [[0], [0, 1], [1]] and obs == [[], [], []]
+    assert capi.build_detector_graph(dem) == [[1], [0]]
+    assert capi.get_detector_coords(dem) == [[0.0, 0.0, 0.0], [1.0, 0.0, 0.0]]
+    # failures are the reference's: malformed text and probabilities outside [0, 1] are invalid arguments
+    for fn in (capi.merge_indistinguishable_errors, capi.get_errors_from_dem):
+        with pytest.raises(ValueError):
+            fn("error(1.5) D0")
+    with pytest.raises(ValueError):
+        capi.build_detector_graph("error(0.1) D0 Q1")

@@ -51,6 +51,59 @@ def test_det_order_shapes():  # utils_test.py:37-76
         assert len(orders) == 4 and all(sorted(o) == list(range(96)) for o in orders)
 
 
+def test_utils_module_functions():  # utils_test.py:33-93
+    dem3 = Dem("error(0.125) D0\nerror(0.375) D0 D1\nerror(0.25) D1")
+    dem10 = Dem("\n".join(f"error(0.1) D{i}" for i in range(10)))
+    assert td.utils.EPSILON <= 1e-7 and not math.isfinite(td.utils.INF)
+    assert td.utils.get_detector_coords(dem3) == []
+    assert td.utils.get_detector_coords(Dem(_DETECTOR_ERROR_MODEL)) == [[0.0, 0.0, 0.0], [1.0, 0.0, 0.0]]
+    assert td.utils.build_detector_graph(dem3) == [[1], [0]]
+    asc = list(range(10))
+    assert td.utils.build_det_orders(dem10, num_det_orders=1, seed=0) in ([asc], [asc[::-1]])  # the default method is DetIndex
+    assert td.utils.build_det_orders(dem10, num_det_orders=1, seed=0) == \
+        td.utils.build_det_orders(dem10, num_det_orders=1, method=td.utils.DetOrder.DetIndex, seed=0)
+    assert td.utils.build_det_orders(dem3, num_det_orders=1, method=td.utils.DetOrder.DetBFS, seed=0) == [[0, 1]]
+    assert td.utils.build_det_orders(dem3, num_det_orders=1, method=td.utils.DetOrder.DetCoordinate, seed=0) == [[0, 1]]
+    assert ", ".join(map(str, td.utils.get_errors_from_dem(dem3))) == \
+        "Error{cost=1.945910, symptom=Symptom{detectors=[0], observables=[]}}, " \
+        "Error{cost=0.510826, symptom=Symptom{detectors=[0 1], observables=[]}}, " \
+        "Error{cost=1.098612, symptom=Symptom{detectors=[1], observables=[]}}"
+
+
+def test_common_module_classes_and_functions():  # common_test.py:42-151
+    def set_bits(n):
+        return [i for i in range(n.bit_length()) if (n >> i) & 1]
+
+    error = td.common.Error(1.945910, [1, 2], set_bits(4324))
+    assert error.likelihood_cost == pytest.approx(1.945910)
+    assert error.symptom.detectors == [1, 2] and error.symptom.observables == [2, 5, 6, 7, 12]
+    assert str(td.common.Error(5.5, [1, 2], [5, 10])) == "Error{cost=5.500000, symptom=Symptom{detectors=[1 2], observables=[5 10]}}"
+    s = td.common.Symptom([1, 2], set_bits(4324))
+    assert str(s) == "Symptom{detectors=[1 2], observables=[2 5 6 7 12]}"
+    assert s == td.common.Symptom([1, 2], [2, 5, 6, 7, 12]) and s != td.common.Symptom([1], [2, 5, 6, 7, 12])
+    assert td.common.Symptom().detectors == [] and td.common.Symptom().observables == []
+    assert [str(t) for t in s.as_dem_instruction_targets()] == ["D1", "D2", "L2", "L5", "L6", "L7", "L12"]
+    # an Error from a DEM error instruction (here: its text, what str(stim.DemInstruction) gives)
+    assert str(td.common.Error("error(0.125) L3")) == "Error{cost=1.945910, symptom=Symptom{detectors=[], observables=[3]}}"
+    with pytest.raises(ValueError):
+        td.common.Error("detector(1, 2) D0")
+    e = td.common.Error()
+    for p, cost in ((0.125, 1.9459101490553132), (0.5, 0.0)):
+        e.set_with_probability(p)
+        assert e.likelihood_cost == pytest.approx(cost) and e.get_probability() == pytest.approx(p)
+    for bad in (0.0, 1.0, -0.1, 1.1):
+        with pytest.raises(ValueError):
+            e.set_with_probability(bad)
+    # DEM in, DEM (text) out: stim.DetectorErrorModel(text) where stim is available
+    assert td.common.merge_indistinguishable_errors(Dem("")) == ""
+    assert td.common.remove_zero_probability_errors(Dem("")) == ""
+    assert td.common.dem_from_counts(Dem(""), [], 3) == ""
+    merged = td.common.merge_indistinguishable_errors(Dem("error(0.1) D0 D1\nerror(0.2) D1 D0\nerror(0) D2"))
+    assert [ln.split(")")[1] for ln in merged.splitlines()] == [" D0 D1", " D2"]
+    assert td.common.remove_zero_probability_errors(Dem(merged)).count("error") == 1
+    assert td.common.merge_weights(1.0, 2.0) == capi.merge_weights(1.0, 2.0)
+
+
 def test_sinter_decoder_object():  # tesseract_sinter_compat_test.py:691-795
     d = TesseractSinterDecoder()
     assert (d.det_beam, d.no_revisit_dets, d.pqlimit, d.num_det_orders, d.seed) == (5, True, 200000, 0, 2384753)
