@@ -64,8 +64,7 @@ def load_golden(name: str) -> dict:
 
 
 def golden_names(sparsify: bool = False) -> list[str]:
-    """Committed golden sets; names starting with "s_" use --sparsify-errors (reference outputs pinned for the next
-    hot-path row; the CUDA path does not implement it yet)."""
+    """Committed golden sets; names starting with "s_" decode with --sparsify-errors."""
     names = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
     return [n for n in names if n.startswith("s_") == sparsify]
 
