@@ -2,8 +2,8 @@
 
 Two faces over the same C ABI (include/tesseract_b200.h, libtesseract_b200.so):
   * `capi`  — thin ctypes binding (what the parity tests and bench.py call);
-  * `tesseract`, `utils`, `common`, `tesseract_sinter_compat` — the reference's Python API names
-    (src/tesseract.pybind.h, src/tesseract_sinter_compat.pybind.h) from the pybind11 module `_tesseract_b200`.
+  * `tesseract`, `utils`, `common`, `tesseract_sinter_compat`, `viz`, `ostream_redirect` — the reference's Python API
+    names (src/tesseract.pybind.cc, src/*.pybind.h) from the pybind11 module `_tesseract_b200`.
 Both are built in-tree by `__graft_entry__.build()` / `make -C tesseract_decoder_b200/csrc`.  There is no CPU
 fallback: decoding without an sm_100 GPU raises.
 """
@@ -20,12 +20,14 @@ if _ext is not None:
     utils = _ext.utils
     common = _ext.common
     tesseract_sinter_compat = _ext.tesseract_sinter_compat
+    viz = _ext.viz
+    ostream_redirect = _ext.ostream_redirect
     TesseractSinterDecoder = tesseract_sinter_compat.TesseractSinterDecoder
     make_tesseract_sinter_decoders_dict = tesseract_sinter_compat.make_tesseract_sinter_decoders_dict
 
 
 def __getattr__(name):
-    if name in ("tesseract", "utils", "common", "tesseract_sinter_compat", "TesseractSinterDecoder",
+    if name in ("tesseract", "utils", "common", "tesseract_sinter_compat", "viz", "ostream_redirect", "TesseractSinterDecoder",
                 "make_tesseract_sinter_decoders_dict"):
         raise ImportError(f"tesseract_decoder_b200.{name} needs the pybind11 extension _tesseract_b200, which is not built "
                           f"(run `make -C tesseract_decoder_b200/csrc pybind`): {_ext_error}")

@@ -2,6 +2,7 @@
 // (src/tesseract.pybind.h, src/utils.pybind.h, src/tesseract_sinter_compat.pybind.h) on top of decoder.h.
 // Same class / method / argument names, defaults and exception texts; DEMs cross the boundary as
 // str(dem), as in the reference (stim_utils.pybind.h:22-26), so python-stim is not required.
+#include <pybind11/iostream.h>
 #include <pybind11/numpy.h>
 #include <pybind11/operators.h>
 #include <pybind11/pybind11.h>
@@ -300,6 +301,7 @@ PYBIND11_MODULE(_tesseract_b200, root) {
       "Returns the suggested number of optional high-degree errors to reactivate per shot.");
 
   py::class_<tesseract_b200::Visualizer>(root.def_submodule("viz", "Module containing the visualization tools"), "Visualizer")  // visualization.pybind.h
+      .def(py::init<>())  // visualization.pybind.h:16: a free-standing Visualizer writes an empty log
       .def("write", &tesseract_b200::Visualizer::write, py::arg("fpath"))
       .def("text", &tesseract_b200::Visualizer::text);
 
@@ -531,4 +533,8 @@ PYBIND11_MODULE(_tesseract_b200, root) {
     d["tesseract-short-beam-sparsify-surface-code-like"] = preset(15, 200000, 16, true, 2);
     return d;
   });
+
+  // tesseract.pybind.cc:39-46: `with tesseract_decoder.ostream_redirect(stdout=..., stderr=...)` routes the C++ side's
+  // stdout / stderr (the verbose search log, the merge warning) to Python's.
+  py::add_ostream_redirect(root, "ostream_redirect");
 }

@@ -104,6 +104,21 @@ def test_common_module_classes_and_functions():  # common_test.py:42-151
     assert td.common.merge_weights(1.0, 2.0) == capi.merge_weights(1.0, 2.0)
 
 
+def test_module_layout_and_ostream_redirect(tmp_path):  # tesseract.pybind.cc:27-47, visualization.pybind.h:14-18
+    for sub in ("common", "utils", "viz", "tesseract", "tesseract_sinter_compat"):
+        assert hasattr(td, sub)
+    log = tmp_path / "empty.log"
+    td.viz.Visualizer().write(str(log))  # a free-standing Visualizer has logged nothing
+    assert log.read_text() == ""
+    import contextlib
+    import io
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        with td.ostream_redirect(stdout=True, stderr=True):  # the C++ side's std::cout lands in Python's sys.stdout
+            td.common.merge_indistinguishable_errors(Dem("error(0.1) L0"))
+    assert "errors that do not flip any detectors" in buf.getvalue()  # common.cc:154-157
+
+
 def test_sinter_decoder_object():  # tesseract_sinter_compat_test.py:691-795
     d = TesseractSinterDecoder()
     assert (d.det_beam, d.no_revisit_dets, d.pqlimit, d.num_det_orders, d.seed) == (5, True, 200000, 0, 2384753)
