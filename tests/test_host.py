@@ -354,3 +354,17 @@ def test_ingestion_stage_known_answers():
             fn("error(1.5) D0")
     with pytest.raises(ValueError):
         capi.build_detector_graph("error(0.1) D0 Q1")
+
+
+def test_remaining_reference_known_answers_without_a_device():
+    # tesseract.test.cc:225-237: get_detector_coords skips logical_observable instructions
+    assert capi.get_detector_coords("error(0.1) D0 L0\ndetector(1,2,3) D0\nlogical_observable L0") == [[1.0, 2.0, 3.0]]
+    # tesseract.test.cc:425-432: suggest_sparsify_reactivate_limit
+    suggest = capi.lib().tsr_suggest_sparsify_reactivate_limit
+    assert [suggest(2, 2), suggest(2, 3), suggest(0, 2), suggest(1, 2**31 - 1)] == [1, 3, 0, 2**31 - 1]
+    assert suggest(2, -1) < 0 and b"sparsify_base_degree" in capi.lib().tsr_last_error()
+    # tesseract.test.cc:434-458: the automatic limit is clamped to the error count before it can overflow
+    dem = "error(0.1) D0\n" + "\n".join(f"detector({i}, 0, 0) D{i}" for i in range(10))
+    dec = capi.Decoder(dem, merge_errors=False, sparsify_errors=True, sparsify_base_degree=2**31 - 1,
+                       sparsify_reactivate_limit=-1, host_only=True)
+    assert dec.sparsify_reactivate_limit == 1
