@@ -22,6 +22,17 @@ std::string dem_text(const py::object& dem) {
   return py::cast<std::string>(py::str(dem));
 }
 
+// A DEM leaving the module: stim.DetectorErrorModel(text) where python-stim is importable — what the reference returns
+// (stim_utils.pybind.h:62-69) — and the text itself otherwise.
+py::object dem_object(const std::string& text) {
+  try {
+    return py::module_::import("stim").attr("DetectorErrorModel")(text);
+  } catch (py::error_already_set& e) {
+    if (!e.matches(PyExc_ImportError)) throw;
+    return py::str(text);
+  }
+}
+
 // tesseract.pybind.h:38-73: an empty det_orders argument means 20 DetIndex orders, seed 2384753.
 TesseractConfig make_config(const std::string& dem, int det_beam, bool beam_climbing, bool no_revisit_dets, bool verbose,
                             bool merge_errors, size_t pqlimit, std::vector<std::vector<size_t>> det_orders, double det_penalty,
@@ -265,14 +276,14 @@ PYBIND11_MODULE(_tesseract_b200, root) {
       "merge_indistinguishable_errors",
       [](const py::object& dem) {
         std::vector<size_t> map;
-        return merge_indistinguishable_errors(dem_text(dem), map);
+        return dem_object(merge_indistinguishable_errors(dem_text(dem), map));
       },
       py::arg("dem"));
   cm.def(
       "remove_zero_probability_errors",
       [](const py::object& dem) {
         std::vector<size_t> map;
-        return remove_zero_probability_errors(dem_text(dem), map);
+        return dem_object(remove_zero_probability_errors(dem_text(dem), map));
       },
       py::arg("dem"));
   cm.def("merge_weights", &tsr_merge_weights, py::arg("a"), py::arg("b"));
@@ -283,7 +294,7 @@ PYBIND11_MODULE(_tesseract_b200, root) {
         check(tsr_dem_from_counts(dem_text(dem).c_str(), error_counts.data(), error_counts.size(), num_shots, &out));
         std::string text(out);
         tsr_free(out);
-        return text;
+        return dem_object(text);
       },
       py::arg("orig_dem"), py::arg("error_counts"), py::arg("num_shots"));
 
@@ -334,9 +345,9 @@ PYBIND11_MODULE(_tesseract_b200, root) {
            py::arg("sparsify_max_degree") = -1, py::arg("sparsify_reactivate_limit") = -1,
            py::arg("at_most_two_errors_per_detector") = false)
       .def_property(
-          "dem", [](const TesseractConfig& c) { return c.dem; },
+          "dem", [](const TesseractConfig& c) { return dem_object(c.dem); },
           [](TesseractConfig& c, const py::object& dem) { c.dem = dem_text(dem); },
-          "The detector error model, as text (construct stim.DetectorErrorModel(text) where stim is available).")
+          "The detector error model: a stim.DetectorErrorModel where python-stim is importable, its text otherwise.")
       .def_readwrite("det_beam", &TesseractConfig::det_beam)
       .def_readwrite("beam_climbing", &TesseractConfig::beam_climbing)
       .def_readwrite("no_revisit_dets", &TesseractConfig::no_revisit_dets)
