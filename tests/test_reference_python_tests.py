@@ -27,6 +27,9 @@ DEVICE_FREE = {
                           "test_create_tesseract_config_with_dem_and_custom_args", "test_create_tesseract_config_no_dem",
                           "test_create_tesseract_config_no_dem_with_custom_args", "test_create_tesseract_config_sparsify_defaults",
                           "test_create_tesseract_config_sparsify_custom", "test_suggest_sparsify_reactivate_limit"],
+    "tesseract_sinter_compat_test.py": ["test_tesseract_sinter_obj_exists", "test_tesseract_sinter_decoder_sparsify_attributes",
+                                        "test_tesseract_sinter_decoder_old_positional_constructor_order",
+                                        "test_make_tesseract_sinter_decoders_dict_contains_sparsify"],
 }
 
 
@@ -34,8 +37,16 @@ DEVICE_FREE = {
 def reference_modules():
     import stim_stand_in
     import tesseract_decoder_b200
-    saved = {k: sys.modules.get(k) for k in ("stim", "tesseract_decoder", "shared_decoding_tests")}
+    import types
+    names = ("stim", "tesseract_decoder", "shared_decoding_tests", "sinter", "sinter._decoding", "sinter._decoding._decoding")
+    saved = {k: sys.modules.get(k) for k in names}
     sys.modules["stim"] = stim_stand_in
+    # tesseract_sinter_compat_test.py imports sinter at module level; only its decoding tests (not run here) use it
+    for name in names[3:]:
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["sinter._decoding._decoding"].sample_decode = None
+    sys.modules["sinter"]._decoding = sys.modules["sinter._decoding"]
+    sys.modules["sinter._decoding"]._decoding = sys.modules["sinter._decoding._decoding"]
     sys.modules["tesseract_decoder"] = tesseract_decoder_b200
     sys.path.insert(0, REF_PY)  # tesseract_test.py imports shared_decoding_tests from its own directory
     sys.dont_write_bytecode, old_flag = True, sys.dont_write_bytecode  # never write __pycache__ into the reference tree
@@ -79,6 +90,13 @@ def test_every_device_free_reference_test_is_listed(reference_modules):
                               "test_compile_decoder_caps_auto_sparsify_reactivate_limit_at_error_count",
                               "test_compile_decoder_preserves_explicit_sparsify_reactivate_limit",
                               "test_python_sparsify_changes_predicted_error_set", "test_decoder_compilation_validation"},
+        "tesseract_sinter_compat_test.py": {"test_compile_decoder_for_dem", "test_decode_shots_bit_packed", "test_decode_shots_bit_packed_multi_shot",
+                                            "test_decode_via_files_sanity_check", "test_decode_via_files", "test_decode_via_files_multi_shot",
+                                            "test_sinter_decode_repetition_code", "test_sinter_decode_surface_code", "test_sinter_empty",
+                                            "test_sinter_no_observables", "test_sinter_invincible_observables", "test_sinter_detector_counting",
+                                            "test_full_scale", "test_full_scale_one_worker", "test_decode_shots_bit_packed_vs_decode_batch",
+                                            "test_sinter_collect_different_dems", "test_sinter_compile_sparsify_config_reaches_decoder",
+                                            "test_sinter_decode_with_sparsify_decoders"},
     }
     for fname, mod in reference_modules.items():
         found = {n for n in dir(mod) if n.startswith("test_") and callable(getattr(mod, n))}
