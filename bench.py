@@ -156,11 +156,6 @@ def algorithmic_bytes(c, shots, D, O):
             + 16 * c["S"] + 4 * c["A"] + Wv * c["V"])
 
 
-def oracle_kwargs(kw):
-    """Decoder keywords the CPU checkers understand (the device-resource knobs are the product's own)."""
-    return dict(kw)
-
-
 def cpu_decoder(dem, kw, threads, kind=None):
     from oracle import oracle
     if kind is None:

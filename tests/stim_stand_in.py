@@ -32,7 +32,6 @@ class DetectorErrorModel:
         return hash(tuple(self._lines))
 
     def _count(self, fn):
-        from tesseract_decoder_b200 import capi
         return fn(str(self)) if self._lines else 0
 
     @property

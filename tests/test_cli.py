@@ -1,6 +1,5 @@
 """The `tesseract` CLI (csrc/main.cc): the reference CLI's decode flags, validation and accounting
 (tesseract_main.cc:98-180, 350-538, 592-616, 657-699)."""
-import gzip
 import json
 import os
 import subprocess

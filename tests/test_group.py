@@ -2,7 +2,6 @@
 process per GPU), both summing {shots, logical errors, low confidence} with one ncclAllReduce.  The single-GPU cases run
 on any GPU box; the 2-GPU cases need `gpurun --gpus 2` (skipped otherwise).  tests/test_sharding.py covers the host-side
 partition logic over gloo on CPU."""
-import ctypes
 
 import numpy as np
 import pytest

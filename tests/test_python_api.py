@@ -2,7 +2,6 @@
 pybind11 module over the C ABI.  Tests read like the reference's own (src/py/tesseract_test.py,
 shared_decoding_tests.py, tesseract_sinter_compat_test.py); a DEM is any object whose str() is DEM text."""
 import math
-import os
 import pickle
 
 import numpy as np

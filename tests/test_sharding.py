@@ -1,7 +1,6 @@
 """The N>1 host logic (shot sharding + the single all-reduce of the counters) on CPU: world_size 2 over gloo.
 The shards are decoded by the CPU checker here (no GPU in this container); tests/test_gpu_parity.py covers the
 decoder itself."""
-import os
 import socket
 
 import numpy as np
