@@ -8,7 +8,7 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 SAN=/tmp/tsr_san
 mkdir -p $SAN
 FLAGS="-std=c++20 -O1 -g -fno-fast-math -ffp-contract=off -fPIC -Wall -Wextra -Wno-unused-parameter -pthread -fsanitize=address,undefined -fno-omit-frame-pointer"
-make -s -j8 -C $ROOT/tesseract_decoder_b200/csrc OUT=$SAN BUILD=$SAN/_build/ CXXFLAGS="$FLAGS" \
+make -s -j8 -C $ROOT/tesseract_decoder_b200/csrc OUT=$SAN BUILD=$SAN/_build CXXFLAGS="$FLAGS" \
   $SAN/_build/dem.o $SAN/_build/ingest.o $SAN/_build/detorder.o $SAN/_build/circuit.o $SAN/_build/fast.o \
   $SAN/_build/search.o $SAN/_build/search_fast.o $SAN/_build/capi.o $SAN/_build/group.o
 ASAN_SO=$(gcc -print-file-name=libasan.so); UBSAN_SO=$(gcc -print-file-name=libubsan.so)
