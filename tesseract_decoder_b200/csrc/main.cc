@@ -59,6 +59,15 @@ std::string read_file(const std::string& path) {
   return ss.str();
 }
 
+// A bit index in a text shot file: decimal digits only (std::stoull would take "-3" or "12abc").
+uint64_t parse_index(std::string tok, const std::string& path) {
+  while (!tok.empty() && (tok.back() == ' ' || tok.back() == '\t')) tok.pop_back();
+  tok.erase(0, tok.find_first_not_of(" \t") == std::string::npos ? tok.size() : tok.find_first_not_of(" \t"));
+  if (tok.empty() || tok.size() > 19 || tok.find_first_not_of("0123456789") != std::string::npos)
+    throw std::invalid_argument(path + ": '" + tok + "' is not a bit index");
+  return std::stoull(tok);
+}
+
 // Reads shots as rows of `bits` bits into a [shots][ceil(bits/8)] b8 matrix.
 // (`dets_prefix`: in the dets format, L# tokens index bits after the first dets_prefix bits.)
 std::vector<uint8_t> read_shots(const std::string& path, const std::string& format, uint64_t bits, uint64_t& shots_out,
@@ -98,7 +107,7 @@ std::vector<uint8_t> read_shots(const std::string& path, const std::string& form
       std::string tok;
       while (std::getline(ls, tok, ',')) {
         if (tok.empty()) continue;
-        const uint64_t i = std::stoull(tok);
+        const uint64_t i = parse_index(tok, path);
         if (i >= bits) throw std::invalid_argument(path + ": hit index " + tok + " is out of range");
         row[i / 8] ^= (uint8_t)(1u << (i % 8));
       }
@@ -117,7 +126,7 @@ std::vector<uint8_t> read_shots(const std::string& path, const std::string& form
       uint8_t* row = out.data() + out.size() - nb;
       while (ls >> tok) {
         if (tok.size() < 2 || (tok[0] != 'D' && tok[0] != 'L' && tok[0] != 'M')) throw std::invalid_argument(path + ": bad dets token " + tok);
-        uint64_t i = std::stoull(tok.substr(1));
+        uint64_t i = parse_index(tok.substr(1), path);
         if (tok[0] == 'L') i += dets_prefix;
         if (i >= bits) throw std::invalid_argument(path + ": dets token " + tok + " is out of range");
         row[i / 8] ^= (uint8_t)(1u << (i % 8));

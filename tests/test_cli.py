@@ -127,3 +127,42 @@ def test_shot_file_formats_round_trip(tmp_path):
     assert np.array_equal(np.fromfile(tmp_path / "back_ptb64.b8", dtype=np.uint8).reshape(192, 15), dets[:192])
     r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / "a.b8", "--out", tmp_path / "x", "--out-format", "nope")
     assert r.returncode != 0 and "unsupported" in r.stderr
+
+
+def test_malformed_shot_files_are_refused(tmp_path):
+    """Every reader fails with a message naming the file (never a crash, never a silently shortened batch); the same
+    cases run clean under ASan + UBSan (scripts/host_sanitizers.sh builds the instrumented library)."""
+    dem = W.load_dem("surface_d5_r5_p0.002_X")
+    (tmp_path / "m.dem").write_text(dem)
+    rng = np.random.default_rng(0)
+    cases = {
+        "b8 truncated": ("b8", bytes(15 * 3 - 7), "multiple of the b8 shot size"),
+        "01 short line": ("01", b"0101\n", "does not have 120 bits"),
+        "01 long line": ("01", b"1" * 300 + b"\n", "does not have 120 bits"),
+        "01 bad character": ("01", b"01x1" * 30 + b"\n", "unexpected character"),
+        "hits out of range": ("hits", b"1,5,100000\n", "out of range"),
+        "hits negative": ("hits", b"-3,4\n", "not a bit index"),
+        "hits trailing junk": ("hits", b"12abc\n", "not a bit index"),
+        "hits overflow": ("hits", b"99999999999999999999999\n", "not a bit index"),
+        "dets out of range": ("dets", b"shot D5 D99999\n", "out of range"),
+        "dets bad token": ("dets", b"shot Dx\n", "not a bit index"),
+        "dets no shot": ("dets", b"D1 D2\n", "must start with 'shot'"),
+        "r8 truncated": ("r8", bytes([255, 255, 255]), "ends inside a shot"),
+        "r8 overrun": ("r8", bytes([200, 200, 200, 200]), "passes the end of a shot"),
+        "r8 random": ("r8", rng.integers(0, 256, 1000, dtype=np.uint8).tobytes(), "r8"),
+        "ptb64 truncated": ("ptb64", b"\x01" * 100, "multiple of the ptb64 group size"),
+    }
+    for name, (fmt, data, message) in cases.items():
+        (tmp_path / "x.in").write_bytes(data)
+        r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / "x.in", "--in-format", fmt, "--out", tmp_path / "x.out",
+                "--out-format", "b8")
+        assert r.returncode == 1 and message in r.stderr and "x.in" in r.stderr, (name, r.returncode, r.stderr)
+    # lenient where stim is: blanks around hit indices, an empty file is zero shots
+    (tmp_path / "x.in").write_bytes(b" 3, 4 \n")
+    r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / "x.in", "--in-format", "hits", "--out", tmp_path / "x.out",
+            "--out-format", "hits")
+    assert r.returncode == 0 and (tmp_path / "x.out").read_text() == "3,4\n"
+    (tmp_path / "x.in").write_bytes(b"")
+    r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / "x.in", "--in-format", "01", "--out", tmp_path / "x.out",
+            "--out-format", "b8")
+    assert r.returncode == 0 and (tmp_path / "x.out").read_bytes() == b""
