@@ -1177,10 +1177,21 @@ int tsr_device(const tsr_decoder* h) {
   return h->host_only ? -1 : h->device;
 }
 
+// The helpers below size their work by the DEM's detector count (1 + the largest id mentioned): a stray D99999999999 must
+// be an error message, not a terabyte allocation.  The decoder itself takes at most 65 534 detectors (ingest.cc).
+static void check_detector_count(const DemModel& dem) {
+  constexpr uint64_t kMax = uint64_t{1} << 24;
+  const uint64_t D = dem.count_detectors();
+  if (D > kMax)
+    throw std::invalid_argument("the detector error model mentions detector " + std::to_string(D - 1) + "; at most " +
+                                std::to_string(kMax) + " detectors are supported here");
+}
+
 int tsr_build_det_orders(const char* dem_text, uint64_t num_det_orders, int method, uint64_t seed, uint64_t* out) {
   return guarded([&] {
     if (method < 0 || method > 2) throw std::invalid_argument("Unknown det order method");
     DemModel dem = DemModel::parse(dem_text);
+    check_detector_count(dem);
     auto orders = tsr::build_det_orders(dem, num_det_orders, (tsr::DetOrder)method, seed);
     const uint64_t D = dem.count_detectors();
     for (size_t k = 0; k < orders.size(); ++k) std::copy(orders[k].begin(), orders[k].end(), out + k * D);
@@ -1278,7 +1289,9 @@ int64_t tsr_get_errors_from_dem(const char* dem_text, double* cost, uint64_t* de
 int64_t tsr_build_detector_graph(const char* dem_text, uint64_t* offsets, uint64_t* neighbors) {
   int64_t n = 0;
   const int rc = guarded([&] {
-    const auto graph = tsr::build_detector_graph(DemModel::parse(dem_text));
+    const DemModel dem = DemModel::parse(dem_text);
+    check_detector_count(dem);
+    const auto graph = tsr::build_detector_graph(dem);
     uint64_t at = 0;
     for (size_t d = 0; d < graph.size(); ++d) {
       if (offsets) offsets[d] = at;
@@ -1319,6 +1332,7 @@ int tsr_circuit_to_dem(const char* circuit_text, char** dem_text_out) {
 int tsr_sample_dem_b8(const char* dem_text, uint64_t seed, uint64_t shots, uint8_t* dets_out, uint8_t* obs_out) {
   return guarded([&] {
     DemModel dem = DemModel::parse(dem_text);
+    check_detector_count(dem);
     const uint64_t ds = (dem.count_detectors() + 7) / 8, os = (dem.count_observables() + 7) / 8;
     std::memset(dets_out, 0, (size_t)(shots * ds));
     if (obs_out) std::memset(obs_out, 0, (size_t)(shots * os));

@@ -39,6 +39,10 @@ struct Parser {
   std::string_view s;
   size_t p = 0;
   std::vector<Op>* out;
+  uint64_t work = 0;
+  static constexpr uint64_t kMaxInt = (uint64_t{1} << 62) - 1;
+  static constexpr uint64_t kMaxWork = uint64_t{1} << 28, kMaxOps = uint64_t{1} << 24;
+  static constexpr uint64_t kMaxQubit = (uint64_t{1} << 24) - 1;  // per-qubit frames are allocated up to the largest index
 
   [[noreturn]] void fail(const std::string& why) const {
     size_t line = 1 + (size_t)std::count(s.begin(), s.begin() + (std::ptrdiff_t)std::min(p, s.size()), '\n');
@@ -50,8 +54,17 @@ struct Parser {
   uint64_t uint() {
     if (p >= s.size() || !std::isdigit((unsigned char)s[p])) fail("expected an unsigned integer");
     uint64_t v = 0;
-    while (p < s.size() && std::isdigit((unsigned char)s[p])) v = v * 10 + (uint64_t)(s[p++] - '0');
+    while (p < s.size() && std::isdigit((unsigned char)s[p])) {
+      const uint64_t digit = (uint64_t)(s[p++] - '0');
+      if (v > (kMaxInt - digit) / 10) fail("integer is too large");
+      v = v * 10 + digit;
+    }
     return v;
+  }
+  // Flattening is bounded: REPEAT 1000000000 { ... } must be an error message, not an out-of-memory kill.
+  void spend() {
+    if (++work > kMaxWork) fail("more than " + std::to_string(kMaxWork) + " REPEAT iterations");
+    if (out->size() >= kMaxOps) fail("the flattened circuit would exceed " + std::to_string(kMaxOps) + " instructions");
   }
   size_t skip_body(size_t from) const {
     int depth = 1;
@@ -89,6 +102,23 @@ struct Parser {
       op();
     }
   }
+  // Which target forms an instruction may carry (anything else would index frames that do not exist).
+  void check_targets(const Op& o) const {
+    const bool annotation = o.name == "DETECTOR" || o.name == "OBSERVABLE_INCLUDE";
+    for (size_t i = 0; i < o.targets.size(); ++i) {
+      const Target& t = o.targets[i];
+      if (t.is_rec && !annotation) fail(o.name + " with a measurement-record target (classical control) is not supported");
+      if (o.name == "MPP") {
+        if (!t.pauli) fail("MPP targets must be Pauli products such as X1*Z2");
+        if (t.combine && i == 0) fail("MPP product starts with '*'");
+      } else if (t.pauli || t.combine) {
+        fail(o.name + " with Pauli targets is not supported by this analyzer");
+      }
+    }
+    if (o.name == "OBSERVABLE_INCLUDE" && !o.args.empty() &&
+        !(o.args[0] >= 0 && o.args[0] < (double)(1 << 24) && o.args[0] == std::floor(o.args[0])))
+      fail("OBSERVABLE_INCLUDE index must be an integer below 16777216");
+  }
   void op() {
     size_t b = p;
     while (p < s.size() && (std::isalnum((unsigned char)s[p]) || s[p] == '_')) ++p;
@@ -123,12 +153,18 @@ struct Parser {
       if (p >= s.size() || s[p] != '{') fail("REPEAT needs '{'");
       size_t body = p + 1, after = skip_body(body);
       for (uint64_t r = 0; r < reps; ++r) {
+        spend();
         p = body;
         block(true);
       }
       p = after;
       return;
     }
+    auto qubit = [&]() {
+      const uint64_t q = uint();
+      if (q > kMaxQubit) fail("qubit index " + std::to_string(q) + " is too large");
+      return (uint32_t)q;
+    };
     while (true) {
       blanks();
       if (p >= s.size() || s[p] == '\n' || s[p] == '#' || s[p] == '}') break;
@@ -137,6 +173,7 @@ struct Parser {
         ++p;
         t.combine = true;
         blanks();
+        if (p >= s.size()) fail("'*' needs a target after it");
       }
       char c = s[p];
       if (c == 'r' || c == 'R') {
@@ -151,15 +188,17 @@ struct Parser {
       } else if (c == 'X' || c == 'Y' || c == 'Z' || c == 'x' || c == 'y' || c == 'z') {
         t.pauli = (char)std::toupper((unsigned char)c);
         ++p;
-        t.qubit = (uint32_t)uint();
+        t.qubit = qubit();
       } else if (c == '!') {
         ++p;  // inverted result: irrelevant for error propagation
         continue;
       } else {
-        t.qubit = (uint32_t)uint();
+        t.qubit = qubit();
       }
       o.targets.push_back(t);
     }
+    check_targets(o);
+    spend();
     out->push_back(std::move(o));
   }
 };

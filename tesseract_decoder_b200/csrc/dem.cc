@@ -50,6 +50,10 @@ struct Reader {
   uint64_t det_shift = 0;
   std::vector<double> coord_shift;
   DemModel* out;
+  uint64_t work = 0;
+  static constexpr uint64_t kMaxId = (uint64_t{1} << 62) - 1;  // ids and counts stay clear of the observable bit and the separator
+  static constexpr uint64_t kMaxWork = uint64_t{1} << 28;
+  static constexpr uint64_t kMaxInstructions = uint64_t{1} << 24;  // 245 x the largest model of the test set (BB [[144,12,12]] r=12)
 
   [[noreturn]] void fail(const std::string& why) const {
     size_t line = 1 + (size_t)std::count(s.begin(), s.begin() + (std::ptrdiff_t)std::min(p, s.size()), '\n');
@@ -61,8 +65,18 @@ struct Reader {
   uint64_t uint() {
     if (p >= s.size() || !std::isdigit((unsigned char)s[p])) fail("expected an unsigned integer");
     uint64_t v = 0;
-    while (p < s.size() && std::isdigit((unsigned char)s[p])) v = v * 10 + (uint64_t)(s[p++] - '0');
+    while (p < s.size() && std::isdigit((unsigned char)s[p])) {
+      const uint64_t digit = (uint64_t)(s[p++] - '0');
+      if (v > (kMaxId - digit) / 10) fail("integer is too large");
+      v = v * 10 + digit;
+    }
     return v;
+  }
+  // Flattening is bounded: a `repeat 1000000000 { ... }` must be an error message, not an out-of-memory kill.
+  void spend() {
+    if (++work > kMaxWork) fail("more than " + std::to_string(kMaxWork) + " repeat iterations");
+    if (out->instructions.size() >= kMaxInstructions)
+      fail("the flattened model would exceed " + std::to_string(kMaxInstructions) + " instructions");
   }
   // Skips a balanced `{ ... }` body starting just after the '{'; returns offset just after '}'.
   size_t skip_body(size_t from) const {
@@ -147,6 +161,7 @@ struct Reader {
       size_t body = p + 1;
       size_t after = skip_body(body);
       for (uint64_t r = 0; r < reps; ++r) {
+        spend();
         p = body;
         block(true);
       }
@@ -161,6 +176,7 @@ struct Reader {
         if (coord_shift.size() <= k) coord_shift.push_back(0);
         coord_shift[k] += args[k];
       }
+      if (n > kMaxId - det_shift) fail("detector shift is too large");
       det_shift += n;
       rest_of_line_must_be_empty();
       return;
@@ -189,7 +205,9 @@ struct Reader {
         inst.targets.push_back(DemTarget::sep());
       } else if (t == 'D' || t == 'd') {
         ++p;
-        inst.targets.push_back(DemTarget::det(uint() + det_shift));
+        const uint64_t id = uint();
+        if (id > kMaxId - det_shift) fail("detector id is too large");
+        inst.targets.push_back(DemTarget::det(id + det_shift));
       } else if (t == 'L' || t == 'l') {
         ++p;
         inst.targets.push_back(DemTarget::obs(uint()));
@@ -197,6 +215,7 @@ struct Reader {
         fail(std::string("unexpected target character '") + t + "'");
       }
     }
+    spend();
     out->instructions.push_back(std::move(inst));
   }
 

@@ -368,3 +368,42 @@ def test_remaining_reference_known_answers_without_a_device():
     dec = capi.Decoder(dem, merge_errors=False, sparsify_errors=True, sparsify_base_degree=2**31 - 1,
                        sparsify_reactivate_limit=-1, host_only=True)
     assert dec.sparsify_reactivate_limit == 1
+
+
+def test_hostile_dem_text_is_refused_quickly():
+    """Untrusted DEM text must end in an error message, never in a terabyte allocation or an endless flatten."""
+    for text, message in (("error(0.1) D99999999999999999999999", "integer is too large"),
+                          ("repeat 99999999999999 {\n}", "repeat iterations"),
+                          ("shift_detectors 4611686018427387903\nshift_detectors 5\nerror(0.1) D0", "too large"),
+                          ("repeat 3 {\n error(0.1) D0\n", "unterminated repeat block")):
+        with pytest.raises(ValueError, match=message):
+            capi.dem_count_detectors(text)
+    big = "error(0.1) D99999999999 D1"  # a legal model, but no helper sizes its work by 10^11 detectors
+    assert capi.dem_count_detectors(big) == 10**11
+    for fn in (capi.build_detector_graph, lambda t: capi.sample_dem_b8(t, 1, 1)):
+        with pytest.raises((ValueError, MemoryError), match="detectors are supported|Unable to allocate"):
+            fn(big)
+    with pytest.raises(ValueError, match="at most 65534 detectors"):
+        capi.Decoder(big, host_only=True)
+
+
+def test_hostile_circuit_text_is_refused():
+    """The circuit analyzer (csrc/circuit.cc, the stand-in for stim's error analysis behind --circuit) indexes per-qubit
+    frames and the measurement record by what the text says; everything it cannot index is an error message.  Found by
+    fuzzing the ASan + UBSan build (an `H rec[-1]` used to read outside the frame arrays)."""
+    for text, message in (("H rec[-1]", "measurement-record target"),
+                          ("CX rec[-1] 1", "measurement-record target"),
+                          ("M 0\nH 4294967295", "too large"),
+                          ("R 99999999999999999999999", "integer is too large"),
+                          ("MPP *X1", "starts with"),
+                          ("MPP 1", "Pauli products"),
+                          ("H X1", "Pauli targets"),
+                          ("M 0\nOBSERVABLE_INCLUDE(99999999999) rec[-1]", "OBSERVABLE_INCLUDE index"),
+                          ("M 0\nOBSERVABLE_INCLUDE(1.5) rec[-1]", "OBSERVABLE_INCLUDE index"),
+                          ("M 0\nDETECTOR rec[-2]", "before the first measurement"),
+                          ("REPEAT 999999999999 {\n}", "REPEAT iterations"),
+                          ("REPEAT 2 {\nM 0\n", "unterminated REPEAT block"),
+                          ("SWAP 0 1", "not supported")):
+        with pytest.raises(ValueError, match=message):
+            capi.circuit_to_dem(text)
+    assert capi.circuit_to_dem("R 0\nX_ERROR(0.125) 0\nM 0\nDETECTOR(1, 2) rec[-1]") == "error(0.125) D0\ndetector(1,2) D0\n"
