@@ -260,6 +260,8 @@ int main(int argc, char** argv) {
       {"--in_includes_appended_observables", &a.in_includes_appended_observables}};
   TesseractConfig config_sparsify;  // carries the --sparsify-* flags
   bool has_base = false, has_max = false, has_limit = false;
+  int det_order_flags = 0;
+  bool threads_given = false;
   try {
     for (int i = 1; i < argc; ++i) {
       const std::string k = argv[i];
@@ -267,34 +269,75 @@ int main(int argc, char** argv) {
         if (i + 1 >= argc) usage(k + " needs a value");
         return argv[++i];
       };
+      // numbers: the whole token must parse, and the message names the flag (std::stoull alone says "stoull")
+      auto u64 = [&]() -> uint64_t {
+        const std::string v = need();
+        if (v.empty() || v.size() > 20 || v.find_first_not_of("0123456789") != std::string::npos)
+          throw std::invalid_argument(k + ": '" + v + "' is not an unsigned integer");
+        try {
+          return std::stoull(v);
+        } catch (const std::exception&) {
+          throw std::invalid_argument(k + ": '" + v + "' is out of range");
+        }
+      };
+      auto i32 = [&]() -> int {
+        const std::string v = need();
+        size_t used = 0;
+        try {
+          const int r = std::stoi(v, &used);
+          if (used == v.size()) return r;
+        } catch (const std::exception&) {
+        }
+        throw std::invalid_argument(k + ": '" + v + "' is not an integer");
+      };
+      auto f64 = [&]() -> double {
+        const std::string v = need();
+        size_t used = 0;
+        try {
+          const double r = std::stod(v, &used);
+          if (used == v.size()) return r;
+        } catch (const std::exception&) {
+        }
+        throw std::invalid_argument(k + ": '" + v + "' is not a number");
+      };
       if (str_opts.count(k)) *str_opts[k] = need();
       else if (flag_opts.count(k)) *flag_opts[k] = true;
-      else if (k == "--num-det-orders") a.num_det_orders = std::stoull(need());
-      else if (k == "--det-order-bfs") a.det_order_method = 0;
-      else if (k == "--det-order-index") a.det_order_method = 1;
-      else if (k == "--det-order-coordinate") a.det_order_method = 2;
-      else if (k == "--det-order-seed") a.det_order_seed = std::stoull(need());
-      else if (k == "--sample-num-shots") a.sample_num_shots = std::stoull(need());
-      else if (k == "--sample-seed") a.sample_seed = std::stoull(need());
-      else if (k == "--max-errors") a.max_errors = std::stoull(need());
-      else if (k == "--shot-range-begin") a.shot_range_begin = std::stoull(need());
-      else if (k == "--shot-range-end") a.shot_range_end = std::stoull(need());
-      else if (k == "--beam") a.det_beam = std::stoi(need());
-      else if (k == "--det-penalty") a.det_penalty = std::stod(need());
-      else if (k == "--pqlimit") a.pqlimit = std::stoull(need());
-      else if (k == "--threads") a.num_threads = std::stoi(need());
-      else if (k == "--gpus") a.gpus = std::stoi(need());
-      else if (k == "--batch") a.batch = std::stoull(need());
+      else if (k == "--num-det-orders") a.num_det_orders = u64();
+      else if (k == "--det-order-bfs") a.det_order_method = 0, ++det_order_flags;
+      else if (k == "--det-order-index") a.det_order_method = 1, ++det_order_flags;
+      else if (k == "--det-order-coordinate") a.det_order_method = 2, ++det_order_flags;
+      else if (k == "--det-order-seed") a.det_order_seed = u64();
+      else if (k == "--sample-num-shots") a.sample_num_shots = u64();
+      else if (k == "--sample-seed") a.sample_seed = u64();
+      else if (k == "--max-errors") a.max_errors = u64();
+      else if (k == "--shot-range-begin") a.shot_range_begin = u64();
+      else if (k == "--shot-range-end") a.shot_range_end = u64();
+      else if (k == "--beam") a.det_beam = i32();
+      else if (k == "--det-penalty") a.det_penalty = f64();
+      else if (k == "--pqlimit") a.pqlimit = u64();
+      else if (k == "--threads") a.num_threads = i32(), threads_given = true;
+      else if (k == "--gpus") a.gpus = i32();
+      else if (k == "--batch") a.batch = u64();
       else if (k == "--sparsify-errors") config_sparsify.sparsify_errors = true;
-      else if (k == "--sparsify-base-degree") config_sparsify.sparsify_base_degree = std::stoi(need()), has_base = true;
-      else if (k == "--sparsify-max-degree") config_sparsify.sparsify_max_degree = std::stoi(need()), has_max = true;
-      else if (k == "--sparsify-reactivate-limit") config_sparsify.sparsify_reactivate_limit = std::stoi(need()), has_limit = true;
+      else if (k == "--sparsify-base-degree") config_sparsify.sparsify_base_degree = i32(), has_base = true;
+      else if (k == "--sparsify-max-degree") config_sparsify.sparsify_max_degree = i32(), has_max = true;
+      else if (k == "--sparsify-reactivate-limit") config_sparsify.sparsify_reactivate_limit = i32(), has_limit = true;
       else if (k == "-h" || k == "--help") usage("tesseract (B200): A* most-likely-error decoder");
       else usage("unknown argument " + k);
     }
     // Args::validate (tesseract_main.cc:98-180)
     if (a.circuit_path.empty() == a.dem_path.empty()) usage("Must provide exactly one of --circuit or --dem");
     if ((a.sample_num_shots != 0) == !a.in_fname.empty()) usage("Must provide exactly one of --sample-num-shots or --in");
+    if (det_order_flags > 1)
+      throw std::invalid_argument("Only one of --det-order-bfs, --det-order-index, or --det-order-coordinate may be set.");
+    for (const std::string* f : {&a.in_format, &a.obs_in_format, &a.out_format})
+      if (*f != "01" && *f != "b8" && *f != "r8" && *f != "hits" && *f != "dets" && *f != "ptb64")
+        throw std::invalid_argument("Invalid format: " + *f);
+    if (!a.obs_in_fname.empty() && a.in_fname.empty())
+      throw std::invalid_argument("Cannot load observable flips without a corresponding detection event data file.");
+    if (threads_given && a.num_threads < 1) throw std::invalid_argument("--threads must be at least 1.");  // accepted and ignored otherwise
+    if ((a.shot_range_begin || a.shot_range_end) && a.shot_range_end < a.shot_range_begin)
+      throw std::invalid_argument("Provided shot range must have end >= begin.");
     if (a.beam_climbing && a.det_beam == INF_DET_BEAM) usage("Beam climbing requires a finite beam");
     if (a.gpus < 1) usage("--gpus must be >= 1");
     if (!config_sparsify.sparsify_errors) {  // tesseract_main.cc:155-179

@@ -42,6 +42,17 @@ def test_argument_validation():
     assert r.returncode != 0 and "Must specify --sparsify-base-degree when --sparsify-errors is enabled." in r.stderr
     r = run("--dem", dem, "--sample-num-shots", 5, "--sparsify-errors", "--sparsify-base-degree", 3, "--sparsify-max-degree", 2)
     assert r.returncode != 0 and "--sparsify-max-degree must be >= --sparsify-base-degree." in r.stderr
+    # the rest of Args::validate (tesseract_main.cc:103-147), all before any device is touched
+    for args, message in ((("--det-order-bfs", "--det-order-index"), "Only one of --det-order-bfs, --det-order-index, or --det-order-coordinate may be set."),
+                          (("--out-format", "foo"), "Invalid format: foo"),
+                          (("--obs_in", "x.b8"), "Cannot load observable flips without a corresponding detection event data file."),
+                          (("--threads", 0), "--threads must be at least 1."),
+                          (("--shot-range-begin", 9, "--shot-range-end", 3), "Provided shot range must have end >= begin."),
+                          (("--beam", "abc"), "--beam: 'abc' is not an integer"),
+                          (("--pqlimit", -5), "--pqlimit: '-5' is not an unsigned integer"),
+                          (("--det-penalty", "1.0x"), "--det-penalty: '1.0x' is not a number")):
+        r = run("--dem", dem, "--sample-num-shots", 5, *args)
+        assert r.returncode != 0 and message in r.stderr, (args, r.stderr)
 
 
 @pytest.mark.gpu
@@ -126,7 +137,7 @@ def test_shot_file_formats_round_trip(tmp_path):
     assert r.returncode == 0, r.stderr
     assert np.array_equal(np.fromfile(tmp_path / "back_ptb64.b8", dtype=np.uint8).reshape(192, 15), dets[:192])
     r = run("--convert-only", "--dem", tmp_path / "m.dem", "--in", tmp_path / "a.b8", "--out", tmp_path / "x", "--out-format", "nope")
-    assert r.returncode != 0 and "unsupported" in r.stderr
+    assert r.returncode != 0 and "Invalid format: nope" in r.stderr  # tesseract_main.cc:119-127
 
 
 def test_malformed_shot_files_are_refused(tmp_path):
