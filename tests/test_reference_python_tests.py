@@ -26,7 +26,9 @@ DEVICE_FREE = {
     "tesseract_test.py": ["test_create_tesseract_config", "test_create_tesseract_config_with_dem",
                           "test_create_tesseract_config_with_dem_and_custom_args", "test_create_tesseract_config_no_dem",
                           "test_create_tesseract_config_no_dem_with_custom_args", "test_create_tesseract_config_sparsify_defaults",
-                          "test_create_tesseract_config_sparsify_custom", "test_suggest_sparsify_reactivate_limit"],
+                          "test_create_tesseract_config_sparsify_custom", "test_suggest_sparsify_reactivate_limit",
+                          # rejected by the constructor's validation, which runs before a device is asked for
+                          "test_sparsify_negative_sentinels_rejected", "test_decoder_compilation_validation"],
     "tesseract_sinter_compat_test.py": ["test_tesseract_sinter_obj_exists", "test_tesseract_sinter_decoder_sparsify_attributes",
                                         "test_tesseract_sinter_decoder_old_positional_constructor_order",
                                         "test_make_tesseract_sinter_decoders_dict_contains_sparsify"],
@@ -70,7 +72,16 @@ def reference_modules():
 
 @pytest.mark.parametrize("fname,test", [(f, t) for f, tests in DEVICE_FREE.items() for t in tests])
 def test_reference_test_passes_unmodified(reference_modules, fname, test):
-    getattr(reference_modules[fname], test)()
+    fn = getattr(reference_modules[fname], test)
+    marks = [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]
+    if not marks:
+        fn()
+        return
+    assert len(marks) == 1
+    names = [n.strip() for n in marks[0].args[0].split(",")]
+    for values in marks[0].args[1]:  # every parameter set of @pytest.mark.parametrize, as pytest would call it
+        values = values if isinstance(values, (tuple, list)) and len(names) > 1 else (values,)
+        fn(**dict(zip(names, values)))
 
 
 def test_every_device_free_reference_test_is_listed(reference_modules):
@@ -86,10 +97,10 @@ def test_every_device_free_reference_test_is_listed(reference_modules):
                               "test_tesseract_decode_batch", "test_tesseract_decode_batch_with_complex_model",
                               "test_tesseract_merge_errors_affects_cost", "test_simlpex_decode_with_mismatched_syndrome_size",
                               "test_test_simplex_decode_batch_with_mismatched_syndrome_size",
-                              "test_sparsify_negative_sentinels_rejected", "test_compile_decoder_resolves_auto_sparsify_reactivate_limit",
+                              "test_compile_decoder_resolves_auto_sparsify_reactivate_limit",
                               "test_compile_decoder_caps_auto_sparsify_reactivate_limit_at_error_count",
                               "test_compile_decoder_preserves_explicit_sparsify_reactivate_limit",
-                              "test_python_sparsify_changes_predicted_error_set", "test_decoder_compilation_validation"},
+                              "test_python_sparsify_changes_predicted_error_set"},
         "tesseract_sinter_compat_test.py": {"test_compile_decoder_for_dem", "test_decode_shots_bit_packed", "test_decode_shots_bit_packed_multi_shot",
                                             "test_decode_via_files_sanity_check", "test_decode_via_files", "test_decode_via_files_multi_shot",
                                             "test_sinter_decode_repetition_code", "test_sinter_decode_surface_code", "test_sinter_empty",
